@@ -1,0 +1,176 @@
+/*
+ * pyrope_gpu.h — C ABI of libpyrope_gpu.so: B200 (sm_100a) implementation of Pyrope's vector-scan
+ * hot path (FLAT exact scan, IVF_FLAT coarse-assign + inverted-list scan, IVF_PQ ADC scan, each with
+ * top-k), behind the reference's IVectorIndex surface.
+ *
+ * The reference (takurot/Pyrope) is 100 % managed C# and has NO FFI today; the seam this ABI plugs
+ * into is the interface src/Pyrope.GarnetServer/Vector/IVectorIndex.cs:14-29 (+ ICentroidsProvider.cs:9-15),
+ * constructed in exactly one place, Services/VectorIndexRegistry.cs:81-113.  A C# class
+ * Gpu*VectorIndex : IVectorIndex P/Invokes the functions below (stub in INTEGRATION.md).
+ *
+ * Conventions
+ *  - every function returns a pyrope_status (0 ok, <0 error); pyrope_last_error() returns a
+ *    thread-local message.  The library never aborts/exits (VectorCommandSet.cs:547-554 turns any
+ *    exception into "-ERR <message>"; the shim maps codes to the .NET exception types named below).
+ *  - host pointers unless the function name ends in _device.  Inputs are only read during the call
+ *    (the library copies, as BruteForceVectorIndex.Add does, BruteForceVectorIndex.cs:147-148).
+ *  - string ids stay host-side in the shim (List<string>/Dictionary<string,long> exactly like
+ *    BruteForceVectorIndex.cs:14-15); the library deals in dense int64 ROW ordinals that it assigns
+ *    at add time (0,1,2,... per index), plus an optional caller-chosen int64 LABEL per row that
+ *    search returns instead of the ordinal (used for global row numbers when sharded across GPUs).
+ *  - scores are "higher is better" for every metric: L2 -> -||q-x||^2, InnerProduct -> q.x,
+ *    Cosine -> q.x/(|q||x|) (0 if either norm < 1e-6), as in the reference.
+ *  - one process drives one GPU (torch.distributed / NCCL provides the cross-GPU exchange in the
+ *    harness); search is thread-safe for concurrent callers on one handle, mutation must be
+ *    serialised by the caller (the shim's ReaderWriterLockSlim already does).
+ */
+#ifndef PYROPE_GPU_H
+#define PYROPE_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pyrope_index pyrope_index; /* opaque */
+
+typedef enum pyrope_status {
+    PYROPE_OK = 0,
+    PYROPE_ERR_INVALID_ARG = -1,   /* -> ArgumentException / ArgumentNullException            */
+    PYROPE_ERR_DIMENSION = -2,     /* -> ArgumentException("Vector dimension mismatch") => VEC_ERR_DIM */
+    PYROPE_ERR_OUT_OF_RANGE = -3,  /* -> ArgumentOutOfRangeException (topK <= 0, dim <= 0)     */
+    PYROPE_ERR_INVALID_STATE = -4, /* -> InvalidOperationException (e.g. "PQ not trained")     */
+    PYROPE_ERR_NOT_FOUND = -5,     /* row does not exist / already deleted                    */
+    PYROPE_ERR_CUDA = -6,          /* CUDA runtime failure; message carries cudaGetErrorString */
+    PYROPE_ERR_OOM = -7,           /* device or host allocation failed                         */
+    PYROPE_ERR_UNSUPPORTED = -8    /* shape outside what the kernels cover (documented limits) */
+} pyrope_status;
+
+/* VectorIndexRegistry.cs:87-108 picks the tail by Algorithm string; these are the GPU kinds. */
+typedef enum pyrope_kind { PYROPE_FLAT = 0, PYROPE_IVF_FLAT = 1, PYROPE_IVF_PQ = 2 } pyrope_kind;
+/* IVectorIndex.cs:5-10 VectorMetric (same numeric values) */
+typedef enum pyrope_metric { PYROPE_L2 = 0, PYROPE_INNER_PRODUCT = 1, PYROPE_COSINE = 2 } pyrope_metric;
+
+/* ---- process / device ------------------------------------------------------------------- */
+/* Select the CUDA device this process drives and warm the context.  device < 0 keeps the current. */
+int pyrope_gpu_init(int device);
+int pyrope_gpu_shutdown(void);
+int pyrope_gpu_device_count(int *out);
+const char *pyrope_last_error(void);
+int pyrope_version(void);
+
+/* ---- lifecycle: replaces the index constructors (BruteForceVectorIndex.cs:42-51,
+ *      IvfFlatVectorIndex.cs:27-33 nList=100, IvfPqVectorIndex.cs:27-35; registry defaults
+ *      m=4,k=256,nlist=100 at VectorIndexRegistry.cs:96-106).  nlist/pq_m/pq_k ignored for FLAT. */
+int pyrope_index_create(int kind, int dim, int metric, int nlist, int pq_m, int pq_k,
+                        pyrope_index **out);
+int pyrope_index_destroy(pyrope_index *h);
+/* Pre-size device storage for n_rows raw vectors (optional; avoids regrowth copies). */
+int pyrope_index_reserve(pyrope_index *h, int64_t n_rows);
+
+/* ---- writes: replace IVectorIndex.Add / Upsert / Delete ----------------------------------- */
+/* Append n vectors (X is n x dim row-major).  labels may be NULL (label = row ordinal).
+ * FLAT: rows join the scan order at the end (BruteForceVectorIndex.cs:162-184 InternalAdd).
+ * IVF_*: rows join the pre-build buffer (IvfFlatVectorIndex.cs:39-55, IvfPqVectorIndex.cs:36-45),
+ *        re-using freed buffer slots LIFO like Dictionary<,> does so enumeration order matches.
+ * first_row_out receives the ordinal of the first appended row (ordinals are consecutive). */
+int pyrope_index_add_batch(pyrope_index *h, int64_t n, const float *X, const int64_t *labels,
+                           int64_t *first_row_out);
+int pyrope_index_add_batch_device(pyrope_index *h, int64_t n, const float *dX,
+                                  const int64_t *d_labels, int64_t *first_row_out);
+/* Overwrite a live (or, for FLAT, tombstoned: Upsert un-deletes, BruteForceVectorIndex.cs:200-203)
+ * row in place: Upsert of an existing id keeps its scan position.  IVF rows must be in the buffer. */
+int pyrope_index_update_row(pyrope_index *h, int64_t row, const float *x);
+/* Tombstone a row (BruteForceVectorIndex.cs:231-254; IvfFlatVectorIndex.cs:62-83).
+ * IVF_PQ mirrors the reference: only buffer rows can be deleted (IvfPqVectorIndex.cs:48-53);
+ * a row already encoded into a list returns PYROPE_ERR_NOT_FOUND. */
+int pyrope_index_delete_row(pyrope_index *h, int64_t row);
+/* Hide (1) / unhide (0) a list row that a newer buffer row with the same id shadows
+ * (the seenIds skip at IvfFlatVectorIndex.cs:210, IvfPqVectorIndex.cs:170). */
+int pyrope_index_shadow_row(pyrope_index *h, int64_t row, int shadowed);
+
+/* ---- build: replaces IVectorIndex.Build (IvfFlatVectorIndex.cs:85-145, IvfPqVectorIndex.cs:55-116;
+ *      FLAT is a no-op, BruteForceVectorIndex.cs:56).  Training follows KMeansUtils.Train
+ *      (KMeansUtils.cs:10-68: System.Random init seed 42 / 123 / 42+m, <=10 Lloyd iterations,
+ *      fp32 means in data order) and ProductQuantizer.Train/Encode (ProductQuantizer.cs:28-80)
+ *      bit-exactly on device unless codebooks were frozen with pyrope_index_set_codebooks. */
+int pyrope_index_build(pyrope_index *h);
+/* Bound the training set to the first max_train_rows rows (<=0: all, the reference rule) and the
+ * Lloyd iterations (<=0: 10, the reference default).  Opt-in deviation for very large builds. */
+int pyrope_index_set_train_params(pyrope_index *h, int64_t max_train_rows, int max_iter);
+/* Freeze codebooks as given inputs: centroids [n_centroids][dim]; pq_codebooks [m][k][dim/m]
+ * (NULL for IVF_FLAT).  The next pyrope_index_build only assigns (+ encodes). */
+int pyrope_index_set_codebooks(pyrope_index *h, int n_centroids, const float *centroids,
+                               const float *pq_codebooks);
+int pyrope_index_is_built(pyrope_index *h, int *out);
+/* ICentroidsProvider.GetCentroids (IvfFlatVectorIndex.cs:314-325): n_out = 0 until built.
+ * centroids_out may be NULL to query the count. */
+int pyrope_index_get_centroids(pyrope_index *h, float *centroids_out, int *n_out);
+/* pq codebooks [m][k][dim/m] (zero padded) and trained codewords per subspace ksub[m]. */
+int pyrope_index_get_codebooks(pyrope_index *h, float *codebooks_out, int32_t *ksub_out);
+/* Inverted-list layout for parity checks: offsets [n_centroids+1]; rows (ordinals) and, for IVF_PQ,
+ * codes [total][m], both list-major in list order.  Any output may be NULL. total_out = entries. */
+int pyrope_index_get_lists(pyrope_index *h, int64_t *offsets_out, int64_t *rows_out,
+                           uint8_t *codes_out, int64_t *total_out);
+
+/* ---- stats: replaces IVectorIndex.GetStats (O(1), host-side, never a device sync;
+ *      BruteForceVectorIndex.cs:119-131, IvfFlatVectorIndex.cs:300-312).  live_rows counts every
+ *      searchable row; the shim reproduces IvfPqVectorIndex.cs:230's hard-coded 0 itself. */
+int pyrope_index_stats(pyrope_index *h, int64_t *live_rows, int64_t *buffer_rows, int *dim,
+                       int *metric);
+
+/* ---- search: replaces IVectorIndex.Search for nq queries at once (VectorCommandSet.cs:458 calls it
+ *      one query at a time; the host micro-batcher funnels concurrent callers into this).
+ *      Q is nq x dim.  max_scans < 0 = SearchOptions.MaxScans null; nprobe < 0 = NProbe null
+ *      (defaults 3 / 1: IvfFlatVectorIndex.cs:14, IvfPqVectorIndex.cs:125).
+ *      Outputs are nq x topk, best first; slots past counts[i] hold score 0 / row -1.
+ *      Errors: topk <= 0 -> OUT_OF_RANGE for FLAT (BruteForceVectorIndex.cs:278), empty result for
+ *      IVF (no validation in the reference); topk > 1024 -> UNSUPPORTED. */
+int pyrope_index_search_batch(pyrope_index *h, int64_t nq, const float *Q, int topk,
+                              int64_t max_scans, int nprobe, float *scores_out, int64_t *rows_out,
+                              int32_t *counts_out);
+/* Same with device-resident queries/outputs, enqueued on `stream` (a cudaStream_t; NULL = the
+ * library's own stream, synchronised before return). */
+int pyrope_index_search_batch_device(pyrope_index *h, int64_t nq, const float *dQ, int topk,
+                                     int64_t max_scans, int nprobe, float *d_scores,
+                                     int64_t *d_rows, int32_t *d_counts, void *stream);
+/* Kernel-only time (ms, CUDA events) of the most recent search on this handle, split by stage:
+ * out[0]=total, [1]=coarse probe, [2]=list/base scan, [3]=merge.  Feeds TraceInfo. */
+int pyrope_index_last_search_ms(pyrope_index *h, float *out4);
+/* Number of kernel launches issued by the most recent search on this handle. */
+int pyrope_index_last_search_launches(pyrope_index *h, int *out);
+
+/* ---- cross-shard merge (the step after ncclAllGather; semantics of DeltaVectorIndex.cs:95-121
+ *      without the id-dedupe, which sharding makes unnecessary): parts x nq x k_in candidate lists
+ *      -> nq x k_out, best first, ties to the lower part index.  rows < 0 mark empty slots. */
+int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float *d_scores,
+                             const int64_t *d_rows, float *d_scores_out, int64_t *d_rows_out,
+                             int32_t *d_counts_out, void *stream);
+
+/* ---- building blocks exposed for parity tests and for "next" rows --------------- */
+/* KMeansUtils.FindNearestCentroid (KMeansUtils.cs:70-93), bit-exact: assign_out[i] = first index
+ * of the best score.  Host pointers. */
+int pyrope_coarse_assign(int metric, int dim, int64_t n, const float *X, int n_centroids,
+                         const float *centroids, int32_t *assign_out);
+/* KMeansUtils.Train (KMeansUtils.cs:10-68) on device, bit-exact w.r.t. the conventions in DESIGN.md.
+ * data is n x dim with leading dimension ld.  Returns centroids (k_out rows) on the host. */
+int pyrope_kmeans_train(int metric, int dim, int64_t n, int64_t ld, const float *data, int k,
+                        int max_iter, int32_t seed, float *centroids_out, int *k_out,
+                        int *iters_out);
+/* ProductQuantizer.Encode (ProductQuantizer.cs:60-80), bit-exact.  codebooks [m][k][dim/m],
+ * ksub [m] (NULL = k everywhere); X n x dim; codes_out n x m. */
+int pyrope_pq_encode(int dim, int m, int k, const float *codebooks, const int32_t *ksub, int64_t n,
+                     const float *X, uint8_t *codes_out);
+/* ProductQuantizer.ComputeDistanceTable (ProductQuantizer.cs:98-120): table_out nq x m x k. */
+int pyrope_pq_distance_table(int dim, int m, int k, const float *codebooks, int64_t nq,
+                             const float *Q, float *table_out);
+/* Fill a device buffer with uniform [0,1) fp32 from a counter-based generator (bench data for
+ * configs too large for the sequential System.Random stream; documented in DESIGN.md). */
+int pyrope_fill_uniform_device(float *d_out, int64_t n, uint64_t seed, uint64_t offset,
+                               void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYROPE_GPU_H */

@@ -1,0 +1,291 @@
+"""ctypes binding of libpyrope_gpu.so (the C ABI in include/pyrope_gpu.h).
+
+There is no CPU fallback: if the CUDA library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpyrope_gpu.so")
+
+FLAT, IVF_FLAT, IVF_PQ = 0, 1, 2
+L2, INNER_PRODUCT, COSINE = 0, 1, 2
+
+OK = 0
+ERR_INVALID_ARG, ERR_DIMENSION, ERR_OUT_OF_RANGE, ERR_INVALID_STATE = -1, -2, -3, -4
+ERR_NOT_FOUND, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = -5, -6, -7, -8
+
+
+class PyropeGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.message = msg
+
+
+f32p = C.POINTER(C.c_float)
+i64p = C.POINTER(C.c_int64)
+i32p = C.POINTER(C.c_int32)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+# name -> (restype, argtypes): exactly the symbols include/pyrope_gpu.h declares
+SIGNATURES = {
+    "pyrope_gpu_init": (C.c_int, [C.c_int]),
+    "pyrope_gpu_shutdown": (C.c_int, []),
+    "pyrope_gpu_device_count": (C.c_int, [i32p]),
+    "pyrope_last_error": (C.c_char_p, []),
+    "pyrope_version": (C.c_int, []),
+    "pyrope_index_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "pyrope_index_destroy": (C.c_int, [vp]),
+    "pyrope_index_reserve": (C.c_int, [vp, C.c_int64]),
+    "pyrope_index_add_batch": (C.c_int, [vp, C.c_int64, vp, vp, i64p]),
+    "pyrope_index_add_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, i64p]),
+    "pyrope_index_update_row": (C.c_int, [vp, C.c_int64, vp]),
+    "pyrope_index_delete_row": (C.c_int, [vp, C.c_int64]),
+    "pyrope_index_shadow_row": (C.c_int, [vp, C.c_int64, C.c_int]),
+    "pyrope_index_build": (C.c_int, [vp]),
+    "pyrope_index_set_train_params": (C.c_int, [vp, C.c_int64, C.c_int]),
+    "pyrope_index_set_codebooks": (C.c_int, [vp, C.c_int, vp, vp]),
+    "pyrope_index_is_built": (C.c_int, [vp, i32p]),
+    "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
+    "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
+    "pyrope_index_get_lists": (C.c_int, [vp, vp, vp, vp, i64p]),
+    "pyrope_index_stats": (C.c_int, [vp, i64p, i64p, i32p, i32p]),
+    "pyrope_index_search_batch": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
+    "pyrope_index_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp]),
+    "pyrope_index_last_search_ms": (C.c_int, [vp, f32p]),
+    "pyrope_index_last_search_launches": (C.c_int, [vp, i32p]),
+    "pyrope_topk_merge_device": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "pyrope_coarse_assign": (C.c_int, [C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]),
+    "pyrope_kmeans_train": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int32, vp, i32p, i32p]),
+    "pyrope_pq_encode": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp, vp]),
+    "pyrope_pq_distance_table": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_int64, vp, vp]),
+    "pyrope_fill_uniform_device": (C.c_int, [vp, C.c_int64, C.c_uint64, C.c_uint64, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library.  Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PyropeGpuError(ERR_INVALID_STATE,
+                             f"{LIB_PATH} is missing: build it with `python -m pyrope_b200.build` "
+                             "(pyrope_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(code: int):
+    if code != OK:
+        msg = load().pyrope_last_error()
+        raise PyropeGpuError(code, msg.decode("utf-8", "replace") if msg else "")
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return a.ctypes.data_as(vp) if a is not None else None
+
+
+class GpuIndex:
+    """Thin, typed view of one pyrope_index handle (dense row ordinals, numpy in/out)."""
+
+    def __init__(self, kind: int, dim: int, metric: int = L2, nlist: int = 100, m: int = 4, k: int = 256,
+                 device: int | None = None):
+        L = load()
+        if device is not None:
+            check(L.pyrope_gpu_init(device))
+        h = vp()
+        check(L.pyrope_index_create(kind, dim, metric, nlist, m, k, C.byref(h)))
+        self._h = h
+        self.kind, self.dim, self.metric, self.nlist, self.m, self.k = kind, dim, metric, nlist, m, k
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().pyrope_index_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- writes
+    def reserve(self, n):
+        check(load().pyrope_index_reserve(self._h, n))
+
+    def add(self, X, labels=None) -> int:
+        X = _np(X, np.float32)
+        if X.ndim == 1:
+            X = X[None, :]
+        if X.shape[1] != self.dim:
+            raise PyropeGpuError(ERR_DIMENSION, "Vector dimension mismatch")
+        lab = _np(labels, np.int64) if labels is not None else None
+        first = C.c_int64(-1)
+        check(load().pyrope_index_add_batch(self._h, X.shape[0], _p(X), _p(lab), C.byref(first)))
+        return first.value
+
+    def add_device(self, ptr: int, n: int, labels_ptr: int | None = None) -> int:
+        first = C.c_int64(-1)
+        check(load().pyrope_index_add_batch_device(self._h, n, vp(ptr), vp(labels_ptr) if labels_ptr else None,
+                                                   C.byref(first)))
+        return first.value
+
+    def update_row(self, row, x):
+        x = _np(x, np.float32).reshape(-1)
+        if x.size != self.dim:
+            raise PyropeGpuError(ERR_DIMENSION, "Vector dimension mismatch")
+        check(load().pyrope_index_update_row(self._h, row, _p(x)))
+
+    def delete_row(self, row) -> bool:
+        rc = load().pyrope_index_delete_row(self._h, row)
+        if rc == ERR_NOT_FOUND:
+            return False
+        check(rc)
+        return True
+
+    def shadow_row(self, row, shadowed=True):
+        check(load().pyrope_index_shadow_row(self._h, row, 1 if shadowed else 0))
+
+    # ---- build
+    def build(self):
+        check(load().pyrope_index_build(self._h))
+
+    def set_train_params(self, max_train_rows=0, max_iter=0):
+        check(load().pyrope_index_set_train_params(self._h, max_train_rows, max_iter))
+
+    def set_codebooks(self, centroids, pq_codebooks=None):
+        c = _np(centroids, np.float32)
+        cb = _np(pq_codebooks, np.float32) if pq_codebooks is not None else None
+        check(load().pyrope_index_set_codebooks(self._h, c.shape[0], _p(c), _p(cb)))
+
+    def is_built(self) -> bool:
+        out = C.c_int32(0)
+        check(load().pyrope_index_is_built(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def centroids(self):
+        n = C.c_int32(0)
+        check(load().pyrope_index_get_centroids(self._h, None, C.byref(n)))
+        if n.value == 0:
+            return None
+        out = np.zeros((n.value, self.dim), np.float32)
+        check(load().pyrope_index_get_centroids(self._h, _p(out), C.byref(n)))
+        return out
+
+    def codebooks(self):
+        cb = np.zeros((self.m, self.k, self.dim // self.m), np.float32)
+        ks = np.zeros(self.m, np.int32)
+        check(load().pyrope_index_get_codebooks(self._h, _p(cb), _p(ks)))
+        return cb, ks
+
+    def lists(self):
+        """-> (offsets[nc+1], rows[total], codes[total][m] or None)"""
+        tot = C.c_int64(0)
+        check(load().pyrope_index_get_lists(self._h, None, None, None, C.byref(tot)))
+        c = self.centroids()
+        nc = 0 if c is None else c.shape[0]
+        off = np.zeros(nc + 1, np.int64)
+        rows = np.zeros(max(tot.value, 1), np.int64)
+        codes = np.zeros((max(tot.value, 1), self.m), np.uint8) if self.kind == IVF_PQ else None
+        check(load().pyrope_index_get_lists(self._h, _p(off), _p(rows), _p(codes), C.byref(tot)))
+        return off, rows[:tot.value], (codes[:tot.value] if codes is not None else None)
+
+    def stats(self):
+        live, buf = C.c_int64(0), C.c_int64(0)
+        dim, metric = C.c_int32(0), C.c_int32(0)
+        check(load().pyrope_index_stats(self._h, C.byref(live), C.byref(buf), C.byref(dim), C.byref(metric)))
+        return {"live": live.value, "buffer": buf.value, "dim": dim.value, "metric": metric.value}
+
+    # ---- search
+    def search(self, Q, topk: int, max_scans: int = -1, nprobe: int = -1):
+        Q = _np(Q, np.float32)
+        if Q.ndim == 1:
+            Q = Q[None, :]
+        if Q.shape[1] != self.dim:
+            raise PyropeGpuError(ERR_DIMENSION, "Vector dimension mismatch")
+        nq = Q.shape[0]
+        kk = max(topk, 1)
+        scores = np.zeros((nq, kk), np.float32)
+        rows = np.full((nq, kk), -1, np.int64)
+        counts = np.zeros(nq, np.int32)
+        check(load().pyrope_index_search_batch(self._h, nq, _p(Q), topk, max_scans, nprobe, _p(scores), _p(rows),
+                                               _p(counts)))
+        return scores, rows, counts
+
+    def search_device(self, q_ptr: int, nq: int, topk: int, scores_ptr: int, rows_ptr: int, counts_ptr: int,
+                      max_scans: int = -1, nprobe: int = -1, stream: int | None = None):
+        check(load().pyrope_index_search_batch_device(self._h, nq, vp(q_ptr), topk, max_scans, nprobe, vp(scores_ptr),
+                                                      vp(rows_ptr), vp(counts_ptr), vp(stream) if stream else None))
+
+    def last_search_ms(self):
+        out = (C.c_float * 4)()
+        check(load().pyrope_index_last_search_ms(self._h, out))
+        return {"total": out[0], "coarse": out[1], "scan": out[2], "merge": out[3]}
+
+    def last_search_launches(self) -> int:
+        out = C.c_int32(0)
+        check(load().pyrope_index_last_search_launches(self._h, C.byref(out)))
+        return out.value
+
+
+# ---- building blocks ---------------------------------------------------------------------------
+def coarse_assign(X, centroids, metric=L2):
+    X = _np(X, np.float32)
+    c = _np(centroids, np.float32)
+    out = np.zeros(X.shape[0], np.int32)
+    check(load().pyrope_coarse_assign(metric, X.shape[1], X.shape[0], _p(X), c.shape[0], _p(c), _p(out)))
+    return out
+
+
+def kmeans_train(data, k, metric=L2, max_iter=10, seed=42):
+    d = _np(data, np.float32)
+    n, dim = d.shape
+    kk = max(1, min(k if k > 0 else 1, n))
+    out = np.zeros((kk, dim), np.float32)
+    ko, it = C.c_int32(0), C.c_int32(0)
+    check(load().pyrope_kmeans_train(metric, dim, n, dim, _p(d), k, max_iter, seed, _p(out), C.byref(ko), C.byref(it)))
+    return out[:ko.value], it.value
+
+
+def pq_encode(codebooks, X, ksub=None):
+    cb = _np(codebooks, np.float32)
+    m, k, sub = cb.shape
+    X = _np(X, np.float32)
+    ks = _np(ksub, np.int32) if ksub is not None else None
+    out = np.zeros((X.shape[0], m), np.uint8)
+    check(load().pyrope_pq_encode(m * sub, m, k, _p(cb), _p(ks), X.shape[0], _p(X), _p(out)))
+    return out
+
+
+def pq_distance_table(codebooks, Q):
+    cb = _np(codebooks, np.float32)
+    m, k, sub = cb.shape
+    Q = _np(Q, np.float32)
+    out = np.zeros((Q.shape[0], m, k), np.float32)
+    check(load().pyrope_pq_distance_table(m * sub, m, k, _p(cb), Q.shape[0], _p(Q), _p(out)))
+    return out
+
+
+def topk_merge_device(nq, parts, k_in, k_out, scores_ptr, rows_ptr, out_scores_ptr, out_rows_ptr, out_counts_ptr,
+                      stream=None):
+    check(load().pyrope_topk_merge_device(nq, parts, k_in, k_out, vp(scores_ptr), vp(rows_ptr), vp(out_scores_ptr),
+                                          vp(out_rows_ptr), vp(out_counts_ptr) if out_counts_ptr else None,
+                                          vp(stream) if stream else None))
+
+
+def fill_uniform_device(ptr, n, seed, offset=0, stream=None):
+    check(load().pyrope_fill_uniform_device(vp(ptr), n, seed, offset, vp(stream) if stream else None))

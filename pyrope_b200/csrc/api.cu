@@ -1,0 +1,1216 @@
+// api.cu — host side of libpyrope_gpu.so: index objects, storage in HBM, build pipeline, search
+// orchestration and the C ABI declared in include/pyrope_gpu.h.
+//
+// HBM layout (one index, one GPU):
+//   Segment (FLAT rows / IVF pre-build buffer): X[cap][dim] fp32 row-major, dead[cap] u8,
+//     labels[cap] i64, norms[cap] fp32 (Cosine only).  Scan order = slot order.
+//   IVF lists: list_off[nc+1] i64; entries list-major: list_vecs[total][dim] fp32 (IVF_FLAT) or
+//     list_codes[total][m] u8 (IVF_PQ), list_rows/list_labels[total] i64, list_dead[total] u8
+//     (allocated on first delete), list_norms (Cosine IVF_FLAT); centroids[nc][dim], cnorms[nc],
+//     codebook[m][k][dim/m] fp32 zero padded, ksub[m].
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pyrope_gpu.h"
+#include "common.cuh"
+#include "dotnet_random.h"
+#include "kernels.h"
+
+using namespace pyrope;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? PYROPE_ERR_OOM : PYROPE_ERR_CUDA,        \
+                        "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,    \
+                        cudaGetErrorString(_e));                                                   \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != PYROPE_OK) return _r; \
+    } while (0)
+
+int g_num_sms = 148;
+bool g_inited = false;
+
+int ensure_init() {
+    if (g_inited) return PYROPE_OK;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    g_num_sms = prop.multiProcessorCount;
+    g_inited = true;
+    return PYROPE_OK;
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    // ensure capacity; keep = preserve first keep_bytes
+    int ensure(size_t need, size_t keep_bytes, cudaStream_t st, bool exact = false) {
+        if (need <= bytes) return PYROPE_OK;
+        size_t nb = exact ? need : std::max(need, bytes + bytes / 2);
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, nb);
+        if (e != cudaSuccess && nb > need) {
+            cudaGetLastError();
+            nb = need;
+            e = cudaMalloc(&np, nb);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PYROPE_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", nb, cudaGetErrorString(e));
+        }
+        if (p && keep_bytes) {
+            CK(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (p) cudaFree(p);
+        p = np;
+        bytes = nb;
+        return PYROPE_OK;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Segment {
+    int dim = 0;
+    bool cosine = false;
+    bool reuse_slots = false;  // Dictionary<,> semantics (IVF buffers) vs List<> (FLAT)
+    int64_t nslots = 0, cap = 0, live = 0, ndead = 0;
+    DevBuf X, dead, labels, norms;
+    std::vector<uint8_t> dead_h;
+    std::vector<int64_t> slot_row;    // IVF buffers only
+    std::vector<int64_t> free_stack;  // LIFO, IVF buffers only
+
+    int reserve(int64_t n, cudaStream_t st, bool exact) {
+        if (n <= cap) return PYROPE_OK;
+        int64_t nc = exact ? n : std::max<int64_t>(n, cap + cap / 2 + 1024);
+        TRY(X.ensure((size_t)nc * dim * sizeof(float), (size_t)nslots * dim * sizeof(float), st, true));
+        size_t old_dead = dead.bytes;
+        TRY(dead.ensure((size_t)nc, (size_t)nslots, st, true));
+        if (dead.bytes > old_dead)
+            CK(cudaMemsetAsync(dead.as<uint8_t>() + nslots, 0, dead.bytes - (size_t)nslots, st));
+        TRY(labels.ensure((size_t)nc * sizeof(int64_t), (size_t)nslots * sizeof(int64_t), st, true));
+        if (cosine) TRY(norms.ensure((size_t)nc * sizeof(float), (size_t)nslots * sizeof(float), st, true));
+        cap = nc;
+        return PYROPE_OK;
+    }
+    void clear() {
+        nslots = live = ndead = 0;
+        dead_h.clear();
+        slot_row.clear();
+        free_stack.clear();
+    }
+    void release() {
+        clear();
+        cap = 0;
+        X.release();
+        dead.release();
+        labels.release();
+        norms.release();
+    }
+};
+
+struct Workspace {
+    DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probe_scores, probe_cnt, allow, qnorm,
+        hq, hs, hl, hc;  // h*: staging for the host-pointer entry point
+};
+
+}  // namespace
+
+struct pyrope_index {
+    int kind = 0, dim = 0, metric = 0, nlist = 0, m = 0, k = 0, sub = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+    std::mutex mu;
+
+    Segment seg;
+    int64_t next_row = 0;
+
+    // IVF state
+    bool built = false;
+    int nc = 0;
+    DevBuf centroids, cnorms, codebook, list_off, list_rows, list_labels, list_dead, list_vecs, list_codes,
+        list_norms;
+    std::vector<int64_t> list_off_h;
+    std::vector<uint8_t> list_dead_h;
+    int64_t list_total = 0, list_ndead = 0;
+    std::vector<int32_t> ksub;
+    DevBuf ksub_d;
+    bool frozen = false;  // codebooks supplied by the caller
+    int64_t max_train_rows = 0;
+    int max_iter = 0;
+
+    // row ordinal -> location: >=0 buffer slot, <=-2 list position (-2-pos), -1 gone
+    std::vector<int64_t> row_loc;
+    bool lists_loc_valid = true;
+
+    Workspace ws;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int last_launches = 0;
+    int pq_force_generic = 0;
+};
+
+namespace {
+
+typedef pyrope_index Index;
+
+// ------------------------------------------------------------------------------------------
+// segment writes
+// ------------------------------------------------------------------------------------------
+int seg_append(Index* h, int64_t n, const float* X, bool x_on_device, const int64_t* labels,
+               bool labels_on_device, int64_t first_row) {
+    Segment& s = h->seg;
+    cudaStream_t st = h->stream;
+    const size_t rowb = (size_t)s.dim * sizeof(float);
+    const cudaMemcpyKind xk = x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind lk = labels_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int64_t i = 0;
+    // Dictionary<,> re-uses freed slots LIFO before growing
+    while (s.reuse_slots && i < n && !s.free_stack.empty()) {
+        int64_t slot = s.free_stack.back();
+        s.free_stack.pop_back();
+        CK(cudaMemcpyAsync(s.X.as<float>() + slot * s.dim, X + i * s.dim, rowb, xk, st));
+        if (labels) CK(cudaMemcpyAsync(s.labels.as<int64_t>() + slot, labels + i, sizeof(int64_t), lk, st));
+        else CK(launch_iota64(s.labels.as<int64_t>() + slot, 1, first_row + i, st));
+        CK(cudaMemsetAsync(s.dead.as<uint8_t>() + slot, 0, 1, st));
+        if (s.cosine) CK(launch_row_norms_exact(s.X.as<float>() + slot * s.dim, 1, s.dim, s.dim, s.norms.as<float>() + slot, st));
+        s.dead_h[(size_t)slot] = 0;
+        s.slot_row[(size_t)slot] = first_row + i;
+        s.ndead--;
+        s.live++;
+        if (h->kind != PYROPE_FLAT) h->row_loc[(size_t)(first_row + i)] = slot;
+        ++i;
+    }
+    const int64_t rest = n - i;
+    if (rest > 0) {
+        TRY(s.reserve(s.nslots + rest, st, false));
+        const int64_t slot0 = s.nslots;
+        CK(cudaMemcpyAsync(s.X.as<float>() + slot0 * s.dim, X + i * s.dim, rowb * (size_t)rest, xk, st));
+        if (labels) CK(cudaMemcpyAsync(s.labels.as<int64_t>() + slot0, labels + i, sizeof(int64_t) * (size_t)rest, lk, st));
+        else CK(launch_iota64(s.labels.as<int64_t>() + slot0, rest, first_row + i, st));
+        if (s.cosine) CK(launch_row_norms_exact(s.X.as<float>() + slot0 * s.dim, rest, s.dim, s.dim, s.norms.as<float>() + slot0, st));
+        s.dead_h.resize((size_t)(slot0 + rest), 0);
+        if (h->kind != PYROPE_FLAT) {
+            s.slot_row.resize((size_t)(slot0 + rest));
+            for (int64_t j = 0; j < rest; ++j) {
+                s.slot_row[(size_t)(slot0 + j)] = first_row + i + j;
+                h->row_loc[(size_t)(first_row + i + j)] = slot0 + j;
+            }
+        }
+        s.nslots += rest;
+        s.live += rest;
+    }
+    CK(cudaStreamSynchronize(st));  // inputs are only borrowed for the duration of the call
+    return PYROPE_OK;
+}
+
+int add_common(Index* h, int64_t n, const float* X, bool dev, const int64_t* labels, int64_t* first_row_out) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (n < 0 || (n > 0 && !X)) return fail(PYROPE_ERR_INVALID_ARG, "vector is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    const int64_t first = h->next_row;
+    if (first_row_out) *first_row_out = first;
+    if (n == 0) return PYROPE_OK;
+    if (h->kind != PYROPE_FLAT) h->row_loc.resize((size_t)(first + n), -1);
+    h->next_row += n;
+    int r = seg_append(h, n, X, dev, labels, dev, first);
+    if (r != PYROPE_OK) h->next_row = first;  // nothing was published
+    return r;
+}
+
+int rebuild_row_loc(Index* h) {
+    if (h->lists_loc_valid) return PYROPE_OK;
+    std::fill(h->row_loc.begin(), h->row_loc.end(), (int64_t)-1);
+    if (h->list_total > 0) {
+        std::vector<int64_t> rows((size_t)h->list_total);
+        CK(cudaMemcpy(rows.data(), h->list_rows.p, sizeof(int64_t) * rows.size(), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < h->list_total; ++i)
+            if (h->list_dead_h.empty() || !(h->list_dead_h[(size_t)i] & 1)) h->row_loc[(size_t)rows[(size_t)i]] = -2 - i;
+    }
+    for (int64_t s = 0; s < h->seg.nslots; ++s)
+        if (!h->seg.dead_h[(size_t)s]) h->row_loc[(size_t)h->seg.slot_row[(size_t)s]] = s;
+    h->lists_loc_valid = true;
+    return PYROPE_OK;
+}
+
+int ensure_list_dead(Index* h) {
+    if (h->list_dead.p && h->list_dead_h.size() == (size_t)h->list_total) return PYROPE_OK;
+    TRY(h->list_dead.ensure((size_t)std::max<int64_t>(h->list_total, 1), 0, h->stream, true));
+    CK(cudaMemsetAsync(h->list_dead.p, 0, (size_t)std::max<int64_t>(h->list_total, 1), h->stream));
+    h->list_dead_h.assign((size_t)h->list_total, 0);
+    h->list_ndead = 0;
+    return PYROPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// training (KMeansUtils.Train on device)
+// ------------------------------------------------------------------------------------------
+__global__ void hist_kernel(const int32_t* a, int64_t n, unsigned long long* counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&counts[a[i]], 1ull);
+}
+__global__ void iota32_kernel(int32_t* out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+__global__ void widen_rows_kernel(const int32_t* order, const int64_t* src, int64_t n, int64_t* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[order[i]];
+}
+__global__ void order_to_i64_kernel(const int32_t* order, int64_t n, int64_t* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = order[i];
+}
+
+struct SortScratch {
+    DevBuf keys_out, vals_in, vals_out, temp, counts, offs;
+};
+
+// stable sort of row indices by cluster id -> order[n], offs[nc+1] (device, int64)
+int group_by_cluster(const int32_t* d_assign, int64_t n, int nc, SortScratch& sc, cudaStream_t st) {
+    if (n >= (int64_t)1 << 31) return fail(PYROPE_ERR_UNSUPPORTED, "more than 2^31-1 rows per build");
+    TRY(sc.keys_out.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
+    TRY(sc.vals_in.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
+    TRY(sc.vals_out.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
+    TRY(sc.counts.ensure(sizeof(unsigned long long) * ((size_t)nc + 1), 0, st, true));
+    TRY(sc.offs.ensure(sizeof(int64_t) * ((size_t)nc + 1), 0, st, true));
+    iota32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_in.as<int32_t>(), n);
+    CK(cudaGetLastError());
+    int end_bit = 1;
+    while ((1ll << end_bit) < nc) ++end_bit;
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_assign, sc.keys_out.as<int32_t>(), sc.vals_in.as<int32_t>(),
+                                       sc.vals_out.as<int32_t>(), (int)n, 0, end_bit, st));
+    size_t tb2 = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, sc.counts.as<unsigned long long>(), sc.offs.as<unsigned long long>(),
+                                     nc + 1, st));
+    TRY(sc.temp.ensure(std::max(tb, tb2) + 16, 0, st, true));
+    CK(cub::DeviceRadixSort::SortPairs(sc.temp.p, tb, d_assign, sc.keys_out.as<int32_t>(), sc.vals_in.as<int32_t>(),
+                                       sc.vals_out.as<int32_t>(), (int)n, 0, end_bit, st));
+    CK(cudaMemsetAsync(sc.counts.p, 0, sizeof(unsigned long long) * ((size_t)nc + 1), st));
+    hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_assign, n, sc.counts.as<unsigned long long>());
+    CK(cudaGetLastError());
+    CK(cub::DeviceScan::ExclusiveSum(sc.temp.p, tb2, sc.counts.as<unsigned long long>(),
+                                     sc.offs.as<unsigned long long>(), nc + 1, st));
+    return PYROPE_OK;
+}
+
+// KMeansUtils.Train: data n x dim (leading dimension ld) on device -> d_centroids [k][dim].
+int kmeans_train_device(int metric, int dim, int64_t n, int64_t ld, const float* d_data, int k, int max_iter,
+                        int32_t seed, float* d_centroids, int* k_out, int* iters_out, cudaStream_t st) {
+    if (iters_out) *iters_out = 0;
+    if (n == 0) { *k_out = 0; return PYROPE_OK; }
+    if (k <= 0) k = 1;
+    if (k > n) k = (int)n;
+    *k_out = k;
+    // init: data.OrderBy(_ => rnd.Next()).Take(k)
+    std::vector<int64_t> init = kmeans_init_indices(n, k, seed);
+    for (int c = 0; c < k; ++c)
+        CK(cudaMemcpyAsync(d_centroids + (size_t)c * dim, d_data + (size_t)init[(size_t)c] * ld, sizeof(float) * dim,
+                           cudaMemcpyDeviceToDevice, st));
+    DevBuf assign, cn, changed;
+    SortScratch sc;
+    TRY(assign.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
+    TRY(changed.ensure(sizeof(int), 0, st, true));
+    if (metric == kCosine) TRY(cn.ensure(sizeof(float) * (size_t)k, 0, st, true));
+    for (int it = 0; it < max_iter; ++it) {
+        if (iters_out) *iters_out = it + 1;
+        if (metric == kCosine) CK(launch_row_norms_exact(d_centroids, k, dim, dim, cn.as<float>(), st));
+        CK(launch_assign_exact(metric, dim, n, d_data, ld, k, d_centroids, cn.as<float>(), assign.as<int32_t>(), st));
+        TRY(group_by_cluster(assign.as<int32_t>(), n, k, sc, st));
+        CK(cudaMemsetAsync(changed.p, 0, sizeof(int), st));
+        CK(launch_kmeans_update(d_data, ld, dim, k, sc.offs.as<int64_t>(), sc.vals_out.as<int32_t>(), d_centroids,
+                                changed.as<int>(), st));
+        int ch = 0;
+        CK(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!ch) break;
+    }
+    return PYROPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------------
+struct BuildData {
+    const float* X = nullptr;  // [n][dim] device
+    int64_t n = 0;
+    DevBuf Xown, rows, labels;  // rows/labels per data row (device int64)
+};
+
+// Collect the rows a Build sees, in the reference's order: live list entries (list order) then
+// live buffer slots (slot order).  IVF_PQ passes lists=false (IvfPqVectorIndex.cs:64).
+int gather_build_data(Index* h, bool include_lists, BuildData& bd) {
+    cudaStream_t st = h->stream;
+    Segment& s = h->seg;
+    const int dim = h->dim;
+    std::vector<int64_t> list_pos;
+    if (include_lists && h->built) {
+        list_pos.reserve((size_t)h->list_total);
+        for (int64_t i = 0; i < h->list_total; ++i)
+            if (h->list_dead_h.empty() || !h->list_dead_h[(size_t)i]) list_pos.push_back(i);
+    }
+    std::vector<int64_t> slots;
+    const bool dense_buffer = (s.ndead == 0);
+    if (!dense_buffer) {
+        slots.reserve((size_t)s.live);
+        for (int64_t i = 0; i < s.nslots; ++i)
+            if (!s.dead_h[(size_t)i]) slots.push_back(i);
+    }
+    const int64_t nb = dense_buffer ? s.nslots : (int64_t)slots.size();
+    const int64_t nl = (int64_t)list_pos.size();
+    bd.n = nl + nb;
+    if (bd.n == 0) return PYROPE_OK;
+    TRY(bd.rows.ensure(sizeof(int64_t) * (size_t)bd.n, 0, st, true));
+    TRY(bd.labels.ensure(sizeof(int64_t) * (size_t)bd.n, 0, st, true));
+    // rows of buffer slots come from the host map
+    if (nl == 0 && dense_buffer) {
+        bd.X = s.X.as<float>();  // zero-copy fast path
+        CK(cudaMemcpyAsync(bd.rows.p, s.slot_row.data(), sizeof(int64_t) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(bd.labels.p, s.labels.p, sizeof(int64_t) * (size_t)nb, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        return PYROPE_OK;
+    }
+    TRY(bd.Xown.ensure(sizeof(float) * (size_t)bd.n * dim, 0, st, true));
+    bd.X = bd.Xown.as<float>();
+    DevBuf idx;
+    TRY(idx.ensure(sizeof(int64_t) * (size_t)std::max(nl, nb), 0, st, true));
+    if (nl) {
+        CK(cudaMemcpyAsync(idx.p, list_pos.data(), sizeof(int64_t) * (size_t)nl, cudaMemcpyHostToDevice, st));
+        CK(launch_gather_rows(h->list_vecs.p, (int64_t)dim * 4, idx.as<int64_t>(), nl, bd.Xown.p, st));
+        CK(launch_gather_rows(h->list_rows.p, 8, idx.as<int64_t>(), nl, bd.rows.p, st));
+        CK(launch_gather_rows(h->list_labels.p, 8, idx.as<int64_t>(), nl, bd.labels.p, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (nb) {
+        std::vector<int64_t> brow((size_t)nb);
+        if (dense_buffer) {
+            slots.resize((size_t)nb);
+            for (int64_t i = 0; i < nb; ++i) slots[(size_t)i] = i;
+        }
+        for (int64_t i = 0; i < nb; ++i) brow[(size_t)i] = s.slot_row[(size_t)slots[(size_t)i]];
+        CK(cudaMemcpyAsync(idx.p, slots.data(), sizeof(int64_t) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        CK(launch_gather_rows(s.X.p, (int64_t)dim * 4, idx.as<int64_t>(), nb, bd.Xown.as<float>() + (size_t)nl * dim, st));
+        CK(launch_gather_rows(s.labels.p, 8, idx.as<int64_t>(), nb, bd.labels.as<int64_t>() + nl, st));
+        CK(cudaMemcpyAsync(bd.rows.as<int64_t>() + nl, brow.data(), sizeof(int64_t) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return PYROPE_OK;
+}
+
+int finish_lists(Index* h, const BuildData& bd, const int32_t* d_assign, int nc, SortScratch& sc,
+                 const void* payload, int64_t payload_row_bytes, DevBuf& payload_out) {
+    cudaStream_t st = h->stream;
+    const int64_t n = bd.n;
+    TRY(group_by_cluster(d_assign, n, nc, sc, st));
+    DevBuf order64;
+    TRY(order64.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+    order_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_out.as<int32_t>(), n, order64.as<int64_t>());
+    CK(cudaGetLastError());
+    TRY(payload_out.ensure((size_t)n * (size_t)payload_row_bytes, 0, st, true));
+    CK(launch_gather_rows(payload, payload_row_bytes, order64.as<int64_t>(), n, payload_out.p, st));
+    TRY(h->list_rows.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+    TRY(h->list_labels.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+    widen_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_out.as<int32_t>(), bd.rows.as<int64_t>(), n, h->list_rows.as<int64_t>());
+    widen_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_out.as<int32_t>(), bd.labels.as<int64_t>(), n, h->list_labels.as<int64_t>());
+    CK(cudaGetLastError());
+    TRY(h->list_off.ensure(sizeof(int64_t) * ((size_t)nc + 1), 0, st, true));
+    CK(cudaMemcpyAsync(h->list_off.p, sc.offs.p, sizeof(int64_t) * ((size_t)nc + 1), cudaMemcpyDeviceToDevice, st));
+    h->list_off_h.resize((size_t)nc + 1);
+    CK(cudaMemcpyAsync(h->list_off_h.data(), sc.offs.p, sizeof(int64_t) * ((size_t)nc + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->list_total = n;
+    h->list_dead_h.clear();
+    h->list_dead.release();
+    h->list_ndead = 0;
+    h->nc = nc;
+    h->built = true;
+    h->lists_loc_valid = false;
+    // the write buffer is consumed by Build (IvfFlatVectorIndex.cs:143, IvfPqVectorIndex.cs:109);
+    // give large buffers back to the allocator, keep small ones for the next writes
+    if ((size_t)h->seg.cap * h->dim * sizeof(float) > ((size_t)256 << 20)) h->seg.release();
+    else h->seg.clear();
+    return PYROPE_OK;
+}
+
+int build_ivfflat(Index* h) {
+    cudaStream_t st = h->stream;
+    const int dim = h->dim;
+    BuildData bd;
+    TRY(gather_build_data(h, true, bd));
+    if (bd.n == 0) return PYROPE_OK;  // IvfFlatVectorIndex.cs:112
+    int nc;
+    if (h->frozen) {
+        nc = h->nc;
+    } else {
+        int k = (int)std::min<int64_t>(h->nlist, bd.n);
+        if (k <= 0) k = 1;
+        int64_t ntrain = (h->max_train_rows > 0) ? std::min<int64_t>(h->max_train_rows, bd.n) : bd.n;
+        if (k > ntrain) k = (int)ntrain;
+        DevBuf cent;
+        TRY(cent.ensure(sizeof(float) * (size_t)k * dim, 0, st, true));
+        int iters = 0;
+        TRY(kmeans_train_device(h->metric, dim, ntrain, dim, bd.X, k, h->max_iter > 0 ? h->max_iter : 10, 42,
+                                cent.as<float>(), &nc, &iters, st));
+        TRY(h->centroids.ensure(sizeof(float) * (size_t)nc * dim, 0, st, true));
+        CK(cudaMemcpyAsync(h->centroids.p, cent.p, sizeof(float) * (size_t)nc * dim, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    TRY(h->cnorms.ensure(sizeof(float) * (size_t)nc, 0, st, true));
+    if (h->metric == kCosine) CK(launch_row_norms_exact(h->centroids.as<float>(), nc, dim, dim, h->cnorms.as<float>(), st));
+    DevBuf assign;
+    TRY(assign.ensure(sizeof(int32_t) * (size_t)bd.n, 0, st, true));
+    CK(launch_assign_exact(h->metric, dim, bd.n, bd.X, dim, nc, h->centroids.as<float>(), h->cnorms.as<float>(),
+                           assign.as<int32_t>(), st));
+    SortScratch sc;
+    DevBuf newvecs;
+    TRY(finish_lists(h, bd, assign.as<int32_t>(), nc, sc, bd.X, (int64_t)dim * 4, newvecs));
+    std::swap(h->list_vecs.p, newvecs.p);
+    std::swap(h->list_vecs.bytes, newvecs.bytes);
+    if (h->metric == kCosine) {
+        TRY(h->list_norms.ensure(sizeof(float) * (size_t)bd.n, 0, st, true));
+        CK(launch_row_norms_exact(h->list_vecs.as<float>(), bd.n, dim, dim, h->list_norms.as<float>(), st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int build_ivfpq(Index* h) {
+    cudaStream_t st = h->stream;
+    const int dim = h->dim, m = h->m, K = h->k, sub = h->sub;
+    BuildData bd;
+    TRY(gather_build_data(h, false, bd));
+    if (bd.n == 0) return PYROPE_OK;  // IvfPqVectorIndex.cs:62,65
+    const int64_t n = bd.n;
+    int nc;
+    const int64_t ntrain = (h->max_train_rows > 0) ? std::min<int64_t>(h->max_train_rows, n) : n;
+    const int iters_max = h->max_iter > 0 ? h->max_iter : 10;
+    if (h->frozen) {
+        nc = h->nc;
+    } else {
+        int k = (int)std::min<int64_t>(h->nlist, n);
+        if (k > ntrain) k = (int)ntrain;
+        if (k <= 0) k = 1;
+        DevBuf cent;
+        TRY(cent.ensure(sizeof(float) * (size_t)k * dim, 0, st, true));
+        int iters = 0;
+        TRY(kmeans_train_device(h->metric, dim, ntrain, dim, bd.X, k, iters_max, 123, cent.as<float>(), &nc, &iters, st));
+        TRY(h->centroids.ensure(sizeof(float) * (size_t)nc * dim, 0, st, true));
+        CK(cudaMemcpyAsync(h->centroids.p, cent.p, sizeof(float) * (size_t)nc * dim, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    TRY(h->cnorms.ensure(sizeof(float) * (size_t)nc, 0, st, true));
+    if (h->metric == kCosine) CK(launch_row_norms_exact(h->centroids.as<float>(), nc, dim, dim, h->cnorms.as<float>(), st));
+    DevBuf assign;
+    TRY(assign.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
+    CK(launch_assign_exact(h->metric, dim, n, bd.X, dim, nc, h->centroids.as<float>(), h->cnorms.as<float>(),
+                           assign.as<int32_t>(), st));
+    // PQ training on the residuals of the training rows (ProductQuantizer.cs:28-58)
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)4 << 20);
+    DevBuf res;
+    TRY(res.ensure(sizeof(float) * (size_t)std::max(chunk, h->frozen ? (int64_t)0 : ntrain) * dim, 0, st, true));
+    if (!h->frozen) {
+        CK(launch_residuals(bd.X, ntrain, dim, h->centroids.as<float>(), assign.as<int32_t>(), res.as<float>(), st));
+        TRY(h->codebook.ensure(sizeof(float) * (size_t)m * K * sub, 0, st, true));
+        CK(cudaMemsetAsync(h->codebook.p, 0, sizeof(float) * (size_t)m * K * sub, st));
+        h->ksub.assign((size_t)m, 0);
+        DevBuf cb1;
+        TRY(cb1.ensure(sizeof(float) * (size_t)K * sub, 0, st, true));
+        for (int mi = 0; mi < m; ++mi) {
+            int kk = 0, iters = 0;
+            TRY(kmeans_train_device(kL2, sub, ntrain, dim, res.as<float>() + (size_t)mi * sub, K, 10, 42 + mi,
+                                    cb1.as<float>(), &kk, &iters, st));
+            h->ksub[(size_t)mi] = kk;
+            CK(cudaMemcpyAsync(h->codebook.as<float>() + (size_t)mi * K * sub, cb1.p, sizeof(float) * (size_t)kk * sub,
+                               cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    TRY(h->ksub_d.ensure(sizeof(int32_t) * (size_t)m, 0, st, true));
+    CK(cudaMemcpyAsync(h->ksub_d.p, h->ksub.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    // encode in chunks
+    DevBuf codes;
+    TRY(codes.ensure((size_t)n * m, 0, st, true));
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        int64_t cn = std::min(chunk, n - c0);
+        CK(launch_residuals(bd.X + (size_t)c0 * dim, cn, dim, h->centroids.as<float>(), assign.as<int32_t>() + c0,
+                            res.as<float>(), st));
+        CK(launch_pq_encode_exact(res.as<float>(), cn, dim, m, K, h->codebook.as<float>(), h->ksub_d.as<int32_t>(),
+                                  codes.as<uint8_t>() + (size_t)c0 * m, st));
+    }
+    SortScratch sc;
+    DevBuf newcodes;
+    TRY(finish_lists(h, bd, assign.as<int32_t>(), nc, sc, codes.p, m, newcodes));
+    std::swap(h->list_codes.p, newcodes.p);
+    std::swap(h->list_codes.bytes, newcodes.bytes);
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+// physically drop dead/shadowed list entries (IVF_FLAT; needed before a MaxScans-limited search)
+int compact_lists(Index* h) {
+    if (h->list_ndead == 0) return PYROPE_OK;
+    cudaStream_t st = h->stream;
+    std::vector<int64_t> keep;
+    keep.reserve((size_t)h->list_total);
+    std::vector<int64_t> noff((size_t)h->nc + 1, 0);
+    for (int c = 0; c < h->nc; ++c) {
+        for (int64_t i = h->list_off_h[(size_t)c]; i < h->list_off_h[(size_t)c + 1]; ++i)
+            if (!h->list_dead_h[(size_t)i]) keep.push_back(i);
+        noff[(size_t)c + 1] = (int64_t)keep.size();
+    }
+    const int64_t n = (int64_t)keep.size();
+    DevBuf idx, nv, nr, nl, nn;
+    TRY(idx.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
+    CK(cudaMemcpyAsync(idx.p, keep.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    TRY(nv.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1) * h->dim, 0, st, true));
+    TRY(nr.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
+    TRY(nl.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
+    CK(launch_gather_rows(h->list_vecs.p, (int64_t)h->dim * 4, idx.as<int64_t>(), n, nv.p, st));
+    CK(launch_gather_rows(h->list_rows.p, 8, idx.as<int64_t>(), n, nr.p, st));
+    CK(launch_gather_rows(h->list_labels.p, 8, idx.as<int64_t>(), n, nl.p, st));
+    if (h->metric == kCosine) {
+        TRY(nn.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
+        CK(launch_gather_rows(h->list_norms.p, 4, idx.as<int64_t>(), n, nn.p, st));
+    }
+    CK(cudaMemcpyAsync(h->list_off.p, noff.data(), sizeof(int64_t) * noff.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    std::swap(h->list_vecs.p, nv.p); std::swap(h->list_vecs.bytes, nv.bytes);
+    std::swap(h->list_rows.p, nr.p); std::swap(h->list_rows.bytes, nr.bytes);
+    std::swap(h->list_labels.p, nl.p); std::swap(h->list_labels.bytes, nl.bytes);
+    if (h->metric == kCosine) { std::swap(h->list_norms.p, nn.p); std::swap(h->list_norms.bytes, nn.bytes); }
+    h->list_off_h = noff;
+    h->list_total = n;
+    h->list_dead_h.clear();
+    h->list_dead.release();
+    h->list_ndead = 0;
+    h->lists_loc_valid = false;
+    return PYROPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------
+// scan position cut-off so that exactly min(max_scans, live) live rows precede it
+int64_t segment_cutoff(const Segment& s, int64_t max_scans) {
+    if (max_scans < 0) return s.nslots;
+    if (max_scans == 0) return 0;
+    if (s.ndead == 0) return std::min<int64_t>(max_scans, s.nslots);
+    int64_t seen = 0;
+    for (int64_t i = 0; i < s.nslots; ++i) {
+        if (!s.dead_h[(size_t)i]) {
+            if (++seen == max_scans) return i + 1;
+        }
+    }
+    return s.nslots;
+}
+
+__global__ void fill_empty_kernel(float* s, int64_t* l, int32_t* c, int64_t nq, int k) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k) { s[i] = 0.f; l[i] = -1; }
+    if (c && i < nq) c[i] = 0;
+}
+
+int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_scans, int nprobe, float* d_scores,
+                  int64_t* d_rows, int32_t* d_counts, cudaStream_t st) {
+    Workspace& ws = h->ws;
+    const int dim = h->dim, k = topk;
+    int launches = 0;
+    if (h->last_stream && h->last_stream != st) CK(cudaStreamSynchronize(h->last_stream));
+    h->last_stream = st;
+    if (!h->ev[0])
+        for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&h->ev[i]));
+    h->ev_valid = false;
+    CK(cudaEventRecord(h->ev[0], st));
+
+    auto fill_empty = [&]() -> int {
+        int64_t tot = std::max<int64_t>(nq * std::max(k, 1), nq);
+        fill_empty_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_scores, d_rows, d_counts, nq, std::max(k, 0));
+        CK(cudaGetLastError());
+        ++launches;
+        return PYROPE_OK;
+    };
+
+    // ---- plan the parts
+    Segment& seg = h->seg;
+    const bool ivf = h->kind != PYROPE_FLAT;
+    const int64_t seg_scan = (h->kind == PYROPE_IVF_PQ) ? seg.nslots : segment_cutoff(seg, max_scans);
+    const bool scan_seg = seg_scan > 0 && seg.live > 0;
+    int64_t seg_live_scanned = 0;
+    if (scan_seg) seg_live_scanned = (max_scans >= 0 && h->kind != PYROPE_IVF_PQ) ? std::min<int64_t>(max_scans, seg.live) : seg.live;
+
+    int P = 0;  // probes
+    bool scan_lists = false;
+    if (ivf && h->built && h->nc > 0 && h->list_total > 0) {
+        int np = nprobe >= 0 ? nprobe : (h->kind == PYROPE_IVF_FLAT ? 3 : 1);
+        P = std::min(np, h->nc);
+        scan_lists = P > 0;
+        if (h->kind == PYROPE_IVF_FLAT && max_scans >= 0 && seg_live_scanned >= max_scans) scan_lists = false;
+    }
+    if (P > kMaxTopK) return fail(PYROPE_ERR_UNSUPPORTED, "nprobe %d exceeds the supported maximum %d", P, kMaxTopK);
+    if (k <= 0 || (!scan_seg && !scan_lists)) {
+        TRY(fill_empty());
+        CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); CK(cudaEventRecord(h->ev[3], st));
+        h->ev_valid = true;
+        h->last_launches = launches;
+        return PYROPE_OK;
+    }
+
+    int groups = 0;
+    if (scan_lists) {
+        int64_t want = (2 * (int64_t)g_num_sms + nq - 1) / nq;
+        groups = (int)std::max<int64_t>(1, std::min<int64_t>(want, P));
+    }
+    int max_parts = kMergeMaxCandidates / k;
+    if (max_parts < 1) max_parts = 1;
+    if (groups > max_parts - (scan_seg ? 1 : 0)) groups = std::max(1, max_parts - (scan_seg ? 1 : 0));
+    int seg_splits = 0;
+    if (scan_seg) seg_splits = flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
+    const int parts = seg_splits + groups;
+    if ((int64_t)parts * k > kMergeMaxCandidates)
+        return fail(PYROPE_ERR_UNSUPPORTED, "topK %d too large for %d partial lists", k, parts);
+
+    TRY(ws.pairs_s.ensure(sizeof(float) * (size_t)nq * parts * k, 0, st));
+    TRY(ws.pairs_l.ensure(sizeof(int64_t) * (size_t)nq * parts * k, 0, st));
+    PairOut out{ws.pairs_s.as<float>(), ws.pairs_l.as<int64_t>(), parts, 0};
+
+    const float* qnorm = nullptr;
+    if (h->metric == kCosine) {
+        TRY(ws.qnorm.ensure(sizeof(float) * (size_t)nq, 0, st));
+        CK(launch_row_norms_exact(dQ, nq, dim, dim, ws.qnorm.as<float>(), st));
+        ++launches;
+        qnorm = ws.qnorm.as<float>();
+    }
+
+    // ---- coarse probe: exact FLAT top-P over the centroids
+    if (scan_lists) {
+        int csplits = flat_scan_pick_splits(nq, h->nc, P, g_num_sms, 0);
+        int ccap = flat_scan_cap(P);
+        TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)csplits * nq * ccap, 0, st));
+        TRY(ws.cpairs_s.ensure(sizeof(float) * (size_t)nq * csplits * P, 0, st));
+        TRY(ws.cpairs_l.ensure(sizeof(int64_t) * (size_t)nq * csplits * P, 0, st));
+        TRY(ws.probes.ensure(sizeof(int64_t) * (size_t)nq * P, 0, st));
+        TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * P, 0, st));
+        FlatScanParams cp{};
+        cp.Q = dQ; cp.nq = nq; cp.dim = dim; cp.X = h->centroids.as<float>(); cp.n_scan = h->nc;
+        cp.dead = nullptr; cp.xnorm = h->cnorms.as<float>(); cp.qnorm = qnorm; cp.labels = nullptr;
+        cp.metric = h->metric; cp.k = P; cp.splits = csplits; cp.queue = ws.queue.as<uint64_t>(); cp.cap = ccap;
+        cp.out = PairOut{ws.cpairs_s.as<float>(), ws.cpairs_l.as<int64_t>(), csplits, 0};
+        CK(launch_flat_scan(cp, st));
+        CK(launch_merge_pairs(nq, csplits, P, P, ws.cpairs_s.as<float>(), ws.cpairs_l.as<int64_t>(), P, (int64_t)csplits * P,
+                              ws.probe_scores.as<float>(), ws.probes.as<int64_t>(), nullptr, st));
+        launches += 2;
+    }
+    CK(cudaEventRecord(h->ev[1], st));
+
+    // ---- buffer / base scan
+    if (scan_seg) {
+        int cap = flat_scan_cap(k);
+        TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)seg_splits * nq * cap, 0, st));
+        FlatScanParams fp{};
+        fp.Q = dQ; fp.nq = nq; fp.dim = dim; fp.X = seg.X.as<float>(); fp.n_scan = seg_scan;
+        fp.dead = seg.ndead > 0 ? seg.dead.as<uint8_t>() : nullptr;
+        fp.xnorm = seg.norms.as<float>(); fp.qnorm = qnorm; fp.labels = seg.labels.as<int64_t>();
+        fp.metric = h->metric; fp.k = k; fp.splits = seg_splits; fp.queue = ws.queue.as<uint64_t>(); fp.cap = cap;
+        fp.out = out; fp.out.part_base = 0;
+        CK(launch_flat_scan(fp, st));
+        ++launches;
+    }
+    // ---- list scan
+    if (scan_lists) {
+        const uint8_t* ldead = h->list_ndead > 0 ? h->list_dead.as<uint8_t>() : nullptr;
+        if (h->kind == PYROPE_IVF_FLAT) {
+            const int32_t* allow = nullptr;
+            if (max_scans >= 0) {
+                TRY(ws.allow.ensure(sizeof(int32_t) * (size_t)nq * P, 0, st));
+                CK(launch_probe_allow(ws.probes.as<int64_t>(), nq, P, h->list_off.as<int64_t>(),
+                                      max_scans - seg_live_scanned, ws.allow.as<int32_t>(), st));
+                ++launches;
+                allow = ws.allow.as<int32_t>();
+            }
+            IvfFlatScanParams ip{};
+            ip.Q = dQ; ip.nq = nq; ip.dim = dim; ip.probes = ws.probes.as<int64_t>(); ip.nprobe = P; ip.allow = allow;
+            ip.list_off = h->list_off.as<int64_t>(); ip.vecs = h->list_vecs.as<float>(); ip.dead = ldead;
+            ip.norms = h->list_norms.as<float>(); ip.labels = h->list_labels.as<int64_t>(); ip.qnorm = qnorm;
+            ip.metric = h->metric; ip.k = k; ip.groups = groups;
+            ip.out = out; ip.out.part_base = seg_splits;
+            CK(launch_ivfflat_scan(ip, st));
+        } else {
+            IvfPqScanParams pp{};
+            pp.Q = dQ; pp.nq = nq; pp.dim = dim; pp.probes = ws.probes.as<int64_t>(); pp.nprobe = P;
+            pp.list_off = h->list_off.as<int64_t>(); pp.centroids = h->centroids.as<float>();
+            pp.codebook = h->codebook.as<float>(); pp.m = h->m; pp.ksub = h->k;
+            pp.codes = h->list_codes.as<uint8_t>(); pp.dead = ldead; pp.labels = h->list_labels.as<int64_t>();
+            pp.k = k; pp.groups = groups; pp.force_generic = h->pq_force_generic;
+            pp.out = out; pp.out.part_base = seg_splits;
+            CK(launch_ivfpq_scan(pp, st));
+        }
+        ++launches;
+    }
+    CK(cudaEventRecord(h->ev[2], st));
+    CK(launch_merge_pairs(nq, parts, k, k, out.scores, out.labels, k, (int64_t)parts * k, d_scores, d_rows, d_counts, st));
+    ++launches;
+    CK(cudaEventRecord(h->ev[3], st));
+    h->ev_valid = true;
+    h->last_launches = launches;
+    return PYROPE_OK;
+}
+
+int validate_search(Index* h, int64_t nq, const float* Q, int topk) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (nq < 0 || (nq > 0 && !Q)) return fail(PYROPE_ERR_INVALID_ARG, "query is null");
+    if (h->kind == PYROPE_FLAT && topk <= 0) return fail(PYROPE_ERR_OUT_OF_RANGE, "topK must be positive.");
+    if (topk > kMaxTopK) return fail(PYROPE_ERR_UNSUPPORTED, "topK %d exceeds the supported maximum %d", topk, kMaxTopK);
+    return PYROPE_OK;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// C ABI
+// ==============================================================================================
+extern "C" {
+
+const char* pyrope_last_error(void) { return g_err.c_str(); }
+int pyrope_version(void) { return 100; }
+
+int pyrope_gpu_device_count(int* out) {
+    if (!out) return fail(PYROPE_ERR_INVALID_ARG, "out is null");
+    CK(cudaGetDeviceCount(out));
+    return PYROPE_OK;
+}
+
+int pyrope_gpu_init(int device) {
+    if (device >= 0) CK(cudaSetDevice(device));
+    CK(cudaFree(0));
+    g_inited = false;
+    return ensure_init();
+}
+
+int pyrope_gpu_shutdown(void) {
+    g_inited = false;
+    return PYROPE_OK;
+}
+
+int pyrope_index_create(int kind, int dim, int metric, int nlist, int pq_m, int pq_k, pyrope_index** out) {
+    if (!out) return fail(PYROPE_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    if (kind < PYROPE_FLAT || kind > PYROPE_IVF_PQ) return fail(PYROPE_ERR_INVALID_ARG, "unknown index kind %d", kind);
+    if (metric < PYROPE_L2 || metric > PYROPE_COSINE) return fail(PYROPE_ERR_INVALID_ARG, "unknown metric %d", metric);
+    if (dim <= 0) return fail(PYROPE_ERR_OUT_OF_RANGE, "Dimension must be positive.");
+    if (kind == PYROPE_IVF_PQ) {
+        if (pq_m <= 0 || dim % pq_m != 0) return fail(PYROPE_ERR_INVALID_ARG, "Dimension must be divisible by M");
+        if (pq_k > 256) return fail(PYROPE_ERR_INVALID_ARG, "K must be <= 256 for byte encoding");
+        if (pq_k <= 0) return fail(PYROPE_ERR_INVALID_ARG, "K must be positive");
+    }
+    TRY(ensure_init());
+    Index* h = new (std::nothrow) Index();
+    if (!h) return fail(PYROPE_ERR_OOM, "out of host memory");
+    h->kind = kind; h->dim = dim; h->metric = metric; h->nlist = nlist;
+    if (kind == PYROPE_IVF_PQ) { h->m = pq_m; h->k = pq_k; h->sub = dim / pq_m; }
+    h->seg.dim = dim;
+    h->seg.cosine = (metric == PYROPE_COSINE);
+    h->seg.reuse_slots = (kind != PYROPE_FLAT);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(PYROPE_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    const char* g = getenv("PYROPE_PQ_GENERIC");
+    h->pq_force_generic = (g && g[0] == '1') ? 1 : 0;
+    *out = h;
+    return PYROPE_OK;
+}
+
+int pyrope_index_destroy(pyrope_index* h) {
+    if (!h) return PYROPE_OK;
+    cudaStreamSynchronize(h->stream);
+    if (h->last_stream) cudaStreamSynchronize(h->last_stream);
+    for (int i = 0; i < 5; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return PYROPE_OK;
+}
+
+int pyrope_index_reserve(pyrope_index* h, int64_t n_rows) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    TRY(h->seg.reserve(n_rows, h->stream, true));
+    CK(cudaStreamSynchronize(h->stream));
+    return PYROPE_OK;
+}
+
+int pyrope_index_add_batch(pyrope_index* h, int64_t n, const float* X, const int64_t* labels, int64_t* first_row_out) {
+    return add_common(h, n, X, false, labels, first_row_out);
+}
+int pyrope_index_add_batch_device(pyrope_index* h, int64_t n, const float* dX, const int64_t* d_labels,
+                                  int64_t* first_row_out) {
+    return add_common(h, n, dX, true, d_labels, first_row_out);
+}
+
+int pyrope_index_update_row(pyrope_index* h, int64_t row, const float* x) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (!x) return fail(PYROPE_ERR_INVALID_ARG, "vector is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    Segment& s = h->seg;
+    int64_t slot;
+    if (h->kind == PYROPE_FLAT) {
+        if (row < 0 || row >= s.nslots) return fail(PYROPE_ERR_NOT_FOUND, "row %lld does not exist", (long long)row);
+        slot = row;
+    } else {
+        if (row < 0 || row >= h->next_row) return fail(PYROPE_ERR_NOT_FOUND, "row %lld does not exist", (long long)row);
+        TRY(rebuild_row_loc(h));
+        slot = h->row_loc[(size_t)row];
+        if (slot < 0) return fail(PYROPE_ERR_NOT_FOUND, "row %lld is not in the write buffer", (long long)row);
+    }
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(s.X.as<float>() + slot * s.dim, x, sizeof(float) * s.dim, cudaMemcpyHostToDevice, st));
+    if (s.cosine) CK(launch_row_norms_exact(s.X.as<float>() + slot * s.dim, 1, s.dim, s.dim, s.norms.as<float>() + slot, st));
+    if (s.dead_h[(size_t)slot]) {  // FLAT Upsert un-deletes (BruteForceVectorIndex.cs:200-203)
+        CK(cudaMemsetAsync(s.dead.as<uint8_t>() + slot, 0, 1, st));
+        s.dead_h[(size_t)slot] = 0;
+        s.ndead--;
+        s.live++;
+    }
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_index_delete_row(pyrope_index* h, int64_t row) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    Segment& s = h->seg;
+    cudaStream_t st = h->stream;
+    if (h->kind == PYROPE_FLAT) {
+        if (row < 0 || row >= s.nslots || s.dead_h[(size_t)row]) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
+        CK(cudaMemsetAsync(s.dead.as<uint8_t>() + row, 1, 1, st));
+        s.dead_h[(size_t)row] = 1;
+        s.ndead++;
+        s.live--;
+        CK(cudaStreamSynchronize(st));
+        return PYROPE_OK;
+    }
+    if (row < 0 || row >= h->next_row) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
+    TRY(rebuild_row_loc(h));
+    int64_t loc = h->row_loc[(size_t)row];
+    if (loc == -1) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
+    if (loc >= 0) {
+        CK(cudaMemsetAsync(s.dead.as<uint8_t>() + loc, 1, 1, st));
+        s.dead_h[(size_t)loc] = 1;
+        s.slot_row[(size_t)loc] = -1;
+        s.ndead++;
+        s.live--;
+        s.free_stack.push_back(loc);
+        h->row_loc[(size_t)row] = -1;
+    } else {
+        if (h->kind == PYROPE_IVF_PQ)  // IvfPqVectorIndex.cs:48-53: Delete only touches the buffer
+            return fail(PYROPE_ERR_NOT_FOUND, "row %lld is encoded in a list; IVF_PQ deletes only buffered rows", (long long)row);
+        int64_t pos = -2 - loc;
+        TRY(ensure_list_dead(h));
+        if (!(h->list_dead_h[(size_t)pos])) h->list_ndead++;
+        h->list_dead_h[(size_t)pos] |= 1;
+        CK(cudaMemcpyAsync(h->list_dead.as<uint8_t>() + pos, &h->list_dead_h[(size_t)pos], 1, cudaMemcpyHostToDevice, st));
+        h->row_loc[(size_t)row] = -1;
+    }
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_index_shadow_row(pyrope_index* h, int64_t row, int shadowed) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->kind == PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "FLAT rows cannot be shadowed");
+    if (row < 0 || row >= h->next_row) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
+    TRY(rebuild_row_loc(h));
+    int64_t loc = h->row_loc[(size_t)row];
+    if (loc > -2) return fail(PYROPE_ERR_NOT_FOUND, "row %lld is not in an inverted list", (long long)row);
+    int64_t pos = -2 - loc;
+    TRY(ensure_list_dead(h));
+    uint8_t old = h->list_dead_h[(size_t)pos];
+    uint8_t nv = shadowed ? (old | 2) : (old & ~2);
+    if (!old && nv) h->list_ndead++;
+    if (old && !nv) h->list_ndead--;
+    h->list_dead_h[(size_t)pos] = nv;
+    CK(cudaMemcpyAsync(h->list_dead.as<uint8_t>() + pos, &h->list_dead_h[(size_t)pos], 1, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PYROPE_OK;
+}
+
+int pyrope_index_build(pyrope_index* h) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->last_stream) CK(cudaStreamSynchronize(h->last_stream));
+    if (h->kind == PYROPE_FLAT) return PYROPE_OK;  // BruteForceVectorIndex.cs:56
+    if (h->kind == PYROPE_IVF_FLAT) return build_ivfflat(h);
+    return build_ivfpq(h);
+}
+
+int pyrope_index_set_train_params(pyrope_index* h, int64_t max_train_rows, int max_iter) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    h->max_train_rows = max_train_rows;
+    h->max_iter = max_iter;
+    return PYROPE_OK;
+}
+
+int pyrope_index_set_codebooks(pyrope_index* h, int n_centroids, const float* centroids, const float* pq_codebooks) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (h->kind == PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "FLAT has no codebooks");
+    if (n_centroids <= 0 || !centroids) return fail(PYROPE_ERR_INVALID_ARG, "centroids missing");
+    if (h->kind == PYROPE_IVF_PQ && !pq_codebooks) return fail(PYROPE_ERR_INVALID_ARG, "pq codebooks missing");
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaStream_t st = h->stream;
+    TRY(h->centroids.ensure(sizeof(float) * (size_t)n_centroids * h->dim, 0, st, true));
+    CK(cudaMemcpyAsync(h->centroids.p, centroids, sizeof(float) * (size_t)n_centroids * h->dim, cudaMemcpyDefault, st));
+    if (h->kind == PYROPE_IVF_PQ) {
+        size_t cb = sizeof(float) * (size_t)h->m * h->k * h->sub;
+        TRY(h->codebook.ensure(cb, 0, st, true));
+        CK(cudaMemcpyAsync(h->codebook.p, pq_codebooks, cb, cudaMemcpyDefault, st));
+        h->ksub.assign((size_t)h->m, h->k);
+    }
+    CK(cudaStreamSynchronize(st));
+    h->nc = n_centroids;
+    h->frozen = true;
+    return PYROPE_OK;
+}
+
+int pyrope_index_is_built(pyrope_index* h, int* out) {
+    if (!h || !out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    *out = h->built ? 1 : 0;
+    return PYROPE_OK;
+}
+
+int pyrope_index_get_centroids(pyrope_index* h, float* centroids_out, int* n_out) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    int n = h->built ? h->nc : 0;
+    if (n_out) *n_out = n;
+    if (centroids_out && n > 0)
+        CK(cudaMemcpy(centroids_out, h->centroids.p, sizeof(float) * (size_t)n * h->dim, cudaMemcpyDeviceToHost));
+    return PYROPE_OK;
+}
+
+int pyrope_index_get_codebooks(pyrope_index* h, float* codebooks_out, int32_t* ksub_out) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (h->kind != PYROPE_IVF_PQ) return fail(PYROPE_ERR_INVALID_STATE, "not an IVF_PQ index");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->ksub.empty()) return fail(PYROPE_ERR_INVALID_STATE, "PQ not trained");
+    if (codebooks_out)
+        CK(cudaMemcpy(codebooks_out, h->codebook.p, sizeof(float) * (size_t)h->m * h->k * h->sub, cudaMemcpyDeviceToHost));
+    if (ksub_out) memcpy(ksub_out, h->ksub.data(), sizeof(int32_t) * (size_t)h->m);
+    return PYROPE_OK;
+}
+
+int pyrope_index_get_lists(pyrope_index* h, int64_t* offsets_out, int64_t* rows_out, uint8_t* codes_out, int64_t* total_out) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->built) {
+        if (total_out) *total_out = 0;
+        return PYROPE_OK;
+    }
+    if (total_out) *total_out = h->list_total;
+    if (offsets_out) memcpy(offsets_out, h->list_off_h.data(), sizeof(int64_t) * ((size_t)h->nc + 1));
+    if (rows_out && h->list_total)
+        CK(cudaMemcpy(rows_out, h->list_rows.p, sizeof(int64_t) * (size_t)h->list_total, cudaMemcpyDeviceToHost));
+    if (codes_out && h->list_total && h->kind == PYROPE_IVF_PQ)
+        CK(cudaMemcpy(codes_out, h->list_codes.p, (size_t)h->list_total * h->m, cudaMemcpyDeviceToHost));
+    return PYROPE_OK;
+}
+
+int pyrope_index_stats(pyrope_index* h, int64_t* live_rows, int64_t* buffer_rows, int* dim, int* metric) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (live_rows) *live_rows = h->seg.live + (h->built ? h->list_total - h->list_ndead : 0);
+    if (buffer_rows) *buffer_rows = h->seg.live;
+    if (dim) *dim = h->dim;
+    if (metric) *metric = h->metric;
+    return PYROPE_OK;
+}
+
+int pyrope_index_search_batch_device(pyrope_index* h, int64_t nq, const float* dQ, int topk, int64_t max_scans,
+                                     int nprobe, float* d_scores, int64_t* d_rows, int32_t* d_counts, void* stream) {
+    TRY(validate_search(h, nq, dQ, topk));
+    if (nq == 0) return PYROPE_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->kind == PYROPE_IVF_FLAT && max_scans >= 0 && h->list_ndead > 0) TRY(compact_lists(h));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    TRY(search_device(h, nq, dQ, topk, max_scans, nprobe, d_scores, d_rows, d_counts, st));
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_index_search_batch(pyrope_index* h, int64_t nq, const float* Q, int topk, int64_t max_scans, int nprobe,
+                              float* scores_out, int64_t* rows_out, int32_t* counts_out) {
+    TRY(validate_search(h, nq, Q, topk));
+    if (nq == 0) return PYROPE_OK;
+    if (!scores_out || !rows_out || !counts_out) return fail(PYROPE_ERR_INVALID_ARG, "output buffer is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->kind == PYROPE_IVF_FLAT && max_scans >= 0 && h->list_ndead > 0) TRY(compact_lists(h));
+    cudaStream_t st = h->stream;
+    Workspace& ws = h->ws;
+    const int kk = std::max(topk, 1);
+    TRY(ws.hq.ensure(sizeof(float) * (size_t)nq * h->dim, 0, st));
+    TRY(ws.hs.ensure(sizeof(float) * (size_t)nq * kk, 0, st));
+    TRY(ws.hl.ensure(sizeof(int64_t) * (size_t)nq * kk, 0, st));
+    TRY(ws.hc.ensure(sizeof(int32_t) * (size_t)nq, 0, st));
+    CK(cudaMemcpyAsync(ws.hq.p, Q, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
+    TRY(search_device(h, nq, ws.hq.as<float>(), topk, max_scans, nprobe, ws.hs.as<float>(), ws.hl.as<int64_t>(),
+                      ws.hc.as<int32_t>(), st));
+    if (topk > 0) {
+        CK(cudaMemcpyAsync(scores_out, ws.hs.p, sizeof(float) * (size_t)nq * topk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rows_out, ws.hl.p, sizeof(int64_t) * (size_t)nq * topk, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(counts_out, ws.hc.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_index_last_search_ms(pyrope_index* h, float* out4) {
+    if (!h || !out4) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.f;
+    if (!h->ev_valid) return PYROPE_OK;
+    CK(cudaEventSynchronize(h->ev[3]));
+    CK(cudaEventElapsedTime(&out4[0], h->ev[0], h->ev[3]));
+    CK(cudaEventElapsedTime(&out4[1], h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&out4[2], h->ev[1], h->ev[2]));
+    CK(cudaEventElapsedTime(&out4[3], h->ev[2], h->ev[3]));
+    return PYROPE_OK;
+}
+
+int pyrope_index_last_search_launches(pyrope_index* h, int* out) {
+    if (!h || !out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    *out = h->last_launches;
+    return PYROPE_OK;
+}
+
+int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float* d_scores, const int64_t* d_rows,
+                             float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream) {
+    if (nq < 0 || parts <= 0 || k_in <= 0 || k_out <= 0) return fail(PYROPE_ERR_INVALID_ARG, "bad merge shape");
+    if ((int64_t)parts * k_in > kMergeMaxCandidates)
+        return fail(PYROPE_ERR_UNSUPPORTED, "parts*k_in = %lld exceeds %d", (long long)parts * k_in, kMergeMaxCandidates);
+    CK(launch_merge_pairs(nq, parts, k_in, k_out, d_scores, d_rows, nq * (int64_t)k_in, k_in, d_scores_out, d_rows_out,
+                          d_counts_out, (cudaStream_t)stream));
+    if (!stream) CK(cudaStreamSynchronize(nullptr));
+    return PYROPE_OK;
+}
+
+// ---- building blocks (host pointers) -------------------------------------------------------------
+int pyrope_coarse_assign(int metric, int dim, int64_t n, const float* X, int n_centroids, const float* centroids,
+                         int32_t* assign_out) {
+    if (!X || !centroids || !assign_out || dim <= 0 || n < 0 || n_centroids <= 0)
+        return fail(PYROPE_ERR_INVALID_ARG, "bad arguments");
+    TRY(ensure_init());
+    if (n == 0) return PYROPE_OK;
+    DevBuf dx, dc, dn, da;
+    cudaStream_t st = nullptr;
+    TRY(dx.ensure(sizeof(float) * (size_t)n * dim, 0, st, true));
+    TRY(dc.ensure(sizeof(float) * (size_t)n_centroids * dim, 0, st, true));
+    TRY(dn.ensure(sizeof(float) * (size_t)n_centroids, 0, st, true));
+    TRY(da.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
+    CK(cudaMemcpy(dx.p, X, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, centroids, sizeof(float) * (size_t)n_centroids * dim, cudaMemcpyHostToDevice));
+    if (metric == kCosine) CK(launch_row_norms_exact(dc.as<float>(), n_centroids, dim, dim, dn.as<float>(), st));
+    CK(launch_assign_exact(metric, dim, n, dx.as<float>(), dim, n_centroids, dc.as<float>(), dn.as<float>(), da.as<int32_t>(), st));
+    CK(cudaMemcpy(assign_out, da.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    return PYROPE_OK;
+}
+
+int pyrope_kmeans_train(int metric, int dim, int64_t n, int64_t ld, const float* data, int k, int max_iter, int32_t seed,
+                        float* centroids_out, int* k_out, int* iters_out) {
+    if (!data || !centroids_out || !k_out || dim <= 0 || n < 0 || ld < dim) return fail(PYROPE_ERR_INVALID_ARG, "bad arguments");
+    TRY(ensure_init());
+    *k_out = 0;
+    if (n == 0) return PYROPE_OK;
+    int kk = k <= 0 ? 1 : (int)std::min<int64_t>(k, n);
+    DevBuf dx, dc;
+    cudaStream_t st = nullptr;
+    TRY(dx.ensure(sizeof(float) * (size_t)n * ld, 0, st, true));
+    TRY(dc.ensure(sizeof(float) * (size_t)kk * dim, 0, st, true));
+    CK(cudaMemcpy(dx.p, data, sizeof(float) * (size_t)n * ld, cudaMemcpyHostToDevice));
+    TRY(kmeans_train_device(metric, dim, n, ld, dx.as<float>(), k, max_iter, seed, dc.as<float>(), k_out, iters_out, st));
+    CK(cudaMemcpy(centroids_out, dc.p, sizeof(float) * (size_t)(*k_out) * dim, cudaMemcpyDeviceToHost));
+    return PYROPE_OK;
+}
+
+int pyrope_pq_encode(int dim, int m, int k, const float* codebooks, const int32_t* ksub, int64_t n, const float* X,
+                     uint8_t* codes_out) {
+    if (!codebooks || !X || !codes_out || dim <= 0 || m <= 0 || dim % m || k <= 0 || k > 256 || n < 0)
+        return fail(PYROPE_ERR_INVALID_ARG, "bad arguments");
+    TRY(ensure_init());
+    if (n == 0) return PYROPE_OK;
+    DevBuf dx, dc, dk, dcode;
+    cudaStream_t st = nullptr;
+    const int sub = dim / m;
+    TRY(dx.ensure(sizeof(float) * (size_t)n * dim, 0, st, true));
+    TRY(dc.ensure(sizeof(float) * (size_t)m * k * sub, 0, st, true));
+    TRY(dk.ensure(sizeof(int32_t) * (size_t)m, 0, st, true));
+    TRY(dcode.ensure((size_t)n * m, 0, st, true));
+    std::vector<int32_t> ks((size_t)m, k);
+    if (ksub) memcpy(ks.data(), ksub, sizeof(int32_t) * (size_t)m);
+    CK(cudaMemcpy(dx.p, X, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, codebooks, sizeof(float) * (size_t)m * k * sub, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.p, ks.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice));
+    CK(launch_pq_encode_exact(dx.as<float>(), n, dim, m, k, dc.as<float>(), dk.as<int32_t>(), dcode.as<uint8_t>(), st));
+    CK(cudaMemcpy(codes_out, dcode.p, (size_t)n * m, cudaMemcpyDeviceToHost));
+    return PYROPE_OK;
+}
+
+int pyrope_pq_distance_table(int dim, int m, int k, const float* codebooks, int64_t nq, const float* Q, float* table_out) {
+    if (!codebooks || !Q || !table_out || dim <= 0 || m <= 0 || dim % m || k <= 0 || nq < 0)
+        return fail(PYROPE_ERR_INVALID_ARG, "bad arguments");
+    TRY(ensure_init());
+    if (nq == 0) return PYROPE_OK;
+    DevBuf dq, dc, dt;
+    cudaStream_t st = nullptr;
+    TRY(dq.ensure(sizeof(float) * (size_t)nq * dim, 0, st, true));
+    TRY(dc.ensure(sizeof(float) * (size_t)k * dim, 0, st, true));
+    TRY(dt.ensure(sizeof(float) * (size_t)nq * m * k, 0, st, true));
+    CK(cudaMemcpy(dq.p, Q, sizeof(float) * (size_t)nq * dim, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, codebooks, sizeof(float) * (size_t)k * dim, cudaMemcpyHostToDevice));
+    CK(launch_pq_distance_table(dq.as<float>(), nq, dim, dc.as<float>(), m, k, dt.as<float>(), st));
+    CK(cudaMemcpy(table_out, dt.p, sizeof(float) * (size_t)nq * m * k, cudaMemcpyDeviceToHost));
+    return PYROPE_OK;
+}
+
+int pyrope_fill_uniform_device(float* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (!d_out || n < 0) return fail(PYROPE_ERR_INVALID_ARG, "bad arguments");
+    CK(launch_fill_uniform(d_out, n, seed, offset, (cudaStream_t)stream));
+    return PYROPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// build.cu — bit-exact build-time kernels: coarse assignment, PQ encoding, k-means update.
+//
+// "Centroid assignment and PQ code IDs must be bit-exact given the same trained codebooks": these
+// kernels reproduce the reference's fp32 evaluation order (8-lane Vector<float> accumulators,
+// separate multiply and add, pairwise horizontal sum — the conventions documented in DESIGN.md) with
+// __fmul_rn/__fadd_rn/__fsub_rn so nvcc can never contract them into FMAs.
+//   assign : KMeansUtils.FindNearestCentroid  (KMeansUtils.cs:70-93)  via VectorMath.L2Squared /
+//            DotProduct / Cosine (VectorMath.cs:8-109)
+//   encode : ProductQuantizer.Encode/FindNearest (ProductQuantizer.cs:60-80,122-136) via
+//            VectorMath.L2SquaredUnsafe (VectorMath.cs:188-253)
+//   update : KMeansUtils.Train mean update (KMeansUtils.cs:46-63)
+#include "common.cuh"
+#include "kernels.h"
+
+#include <float.h>
+
+namespace pyrope {
+namespace {
+
+__device__ __forceinline__ float hsum8(const float (&v)[8]) {
+    float lo = __fadd_rn(__fadd_rn(v[0], v[1]), __fadd_rn(v[2], v[3]));
+    float hi = __fadd_rn(__fadd_rn(v[4], v[5]), __fadd_rn(v[6], v[7]));
+    return __fadd_rn(lo, hi);
+}
+
+enum Arith { A2_L2 = 0, A2_DOT = 1, A1_L2 = 2 };
+
+template <int OP>  // 0 l2, 1 dot
+__device__ __forceinline__ float term(float a, float b) {
+    if (OP == 0) { float d = __fsub_rn(a, b); return __fmul_rn(d, d); }
+    return __fmul_rn(a, b);
+}
+
+// VectorMath.L2Squared / DotProduct: one 8-lane accumulator, scalar tail.  a: shared/global, b: global
+template <int OP>
+__device__ float a2_eval(const float* a, const float* b, int n) {
+    int i = 0;
+    float sum = 0.f;
+    if (n >= 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (; i <= n - 8; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], term<OP>(a[i + j], __ldg(b + i + j)));
+        }
+        sum = __fadd_rn(sum, hsum8(acc));
+    }
+    for (; i < n; ++i) sum = __fadd_rn(sum, term<OP>(a[i], __ldg(b + i)));
+    return sum;
+}
+
+// VectorMath.L2SquaredUnsafe: 4 accumulators for len >= 32, remainder accumulator, scalar tail
+__device__ float a1_l2_eval(const float* a, const float* b, int n) {
+    int i = 0;
+    float sum = 0.f;
+    if (n >= 32) {
+        float a1[8], a2[8], a3[8], a4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a1[j] = a2[j] = a3[j] = a4[j] = 0.f;
+        for (; i <= n - 32; i += 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a1[j] = __fadd_rn(a1[j], term<0>(a[i + j], __ldg(b + i + j)));
+                a2[j] = __fadd_rn(a2[j], term<0>(a[i + 8 + j], __ldg(b + i + 8 + j)));
+                a3[j] = __fadd_rn(a3[j], term<0>(a[i + 16 + j], __ldg(b + i + 16 + j)));
+                a4[j] = __fadd_rn(a4[j], term<0>(a[i + 24 + j], __ldg(b + i + 24 + j)));
+            }
+        }
+        float fin[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fin[j] = __fadd_rn(__fadd_rn(__fadd_rn(a1[j], a2[j]), a3[j]), a4[j]);
+        sum = __fadd_rn(sum, hsum8(fin));
+    }
+    if (i <= n - 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (; i <= n - 8; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], term<0>(a[i + j], __ldg(b + i + j)));
+        }
+        sum = __fadd_rn(sum, hsum8(acc));
+    }
+    for (; i < n; ++i) sum = __fadd_rn(sum, term<0>(a[i], __ldg(b + i)));
+    return sum;
+}
+
+// ComputeNorm (VectorMath.cs:72-100)
+__device__ float norm_eval(const float* v, int n) {
+    int i = 0;
+    float sum = 0.f;
+    if (n >= 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (; i <= n - 8; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(v[i + j], v[i + j]));
+        }
+        sum = __fadd_rn(sum, hsum8(acc));
+    }
+    for (; i < n; ++i) sum = __fadd_rn(sum, __fmul_rn(v[i], v[i]));
+    return __fsqrt_rn(sum);
+}
+
+// One warp per (vector, subspace): lanes stride over candidates in increasing index order, keep
+// the first best (strict '>'), then a warp arg-max that prefers the lower index on ties —
+// exactly "lowest index wins" of the sequential reference loops.
+// MODE 0: score = -L2Squared (a2)   1: DotProduct (a2)   2: Cosine (a2)   3: -L2SquaredUnsafe (a1)
+template <int MODE, typename OutT>
+__global__ void __launch_bounds__(256) nearest_exact_kernel(const float* __restrict__ X, int64_t n,
+                                                            int64_t ldx, int dd, int nsub,
+                                                            const float* __restrict__ Cn, int ncmax,
+                                                            const int32_t* __restrict__ ncs,
+                                                            const float* __restrict__ cnorms,
+                                                            OutT* out) {
+    extern __shared__ float vs[];  // [8 warps][dd]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    const int mi = blockIdx.y;
+    if (row >= n) return;
+    float* v = vs + warp * dd;
+    const float* x = X + row * ldx + (int64_t)mi * dd;
+    for (int i = lane; i < dd; i += 32) v[i] = x[i];
+    __syncwarp();
+    const int nc = ncs ? ncs[mi] : ncmax;
+    const float* C = Cn + (int64_t)mi * ncmax * dd;
+    float vnorm = 0.f;
+    if (MODE == 2) vnorm = norm_eval(v, dd);
+    float best = -FLT_MAX;
+    int besti = 0;
+    for (int c = lane; c < nc; c += 32) {
+        const float* cv = C + (int64_t)c * dd;
+        float s;
+        if (MODE == 0) s = -a2_eval<0>(v, cv, dd);
+        else if (MODE == 1) s = a2_eval<1>(v, cv, dd);
+        else if (MODE == 2) {
+            float cn = cnorms[c];
+            if (vnorm < 1e-6f || cn < 1e-6f) s = 0.f;
+            else s = __fdiv_rn(a2_eval<1>(v, cv, dd), __fmul_rn(vnorm, cn));
+        } else s = -a1_l2_eval(v, cv, dd);
+        if (s > best) { best = s; besti = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (os > best || (os == best && oi < besti)) { best = os; besti = oi; }
+    }
+    if (lane == 0) out[row * nsub + mi] = (OutT)besti;
+}
+
+__global__ void row_norms_kernel(const float* X, int64_t n, int dim, int64_t ldx, float* out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    out[r] = norm_eval(X + r * ldx, dim);
+}
+
+__global__ void residual_kernel(const float* X, int64_t n, int dim, const float* C, const int32_t* assign,
+                                float* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    int64_t r = i / dim;
+    int d = (int)(i - r * dim);
+    out[i] = __fsub_rn(X[i], C[(int64_t)assign[r] * dim + d]);
+}
+
+// one CTA per cluster; thread per dimension keeps the running fp32 sum in data order
+__global__ void __launch_bounds__(128) kmeans_update_kernel(const float* __restrict__ X, int64_t ldx, int dim,
+                                                            const int64_t* __restrict__ offs,
+                                                            const int32_t* __restrict__ order,
+                                                            float* centroids, int* changed) {
+    const int c = blockIdx.x;
+    const int64_t b = offs[c], e = offs[c + 1];
+    if (e == b) return;  // empty cluster keeps its centroid (KMeansUtils.cs:48)
+    const float fc = (float)(int)(e - b);
+    int differs = 0;
+    // pass 1: decide whether any dimension moved by more than 1e-6 (ArraysEqual :95-101)
+    for (int d0 = 0; d0 < dim; d0 += blockDim.x) {
+        int d = d0 + threadIdx.x;
+        if (d < dim) {
+            float s = 0.f;
+            for (int64_t j = b; j < e; ++j) s = __fadd_rn(s, __ldg(X + (int64_t)order[j] * ldx + d));
+            float nv = __fdiv_rn(s, fc);
+            float df = __fsub_rn(centroids[(int64_t)c * dim + d], nv);
+            if ((double)fabsf(df) > 1e-6) differs = 1;
+        }
+    }
+    differs = __syncthreads_or(differs);
+    if (!differs) return;
+    for (int d0 = 0; d0 < dim; d0 += blockDim.x) {
+        int d = d0 + threadIdx.x;
+        if (d < dim) {
+            float s = 0.f;
+            for (int64_t j = b; j < e; ++j) s = __fadd_rn(s, __ldg(X + (int64_t)order[j] * ldx + d));
+            centroids[(int64_t)c * dim + d] = __fdiv_rn(s, fc);
+        }
+    }
+    if (threadIdx.x == 0) *changed = 1;
+}
+
+__global__ void gather_rows_kernel(const uint8_t* X, int64_t row_bytes, const int64_t* idx, int64_t n,
+                                   uint8_t* out) {
+    // one warp per row; 16-byte words when aligned
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const uint8_t* src = X + idx[r] * row_bytes;
+    uint8_t* dst = out + r * row_bytes;
+    if ((row_bytes & 15) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int64_t i = lane; i < row_bytes / 16; i += 32) d4[i] = s4[i];
+    } else {
+        for (int64_t i = lane; i < row_bytes; i += 32) dst[i] = src[i];
+    }
+}
+
+__global__ void iota64_kernel(int64_t* out, int64_t n, int64_t base) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = base + i;
+}
+
+// counter-based uniform [0,1) generator (splitmix64 finaliser), 24 random mantissa bits
+__global__ void fill_uniform_kernel(float* out, int64_t n, uint64_t seed, uint64_t offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t z = (offset + (uint64_t)i) * 0x9E3779B97F4A7C15ull + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    out[i] = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+cudaError_t launch_assign_exact(int metric, int dim, int64_t n, const float* X, int64_t ldx, int nc,
+                                const float* centroids, const float* cnorms, int32_t* assign,
+                                cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid(blocks_for(n, 8), 1);
+    size_t smem = sizeof(float) * 8 * (size_t)dim;
+    cudaError_t e = cudaSuccess;
+#define PYROPE_LAUNCH_NEAREST(MODE)                                                                  \
+    if (smem > 48 * 1024)                                                                            \
+        e = cudaFuncSetAttribute(nearest_exact_kernel<MODE, int32_t>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    if (e != cudaSuccess) return e;                                                                  \
+    nearest_exact_kernel<MODE, int32_t><<<grid, 256, smem, st>>>(X, n, ldx, dim, 1, centroids, nc,   \
+                                                                  nullptr, cnorms, assign);
+    if (metric == kL2) { PYROPE_LAUNCH_NEAREST(0) }
+    else if (metric == kIP) { PYROPE_LAUNCH_NEAREST(1) }
+    else { PYROPE_LAUNCH_NEAREST(2) }
+#undef PYROPE_LAUNCH_NEAREST
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pq_encode_exact(const float* R, int64_t n, int dim, int m, int kpad,
+                                   const float* codebook, const int32_t* ksub, uint8_t* codes,
+                                   cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int sub = dim / m;
+    dim3 grid(blocks_for(n, 8), (unsigned)m);
+    size_t smem = sizeof(float) * 8 * (size_t)sub;
+    nearest_exact_kernel<3, uint8_t><<<grid, 256, smem, st>>>(R, n, dim, sub, m, codebook, kpad, ksub,
+                                                              nullptr, codes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_norms_exact(const float* X, int64_t n, int dim, int64_t ldx, float* out,
+                                   cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    row_norms_kernel<<<blocks_for(n, 128), 128, 0, st>>>(X, n, dim, ldx, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_residuals(const float* X, int64_t n, int dim, const float* centroids,
+                             const int32_t* assign, float* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    residual_kernel<<<blocks_for(n * dim, 256), 256, 0, st>>>(X, n, dim, centroids, assign, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans_update(const float* X, int64_t ldx, int dim, int nc, const int64_t* offs,
+                                 const int32_t* order, float* centroids, int* changed, cudaStream_t st) {
+    if (nc <= 0) return cudaSuccess;
+    kmeans_update_kernel<<<(unsigned)nc, 128, 0, st>>>(X, ldx, dim, offs, order, centroids, changed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const void* X, int64_t row_bytes, const int64_t* idx, int64_t n, void* out,
+                               cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    gather_rows_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>((const uint8_t*)X, row_bytes, idx, n,
+                                                               (uint8_t*)out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_iota64(int64_t* out, int64_t n, int64_t base, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    iota64_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, base);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    fill_uniform_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, seed, offset);
+    return cudaGetLastError();
+}
+
+}  // namespace pyrope

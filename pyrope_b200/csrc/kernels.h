@@ -1,0 +1,110 @@
+// kernels.h — launchers of the sm_100a kernels behind libpyrope_gpu.so (internal; not the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pyrope {
+
+enum Metric { kL2 = 0, kIP = 1, kCosine = 2 };
+
+// Every scan kernel emits, per query and per "part" (a base split, a probe group, the buffer ...),
+// its local top-k as (score, label) pairs into one combined array laid out [nq][parts_total][k];
+// label < 0 marks an empty slot.  merge_pairs() then reduces parts_total*k -> k_out per query.
+struct PairOut {
+    float* scores;
+    int64_t* labels;
+    int parts_total;  // S
+    int part_base;    // first part index this launch writes
+};
+
+// ---- K1: exact FLAT scan + top-k (CUDA-core path) -------------------------------------------
+// Replaces BruteForceVectorIndex.Search:341-360 (and, over centroids, the coarse ranking at
+// IvfFlatVectorIndex.cs:186-198 / IvfPqVectorIndex.cs:141-150).
+struct FlatScanParams {
+    const float* Q; int64_t nq; int dim;
+    const float* X; int64_t n_scan;          // scan positions [0, n_scan)
+    const uint8_t* dead;                     // nullable: non-zero = skip
+    const float* xnorm; const float* qnorm;  // cosine only
+    const int64_t* labels;                   // nullable: label = position
+    int metric; int k;
+    int splits;                              // parts written: [part_base, part_base+splits)
+    uint64_t* queue; int cap;                // scratch [splits][nq][cap]
+    PairOut out;
+};
+int flat_scan_cap(int k);
+int flat_scan_pick_splits(int64_t nq, int64_t n_scan, int k, int num_sms, int max_parts);
+cudaError_t launch_flat_scan(const FlatScanParams& p, cudaStream_t st);
+
+// ---- K6: merge ------------------------------------------------------------------------------
+// in: candidate (score,label) at address part*part_stride + q*q_stride + j, j < k_in.
+cudaError_t launch_merge_pairs(int64_t nq, int parts, int k_in, int k_out, const float* in_scores,
+                               const int64_t* in_labels, int64_t part_stride, int64_t q_stride,
+                               float* out_scores, int64_t* out_labels, int32_t* out_counts,
+                               cudaStream_t st);
+constexpr int kMergeMaxCandidates = 4096;
+
+// ---- K4: IVF_FLAT inverted-list scan ----------------------------------------------------------
+// Replaces IvfFlatVectorIndex.Search:200-218.
+struct IvfFlatScanParams {
+    const float* Q; int64_t nq; int dim;
+    const int64_t* probes; int nprobe;       // [nq][nprobe] list ids in rank order, <0 = none
+    const int32_t* allow;                    // nullable [nq][nprobe]: entries allowed per probe (MaxScans)
+    const int64_t* list_off;                 // [nlist+1]
+    const float* vecs; const uint8_t* dead; const float* norms; const int64_t* labels;
+    const float* qnorm;
+    int metric; int k; int groups;           // grid.y: probe groups (parts)
+    PairOut out;
+};
+cudaError_t launch_ivfflat_scan(const IvfFlatScanParams& p, cudaStream_t st);
+
+// ---- K5: IVF_PQ LUT build + ADC scan ----------------------------------------------------------
+// Replaces ProductQuantizer.ComputeDistanceTable:98-120 + IvfPqVectorIndex.Search:152-199.
+struct IvfPqScanParams {
+    const float* Q; int64_t nq; int dim;
+    const int64_t* probes; int nprobe;
+    const int64_t* list_off;
+    const float* centroids;                  // [nlist][dim]
+    const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
+    const uint8_t* codes; const uint8_t* dead; const int64_t* labels;
+    int k; int groups;
+    int force_generic;                       // tests: run the simple kernel
+    PairOut out;
+};
+cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
+// ProductQuantizer.ComputeDistanceTable for nq queries (parity tests): table [nq][m][k]
+cudaError_t launch_pq_distance_table(const float* Q, int64_t nq, int dim, const float* codebook,
+                                     int m, int k, float* table, cudaStream_t st);
+
+// ---- MaxScans bookkeeping (IvfFlatVectorIndex.cs:172,202,209) ---------------------------------
+cudaError_t launch_probe_allow(const int64_t* probes, int64_t nq, int nprobe,
+                               const int64_t* list_off, int64_t budget, int32_t* allow,
+                               cudaStream_t st);
+
+// ---- bit-exact build kernels -------------------------------------------------------------------
+// KMeansUtils.FindNearestCentroid:70-93 (VectorMath.L2Squared/DotProduct/Cosine order, no FMA)
+cudaError_t launch_assign_exact(int metric, int dim, int64_t n, const float* X, int64_t ldx,
+                                int nc, const float* centroids, const float* cnorms,
+                                int32_t* assign, cudaStream_t st);
+// ComputeNorm:72-100 in the reference's order, one row per thread group
+cudaError_t launch_row_norms_exact(const float* X, int64_t n, int dim, int64_t ldx, float* out,
+                                   cudaStream_t st);
+// residual = x - centroid[assign]   (IvfPqVectorIndex.cs:82-85)
+cudaError_t launch_residuals(const float* X, int64_t n, int dim, const float* centroids,
+                             const int32_t* assign, float* out, cudaStream_t st);
+// ProductQuantizer.Encode:60-80 + FindNearest:122-136 (L2SquaredUnsafe order, no FMA)
+cudaError_t launch_pq_encode_exact(const float* R, int64_t n, int dim, int m, int kpad,
+                                   const float* codebook, const int32_t* ksub, uint8_t* codes,
+                                   cudaStream_t st);
+// KMeansUtils.Train:46-63 update: order[offs[c]..offs[c+1]) lists the rows of cluster c in data
+// order; fp32 running sums in that order, /= count, ArraysEqual(1e-6) gate.  changed: int flag.
+cudaError_t launch_kmeans_update(const float* X, int64_t ldx, int dim, int nc,
+                                 const int64_t* offs, const int32_t* order, float* centroids,
+                                 int* changed, cudaStream_t st);
+// gather rows: out[i] = X[idx[i]]  (rows of `width` elements of `elem` bytes)
+cudaError_t launch_gather_rows(const void* X, int64_t row_bytes, const int64_t* idx, int64_t n,
+                               void* out, cudaStream_t st);
+cudaError_t launch_iota64(int64_t* out, int64_t n, int64_t base, cudaStream_t st);
+cudaError_t launch_fill_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset,
+                                cudaStream_t st);
+
+}  // namespace pyrope
