@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — batched VEC.SEARCH throughput of the B200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c1|c2|c3] [--scale S]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm (oracle port of the reference's C# loops)
+
+A step = one pass of the hot path over one batch of synthetic queries.  `value` = whole-job QPS with
+queries and outputs resident in HBM (CUDA events on the launching stream, max over ranks);
+`e2e` = the same through the C-ABI host entry point with HOST buffers (H2D of the queries and D2H of
+the results inside the timed region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC_NAME = "batched VEC.SEARCH QPS at fixed recall@10"
+
+
+def workload(name: str, scale: float) -> dict:
+    """BASELINE.json configs.  scale < 1 shrinks N and nlist together (list length,
+    nprobe and per-query work unchanged) for development runs; such lines carry "reduced": true."""
+    if name == "c5":
+        w = dict(kind="IVF_PQ", metric="L2", dim=128, n=100_000_000, nq=10_000, topk=10, nlist=65536, m=16, k=256,
+                 nprobe=64)
+        w["n"] = max(4096, int(round(w["n"] * scale)))
+        w["nlist"] = max(64, int(round(w["nlist"] * scale)))
+    elif name == "c4":
+        w = dict(kind="FLAT", metric="IP", dim=768, n=10_000_000, nq=10_000, topk=100)
+        w["n"] = max(4096, int(round(w["n"] * scale)))
+    elif name == "c1":
+        w = dict(kind="FLAT", metric="L2", dim=128, n=10_000, nq=100, topk=10)
+    elif name == "c2":
+        w = dict(kind="IVF_FLAT", metric="L2", dim=128, n=10_000, nq=100, topk=10, nlist=100, nprobe=3)
+    elif name == "c3":
+        w = dict(kind="IVF_PQ", metric="L2", dim=128, n=10_000, nq=100, topk=10, nlist=100, m=4, k=256, nprobe=1)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    w["name"] = name
+    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5"))
+    return w
+
+
+def describe(w: dict) -> str:
+    if w["kind"] == "IVF_PQ":
+        return (f"{w['name']}: IVF_PQ nlist={w['nlist']} m={w['m']} k={w['k']} synthetic dim={w['dim']}, "
+                f"{w['n']} base, nprobe={w['nprobe']}, {w['nq']}-query batch, TOPK {w['topk']}")
+    if w["kind"] == "IVF_FLAT":
+        return (f"{w['name']}: IVF_FLAT nlist={w['nlist']} synthetic dim={w['dim']}, {w['n']} base, "
+                f"nprobe={w['nprobe']}, {w['nq']} queries, TOPK {w['topk']}")
+    return f"{w['name']}: FLAT {w['metric']} synthetic dim={w['dim']}, {w['n']} base, {w['nq']}-query batch, TOPK {w['topk']}"
+
+
+def algorithmic_work(w: dict, world: int) -> dict:
+    """Per search launch on ONE rank: HBM bytes for the scan paths, FLOPs for FLAT."""
+    if w["kind"] == "IVF_PQ":  # codes only: nprobe * avg_list * m bytes per query
+        b = w["nq"] * w["nprobe"] * (w["n"] / w["nlist"]) * w["m"] / world
+        return {"bound": "hbm", "work": b, "unit": "GB/s"}
+    if w["kind"] == "IVF_FLAT":
+        b = w["nq"] * (w["nprobe"] * (w["n"] / w["nlist"]) * w["dim"] * 4) / world
+        return {"bound": "hbm", "work": b, "unit": "GB/s"}
+    f = 2.0 * w["nq"] * (w["n"] / world) * w["dim"]
+    return {"bound": "tensor", "work": f, "unit": "TFLOP/s"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# index construction on the GPU (setup, untimed)
+# ------------------------------------------------------------------------------------------------
+def build_gpu_index(pg, torch, w: dict, rank: int, world: int, log):
+    from pyrope_b200 import _lib
+    kind = {"FLAT": pg.FLAT, "IVF_FLAT": pg.IVF_FLAT, "IVF_PQ": pg.IVF_PQ}[w["kind"]]
+    metric = {"L2": pg.L2, "IP": pg.INNER_PRODUCT, "COSINE": pg.COSINE}[w["metric"]]
+    dim, n = w["dim"], w["n"]
+    ix = pg.GpuIndex(kind, dim, metric, nlist=w.get("nlist", 100), m=w.get("m", 4), k=w.get("k", 256))
+    t0 = time.time()
+    if kind == pg.FLAT:
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world  # contiguous row blocks per rank
+    else:
+        lo, hi = 0, n  # every rank sees every row; lists are sharded by list id at build time
+        if world > 1:
+            ix.set_shard(rank, world)
+        ntrain = min(n, max(40 * w["nlist"], 65536))
+        ix.set_train_params(ntrain, 4 if w["nlist"] > 1024 else 10)
+    ix.reserve(hi - lo)
+    chunk = min(hi - lo, (1 << 31) // (dim * 4) // 2)  # ~1 GiB staging
+    stage = torch.empty(chunk * dim, dtype=torch.float32, device="cuda")
+    labels = torch.empty(chunk, dtype=torch.int64, device="cuda") if kind == pg.FLAT and world > 1 else None
+    r = lo
+    while r < hi:
+        c = min(chunk, hi - r)
+        _lib.fill_uniform_device(stage.data_ptr(), c * dim, 42, r * dim, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        if labels is not None:
+            labels[:c] = torch.arange(r, r + c, device="cuda")
+            ix.add_device(stage.data_ptr(), c, labels.data_ptr())
+        else:
+            ix.add_device(stage.data_ptr(), c)
+        r += c
+    del stage
+    t1 = time.time()
+    if kind != pg.FLAT:
+        ix.build()
+    t2 = time.time()
+    log(f"rank {rank}: added {hi - lo} rows in {t1 - t0:.1f}s, build {t2 - t1:.1f}s, stats {ix.stats()}")
+    return ix, {"add_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2)}
+
+
+def make_queries(torch, w: dict):
+    from pyrope_b200 import _lib
+    q = torch.empty(w["nq"] * w["dim"], dtype=torch.float32, device="cuda")
+    _lib.fill_uniform_device(q.data_ptr(), q.numel(), 1337, 0, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return q.view(w["nq"], w["dim"])
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's loops on the index the GPU built
+# ------------------------------------------------------------------------------------------------
+def oracle_index_from_gpu(ix, w: dict, base_rows=None):
+    from oracle import pyoracle as orc
+    metric = {"L2": orc.L2, "IP": orc.IP, "COSINE": orc.COSINE}[w["metric"]]
+    if w["kind"] == "IVF_PQ":
+        o = orc.IvfPqIndex(w["dim"], metric, m=w["m"], k=w["k"], nlist=w["nlist"])
+        off, rows, codes = ix.lists()
+        cb, _ = ix.codebooks()
+        o.adopt(ix.centroids(), cb, off, rows, codes)
+        return o
+    raise NotImplementedError
+
+
+def time_cpu_baseline(oidx, Qh: np.ndarray, w: dict, budget_s: float):
+    from oracle import pyoracle as orc
+    threads = orc.max_threads()
+    nprobe = w.get("nprobe", -1)
+    probe = min(len(Qh), 2 * threads)
+    t0 = time.perf_counter()
+    oidx.search_batch(Qh[:probe], w["topk"], nprobe=nprobe)
+    per_q = (time.perf_counter() - t0) / probe
+    s = int(max(threads, min(len(Qh), budget_s / max(per_q, 1e-9))))
+    t0 = time.perf_counter()
+    oidx.search_batch(Qh[:s], w["topk"], nprobe=nprobe)
+    dt = time.perf_counter() - t0
+    return {"value": s / dt, "unit": "QPS", "cores": threads, "kind": "port",
+            "sample": f"{s} of the batch's {len(Qh)} queries over the same GPU-built index, one query per thread, "
+                      f"{dt:.1f}s wall"}, s, dt
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    import pyrope_b200 as pg
+    from pyrope_b200 import _lib
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.check(pg.load().pyrope_gpu_init(local))
+    log = (lambda s: print(s, file=sys.stderr, flush=True))
+    w = workload(args.workload, args.scale)
+    nq, dim, k = w["nq"], w["dim"], w["topk"]
+    nprobe = w.get("nprobe", -1)
+
+    ix, build_info = build_gpu_index(pg, torch, w, rank, world, log)
+    Q = make_queries(torch, w)
+    stream = torch.cuda.current_stream().cuda_stream
+    sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    rw = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    cn = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    if world > 1:
+        g_sc = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
+        g_rw = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
+        m_sc, m_rw, m_cn = torch.empty_like(sc), torch.empty_like(rw), torch.empty_like(cn)
+
+    launches = [0]
+
+    def step():
+        ix.search_device(Q.data_ptr(), nq, k, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), nprobe=nprobe, stream=stream)
+        launches[0] = ix.last_search_launches()
+        if world > 1:
+            dist.all_gather_into_tensor(g_sc.view(-1), sc.view(-1))
+            dist.all_gather_into_tensor(g_rw.view(-1), rw.view(-1))
+            _lib.topk_merge_device(nq, world, k, k, g_sc.data_ptr(), g_rw.data_ptr(), m_sc.data_ptr(), m_rw.data_ptr(),
+                                   m_cn.data_ptr(), stream=stream)
+            launches[0] += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = nq * args.steps / (ms / 1e3)
+
+    # ---- dominant-kernel time (CUDA events inside the library around the scan stage), per launch
+    stage_ms = {"total": 0.0, "coarse": 0.0, "scan": 0.0, "merge": 0.0}
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        ix.search_device(Q.data_ptr(), nq, k, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), nprobe=nprobe, stream=stream)
+        torch.cuda.synchronize()
+        for kk, v in ix.last_search_ms().items():
+            stage_ms[kk] += v / reps
+    alg = algorithmic_work(w, world)
+    dom = "scan"
+    dom_ms = stage_ms[dom]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if alg["bound"] == "hbm":
+        achieved = alg["work"] / (dom_ms / 1e3) / 1e9
+        peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (of fallback)"
+    else:
+        achieved = alg["work"] / (dom_ms / 1e3) / 1e12
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        peak = bf16 / 2.0  # TF32 dense = 1/2 bf16; 3xTF32 issues 3x the algorithmic FLOPs
+        peak_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense, of measured)" if "bf16_tflops" in peaks else "fallback"
+    roofline = {"bound": alg["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": alg["unit"],
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "ivfpq_scan_fast_kernel" if w["kind"] == "IVF_PQ" else w["kind"].lower() + "_scan",
+                "kernel_ms": round(dom_ms, 4), "algorithmic_per_launch": alg["work"], "peak_source": peak_src,
+                "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()}}
+
+    # ---- end to end through the host entry point: pinned host queries in, host results out
+    Qh_t = torch.empty((nq, dim), dtype=torch.float32, pin_memory=True)
+    Qh_t.copy_(Q)
+    torch.cuda.synchronize()
+    Qh = Qh_t.numpy()
+    hs = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+    hr = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+    hc = torch.empty((nq,), dtype=torch.int32, pin_memory=True)
+    L = pg.load()
+    import ctypes as C
+
+    def e2e_step():
+        if world == 1:
+            _lib.check(L.pyrope_index_search_batch(ix._h, nq, C.c_void_p(Qh_t.data_ptr()), k, -1, nprobe,
+                                                   C.c_void_p(hs.data_ptr()), C.c_void_p(hr.data_ptr()),
+                                                   C.c_void_p(hc.data_ptr())))
+        else:
+            Q.copy_(Qh_t, non_blocking=True)
+            step()
+            hs.copy_(m_sc, non_blocking=True)
+            hr.copy_(m_rw, non_blocking=True)
+            hc.copy_(m_cn, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": round(nq * args.steps / e2e_s, 1), "unit": "QPS", "h2d_bytes_per_step": nq * dim * 4,
+           "d2h_bytes_per_step": nq * k * 12 + nq * 4}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            oidx = oracle_index_from_gpu(ix, w)
+            cpu, _, _ = time_cpu_baseline(oidx, Qh, w, args.cpu_budget)
+            cpu["value"] = round(cpu["value"], 2)
+            del oidx
+        except NotImplementedError:
+            cpu = {"value": None, "unit": "QPS", "cores": 0, "kind": "port", "sample": "not wired for this workload"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC_NAME, "value": round(value, 1), "unit": "QPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w["kind"] != "IVF_PQ" else "f32 LUT / u8 codes",
+            "data": "synthetic uniform[0,1) fp32, counter-based generator (base seed 42, query seed 1337), "
+                    "codebooks trained on device and frozen",
+            "config": {"workload": describe(w), "reduced": w["reduced"], "l2_policy": "inputs larger than L2 (index "
+                       f"{w['n'] * w.get('m', w['dim'] * 4) / 1e6:.0f} MB scanned region vs 126 MB L2)",
+                       "parallelism": f"lists sharded list_id % {world}" if w["kind"] != "FLAT" else f"rows sharded in {world} blocks",
+                       "exchange": "nccl all_gather + on-device merge" if world > 1 else "none", **build_info},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * args.steps),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  The C# engine cannot be built in this image
+    (no dotnet), so this arm times the oracle port of its loops (oracle/oracle.c) with all host threads,
+    on the same config; the index it searches is the one the GPU builds (setup only, untimed)."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import torch
+
+    import pyrope_b200 as pg
+    from oracle import pyoracle as orc
+    from pyrope_b200 import _lib
+    torch.cuda.set_device(0)
+    _lib.check(pg.load().pyrope_gpu_init(0))
+    log = (lambda s: print(s, file=sys.stderr, flush=True))
+    w = workload(args.workload, args.scale)
+    ix, build_info = build_gpu_index(pg, torch, w, 0, 1, log)
+    Q = make_queries(torch, w)
+    Qh = Q.cpu().numpy()
+    oidx = oracle_index_from_gpu(ix, w)
+    del ix
+    torch.cuda.empty_cache()
+    threads = orc.max_threads()
+    nprobe = w.get("nprobe", -1)
+    # size one step to ~ (budget / (steps+warmup)) seconds
+    probe = min(len(Qh), 2 * threads)
+    t0 = time.perf_counter()
+    oidx.search_batch(Qh[:probe], w["topk"], nprobe=nprobe)
+    per_q = (time.perf_counter() - t0) / probe
+    per_step_budget = max(1.0, args.cpu_budget * 6 / max(1, args.steps + args.warmup))
+    s = int(max(threads, min(len(Qh), per_step_budget / max(per_q, 1e-9))))
+    for i in range(args.warmup):
+        oidx.search_batch(Qh[:s], w["topk"], nprobe=nprobe)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        off = (i * s) % max(1, len(Qh) - s + 1)
+        oidx.search_batch(Qh[off:off + s], w["topk"], nprobe=nprobe)
+    dt = time.perf_counter() - t0
+    value = s * args.steps / dt
+    sample = f"{s} of the batch's {len(Qh)} queries per step over the GPU-built index, one query per thread"
+    line = {"impl": "reference", "metric": METRIC_NAME, "value": round(value, 2), "unit": "QPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 LUT / u8 codes",
+            "data": "synthetic uniform[0,1) fp32 (same generator and seeds as the GPU arm)",
+            "config": {"workload": describe(w), "reduced": w["reduced"], **build_info},
+            "cpu_baseline": {"value": round(value, 2), "unit": "QPS", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 2), "unit": "QPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PYROPE_BENCH_WORKLOAD", "c5"))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("PYROPE_BENCH_SCALE", "1.0")))
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

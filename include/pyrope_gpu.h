@@ -103,6 +103,11 @@ int pyrope_index_set_train_params(pyrope_index *h, int64_t max_train_rows, int m
  * (NULL for IVF_FLAT).  The next pyrope_index_build only assigns (+ encodes). */
 int pyrope_index_set_codebooks(pyrope_index *h, int n_centroids, const float *centroids,
                                const float *pq_codebooks);
+/* Multi-GPU sharding of an IVF index: this process keeps only the inverted lists with
+ * list_id % world == rank (centroids and PQ codebooks stay replicated); rows assigned to other lists
+ * are dropped at the next pyrope_index_build.  Every rank sees all rows and all queries; per-rank
+ * top-k lists are exchanged with NCCL allgather and reduced by pyrope_topk_merge_device. */
+int pyrope_index_set_shard(pyrope_index *h, int rank, int world);
 int pyrope_index_is_built(pyrope_index *h, int *out);
 /* ICentroidsProvider.GetCentroids (IvfFlatVectorIndex.cs:314-325): n_out = 0 until built.
  * centroids_out may be NULL to query the count. */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pyrope_index_build": (C.c_int, [vp]),
     "pyrope_index_set_train_params": (C.c_int, [vp, C.c_int64, C.c_int]),
     "pyrope_index_set_codebooks": (C.c_int, [vp, C.c_int, vp, vp]),
+    "pyrope_index_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
     "pyrope_index_is_built": (C.c_int, [vp, i32p]),
     "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
@@ -171,6 +172,9 @@ class GpuIndex:
         c = _np(centroids, np.float32)
         cb = _np(pq_codebooks, np.float32) if pq_codebooks is not None else None
         check(load().pyrope_index_set_codebooks(self._h, c.shape[0], _p(c), _p(cb)))
+
+    def set_shard(self, rank, world):
+        check(load().pyrope_index_set_shard(self._h, rank, world))
 
     def is_built(self) -> bool:
         out = C.c_int32(0)

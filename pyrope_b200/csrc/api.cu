@@ -173,6 +173,7 @@ struct pyrope_index {
     bool frozen = false;  // codebooks supplied by the caller
     int64_t max_train_rows = 0;
     int max_iter = 0;
+    int shard_rank = 0, shard_world = 1;
 
     // row ordinal -> location: >=0 buffer slot, <=-2 list position (-2-pos), -1 gone
     std::vector<int64_t> row_loc;
@@ -295,6 +296,11 @@ __global__ void widen_rows_kernel(const int32_t* order, const int64_t* src, int6
 __global__ void order_to_i64_kernel(const int32_t* order, int64_t n, int64_t* dst) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = order[i];
+}
+
+__global__ void shard_mask_kernel(int32_t* a, int64_t n, int nc, int rank, int world) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (a[i] % world) != rank) a[i] = nc;  // parked in a dummy trailing cluster, dropped below
 }
 
 struct SortScratch {
@@ -433,19 +439,29 @@ int gather_build_data(Index* h, bool include_lists, BuildData& bd) {
     return PYROPE_OK;
 }
 
-int finish_lists(Index* h, const BuildData& bd, const int32_t* d_assign, int nc, SortScratch& sc,
+int finish_lists(Index* h, const BuildData& bd, int32_t* d_assign, int nc, SortScratch& sc,
                  const void* payload, int64_t payload_row_bytes, DevBuf& payload_out) {
     cudaStream_t st = h->stream;
-    const int64_t n = bd.n;
-    TRY(group_by_cluster(d_assign, n, nc, sc, st));
+    int64_t n = bd.n;
+    if (h->shard_world > 1) {
+        shard_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_assign, n, nc, h->shard_rank, h->shard_world);
+        CK(cudaGetLastError());
+        TRY(group_by_cluster(d_assign, n, nc + 1, sc, st));
+        int64_t kept = 0;
+        CK(cudaMemcpyAsync(&kept, sc.offs.as<int64_t>() + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n = kept;  // rows of foreign lists sort to the tail and are cut off
+    } else {
+        TRY(group_by_cluster(d_assign, n, nc, sc, st));
+    }
     DevBuf order64;
-    TRY(order64.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+    TRY(order64.ensure(sizeof(int64_t) * (size_t)bd.n, 0, st, true));
     order_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_out.as<int32_t>(), n, order64.as<int64_t>());
     CK(cudaGetLastError());
-    TRY(payload_out.ensure((size_t)n * (size_t)payload_row_bytes, 0, st, true));
+    TRY(payload_out.ensure((size_t)std::max<int64_t>(n, 1) * (size_t)payload_row_bytes, 0, st, true));
     CK(launch_gather_rows(payload, payload_row_bytes, order64.as<int64_t>(), n, payload_out.p, st));
-    TRY(h->list_rows.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
-    TRY(h->list_labels.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+    TRY(h->list_rows.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
+    TRY(h->list_labels.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
     widen_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_out.as<int32_t>(), bd.rows.as<int64_t>(), n, h->list_rows.as<int64_t>());
     widen_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.vals_out.as<int32_t>(), bd.labels.as<int64_t>(), n, h->list_labels.as<int64_t>());
     CK(cudaGetLastError());
@@ -503,8 +519,8 @@ int build_ivfflat(Index* h) {
     std::swap(h->list_vecs.p, newvecs.p);
     std::swap(h->list_vecs.bytes, newvecs.bytes);
     if (h->metric == kCosine) {
-        TRY(h->list_norms.ensure(sizeof(float) * (size_t)bd.n, 0, st, true));
-        CK(launch_row_norms_exact(h->list_vecs.as<float>(), bd.n, dim, dim, h->list_norms.as<float>(), st));
+        TRY(h->list_norms.ensure(sizeof(float) * (size_t)std::max<int64_t>(h->list_total, 1), 0, st, true));
+        CK(launch_row_norms_exact(h->list_vecs.as<float>(), h->list_total, dim, dim, h->list_norms.as<float>(), st));
     }
     CK(cudaStreamSynchronize(st));
     return PYROPE_OK;
@@ -1006,6 +1022,15 @@ int pyrope_index_set_codebooks(pyrope_index* h, int n_centroids, const float* ce
     CK(cudaStreamSynchronize(st));
     h->nc = n_centroids;
     h->frozen = true;
+    return PYROPE_OK;
+}
+
+int pyrope_index_set_shard(pyrope_index* h, int rank, int world) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (h->kind == PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "FLAT shards by rows: add only this rank's rows");
+    if (world < 1 || rank < 0 || rank >= world) return fail(PYROPE_ERR_INVALID_ARG, "bad shard %d/%d", rank, world);
+    h->shard_rank = rank;
+    h->shard_world = world;
     return PYROPE_OK;
 }
 
