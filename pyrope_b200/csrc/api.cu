@@ -128,7 +128,9 @@ struct Segment {
         cap = nc;
         return PYROPE_OK;
     }
+    bool tc_dirty = true;  // hi/lo split copies stale (row overwritten, deleted or slot re-used)
     void clear() {
+        tc_dirty = true;
         nslots = live = ndead = 0;
         dead_h.clear();
         slot_row.clear();
@@ -146,7 +148,16 @@ struct Segment {
 
 struct Workspace {
     DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probe_scores, probe_cnt, allow, qnorm,
-        hq, hs, hl, hc;  // h*: staging for the host-pointer entry point
+        qhi, qlo, tcq, tcc,  // tensor-core path: split queries, candidate queues, counts
+        hq, hs, hl, hc;      // h*: staging for the host-pointer entry point
+};
+
+// tf32 hi/lo split + per-row proxy terms of one operand table (base rows or centroids)
+struct TcOperand {
+    DevBuf hi, lo, scale, bias;
+    int64_t rows_valid = 0;
+    bool dirty = true;
+    void invalidate() { dirty = true; }
 };
 
 }  // namespace
@@ -180,6 +191,8 @@ struct pyrope_index {
     bool lists_loc_valid = true;
 
     Workspace ws;
+    TcOperand tc_seg, tc_cent;
+    int tc_mode = -1;  // -1 auto, 0 off, 1 force (PYROPE_FLAT_TC)
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     int last_launches = 0;
@@ -210,6 +223,7 @@ int seg_append(Index* h, int64_t n, const float* X, bool x_on_device, const int6
         else CK(launch_iota64(s.labels.as<int64_t>() + slot, 1, first_row + i, st));
         CK(cudaMemsetAsync(s.dead.as<uint8_t>() + slot, 0, 1, st));
         if (s.cosine) CK(launch_row_norms_exact(s.X.as<float>() + slot * s.dim, 1, s.dim, s.dim, s.norms.as<float>() + slot, st));
+        s.tc_dirty = true;
         s.dead_h[(size_t)slot] = 0;
         s.slot_row[(size_t)slot] = first_row + i;
         s.ndead--;
@@ -476,6 +490,7 @@ int finish_lists(Index* h, const BuildData& bd, int32_t* d_assign, int nc, SortS
     h->list_ndead = 0;
     h->nc = nc;
     h->built = true;
+    h->tc_cent.invalidate();
     h->lists_loc_valid = false;
     // the write buffer is consumed by Build (IvfFlatVectorIndex.cs:143, IvfPqVectorIndex.cs:109);
     // give large buffers back to the allocator, keep small ones for the next writes
@@ -656,6 +671,22 @@ int64_t segment_cutoff(const Segment& s, int64_t max_scans) {
     return s.nslots;
 }
 
+int ensure_tc_operand(TcOperand& op, const float* X, int64_t n, int dim, int metric, const uint8_t* dead,
+                      cudaStream_t st) {
+    if (op.dirty) op.rows_valid = 0;
+    const size_t keep_e = (size_t)op.rows_valid * dim * sizeof(float), keep_r = (size_t)op.rows_valid * sizeof(float);
+    TRY(op.hi.ensure(sizeof(float) * (size_t)n * dim, keep_e, st));
+    TRY(op.lo.ensure(sizeof(float) * (size_t)n * dim, keep_e, st));
+    TRY(op.scale.ensure(sizeof(float) * (size_t)n, keep_r, st));
+    TRY(op.bias.ensure(sizeof(float) * (size_t)n, keep_r, st));
+    if (op.rows_valid < n)
+        CK(launch_tc_prepare(X, n, dim, metric, dead, op.hi.as<float>(), op.lo.as<float>(), op.scale.as<float>(),
+                             op.bias.as<float>(), op.rows_valid, st));
+    op.rows_valid = n;
+    op.dirty = false;
+    return PYROPE_OK;
+}
+
 __global__ void fill_empty_kernel(float* s, int64_t* l, int32_t* c, int64_t nq, int k) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq * k) { s[i] = 0.f; l[i] = -1; }
@@ -715,8 +746,12 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     int max_parts = kMergeMaxCandidates / k;
     if (max_parts < 1) max_parts = 1;
     if (groups > max_parts - (scan_seg ? 1 : 0)) groups = std::max(1, max_parts - (scan_seg ? 1 : 0));
+    const bool use_tc_seg = scan_seg && h->tc_mode != 0 && flat_tc_supported(dim, k) &&
+                            (h->tc_mode == 1 || seg_scan >= 8192);
+    const bool use_tc_coarse = scan_lists && h->tc_mode != 0 && flat_tc_supported(dim, P) &&
+                               (h->tc_mode == 1 || h->nc >= 2048);
     int seg_splits = 0;
-    if (scan_seg) seg_splits = flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
+    if (scan_seg) seg_splits = use_tc_seg ? 1 : flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
     const int parts = seg_splits + groups;
     if ((int64_t)parts * k > kMergeMaxCandidates)
         return fail(PYROPE_ERR_UNSUPPORTED, "topK %d too large for %d partial lists", k, parts);
@@ -733,8 +768,38 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         qnorm = ws.qnorm.as<float>();
     }
 
+    if (use_tc_seg || use_tc_coarse) {
+        TRY(ws.qhi.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
+        TRY(ws.qlo.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
+        CK(launch_tc_prepare(dQ, nq, dim, h->metric, nullptr, ws.qhi.as<float>(), ws.qlo.as<float>(), nullptr, nullptr, 0, st));
+        ++launches;
+    }
+    auto run_tc = [&](TcOperand& op, const float* X, int64_t n_rows, int64_t n_scan_rows, const uint8_t* dead,
+                      const float* xnorm, const int64_t* labels, int kk, PairOut po) -> int {
+        if (op.dirty || op.rows_valid < n_rows) ++launches;
+        TRY(ensure_tc_operand(op, X, n_rows, dim, h->metric, dead, st));
+        FlatTcParams tp{};
+        tp.Q = dQ; tp.Qhi = ws.qhi.as<float>(); tp.Qlo = ws.qlo.as<float>(); tp.nq = nq; tp.dim = dim;
+        tp.X = X; tp.Xhi = op.hi.as<float>(); tp.Xlo = op.lo.as<float>(); tp.n_rows = n_rows; tp.n_scan = n_scan_rows;
+        tp.scale = op.scale.as<float>(); tp.bias = op.bias.as<float>(); tp.xnorm = xnorm; tp.qnorm = qnorm; tp.labels = labels;
+        tp.metric = h->metric; tp.k = kk; tp.kprime = kk + flat_tc_margin(kk); tp.cap = flat_tc_cap(tp.kprime);
+        tp.splits = flat_tc_pick_splits(nq, n_scan_rows, tp.kprime, g_num_sms);
+        const int64_t nq_pad = flat_tc_nq_pad(nq);
+        TRY(ws.tcq.ensure(sizeof(uint64_t) * (size_t)tp.splits * nq_pad * tp.cap, 0, st));
+        TRY(ws.tcc.ensure(sizeof(int32_t) * (size_t)tp.splits * nq_pad, 0, st));
+        tp.queue = ws.tcq.as<uint64_t>(); tp.counts = ws.tcc.as<int32_t>(); tp.out = po;
+        CK(launch_flat_tc(tp, st));
+        launches += 2;
+        return PYROPE_OK;
+    };
+
     // ---- coarse probe: exact FLAT top-P over the centroids
-    if (scan_lists) {
+    if (scan_lists && use_tc_coarse) {
+        TRY(ws.probes.ensure(sizeof(int64_t) * (size_t)nq * P, 0, st));
+        TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * P, 0, st));
+        TRY(run_tc(h->tc_cent, h->centroids.as<float>(), h->nc, h->nc, nullptr, h->cnorms.as<float>(), nullptr, P,
+                   PairOut{ws.probe_scores.as<float>(), ws.probes.as<int64_t>(), 1, 0}));
+    } else if (scan_lists) {
         int csplits = flat_scan_pick_splits(nq, h->nc, P, g_num_sms, 0);
         int ccap = flat_scan_cap(P);
         TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)csplits * nq * ccap, 0, st));
@@ -755,7 +820,13 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     CK(cudaEventRecord(h->ev[1], st));
 
     // ---- buffer / base scan
-    if (scan_seg) {
+    if (scan_seg && use_tc_seg) {
+        PairOut po = out;
+        po.part_base = 0;
+        if (seg.tc_dirty) { h->tc_seg.invalidate(); seg.tc_dirty = false; }
+        TRY(run_tc(h->tc_seg, seg.X.as<float>(), seg.nslots, seg_scan, seg.ndead > 0 ? seg.dead.as<uint8_t>() : nullptr,
+                   seg.norms.as<float>(), seg.labels.as<int64_t>(), k, po));
+    } else if (scan_seg) {
         int cap = flat_scan_cap(k);
         TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)seg_splits * nq * cap, 0, st));
         FlatScanParams fp{};
@@ -869,6 +940,8 @@ int pyrope_index_create(int kind, int dim, int metric, int nlist, int pq_m, int 
     }
     const char* g = getenv("PYROPE_PQ_GENERIC");
     h->pq_force_generic = (g && g[0] == '1') ? 1 : 0;
+    const char* t = getenv("PYROPE_FLAT_TC");
+    h->tc_mode = (t && t[0] == '0') ? 0 : (t && t[0] == '1') ? 1 : -1;
     *out = h;
     return PYROPE_OK;
 }
@@ -918,6 +991,7 @@ int pyrope_index_update_row(pyrope_index* h, int64_t row, const float* x) {
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(s.X.as<float>() + slot * s.dim, x, sizeof(float) * s.dim, cudaMemcpyHostToDevice, st));
     if (s.cosine) CK(launch_row_norms_exact(s.X.as<float>() + slot * s.dim, 1, s.dim, s.dim, s.norms.as<float>() + slot, st));
+    s.tc_dirty = true;
     if (s.dead_h[(size_t)slot]) {  // FLAT Upsert un-deletes (BruteForceVectorIndex.cs:200-203)
         CK(cudaMemsetAsync(s.dead.as<uint8_t>() + slot, 0, 1, st));
         s.dead_h[(size_t)slot] = 0;
@@ -936,6 +1010,7 @@ int pyrope_index_delete_row(pyrope_index* h, int64_t row) {
     if (h->kind == PYROPE_FLAT) {
         if (row < 0 || row >= s.nslots || s.dead_h[(size_t)row]) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
         CK(cudaMemsetAsync(s.dead.as<uint8_t>() + row, 1, 1, st));
+        s.tc_dirty = true;
         s.dead_h[(size_t)row] = 1;
         s.ndead++;
         s.live--;
@@ -948,6 +1023,7 @@ int pyrope_index_delete_row(pyrope_index* h, int64_t row) {
     if (loc == -1) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
     if (loc >= 0) {
         CK(cudaMemsetAsync(s.dead.as<uint8_t>() + loc, 1, 1, st));
+        s.tc_dirty = true;
         s.dead_h[(size_t)loc] = 1;
         s.slot_row[(size_t)loc] = -1;
         s.ndead++;
@@ -1022,6 +1098,7 @@ int pyrope_index_set_codebooks(pyrope_index* h, int n_centroids, const float* ce
     CK(cudaStreamSynchronize(st));
     h->nc = n_centroids;
     h->frozen = true;
+    h->tc_cent.invalidate();
     return PYROPE_OK;
 }
 

@@ -1,0 +1,526 @@
+// flat_tc.cu — K1 on the 5th-gen tensor cores: batched exact FLAT scoring as a 3xTF32 split GEMM
+// (tcgen05.mma kind::tf32, operands staged by TMA into 128B-swizzled shared memory, accumulators in
+// TMEM) with the top-k selection fused into the epilogue, so the Q x N score matrix never exists.
+//
+// Replaces the scoring + heap loop of BruteForceVectorIndex.Search (BruteForceVectorIndex.cs:341-360)
+// for a whole query batch, and — run over the centroid table — the coarse ranking of
+// IvfFlatVectorIndex.cs:186-198 / IvfPqVectorIndex.cs:141-150.
+//
+//   D[q][n] = Qhi.Xhi + Qhi.Xlo + Qlo.Xhi      (hi = tf32(x) rounded to nearest, lo = x - hi, exact)
+//   proxy score  s = scale[n] * D + bias[n]    (L2: 2*q.x - |x|^2 ; IP: q.x ; Cosine: q.x/|x| ;
+//                                               tombstoned / out-of-range rows: bias = -inf)
+// Tile: 128 queries (UMMA M, one TMEM lane each) x 256 base rows (UMMA N), K in 32-float chunks
+// (one 128-byte swizzle atom), 2 shared-memory stages of 96 KiB, 2 TMEM accumulator buffers of 256
+// columns.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (thread <-> query: tcgen05.ld its lane, compare against its private
+// threshold, append survivors to its private queue in L2; a full queue is sorted by the whole warp).
+// The k' = k + margin survivors per (query, split) are re-scored with exact fp32 arithmetic by
+// flat_rescore_kernel, which also does the final ordering — reported distances never come from
+// the TF32 path.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pyrope {
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
+constexpr int TC_THREADS = 256;
+constexpr int QH_BYTES = BM * BK * 4, XH_BYTES = BN * BK * 4;
+constexpr int STAGE_BYTES = 2 * QH_BYTES + 2 * XH_BYTES;  // 96 KiB
+constexpr int TMEM_COLS = 512;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();  // a broken pipeline must fault, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B, 8-row atoms of 1024 bytes
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)0 << 16;                    // leading byte offset (unused: one atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TcParams {
+    int64_t nq, n_scan;
+    int dim, kprime, cap, splits;
+    int64_t ntiles, tiles_per_split;
+    const float* scale;  // [n] nullable (=1)
+    const float* bias;   // [n] nullable (=0)
+    uint64_t* queue;     // [splits][nq_pad][cap]
+    int32_t* counts;     // [splits][nq_pad]
+    int64_t nq_pad;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+               const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // layout: [stage0 | stage1 | barriers | tmem ptr | sbias[2][BN] | sscale[2][BN] | sort staging 4 x cap]
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
+    float* sbias = reinterpret_cast<float*>(tmem_ptr_s + 4);
+    float* sscale = sbias + 2 * BN;
+    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(sscale + 2 * BN);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+    const uint32_t tfull0 = smem_u32(&bars[4]), tempty0 = smem_u32(&bars[6]);
+
+    const int64_t qtiles = (p.nq + BM - 1) / BM;
+    const int64_t qt = blockIdx.x % qtiles, sp = blockIdx.x / qtiles;
+    const int64_t t_begin = sp * p.tiles_per_split;
+    const int64_t t_end = min(p.ntiles, t_begin + p.tiles_per_split);
+    const int ntile = (int)max((int64_t)0, t_end - t_begin);
+    const int KC = (p.dim + BK - 1) / BK;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int ti = 0; ti < ntile; ++ti) {
+                const int n0 = (int)((t_begin + ti) * BN);
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const uint32_t sb = smem_u32(stage_base + s * STAGE_BYTES);
+                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                    tma_load_2d(sb, &map_qhi, full0 + 8 * s, kc * BK, (int)(qt * BM));
+                    tma_load_2d(sb + QH_BYTES, &map_qlo, full0 + 8 * s, kc * BK, (int)(qt * BM));
+                    tma_load_2d(sb + 2 * QH_BYTES, &map_xhi, full0 + 8 * s, kc * BK, n0);
+                    tma_load_2d(sb + 2 * QH_BYTES + XH_BYTES, &map_xlo, full0 + 8 * s, kc * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int ti = 0; ti < ntile; ++ti) {
+                const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(tempty0 + 8 * buf, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(stage_base + s * STAGE_BYTES);
+                    const uint64_t qhi = make_sw128_desc(sb), qlo = make_sw128_desc(sb + QH_BYTES);
+                    const uint64_t xhi = make_sw128_desc(sb + 2 * QH_BYTES), xlo = make_sw128_desc(sb + 2 * QH_BYTES + XH_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 8; ++k4) {
+                        const uint64_t adv = (uint64_t)(k4 * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
+                        tc_mma_tf32(d_tmem, qlo + adv, xhi + adv, kInstrDesc, (kc | k4) != 0);
+                        tc_mma_tf32(d_tmem, qhi + adv, xlo + adv, kInstrDesc, 1);
+                        tc_mma_tf32(d_tmem, qhi + adv, xhi + adv, kInstrDesc, 1);
+                    }
+                    tc_commit(empty0 + 8 * s);  // frees the shared-memory stage when these MMAs retire
+                }
+                tc_commit(tfull0 + 8 * buf);    // accumulator tile complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: thread <-> query =================
+        const int ew = warp - 4;                       // TMEM lane quarter
+        const int et = ew * 32 + lane;                 // 0..127
+        const int64_t gq = qt * BM + et;
+        const bool qvalid = gq < p.nq;
+        uint64_t* myq = p.queue + ((int64_t)sp * p.nq_pad + (qt * BM + et)) * p.cap;
+        uint64_t* st = sortbuf + (int64_t)ew * p.cap;
+        int cnt = 0;
+        float tau = -INFINITY;
+        const int cap = p.cap, kprime = p.kprime;
+
+        auto prune_lane = [&](int l) {
+            uint64_t* src = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)myq, l));
+            const int c = __shfl_sync(0xffffffffu, cnt, l);
+            const int P = next_pow2(max(c, 2));
+            for (int i = lane; i < P; i += 32) st[i] = i < c ? __ldcg(src + i) : 0ull;
+            __syncwarp();
+            bitonic_sort_desc<true>(st, P, lane, 32);
+            const int keep = min(c, kprime);
+            for (int i = lane; i < keep; i += 32) __stcg(src + i, st[i]);
+            __syncwarp();
+            if (lane == l) {
+                cnt = keep;
+                tau = (keep == kprime) ? key_score(st[kprime - 1]) : -INFINITY;
+            }
+            __syncwarp();
+        };
+
+        for (int ti = 0; ti < ntile; ++ti) {
+            const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
+            const int64_t n0 = (t_begin + ti) * BN;
+            // stage this tile's per-row scale/bias (2 columns per epilogue thread)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = et + u * 128;
+                const int64_t pos = n0 + col;
+                float b = -INFINITY, sc = 0.f;
+                if (pos < p.n_scan) {
+                    b = p.bias ? __ldg(p.bias + pos) : 0.f;
+                    sc = p.scale ? __ldg(p.scale + pos) : 1.f;
+                }
+                sbias[buf * BN + col] = b;
+                sscale[buf * BN + col] = sc;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(tfull0 + 8 * buf, aph);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tc_ld32(taddr0 + c * 32, v);
+                if (qvalid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        const float s = fmaf(v[j], sscale[buf * BN + col], sbias[buf * BN + col]);
+                        if (s > tau) {
+                            __stcg(myq + cnt, make_key(s, (uint32_t)(n0 + col)));
+                            ++cnt;
+                        }
+                    }
+                }
+                unsigned full = __ballot_sync(0xffffffffu, cnt > cap - 32);
+                while (full) {
+                    const int l = __ffs(full) - 1;
+                    full &= full - 1;
+                    prune_lane(l);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
+        // final: sort every queue, leave the best k' in place, publish the counts
+        for (int l = 0; l < 32; ++l) prune_lane(l);
+        p.counts[(int64_t)sp * p.nq_pad + qt * BM + et] = qvalid ? cnt : 0;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- exact fp32 re-score of the survivors + final ordering -------------------------------------
+struct RescoreParams {
+    const float* Q; int64_t nq; int dim;
+    const float* X; const float* xnorm; const float* qnorm; const int64_t* labels;
+    int metric, k, cap, splits;
+    const uint64_t* queue; const int32_t* counts; int64_t nq_pad;
+    PairOut out;
+};
+
+__global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [P]
+    __shared__ int s_total;
+    __shared__ int s_off[64];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        int t = 0;
+        for (int s = 0; s < p.splits; ++s) {
+            s_off[s] = t;
+            t += p.counts[(int64_t)s * p.nq_pad + q];
+        }
+        s_total = t;
+    }
+    __syncthreads();
+    const int total = s_total;
+    for (int i = total + tid; i < P; i += blockDim.x) keys[i] = 0ull;
+    const float* qv = p.Q + q * p.dim;
+    const bool vec_ok = (p.dim % 4 == 0);
+    const float qn = p.metric == kCosine ? p.qnorm[q] : 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+        const int c = p.counts[(int64_t)s * p.nq_pad + q];
+        const uint64_t* src = p.queue + ((int64_t)s * p.nq_pad + q) * p.cap;
+        for (int i = warp; i < c; i += 8) {
+            const uint32_t pos = key_pos(__ldcg(src + i));
+            const float* x = p.X + (int64_t)pos * p.dim;
+            float a = 0.f;
+            if (vec_ok) {
+                for (int d = lane * 4; d < p.dim; d += 128) {
+                    float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
+                    float4 qq = __ldg(reinterpret_cast<const float4*>(qv + d));
+                    if (p.metric == kL2) {
+                        float d0 = qq.x - xv.x, d1 = qq.y - xv.y, d2 = qq.z - xv.z, d3 = qq.w - xv.w;
+                        a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
+                    } else {
+                        a = fmaf(qq.x, xv.x, a); a = fmaf(qq.y, xv.y, a); a = fmaf(qq.z, xv.z, a); a = fmaf(qq.w, xv.w, a);
+                    }
+                }
+            } else {
+                for (int d = lane; d < p.dim; d += 32) {
+                    float xv = __ldg(x + d), qq = __ldg(qv + d);
+                    if (p.metric == kL2) { float df = qq - xv; a = fmaf(df, df, a); }
+                    else a = fmaf(qq, xv, a);
+                }
+            }
+            a = warp_sum(a);
+            if (lane == 0) {
+                float score;
+                if (p.metric == kL2) score = -a;
+                else if (p.metric == kIP) score = a;
+                else {
+                    float xn = p.xnorm[pos];
+                    score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : a / (qn * xn);
+                }
+                keys[s_off[s] + i] = make_key(score, pos);
+            }
+        }
+    }
+    __syncthreads();
+    bitonic_sort_desc<false>(keys, P, tid, blockDim.x);
+    const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
+    for (int i = tid; i < p.k; i += blockDim.x) {
+        uint64_t key = (i < P) ? keys[i] : 0ull;
+        if (i < total && key) {
+            uint32_t pos = key_pos(key);
+            p.out.scores[ob + i] = key_score(key);
+            p.out.labels[ob + i] = p.labels ? p.labels[pos] : (int64_t)pos;
+        } else {
+            p.out.scores[ob + i] = 0.f;
+            p.out.labels[ob + i] = -1;
+        }
+    }
+}
+
+// ---- operand preparation -----------------------------------------------------------------------
+__global__ void tc_split_kernel(const float* __restrict__ X, int64_t n_elems, float* __restrict__ hi, float* __restrict__ lo) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n_elems) {
+        float4 x = __ldg(reinterpret_cast<const float4*>(X + i));
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t);
+        l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+        *reinterpret_cast<float4*>(hi + i) = h;
+        *reinterpret_cast<float4*>(lo + i) = l;
+    } else {
+        for (; i < n_elems; ++i) {
+            uint32_t t;
+            float x = X[i];
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+            float h = __uint_as_float(t);
+            hi[i] = h;
+            lo[i] = x - h;
+        }
+    }
+}
+
+// one warp per row: scale/bias of the proxy score
+__global__ void tc_rowterms_kernel(const float* __restrict__ X, int64_t n, int dim, int metric,
+                                   const uint8_t* __restrict__ dead, float* scale, float* bias) {
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    float a = 0.f;
+    if (metric != kIP) {
+        const float* x = X + r * dim;
+        for (int d = lane; d < dim; d += 32) { float v = __ldg(x + d); a = fmaf(v, v, a); }
+        a = warp_sum(a);
+    }
+    if (lane == 0) {
+        float sc = 1.f, b = 0.f;
+        if (metric == kL2) { sc = 2.f; b = -a; }
+        else if (metric == kCosine) { float nrm = sqrtf(a); sc = nrm < 1e-6f ? 0.f : 1.f / nrm; }
+        if (dead && dead[r]) b = -INFINITY;
+        scale[r] = sc;
+        bias[r] = b;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dim, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// ---- public launchers ----------------------------------------------------------------------------
+int flat_tc_margin(int k) { return k < 64 ? 16 : 32; }
+bool flat_tc_supported(int dim, int k) { return dim % 4 == 0 && dim >= 8 && k >= 1 && k + flat_tc_margin(k) <= 224; }
+int flat_tc_cap(int kprime) { return std::max(64, next_pow2(kprime + 32)); }
+int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
+
+int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
+    const int64_t qtiles = (nq + BM - 1) / BM;
+    const int64_t ntiles = std::max<int64_t>(1, (n_scan + BN - 1) / BN);
+    int64_t smax = std::min<int64_t>(std::min<int64_t>(ntiles, 32), std::max<int64_t>(1, 4096 / kprime));
+    int best = 1;
+    double best_eff = -1.0;
+    for (int64_t s = 1; s <= smax; ++s) {
+        const int64_t units = qtiles * s;
+        const int64_t waves = (units + num_sms - 1) / num_sms;
+        // prefer full waves; among equals prefer fewer splits (longer streams tighten thresholds)
+        const double eff = (double)units / (double)(waves * num_sms) - 1e-4 * (double)s;
+        if (eff > best_eff) { best_eff = eff; best = (int)s; }
+    }
+    return best;
+}
+
+cudaError_t launch_tc_prepare(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* hi, float* lo,
+                              float* scale, float* bias, int64_t from_row, cudaStream_t st) {
+    if (n <= from_row) return cudaSuccess;
+    const int64_t rows = n - from_row;
+    const int64_t ne = rows * dim;
+    tc_split_kernel<<<(unsigned)((ne / 4 + 256) / 256), 256, 0, st>>>(X + from_row * dim, ne, hi + from_row * dim, lo + from_row * dim);
+    if (scale && bias)
+        tc_rowterms_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(X + from_row * dim, rows, dim, metric,
+                                                                            dead ? dead + from_row : nullptr, scale + from_row, bias + from_row);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* scale, float* bias,
+                               cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    tc_rowterms_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(X, n, dim, metric, dead, scale, bias);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
+    if (a.nq <= 0) return cudaSuccess;
+    CUtensorMap mqh, mql, mxh, mxl;
+    if (!make_map(&mqh, a.Qhi, a.nq, a.dim, BM) || !make_map(&mql, a.Qlo, a.nq, a.dim, BM) ||
+        !make_map(&mxh, a.Xhi, a.n_rows, a.dim, BN) || !make_map(&mxl, a.Xlo, a.n_rows, a.dim, BN))
+        return cudaErrorInvalidValue;
+    TcParams p{};
+    p.nq = a.nq; p.n_scan = a.n_scan; p.dim = a.dim; p.kprime = a.kprime; p.cap = a.cap; p.splits = a.splits;
+    p.ntiles = (a.n_scan + BN - 1) / BN;
+    p.tiles_per_split = (p.ntiles + a.splits - 1) / a.splits;
+    p.scale = a.scale; p.bias = a.bias; p.queue = a.queue; p.counts = a.counts;
+    const int64_t qtiles = (a.nq + BM - 1) / BM;
+    p.nq_pad = qtiles * BM;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 16 * 8 + 16 + 4 * BN * sizeof(float) + 4 * (size_t)a.cap * 8 + 64;
+    cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    flat_tc_kernel<<<(unsigned)(qtiles * a.splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    RescoreParams r{};
+    r.Q = a.Q; r.nq = a.nq; r.dim = a.dim; r.X = a.X; r.xnorm = a.xnorm; r.qnorm = a.qnorm; r.labels = a.labels;
+    r.metric = a.metric; r.k = a.k; r.cap = a.cap; r.splits = a.splits; r.queue = a.queue; r.counts = a.counts;
+    r.nq_pad = p.nq_pad; r.out = a.out;
+    const int P = next_pow2(std::max(2, a.splits * a.kprime));
+    flat_rescore_kernel<<<(unsigned)a.nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(r, P);
+    return cudaGetLastError();
+}
+
+}  // namespace pyrope

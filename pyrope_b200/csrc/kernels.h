@@ -35,6 +35,31 @@ int flat_scan_cap(int k);
 int flat_scan_pick_splits(int64_t nq, int64_t n_scan, int k, int num_sms, int max_parts);
 cudaError_t launch_flat_scan(const FlatScanParams& p, cudaStream_t st);
 
+// ---- K1 on tensor cores: 3xTF32 tcgen05 GEMM + fused top-k + exact fp32 re-score (flat_tc.cu) ----
+struct FlatTcParams {
+    const float* Q; const float* Qhi; const float* Qlo; int64_t nq; int dim;
+    const float* X; const float* Xhi; const float* Xlo;
+    int64_t n_rows;                          // rows backing X/Xhi/Xlo (tensor-map extent)
+    int64_t n_scan;                          // scan positions [0, n_scan)
+    const float* scale; const float* bias;   // per-row proxy terms (bias = -inf for tombstones)
+    const float* xnorm; const float* qnorm;  // cosine re-score
+    const int64_t* labels;
+    int metric, k, kprime, cap, splits;
+    uint64_t* queue; int32_t* counts;        // scratch [splits][nq_pad][cap], [splits][nq_pad]
+    PairOut out;                             // writes ONE part (splits are reduced by the re-score)
+};
+bool flat_tc_supported(int dim, int k);
+int flat_tc_margin(int k);
+int flat_tc_cap(int kprime);
+int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms);
+int64_t flat_tc_nq_pad(int64_t nq);
+// hi = tf32(x) (round to nearest), lo = x - hi for rows [from_row, n); scale/bias may be null
+cudaError_t launch_tc_prepare(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* hi,
+                              float* lo, float* scale, float* bias, int64_t from_row, cudaStream_t st);
+cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* scale,
+                               float* bias, cudaStream_t st);
+cudaError_t launch_flat_tc(const FlatTcParams& p, cudaStream_t st);
+
 // ---- K6: merge ------------------------------------------------------------------------------
 // in: candidate (score,label) at address part*part_stride + q*q_stride + j, j < k_in.
 cudaError_t launch_merge_pairs(int64_t nq, int parts, int k_in, int k_out, const float* in_scores,
