@@ -313,7 +313,7 @@ def run_ours(args):
         peak = bf16 / 2.0  # TF32 dense = 1/2 bf16; 3xTF32 issues 3x the algorithmic FLOPs
         peak_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense, of measured)" if "bf16_tflops" in peaks else "fallback"
     roofline = {"bound": alg["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": alg["unit"],
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "ivfpq_scan_fast_kernel" if w["kind"] == "IVF_PQ" else w["kind"].lower() + "_scan",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "ivfpq_lm_scan_kernel" if w["kind"] == "IVF_PQ" else w["kind"].lower() + "_scan",
                 "kernel_ms": round(dom_ms, 4), "algorithmic_per_launch": alg["work"], "peak_source": peak_src,
                 "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()}}
 

@@ -149,7 +149,8 @@ struct Segment {
 struct Workspace {
     DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probe_scores, probe_cnt, allow, qnorm,
         qhi, qlo, tcq, tcc,  // tensor-core path: split queries, candidate queues, counts
-        hq, hs, hl, hc;      // h*: staging for the host-pointer entry point
+        hq, hs, hl, hc,      // h*: staging for the host-pointer entry point
+        lm;                  // list-major IVF_PQ scan scratch
 };
 
 // tf32 hi/lo split + per-row proxy terms of one operand table (base rows or centroids)
@@ -197,6 +198,7 @@ struct pyrope_index {
     bool ev_valid = false;
     int last_launches = 0;
     int pq_force_generic = 0;
+    int pq_lm_mode = -1;  // PYROPE_PQ_LM: 0 = query-major kernels only
 };
 
 namespace {
@@ -350,6 +352,77 @@ int group_by_cluster(const int32_t* d_assign, int64_t n, int nc, SortScratch& sc
     return PYROPE_OK;
 }
 
+// forward declaration (defined with the search helpers below)
+int ensure_tc_operand(TcOperand& op, const float* X, int64_t n, int dim, int metric, const uint8_t* dead,
+                      cudaStream_t st);
+
+struct AssignScratch {
+    TcOperand cent;                       // tf32 split + proxy terms of the centroid table
+    DevBuf qhi, qlo, tcq, tcc, flag, idx, nsel, temp, sub_assign, xg;
+};
+
+__global__ void flag_fill_kernel(uint8_t* f, int64_t n, uint8_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = v;
+}
+
+// KMeansUtils.FindNearestCentroid for n rows, bit-exact.  Small tables: exhaustive exact kernel.
+// Large tables (>= 2048 centroids): tensor-core proxy scores shortlist k' = 17 centroids per row, the
+// shortlist is re-evaluated in the reference's fp32 order (first index wins ties), and any row whose
+// shortlist cannot be proven complete (proxy spread below 1e-4 relative) is redone exhaustively.
+int assign_rows(int metric, int dim, int64_t n, const float* X, int64_t ldx, int nc, const float* centroids,
+                const float* cnorms, int32_t* assign, AssignScratch& sc, bool centroids_changed, cudaStream_t st) {
+    if (n <= 0) return PYROPE_OK;
+    const bool tc = nc >= 2048 && ldx == dim && flat_tc_supported(dim, 1) && !getenv("PYROPE_ASSIGN_EXACT");
+    if (!tc) {
+        CK(launch_assign_exact(metric, dim, n, X, ldx, nc, centroids, cnorms, assign, st));
+        return PYROPE_OK;
+    }
+    if (centroids_changed) sc.cent.invalidate();
+    TRY(ensure_tc_operand(sc.cent, centroids, nc, dim, metric, nullptr, st));
+    const int kprime = 1 + flat_tc_margin(1), cap = flat_tc_cap(kprime);
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 20);
+    const int64_t chunk_pad = flat_tc_nq_pad(chunk);
+    TRY(sc.qhi.ensure(sizeof(float) * (size_t)chunk * dim, 0, st, true));
+    TRY(sc.qlo.ensure(sizeof(float) * (size_t)chunk * dim, 0, st, true));
+    TRY(sc.tcq.ensure(sizeof(uint64_t) * (size_t)chunk_pad * cap, 0, st, true));
+    TRY(sc.tcc.ensure(sizeof(int32_t) * (size_t)chunk_pad, 0, st, true));
+    TRY(sc.flag.ensure((size_t)n, 0, st, true));
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t cn = std::min(chunk, n - c0);
+        const float* Xc = X + (size_t)c0 * ldx;
+        CK(launch_tc_prepare(Xc, cn, dim, metric, nullptr, sc.qhi.as<float>(), sc.qlo.as<float>(), nullptr, nullptr, 0, st));
+        FlatTcParams tp{};
+        tp.Q = Xc; tp.Qhi = sc.qhi.as<float>(); tp.Qlo = sc.qlo.as<float>(); tp.nq = cn; tp.dim = dim;
+        tp.X = centroids; tp.Xhi = sc.cent.hi.as<float>(); tp.Xlo = sc.cent.lo.as<float>(); tp.n_rows = nc; tp.n_scan = nc;
+        tp.scale = sc.cent.scale.as<float>(); tp.bias = sc.cent.bias.as<float>();
+        tp.metric = metric; tp.k = 1; tp.kprime = kprime; tp.cap = cap; tp.splits = 1;
+        tp.queue = sc.tcq.as<uint64_t>(); tp.counts = sc.tcc.as<int32_t>();
+        CK(launch_flat_tc_select(tp, st));
+        CK(launch_assign_from_shortlist(metric, dim, cn, Xc, ldx, centroids, cnorms, sc.tcq.as<uint64_t>(),
+                                        sc.tcc.as<int32_t>(), cap, kprime, assign + c0, sc.flag.as<uint8_t>() + c0, st));
+    }
+    // rows whose shortlist may be incomplete: redo exhaustively
+    TRY(sc.idx.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+    TRY(sc.nsel.ensure(sizeof(int64_t), 0, st, true));
+    size_t tb = 0;
+    cub::CountingInputIterator<int64_t> iota(0);
+    CK(cub::DeviceSelect::Flagged(nullptr, tb, iota, sc.flag.as<uint8_t>(), sc.idx.as<int64_t>(), sc.nsel.as<int64_t>(), n, st));
+    TRY(sc.temp.ensure(tb + 16, 0, st, true));
+    CK(cub::DeviceSelect::Flagged(sc.temp.p, tb, iota, sc.flag.as<uint8_t>(), sc.idx.as<int64_t>(), sc.nsel.as<int64_t>(), n, st));
+    int64_t nsel = 0;
+    CK(cudaMemcpyAsync(&nsel, sc.nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nsel > 0) {
+        TRY(sc.xg.ensure(sizeof(float) * (size_t)nsel * dim, 0, st, true));
+        TRY(sc.sub_assign.ensure(sizeof(int32_t) * (size_t)nsel, 0, st, true));
+        CK(launch_gather_rows(X, (int64_t)dim * 4, sc.idx.as<int64_t>(), nsel, sc.xg.p, st));
+        CK(launch_assign_exact(metric, dim, nsel, sc.xg.as<float>(), dim, nc, centroids, cnorms, sc.sub_assign.as<int32_t>(), st));
+        CK(launch_scatter_i32(sc.sub_assign.as<int32_t>(), sc.idx.as<int64_t>(), nsel, assign, st));
+    }
+    return PYROPE_OK;
+}
+
 // KMeansUtils.Train: data n x dim (leading dimension ld) on device -> d_centroids [k][dim].
 int kmeans_train_device(int metric, int dim, int64_t n, int64_t ld, const float* d_data, int k, int max_iter,
                         int32_t seed, float* d_centroids, int* k_out, int* iters_out, cudaStream_t st) {
@@ -365,13 +438,14 @@ int kmeans_train_device(int metric, int dim, int64_t n, int64_t ld, const float*
                            cudaMemcpyDeviceToDevice, st));
     DevBuf assign, cn, changed;
     SortScratch sc;
+    AssignScratch as;
     TRY(assign.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
     TRY(changed.ensure(sizeof(int), 0, st, true));
     if (metric == kCosine) TRY(cn.ensure(sizeof(float) * (size_t)k, 0, st, true));
     for (int it = 0; it < max_iter; ++it) {
         if (iters_out) *iters_out = it + 1;
         if (metric == kCosine) CK(launch_row_norms_exact(d_centroids, k, dim, dim, cn.as<float>(), st));
-        CK(launch_assign_exact(metric, dim, n, d_data, ld, k, d_centroids, cn.as<float>(), assign.as<int32_t>(), st));
+        TRY(assign_rows(metric, dim, n, d_data, ld, k, d_centroids, cn.as<float>(), assign.as<int32_t>(), as, true, st));
         TRY(group_by_cluster(assign.as<int32_t>(), n, k, sc, st));
         CK(cudaMemsetAsync(changed.p, 0, sizeof(int), st));
         CK(launch_kmeans_update(d_data, ld, dim, k, sc.offs.as<int64_t>(), sc.vals_out.as<int32_t>(), d_centroids,
@@ -526,8 +600,12 @@ int build_ivfflat(Index* h) {
     if (h->metric == kCosine) CK(launch_row_norms_exact(h->centroids.as<float>(), nc, dim, dim, h->cnorms.as<float>(), st));
     DevBuf assign;
     TRY(assign.ensure(sizeof(int32_t) * (size_t)bd.n, 0, st, true));
-    CK(launch_assign_exact(h->metric, dim, bd.n, bd.X, dim, nc, h->centroids.as<float>(), h->cnorms.as<float>(),
-                           assign.as<int32_t>(), st));
+    {
+        AssignScratch as;
+        TRY(assign_rows(h->metric, dim, bd.n, bd.X, dim, nc, h->centroids.as<float>(), h->cnorms.as<float>(),
+                        assign.as<int32_t>(), as, true, st));
+        CK(cudaStreamSynchronize(st));
+    }
     SortScratch sc;
     DevBuf newvecs;
     TRY(finish_lists(h, bd, assign.as<int32_t>(), nc, sc, bd.X, (int64_t)dim * 4, newvecs));
@@ -569,8 +647,12 @@ int build_ivfpq(Index* h) {
     if (h->metric == kCosine) CK(launch_row_norms_exact(h->centroids.as<float>(), nc, dim, dim, h->cnorms.as<float>(), st));
     DevBuf assign;
     TRY(assign.ensure(sizeof(int32_t) * (size_t)n, 0, st, true));
-    CK(launch_assign_exact(h->metric, dim, n, bd.X, dim, nc, h->centroids.as<float>(), h->cnorms.as<float>(),
-                           assign.as<int32_t>(), st));
+    {
+        AssignScratch as;
+        TRY(assign_rows(h->metric, dim, n, bd.X, dim, nc, h->centroids.as<float>(), h->cnorms.as<float>(),
+                        assign.as<int32_t>(), as, true, st));
+        CK(cudaStreamSynchronize(st));
+    }
     // PQ training on the residuals of the training rows (ProductQuantizer.cs:28-58)
     const int64_t chunk = std::min<int64_t>(n, (int64_t)4 << 20);
     DevBuf res;
@@ -743,6 +825,9 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         int64_t want = (2 * (int64_t)g_num_sms + nq - 1) / nq;
         groups = (int)std::max<int64_t>(1, std::min<int64_t>(want, P));
     }
+    const bool use_lm = scan_lists && h->kind == PYROPE_IVF_PQ && !h->pq_force_generic && h->pq_lm_mode != 0 &&
+                        ivfpq_lm_supported(dim, h->m, h->k, P, k, nq, h->list_total);
+    if (use_lm) groups = 1;
     int max_parts = kMergeMaxCandidates / k;
     if (max_parts < 1) max_parts = 1;
     if (groups > max_parts - (scan_seg ? 1 : 0)) groups = std::max(1, max_parts - (scan_seg ? 1 : 0));
@@ -860,12 +945,18 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         } else {
             IvfPqScanParams pp{};
             pp.Q = dQ; pp.nq = nq; pp.dim = dim; pp.probes = ws.probes.as<int64_t>(); pp.nprobe = P;
-            pp.list_off = h->list_off.as<int64_t>(); pp.centroids = h->centroids.as<float>();
+            pp.list_off = h->list_off.as<int64_t>(); pp.nlist = h->nc; pp.centroids = h->centroids.as<float>();
             pp.codebook = h->codebook.as<float>(); pp.m = h->m; pp.ksub = h->k;
             pp.codes = h->list_codes.as<uint8_t>(); pp.dead = ldead; pp.labels = h->list_labels.as<int64_t>();
             pp.k = k; pp.groups = groups; pp.force_generic = h->pq_force_generic;
             pp.out = out; pp.out.part_base = seg_splits;
-            CK(launch_ivfpq_scan(pp, st));
+            if (use_lm) {
+                TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc), 0, st));
+                CK(launch_ivfpq_scan_lm(pp, ws.lm.p, g_num_sms, st));
+                launches += ivfpq_lm_launches() - 1;
+            } else {
+                CK(launch_ivfpq_scan(pp, st));
+            }
         }
         ++launches;
     }
@@ -940,6 +1031,8 @@ int pyrope_index_create(int kind, int dim, int metric, int nlist, int pq_m, int 
     }
     const char* g = getenv("PYROPE_PQ_GENERIC");
     h->pq_force_generic = (g && g[0] == '1') ? 1 : 0;
+    const char* lmv = getenv("PYROPE_PQ_LM");
+    h->pq_lm_mode = (lmv && lmv[0] == '0') ? 0 : -1;
     const char* t = getenv("PYROPE_FLAT_TC");
     h->tc_mode = (t && t[0] == '0') ? 0 : (t && t[0] == '1') ? 1 : -1;
     *out = h;
@@ -1247,7 +1340,8 @@ int pyrope_coarse_assign(int metric, int dim, int64_t n, const float* X, int n_c
     CK(cudaMemcpy(dx.p, X, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dc.p, centroids, sizeof(float) * (size_t)n_centroids * dim, cudaMemcpyHostToDevice));
     if (metric == kCosine) CK(launch_row_norms_exact(dc.as<float>(), n_centroids, dim, dim, dn.as<float>(), st));
-    CK(launch_assign_exact(metric, dim, n, dx.as<float>(), dim, n_centroids, dc.as<float>(), dn.as<float>(), da.as<int32_t>(), st));
+    AssignScratch as;
+    TRY(assign_rows(metric, dim, n, dx.as<float>(), dim, n_centroids, dc.as<float>(), dn.as<float>(), da.as<int32_t>(), as, true, st));
     CK(cudaMemcpy(assign_out, da.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
     return PYROPE_OK;
 }

@@ -10,6 +10,7 @@
 //            VectorMath.L2SquaredUnsafe (VectorMath.cs:188-253)
 //   update : KMeansUtils.Train mean update (KMeansUtils.cs:46-63)
 #include "common.cuh"
+#include "exact_arith.cuh"
 #include "kernels.h"
 
 #include <float.h>
@@ -17,86 +18,7 @@
 namespace pyrope {
 namespace {
 
-__device__ __forceinline__ float hsum8(const float (&v)[8]) {
-    float lo = __fadd_rn(__fadd_rn(v[0], v[1]), __fadd_rn(v[2], v[3]));
-    float hi = __fadd_rn(__fadd_rn(v[4], v[5]), __fadd_rn(v[6], v[7]));
-    return __fadd_rn(lo, hi);
-}
-
-enum Arith { A2_L2 = 0, A2_DOT = 1, A1_L2 = 2 };
-
-template <int OP>  // 0 l2, 1 dot
-__device__ __forceinline__ float term(float a, float b) {
-    if (OP == 0) { float d = __fsub_rn(a, b); return __fmul_rn(d, d); }
-    return __fmul_rn(a, b);
-}
-
-// VectorMath.L2Squared / DotProduct: one 8-lane accumulator, scalar tail.  a: shared/global, b: global
-template <int OP>
-__device__ float a2_eval(const float* a, const float* b, int n) {
-    int i = 0;
-    float sum = 0.f;
-    if (n >= 8) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (; i <= n - 8; i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], term<OP>(a[i + j], __ldg(b + i + j)));
-        }
-        sum = __fadd_rn(sum, hsum8(acc));
-    }
-    for (; i < n; ++i) sum = __fadd_rn(sum, term<OP>(a[i], __ldg(b + i)));
-    return sum;
-}
-
-// VectorMath.L2SquaredUnsafe: 4 accumulators for len >= 32, remainder accumulator, scalar tail
-__device__ float a1_l2_eval(const float* a, const float* b, int n) {
-    int i = 0;
-    float sum = 0.f;
-    if (n >= 32) {
-        float a1[8], a2[8], a3[8], a4[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a1[j] = a2[j] = a3[j] = a4[j] = 0.f;
-        for (; i <= n - 32; i += 32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a1[j] = __fadd_rn(a1[j], term<0>(a[i + j], __ldg(b + i + j)));
-                a2[j] = __fadd_rn(a2[j], term<0>(a[i + 8 + j], __ldg(b + i + 8 + j)));
-                a3[j] = __fadd_rn(a3[j], term<0>(a[i + 16 + j], __ldg(b + i + 16 + j)));
-                a4[j] = __fadd_rn(a4[j], term<0>(a[i + 24 + j], __ldg(b + i + 24 + j)));
-            }
-        }
-        float fin[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) fin[j] = __fadd_rn(__fadd_rn(__fadd_rn(a1[j], a2[j]), a3[j]), a4[j]);
-        sum = __fadd_rn(sum, hsum8(fin));
-    }
-    if (i <= n - 8) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (; i <= n - 8; i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], term<0>(a[i + j], __ldg(b + i + j)));
-        }
-        sum = __fadd_rn(sum, hsum8(acc));
-    }
-    for (; i < n; ++i) sum = __fadd_rn(sum, term<0>(a[i], __ldg(b + i)));
-    return sum;
-}
-
-// ComputeNorm (VectorMath.cs:72-100)
-__device__ float norm_eval(const float* v, int n) {
-    int i = 0;
-    float sum = 0.f;
-    if (n >= 8) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (; i <= n - 8; i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(v[i + j], v[i + j]));
-        }
-        sum = __fadd_rn(sum, hsum8(acc));
-    }
-    for (; i < n; ++i) sum = __fadd_rn(sum, __fmul_rn(v[i], v[i]));
-    return __fsqrt_rn(sum);
-}
+using namespace exact;
 
 // One warp per (vector, subspace): lanes stride over candidates in increasing index order, keep
 // the first best (strict '>'), then a warp arg-max that prefers the lower index on ties —
@@ -143,6 +65,64 @@ __global__ void __launch_bounds__(256) nearest_exact_kernel(const float* __restr
         if (os > best || (os == best && oi < besti)) { best = os; besti = oi; }
     }
     if (lane == 0) out[row * nsub + mi] = (OutT)besti;
+}
+
+// Shortlist variant of nearest_exact_kernel: lanes take the (<= 32) shortlisted centroids of the row.
+template <int MODE>
+__global__ void __launch_bounds__(256) assign_shortlist_kernel(const float* __restrict__ X, int64_t n, int64_t ldx,
+                                                               int dd, const float* __restrict__ C,
+                                                               const float* __restrict__ cnorms,
+                                                               const uint64_t* __restrict__ queue,
+                                                               const int32_t* __restrict__ counts, int cap, int kprime,
+                                                               int32_t* assign, uint8_t* flag) {
+    extern __shared__ float vs[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= n) return;
+    float* v = vs + warp * dd;
+    const float* x = X + row * ldx;
+    for (int i = lane; i < dd; i += 32) v[i] = x[i];
+    __syncwarp();
+    const int c = min(counts[row], 32);
+    float vnorm = 0.f;
+    if (MODE == 2) vnorm = norm_eval(v, dd);
+    float best = -FLT_MAX;
+    int besti = 0x7fffffff;
+    float proxy = 0.f;
+    if (lane < c) {
+        const uint64_t key = __ldcg(queue + row * cap + lane);
+        const int cand = (int)key_pos(key);
+        proxy = key_score(key);
+        const float* cv = C + (int64_t)cand * dd;
+        float s;
+        if (MODE == 0) s = -a2_eval<0>(v, cv, dd);
+        else if (MODE == 1) s = a2_eval<1>(v, cv, dd);
+        else {
+            float cn = cnorms[cand];
+            if (vnorm < 1e-6f || cn < 1e-6f) s = 0.f;
+            else s = __fdiv_rn(a2_eval<1>(v, cv, dd), __fmul_rn(vnorm, cn));
+        }
+        if (s > best) { best = s; besti = cand; }
+    }
+    const float p0 = __shfl_sync(0xffffffffu, proxy, 0);
+    const float plast = __shfl_sync(0xffffffffu, proxy, max(c - 1, 0));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (os > best || (os == best && oi < besti)) { best = os; besti = oi; }
+    }
+    if (lane == 0) {
+        const bool incomplete = (c == 0) || besti == 0x7fffffff ||
+                                (c >= kprime && !(plast < p0 - 1e-4f * (fabsf(p0) + 1.f)));
+        assign[row] = incomplete ? 0 : besti;
+        flag[row] = incomplete ? 1 : 0;
+    }
+}
+
+__global__ void scatter_i32_kernel(const int32_t* src, const int64_t* idx, int64_t n, int32_t* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = src[i];
 }
 
 __global__ void row_norms_kernel(const float* X, int64_t n, int dim, int64_t ldx, float* out) {
@@ -249,6 +229,28 @@ cudaError_t launch_assign_exact(int metric, int dim, int64_t n, const float* X, 
     else if (metric == kIP) { PYROPE_LAUNCH_NEAREST(1) }
     else { PYROPE_LAUNCH_NEAREST(2) }
 #undef PYROPE_LAUNCH_NEAREST
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_from_shortlist(int metric, int dim, int64_t n, const float* X, int64_t ldx,
+                                         const float* centroids, const float* cnorms, const uint64_t* queue,
+                                         const int32_t* counts, int cap, int kprime, int32_t* assign,
+                                         uint8_t* flag, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = blocks_for(n, 8);
+    const size_t smem = sizeof(float) * 8 * (size_t)dim;
+    if (metric == kL2)
+        assign_shortlist_kernel<0><<<grid, 256, smem, st>>>(X, n, ldx, dim, centroids, cnorms, queue, counts, cap, kprime, assign, flag);
+    else if (metric == kIP)
+        assign_shortlist_kernel<1><<<grid, 256, smem, st>>>(X, n, ldx, dim, centroids, cnorms, queue, counts, cap, kprime, assign, flag);
+    else
+        assign_shortlist_kernel<2><<<grid, 256, smem, st>>>(X, n, ldx, dim, centroids, cnorms, queue, counts, cap, kprime, assign, flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n, int32_t* dst, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    scatter_i32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, idx, n, dst);
     return cudaGetLastError();
 }
 

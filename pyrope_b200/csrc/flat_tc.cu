@@ -495,7 +495,7 @@ cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
+cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
     CUtensorMap mqh, mql, mxh, mxl;
     if (!make_map(&mqh, a.Qhi, a.nq, a.dim, BM) || !make_map(&mql, a.Qlo, a.nq, a.dim, BM) ||
@@ -512,12 +512,17 @@ cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     flat_tc_kernel<<<(unsigned)(qtiles * a.splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
-    e = cudaGetLastError();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
+    if (a.nq <= 0) return cudaSuccess;
+    cudaError_t e = launch_flat_tc_select(a, st);
     if (e != cudaSuccess) return e;
     RescoreParams r{};
     r.Q = a.Q; r.nq = a.nq; r.dim = a.dim; r.X = a.X; r.xnorm = a.xnorm; r.qnorm = a.qnorm; r.labels = a.labels;
     r.metric = a.metric; r.k = a.k; r.cap = a.cap; r.splits = a.splits; r.queue = a.queue; r.counts = a.counts;
-    r.nq_pad = p.nq_pad; r.out = a.out;
+    r.nq_pad = flat_tc_nq_pad(a.nq); r.out = a.out;
     const int P = next_pow2(std::max(2, a.splits * a.kprime));
     flat_rescore_kernel<<<(unsigned)a.nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(r, P);
     return cudaGetLastError();

@@ -59,6 +59,17 @@ cudaError_t launch_tc_prepare(const float* X, int64_t n, int dim, int metric, co
 cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* scale,
                                float* bias, cudaStream_t st);
 cudaError_t launch_flat_tc(const FlatTcParams& p, cudaStream_t st);
+// selection only: leaves the k' best proxy candidates per (split, query) sorted in queue/counts
+cudaError_t launch_flat_tc_select(const FlatTcParams& p, cudaStream_t st);
+// bit-exact arg-best among the shortlisted centroids of each row (split 0 of queue/counts), in the
+// reference's evaluation order; flag[row] = 1 when the shortlist may be incomplete (full and its
+// last proxy score within eps of the first) so the caller re-runs that row exhaustively.
+cudaError_t launch_assign_from_shortlist(int metric, int dim, int64_t n, const float* X, int64_t ldx,
+                                         const float* centroids, const float* cnorms, const uint64_t* queue,
+                                         const int32_t* counts, int cap, int kprime, int32_t* assign,
+                                         uint8_t* flag, cudaStream_t st);
+// scatter: dst[idx[i]] = src[i]
+cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
 
 // ---- K6: merge ------------------------------------------------------------------------------
 // in: candidate (score,label) at address part*part_stride + q*q_stride + j, j < k_in.
@@ -87,7 +98,7 @@ cudaError_t launch_ivfflat_scan(const IvfFlatScanParams& p, cudaStream_t st);
 struct IvfPqScanParams {
     const float* Q; int64_t nq; int dim;
     const int64_t* probes; int nprobe;
-    const int64_t* list_off;
+    const int64_t* list_off; int nlist;
     const float* centroids;                  // [nlist][dim]
     const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
     const uint8_t* codes; const uint8_t* dead; const int64_t* labels;
@@ -96,6 +107,12 @@ struct IvfPqScanParams {
     PairOut out;
 };
 cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
+// List-major variant (pq_lm.cu): (query, probe) pairs grouped by list, four queries per work item share
+// one pass over the list's codes; writes ONE part (p.groups is ignored).  m = 16, dim/m in {4, 8}.
+bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total);
+size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist);
+int ivfpq_lm_launches();
+cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st);
 // ProductQuantizer.ComputeDistanceTable for nq queries (parity tests): table [nq][m][k]
 cudaError_t launch_pq_distance_table(const float* Q, int64_t nq, int dim, const float* codebook,
                                      int m, int k, float* table, cudaStream_t st);

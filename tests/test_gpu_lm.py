@@ -1,0 +1,163 @@
+"""GPU parity tests of the list-major IVF_PQ scan (pq_lm.cu: pairs grouped by list, four queries per work
+item, interleaved float4 lookup tables, TMA-staged codes, exact re-score of the survivors) and of the
+tensor-core shortlist used for coarse assignment at large nlist.  Same bar as tests/test_gpu_parity.py:
+distances within 1e-4 relative of the oracle, ids identical modulo ties, assignments bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.parity import assert_batch_equivalent, recall_at_k
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import pyrope_b200 as pg
+    pg._lib.check(pg.load().pyrope_gpu_init(0))
+    return pg
+
+
+def _s(ix, Q, k, **kw):
+    sc, rows, cnt = ix.search(Q, k, **kw)
+    return rows, sc, cnt
+
+
+def _pair(gpu, base, dim, nlist, m=16):
+    ref = orc.IvfPqIndex(dim, orc.L2, m=m, k=256, nlist=nlist)
+    ref.add_batch(base)
+    ref.build()
+    ix = gpu.GpuIndex(gpu.IVF_PQ, dim, gpu.L2, nlist=nlist, m=m, k=256)
+    ix.add(base)
+    ix.build()
+    off, rows, codes = ix.lists()
+    for c, (ids, rc) in enumerate(ref.lists()):
+        np.testing.assert_array_equal(rc, codes[off[c]:off[c + 1]])
+    return ref, ix
+
+
+@pytest.fixture(scope="module")
+def mid(gpu):
+    base = orc.random_vectors(20_000, 128, 42)
+    q = orc.random_vectors(300, 128, 1337)
+    ref, ix = _pair(gpu, base, 128, 32)
+    return base, q, ref, ix
+
+
+def test_lm_many_queries_per_list(mid):
+    """300 queries x 8 probes over 32 lists: ~75 queries per list, every slot of most items in use."""
+    base, q, ref, ix = mid
+    assert_batch_equivalent(ref.search_batch(q, 10, nprobe=8), _s(ix, q, 10, nprobe=8), ctx="lm nprobe=8")
+    assert ix.last_search_launches() >= 8  # grouping kernels + scan + final + coarse + merge
+
+
+def test_lm_distances_are_the_reference_values(mid):
+    """Survivors are re-scored in the reference's order: scores must be bit-identical to the oracle's
+    wherever the id matches."""
+    base, q, ref, ix = mid
+    rid, rsc, rcn = ref.search_batch(q[:64], 10, nprobe=4)
+    gid, gsc, gcn = _s(ix, q[:64], 10, nprobe=4)
+    same = rid == gid
+    assert same.mean() > 0.99
+    np.testing.assert_array_equal(rsc[same], gsc[same])
+
+
+@pytest.mark.parametrize("k,nprobe", [(1, 1), (100, 16), (10, 32), (37, 5)])
+def test_lm_topk_and_nprobe_shapes(mid, k, nprobe):
+    base, q, ref, ix = mid
+    assert_batch_equivalent(ref.search_batch(q[:120], k, nprobe=nprobe), _s(ix, q[:120], k, nprobe=nprobe),
+                            ctx=f"lm k={k} nprobe={nprobe}")
+
+
+def test_lm_single_query_and_ragged_groups(mid):
+    base, q, ref, ix = mid
+    for nq in (1, 2, 3, 5, 33):
+        assert_batch_equivalent(ref.search_batch(q[:nq], 10, nprobe=3), _s(ix, q[:nq], 10, nprobe=3), ctx=f"lm nq={nq}")
+
+
+def test_lm_long_lists_multi_segment_and_cold_queues(gpu):
+    """Lists of ~4000 codes: several 1024-code TMA segments per item and, for the first items of every
+    query (no threshold yet), the queue-prune path."""
+    base = orc.random_vectors(16_000, 128, 7)
+    q = orc.random_vectors(40, 128, 8)
+    ref, ix = _pair(gpu, base, 128, 4)
+    for k, nprobe in ((10, 4), (100, 2), (1000, 4)):
+        assert_batch_equivalent(ref.search_batch(q, k, nprobe=nprobe), _s(ix, q, k, nprobe=nprobe),
+                                ctx=f"lm long lists k={k} nprobe={nprobe}")
+
+
+def test_lm_dim64_sub4(gpu):
+    base = orc.random_vectors(6_000, 64, 11)
+    q = orc.random_vectors(50, 64, 12)
+    ref, ix = _pair(gpu, base, 64, 16)
+    assert_batch_equivalent(ref.search_batch(q, 10, nprobe=4), _s(ix, q, 10, nprobe=4), ctx="lm dim=64")
+
+
+def test_lm_agrees_with_query_major_kernel(gpu, mid, monkeypatch):
+    base, q, ref, ix = mid
+    cent = ix.centroids()
+    cb, _ = ix.codebooks()
+    monkeypatch.setenv("PYROPE_PQ_LM", "0")
+    qm = gpu.GpuIndex(gpu.IVF_PQ, 128, gpu.L2, nlist=32, m=16, k=256)
+    qm.set_codebooks(cent, cb)
+    qm.add(base)
+    qm.build()
+    a = _s(qm, q, 10, nprobe=8)
+    assert qm.last_search_launches() < 8
+    b = _s(ix, q, 10, nprobe=8)
+    assert_batch_equivalent(a, b, ctx="query-major vs list-major")
+    assert recall_at_k(a[0], b[0], 10) > 0.999
+
+
+def test_lm_shadowed_rows_and_buffer(gpu):
+    base = orc.random_vectors(5_000, 128, 21)
+    q = orc.random_vectors(30, 128, 22)
+    ref, ix = _pair(gpu, base, 128, 8)
+    # rows re-added after the build live in the exact buffer and shadow their list entries
+    rng = np.random.default_rng(0)
+    upd = rng.choice(5_000, 40, replace=False)
+    for r in upd:
+        v = rng.random(128, dtype=np.float32)
+        ref.add_batch(v[None, :], ids=np.array([int(r)]))
+        new_row = ix.add(v[None, :])
+        ix.shadow_row(int(r), True)
+        assert new_row >= 5_000
+    rid, rsc, rcn = ref.search_batch(q, 10, nprobe=8)
+    gsc, grows, gcn = ix.search(q, 10, nprobe=8)
+    # map the GPU's fresh row ordinals of the re-added vectors back to their ids
+    remap = {5_000 + i: int(r) for i, r in enumerate(upd)}
+    gid = np.vectorize(lambda x: remap.get(int(x), int(x)))(grows)
+    assert_batch_equivalent((rid, rsc, rcn), (gid, gsc, gcn), ctx="lm shadowed + buffer")
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core shortlist for KMeansUtils.FindNearestCentroid at large nlist
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [orc.L2, orc.IP, orc.COSINE])
+def test_tc_shortlist_assign_bit_exact(gpu, monkeypatch, metric):
+    rng = np.random.default_rng(3)
+    dim, nc, n = 128, 3000, 6000
+    cent = rng.random((nc, dim), dtype=np.float32)
+    X = rng.random((n, dim), dtype=np.float32)
+    cent[1500] = cent[7]            # duplicate centroids: the lower index must win
+    cent[2999] = cent[7]
+    X[:50] = cent[rng.choice(nc, 50)]  # rows that coincide with a centroid
+    X[50:60] = cent[7]
+    a = gpu.coarse_assign(X, cent, metric)           # tensor-core shortlist + exact re-evaluation
+    monkeypatch.setenv("PYROPE_ASSIGN_EXACT", "1")
+    b = gpu.coarse_assign(X, cent, metric)           # exhaustive exact kernel
+    np.testing.assert_array_equal(a, b)
+    ref = np.array([orc.find_nearest_centroid(v, cent, metric) for v in X[:400]], np.int32)
+    np.testing.assert_array_equal(a[:400], ref)
+    if metric == orc.L2:
+        assert (a[50:60] == 7).all()
+
+
+def test_tc_shortlist_kmeans_matches_exact_path(gpu, monkeypatch):
+    rng = np.random.default_rng(5)
+    X = rng.random((30_000, 64), dtype=np.float32)
+    c1, it1 = gpu.kmeans_train(X, 2500, gpu.L2, 3, 42)
+    monkeypatch.setenv("PYROPE_ASSIGN_EXACT", "1")
+    c2, it2 = gpu.kmeans_train(X, 2500, gpu.L2, 3, 42)
+    assert it1 == it2
+    np.testing.assert_array_equal(c1, c2)
