@@ -145,6 +145,10 @@ int pyrope_index_search_batch_device(pyrope_index *h, int64_t nq, const float *d
 int pyrope_index_last_search_ms(pyrope_index *h, float *out4);
 /* Number of kernel launches issued by the most recent search on this handle. */
 int pyrope_index_last_search_launches(pyrope_index *h, int *out);
+/* PQ codes scored by the most recent batched IVF_PQ search (sum over its (query, probe) pairs of the
+ * probed list's length; 0 if the search did not take the list-major path).  Measurement only: this is
+ * the unit count behind the bench's algorithmic HBM bytes (m bytes per scored code). */
+int pyrope_index_last_search_scanned(pyrope_index *h, int64_t *codes_out);
 
 /* ---- cross-shard merge (the step after ncclAllGather; semantics of DeltaVectorIndex.cs:95-121
  *      without the id-dedupe, which sharding makes unnecessary): parts x nq x k_in candidate lists

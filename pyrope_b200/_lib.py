@@ -61,6 +61,7 @@ SIGNATURES = {
     "pyrope_index_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp]),
     "pyrope_index_last_search_ms": (C.c_int, [vp, f32p]),
     "pyrope_index_last_search_launches": (C.c_int, [vp, i32p]),
+    "pyrope_index_last_search_scanned": (C.c_int, [vp, i64p]),
     "pyrope_topk_merge_device": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "pyrope_coarse_assign": (C.c_int, [C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]),
     "pyrope_kmeans_train": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int32, vp, i32p, i32p]),
@@ -243,6 +244,12 @@ class GpuIndex:
     def last_search_launches(self) -> int:
         out = C.c_int32(0)
         check(load().pyrope_index_last_search_launches(self._h, C.byref(out)))
+        return out.value
+
+    def last_search_scanned(self) -> int:
+        """PQ codes scored by the last batched IVF_PQ search (sum of probed list lengths)."""
+        out = C.c_int64(0)
+        check(load().pyrope_index_last_search_scanned(self._h, C.byref(out)))
         return out.value
 
 

@@ -179,7 +179,9 @@ struct pyrope_index {
         list_norms;
     std::vector<int64_t> list_off_h;
     std::vector<uint8_t> list_dead_h;
-    int64_t list_total = 0, list_ndead = 0;
+    int64_t list_total = 0, list_ndead = 0, max_list_len = 0;
+    // shape of the most recent list-major IVF_PQ search (for pyrope_index_last_search_scanned)
+    int64_t lm_nq = 0; int lm_P = 0, lm_k = 0;
     std::vector<int32_t> ksub;
     DevBuf ksub_d;
     bool frozen = false;  // codebooks supplied by the caller
@@ -559,6 +561,8 @@ int finish_lists(Index* h, const BuildData& bd, int32_t* d_assign, int nc, SortS
     CK(cudaMemcpyAsync(h->list_off_h.data(), sc.offs.p, sizeof(int64_t) * ((size_t)nc + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     h->list_total = n;
+    h->max_list_len = 0;
+    for (int c = 0; c < nc; ++c) h->max_list_len = std::max(h->max_list_len, h->list_off_h[(size_t)c + 1] - h->list_off_h[(size_t)c]);
     h->list_dead_h.clear();
     h->list_dead.release();
     h->list_ndead = 0;
@@ -728,6 +732,8 @@ int compact_lists(Index* h) {
     std::swap(h->list_labels.p, nl.p); std::swap(h->list_labels.bytes, nl.bytes);
     if (h->metric == kCosine) { std::swap(h->list_norms.p, nn.p); std::swap(h->list_norms.bytes, nn.bytes); }
     h->list_off_h = noff;
+    h->max_list_len = 0;
+    for (int c = 0; c < h->nc; ++c) h->max_list_len = std::max(h->max_list_len, noff[(size_t)c + 1] - noff[(size_t)c]);
     h->list_total = n;
     h->list_dead_h.clear();
     h->list_dead.release();
@@ -826,7 +832,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         groups = (int)std::max<int64_t>(1, std::min<int64_t>(want, P));
     }
     const bool use_lm = scan_lists && h->kind == PYROPE_IVF_PQ && !h->pq_force_generic && h->pq_lm_mode != 0 &&
-                        ivfpq_lm_supported(dim, h->m, h->k, P, k, nq, h->list_total);
+                        ivfpq_lm_supported(dim, h->m, h->k, P, k, nq, h->list_total, h->max_list_len);
     if (use_lm) groups = 1;
     int max_parts = kMergeMaxCandidates / k;
     if (max_parts < 1) max_parts = 1;
@@ -951,8 +957,10 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             pp.k = k; pp.groups = groups; pp.force_generic = h->pq_force_generic;
             pp.out = out; pp.out.part_base = seg_splits;
             if (use_lm) {
-                TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc), 0, st));
+                TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc, dim, h->max_list_len), 0, st));
+                pp.max_list_len = h->max_list_len;
                 CK(launch_ivfpq_scan_lm(pp, ws.lm.p, g_num_sms, st));
+                h->lm_nq = nq; h->lm_P = P; h->lm_k = k;
                 launches += ivfpq_lm_launches() - 1;
             } else {
                 CK(launch_ivfpq_scan(pp, st));
@@ -1310,6 +1318,18 @@ int pyrope_index_last_search_ms(pyrope_index* h, float* out4) {
 int pyrope_index_last_search_launches(pyrope_index* h, int* out) {
     if (!h || !out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
     *out = h->last_launches;
+    return PYROPE_OK;
+}
+
+int pyrope_index_last_search_scanned(pyrope_index* h, int64_t* codes_out) {
+    if (!h || !codes_out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    *codes_out = 0;
+    if (h->lm_nq <= 0 || !h->ws.lm.p) return PYROPE_OK;
+    unsigned long long v = 0;
+    CK(ivfpq_lm_scanned_codes(h->ws.lm.p, h->lm_nq, h->lm_P, h->lm_k, h->nc, h->dim, h->max_list_len, &v,
+                              h->last_stream ? h->last_stream : h->stream));
+    *codes_out = (int64_t)v;
     return PYROPE_OK;
 }
 

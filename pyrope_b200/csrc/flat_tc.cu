@@ -457,7 +457,9 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dim, int box_
 // ---- public launchers ----------------------------------------------------------------------------
 int flat_tc_margin(int k) { return k < 64 ? 16 : 32; }
 bool flat_tc_supported(int dim, int k) { return dim % 4 == 0 && dim >= 8 && k >= 1 && k + flat_tc_margin(k) <= 224; }
-int flat_tc_cap(int kprime) { return std::max(64, next_pow2(kprime + 32)); }
+// queue capacity per (split, query): a prune (warp-wide sort) fires when fewer than 32 slots are left and
+// keeps k', so the headroom cap - 32 - k' is the number of accepted candidates between two prunes.
+int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * kprime))); }
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {

@@ -99,6 +99,7 @@ struct IvfPqScanParams {
     const float* Q; int64_t nq; int dim;
     const int64_t* probes; int nprobe;
     const int64_t* list_off; int nlist;
+    int64_t max_list_len;                    // longest inverted list (list-major path sizing)
     const float* centroids;                  // [nlist][dim]
     const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
     const uint8_t* codes; const uint8_t* dead; const int64_t* labels;
@@ -109,9 +110,11 @@ struct IvfPqScanParams {
 cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
 // List-major variant (pq_lm.cu): (query, probe) pairs grouped by list, four queries per work item share
 // one pass over the list's codes; writes ONE part (p.groups is ignored).  m = 16, dim/m in {4, 8}.
-bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total);
-size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist);
+bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total, int64_t max_list_len);
+size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist, int dim, int64_t max_list_len);
 int ivfpq_lm_launches();
+cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, int k, int nlist, int dim,
+                                   int64_t max_list_len, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st);
 // ProductQuantizer.ComputeDistanceTable for nq queries (parity tests): table [nq][m][k]
 cudaError_t launch_pq_distance_table(const float* Q, int64_t nq, int dim, const float* codebook,

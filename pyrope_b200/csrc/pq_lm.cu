@@ -3,28 +3,40 @@
 // Replaces, for a whole query batch, ProductQuantizer.ComputeDistanceTable (ProductQuantizer.cs:98-120)
 // and the ADC loop of IvfPqVectorIndex.Search (IvfPqVectorIndex.cs:152-199).  The reference walks
 // query -> probed list -> code; a batch of 10^4 queries x 64 probes hits every inverted list ~10 times,
-// so this kernel inverts the loop: (query, probe) pairs are grouped BY LIST and each work item is one
-// list x up to four of the queries that probe it.
+// so this path inverts the loop: (query, probe) pairs are grouped BY LIST and one work item is one
+// list segment (<= 2048 codes) x up to four of the queries that probe it.
 //
-//   * the four queries' lookup tables are interleaved as float4 — LUT[e][m] = {q0,q1,q2,q3} at byte
-//     e*256 + m*16 — so one 128-bit shared-memory load serves four (query, code) lookups;
-//   * during the scan lane l reads table (l+t) mod 16 at step t: the eight lanes of every quarter warp
-//     touch eight distinct 16-byte bank groups whatever the code bytes are — conflict-free by
-//     construction.  The 16 code bytes are rotated once per lane so step t uses a compile-time byte
-//     and the address (code<<8 | table<<4) is a single PRMT;
-//   * the PQ codebook (m*k*sub fp32 = 128 KiB at d=128) stays in REGISTERS for the life of the
-//     persistent CTA (8 codewords per thread) and the table is built with packed FFMA2 as
-//     |p|^2 + |r_m|^2 - 2 r_m.p for the four residual queries at once;
-//   * each list's codes are staged into shared memory with TMA bulk copies (cp.async.bulk +
-//     mbarrier), double buffered, the next segment in flight while the current one is scanned;
-//   * candidates pass a per-query global threshold (the k-th best of any finished item), go to a
-//     per-slot queue, and at most k per item are appended to the query's pool in HBM;
-//   * ivfpq_lm_final_kernel selects the best k of the pool and RE-SCORES them in the reference's exact
-//     fp32 order (L2SquaredUnsafe per sub-vector, sequential sum over m), so reported distances never
-//     come from the fused-multiply-add path.
-// HBM traffic is one pass over the probed lists' codes (shared by all queries of the batch) instead
-// of one pass per (query, probe); the kernel is bound by the 128 B/clk/SM shared-memory crossbar.
+// Pipeline (all on one stream, no host synchronisation):
+//   lm_count / scans / lm_fill_pairs   group the pairs by list (counting sort on device);
+//   lm_prepare_kernel                  one warp per item writes the item block: header (list, code range,
+//                                      four query ids) + the four residual queries -2(q - c) interleaved
+//                                      as float4 per dimension (slot d*16 + m: conflict-free reads);
+//   ivfpq_lm_seed_kernel               per query, an upper bound of its k-th best ADC distance from (a
+//                                      sample of) its nearest list, so no item starts without a threshold;
+//   ivfpq_lm_scan_kernel               persistent CTAs, static item striding.  Per item:
+//       - item block and code segment arrive by TMA bulk copies (cp.async.bulk + mbarrier), issued one
+//         item ahead; codes double buffered, item blocks four deep;
+//       - the PQ codebook (m*k*sub fp32 = 128 KiB at d=128) stays in REGISTERS for the CTA's lifetime
+//         (8 codewords per thread); the four lookup tables are built with packed FFMA2 as
+//         |p|^2 + |r_m|^2 - 2 r_m.p and stored interleaved, LUT[e][m] = {q0,q1,q2,q3} at byte
+//         e*256 + m*16, double buffered so fast warps build item i+1 while slow warps still scan item i;
+//       - scan: lane l reads table (l+t) mod 16 at step t, so the eight lanes of every quarter warp
+//         touch eight distinct 16-byte bank groups whatever the code bytes are (conflict-free by
+//         construction); the 16 code bytes are rotated once per lane so step t uses a compile-time
+//         byte and the address (code<<8 | table<<4) is one PRMT; one LDS.128 = four (query, code) lookups;
+//       - candidates below the query's global threshold go to a small per-slot queue; after the item,
+//         one warp per slot hands at most k of them to the query's pool in HBM and tightens the
+//         threshold (atomicMax).  A queue that overflows sends the (query, item) to the redo list;
+//   ivfpq_lm_redo_kernel               plain per-(query, item) scan for the rare overflows;
+//   ivfpq_lm_final_kernel              best k of the pool, RE-SCORED in the reference's exact fp32 order
+//                                      (L2SquaredUnsafe per sub-vector, sequential sum over m), so
+//                                      reported distances never come from the fused-multiply-add path.
+// HBM traffic is one pass over the probed lists' codes (shared by the batch) instead of one pass per
+// (query, probe); the scan is bound by the 128 B/clk/SM shared-memory crossbar (ncu: 4 wavefronts per
+// LDS.128, zero excess).
 #include <cub/cub.cuh>
+
+#include <cstdio>
 
 #include "common.cuh"
 #include "exact_arith.cuh"
@@ -35,10 +47,26 @@ namespace {
 
 constexpr int LM_THREADS = 512;
 constexpr int LM_QS = 4;            // query slots per work item
-constexpr int LM_CODE_CAP = 1024;   // vectors per staged segment (16 KiB)
-constexpr int LM_QC = 2048;         // candidate queue entries per slot (>= LM_CODE_CAP + kMaxTopK)
+constexpr int LM_CODE_CAP = 2048;   // codes per item (32 KiB)
+constexpr int LM_QC = 256;          // candidate queue entries per slot
+constexpr int LM_RST = 4;           // item-block stages
+constexpr int LM_HDR = 64;          // item-block header bytes
+constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;
-constexpr int LM_SMEM = LM_LUT_BYTES + 2 * LM_CODE_CAP * 16 + LM_QS * LM_QC * 8;
+constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 16;
+constexpr int LM_SMEM = 2 * LM_LUT_BYTES + 2 * LM_CODE_CAP * 16 + LM_RST * LM_BLK_MAX + 2 * LM_QS * LM_QC * 8;
+constexpr int SEED_NQ = 4;          // queries per seed CTA (share the codebook reads)
+constexpr int SEED_CAP = 2048;      // sampled distances per query
+constexpr int REDO_QCAP = 2048;
+
+struct __align__(16) LmHeader {
+    int list, nvec;
+    long long vbeg;
+    int qid[LM_QS];
+    int pslot[LM_QS];  // (probe rank * maxseg + segment): the pair's private slot in the query's pool
+    int pad[4];
+};
+static_assert(sizeof(LmHeader) == LM_HDR, "header size");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,59 +118,269 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
     return d;
 }
 
+
+#ifdef PYROPE_LM_TIMING
+#define LM_T(i) do { long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } while (0)
+#else
+#define LM_T(i) do { } while (0)
+#endif
+
 struct LmParams {
-    const float* Q; int64_t nq; int dim;
-    const float* centroids; const float* codebook; int ksub;
-    const uint8_t* codes; const uint8_t* dead; const int64_t* list_off; int nlist;
-    const int2* items; const int32_t* n_items; const int32_t* pair_off; const int32_t* pairq;
-    unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pool_cap; int k;
-    int32_t* work_ctr;
+    long long* timing;  // [grid][16 warps][8] cycle sums per phase (PYROPE_LM_TIMING builds only)
+    int dim, ksub, k;
+    const float* codebook; const uint8_t* codes; const uint8_t* dead;
+    const unsigned char* iblk; const int32_t* n_items;
+    unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots;  // pool [nq][pslots][k], counts [nq][pslots]
+    int2* redo; int32_t* redo_cnt;
 };
 
 // ---- grouping (query, probe) pairs by list ---------------------------------------------------------
 __global__ void lm_count_kernel(const int64_t* __restrict__ probes, int64_t npairs, const int64_t* __restrict__ list_off,
-                                int32_t* lcnt) {
+                                int32_t* lcnt, unsigned long long* scanned) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npairs) return;
-    const int64_t l = probes[i];
-    if (l >= 0 && list_off[l + 1] > list_off[l]) atomicAdd(&lcnt[l], 1);  // IvfPqVectorIndex.cs:155 skips empty lists
+    unsigned long long len = 0;
+    if (i < npairs) {
+        const int64_t l = probes[i];
+        if (l >= 0) {
+            len = (unsigned long long)(list_off[l + 1] - list_off[l]);
+            if (len) atomicAdd(&lcnt[l], 1);  // IvfPqVectorIndex.cs:155 skips empty lists
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+    if ((threadIdx.x & 31) == 0 && len) atomicAdd(scanned, len);
 }
-__global__ void lm_items_per_list_kernel(const int32_t* __restrict__ lcnt, int n, int32_t* nit) {
+__global__ void lm_items_per_list_kernel(const int32_t* __restrict__ lcnt, const int64_t* __restrict__ list_off, int nlist,
+                                         int32_t* nit) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) nit[i] = (lcnt[i] + LM_QS - 1) / LM_QS;
+    if (i > nlist) return;
+    int v = 0;
+    if (i < nlist) {
+        const int64_t len = list_off[i + 1] - list_off[i];
+        v = ((lcnt[i] + LM_QS - 1) / LM_QS) * (int)((len + LM_CODE_CAP - 1) / LM_CODE_CAP);
+    }
+    nit[i] = v;
 }
 __global__ void lm_fill_pairs_kernel(const int64_t* __restrict__ probes, int64_t npairs, int P,
                                      const int64_t* __restrict__ list_off, const int32_t* __restrict__ loff, int32_t* lcur,
-                                     int32_t* pairq) {
+                                     int32_t* pairq, int32_t* pairp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     const int64_t l = probes[i];
-    if (l >= 0 && list_off[l + 1] > list_off[l]) pairq[loff[l] + atomicAdd(&lcur[l], 1)] = (int32_t)(i / P);
+    if (l >= 0 && list_off[l + 1] > list_off[l]) {
+        const int slot = loff[l] + atomicAdd(&lcur[l], 1);
+        pairq[slot] = (int32_t)(i / P);
+        pairp[slot] = (int32_t)(i % P);
+    }
 }
-__global__ void lm_fill_items_kernel(const int32_t* __restrict__ nit, const int32_t* __restrict__ ioff, int nlist, int2* items) {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlist) return;
-    const int n = nit[l], o = ioff[l];
-    for (int g = 0; g < n; ++g) items[o + g] = make_int2(l, g);
+
+// one warp per item: header + the four residual queries t = -2 (q - c), interleaved per dimension
+struct LmPrep {
+    const int32_t* ioff; const int32_t* loff; const int32_t* pairq; const int32_t* pairp; const int64_t* list_off; int nlist;
+    int maxseg;
+    const float* Q; const float* centroids; int dim;
+    unsigned char* iblk; int blk;
+};
+__global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= a.ioff[a.nlist]) return;
+    int lo = 0, hi = a.nlist;  // last list with ioff[l] <= w
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.ioff + mid) <= w) lo = mid; else hi = mid;
+    }
+    const int l = lo, rel = w - a.ioff[l];
+    const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
+    const int nseg = (int)((len + LM_CODE_CAP - 1) / LM_CODE_CAP);
+    const int g = rel / nseg, sg = rel - g * nseg;
+    const int pbeg = a.loff[l], pend = a.loff[l + 1];
+    int qid[LM_QS], psl[LM_QS];
+#pragma unroll
+    for (int j = 0; j < LM_QS; ++j) {
+        const int idx = pbeg + LM_QS * g + j;
+        qid[j] = idx < pend ? a.pairq[idx] : -1;
+        psl[j] = idx < pend ? a.pairp[idx] * a.maxseg + sg : 0;
+    }
+    unsigned char* blkp = a.iblk + (size_t)w * a.blk;
+    if (lane == 0) {
+        LmHeader h{};
+        h.list = l;
+        h.vbeg = beg + (int64_t)sg * LM_CODE_CAP;
+        h.nvec = (int)min((int64_t)LM_CODE_CAP, len - (int64_t)sg * LM_CODE_CAP);
+#pragma unroll
+        for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = psl[j]; }
+        *reinterpret_cast<LmHeader*>(blkp) = h;
+    }
+    if (lane * 4 < a.dim) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
+        float4 t[LM_QS];
+#pragma unroll
+        for (int j = 0; j < LM_QS; ++j) {
+            float4 q = c;
+            if (qid[j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[j] * a.dim) + lane);
+            t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
+        }
+        // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
+        // table build read 256 contiguous bytes per d (no bank conflicts)
+        float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR);
+        const int sub = a.dim >> 4, D0 = lane * 4;
+        dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+        dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+        dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+        dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+    }
+}
+
+// ---- plain ADC pieces shared by the seed and redo kernels ------------------------------------------------
+// lut[j][m*256 + e] = |r_j,m - codeword(m,e)|^2 for NQ residual queries res[j][dim]; thread e <-> codeword
+template <int NQ>
+__device__ __forceinline__ void lut_direct(const float* __restrict__ codebook, int K, int sub, const float* res, int dim,
+                                           float* lut, int tid, int nthr) {
+    for (int e = tid; e < 256; e += nthr) {
+        for (int mi = 0; mi < 16; ++mi) {
+            float a[NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) a[j] = 0.f;
+            if (e < K) {
+                const float* cw = codebook + ((size_t)mi * K + e) * sub;
+                for (int d = 0; d < sub; ++d) {
+                    const float c = __ldg(cw + d);
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) { const float df = res[j * dim + mi * sub + d] - c; a[j] = fmaf(df, df, a[j]); }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) lut[j * 4096 + mi * 256 + e] = a[j];
+        }
+    }
+}
+__device__ __forceinline__ float adc_plain(const uint8_t* __restrict__ code16, const float* lut) {
+    const uint4 cw = __ldg(reinterpret_cast<const uint4*>(code16));
+    const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+    float d = 0.f;
+#pragma unroll
+    for (int mi = 0; mi < 16; ++mi) d += lut[mi * 256 + ((w[mi >> 2] >> (8 * (mi & 3))) & 0xffu)];
+    return d;
+}
+
+// ---- seed: an upper bound of every query's k-th best ADC distance ---------------------------------------
+struct LmSeed {
+    const float* Q; int64_t nq; int dim; const int64_t* probes; int P;
+    const float* centroids; const float* codebook; int ksub;
+    const uint8_t* codes; const uint8_t* dead; const int64_t* list_off;
+    uint32_t* pool_thr; int k; int sample;
+};
+__global__ void __launch_bounds__(256) ivfpq_lm_seed_kernel(LmSeed a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* lut = reinterpret_cast<float*>(smem_raw);      // [SEED_NQ][16*256]
+    float* dist = lut + SEED_NQ * 4096;                   // [SEED_NQ][SEED_CAP]
+    float* res = dist + SEED_NQ * SEED_CAP;               // [SEED_NQ][dim]
+    __shared__ int s_cnt[SEED_NQ], s_pr[SEED_NQ];
+    __shared__ int64_t s_list[SEED_NQ];
+    __shared__ float s_rr[SEED_NQ];
+    __shared__ int s_more;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * SEED_NQ;
+    const int dim = a.dim, sub = dim / 16;
+    if (tid < SEED_NQ) { s_cnt[tid] = 0; s_pr[tid] = 0; s_rr[tid] = 0.f; }
+    __syncthreads();
+    for (int round = 0; round < a.P; ++round) {
+        // every query still short of k distances takes its next non-empty probed list
+        if (tid < SEED_NQ) {
+            const int64_t q = q0 + tid;
+            int64_t l = -1;
+            if (q < a.nq && s_cnt[tid] < a.k) {
+                int pr = s_pr[tid];
+                while (pr < a.P) {
+                    const int64_t c = a.probes[q * a.P + pr++];
+                    if (c >= 0 && a.list_off[c + 1] > a.list_off[c]) { l = c; break; }
+                }
+                s_pr[tid] = pr;
+            }
+            s_list[tid] = l;
+        }
+        if (tid == 0) s_more = 0;
+        __syncthreads();
+        if (s_list[0] < 0 && s_list[1] < 0 && s_list[2] < 0 && s_list[3] < 0) break;
+        for (int i = tid; i < SEED_NQ * dim; i += 256) {
+            const int j = i / dim, d = i - j * dim;
+            const int64_t l = s_list[j];
+            res[i] = l >= 0 ? a.Q[(q0 + j) * dim + d] - a.centroids[l * dim + d] : 0.f;
+        }
+        __syncthreads();
+        if (warp < SEED_NQ && s_list[warp] >= 0) {  // |q - c|^2 scales the rounding margin below
+            float s = 0.f;
+            for (int d = lane; d < dim; d += 32) s = fmaf(res[warp * dim + d], res[warp * dim + d], s);
+            s = warp_sum(s);
+            if (lane == 0) s_rr[warp] = fmaxf(s_rr[warp], s);
+        }
+        lut_direct<SEED_NQ>(a.codebook, a.ksub, sub, res, dim, lut, tid, 256);
+        __syncthreads();
+        for (int j = 0; j < SEED_NQ; ++j) {
+            const int64_t l = s_list[j];
+            if (l < 0) continue;
+            const int64_t beg = a.list_off[l];
+            const int room = min(a.sample, SEED_CAP) - s_cnt[j];
+            const int nv = (int)min((int64_t)max(room, 0), a.list_off[l + 1] - beg);
+            __syncthreads();  // s_cnt[j] read by everyone before it moves
+            for (int v = tid; v < nv; v += 256) {
+                const int64_t pos = beg + v;
+                if (a.dead && a.dead[pos]) continue;
+                const float d = adc_plain(a.codes + pos * 16, lut + j * 4096);
+                dist[j * SEED_CAP + atomicAdd(&s_cnt[j], 1)] = d;
+            }
+        }
+        __syncthreads();
+        if (tid < SEED_NQ && q0 + tid < a.nq && s_cnt[tid] < a.k && s_pr[tid] < a.P) s_more = 1;
+        __syncthreads();
+        if (!s_more) break;
+    }
+    __syncthreads();
+    // one warp per query: smallest t (within a factor-2 count window) with count(dist <= t) >= k
+    if (warp < SEED_NQ && q0 + warp < a.nq) {
+        const int n = s_cnt[warp];
+        if (n >= a.k) {
+            const float* dj = dist + warp * SEED_CAP;
+            uint32_t hi = 0;
+            for (int i = lane; i < n; i += 32) hi = max(hi, __float_as_uint(fmaxf(dj[i], 0.f)));
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            uint32_t lo = 0;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                int c = 0;
+                for (int i = lane; i < n; i += 32) c += __float_as_uint(fmaxf(dj[i], 0.f)) <= mid;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= a.k) { hi = mid; if (c <= 2 * a.k) break; } else lo = mid + 1;
+            }
+            if (lane == 0) {
+                const float t = __uint_as_float(hi);
+                // the scan kernel evaluates the same distances in |p|^2+|r|^2-2r.p form: cover its rounding
+                const float tp = t + 2e-5f * t + 1e-5f * s_rr[warp] + 1e-12f;
+                a.pool_thr[q0 + warp] = score_to_ord(-tp) - 1u;  // accept iff dist <= tp
+            }
+        }
+    }
 }
 
 // ---- the scan --------------------------------------------------------------------------------------
 template <int SUB>
 __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* lut = smem;                                                         // [256][16] float4
-    unsigned char* cbuf = smem + LM_LUT_BYTES;                                         // [2][CODE_CAP] uint4
-    uint64_t* qkeys = reinterpret_cast<uint64_t*>(cbuf + 2 * LM_CODE_CAP * 16);        // [QS][QC]
-    __shared__ __align__(8) uint64_t s_mbar[2];
-    __shared__ int s_qcnt[LM_QS];
-    __shared__ int s_next;
+    unsigned char* lut = smem;                                                     // [2][256][16] float4
+    unsigned char* cbuf = lut + 2 * LM_LUT_BYTES;                                   // [2][CODE_CAP] uint4
+    unsigned char* rbuf = cbuf + 2 * LM_CODE_CAP * 16;                              // [RST] item blocks
+    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_RST * LM_BLK_MAX);     // [2][QS][QC]
+    __shared__ __align__(8) uint64_t s_mbar[2 + LM_RST];
+    __shared__ int s_qcnt[2 * LM_QS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = p.ksub, dim = p.dim;
+    const int K = p.ksub;
+    const int blk = LM_HDR + p.dim * 16;
     const int m = lane & 15;                 // build: this thread's sub-quantiser
     const int eb = (lane >> 4) + 2 * warp;   // build: its codewords are eb + 32 j, j < 8
     const int n_items = *p.n_items;
-    const uint32_t bar0 = smem_u32(&s_mbar[0]), bar1 = smem_u32(&s_mbar[1]);
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_n = first < n_items ? (n_items - first + stride - 1) / stride : 0;
 
     // codebook slice in registers for the CTA's lifetime
     float cb[8][SUB], pn[8];
@@ -164,181 +402,53 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         op[i] = (uint32_t)(((lane + 2 * i) & 15) << 4) | ((uint32_t)(((lane + 2 * i + 1) & 15) << 4) << 8);
+    // byte 2 of op[] carries the table buffer (item parity): PRMT drops it into bit 16 of the address
     const int rot = lane & 15;
 
-    auto seg_issue = [&](int item, int seg, int b) {  // thread 0 only
-        const int2 it = __ldg(&p.items[item]);
-        const int64_t beg = __ldg(p.list_off + it.x) + (int64_t)seg * LM_CODE_CAP;
-        const int64_t end = __ldg(p.list_off + it.x + 1);
-        const uint32_t bytes = (uint32_t)min((int64_t)LM_CODE_CAP, end - beg) * 16u;
-        const uint32_t bar = b ? bar1 : bar0;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(cbuf + b * LM_CODE_CAP * 16), p.codes + beg * 16, bytes, bar);
-    };
-    // CTA-wide: sort slot j's queue, keep the best k; returns the kept count (all threads call)
-    auto prune_slot = [&](int j) -> int {
-        uint64_t* kq = qkeys + j * LM_QC;
-        const int n = min(s_qcnt[j], LM_QC);
-        const int P2 = next_pow2(max(n, 2));
-        for (int i = n + tid; i < P2; i += LM_THREADS) kq[i] = 0ull;
-        __syncthreads();
-        bitonic_sort_desc<false>(kq, P2, tid, LM_THREADS);
-        const int keep = min(n, p.k);
-        if (tid == 0) s_qcnt[j] = keep;
-        __syncthreads();
-        return keep;
-    };
-
+    const uint32_t bar_c = smem_u32(&s_mbar[0]);  // +8*b: codes buffer b
+    const uint32_t bar_r = smem_u32(&s_mbar[2]);  // +8*s: item-block stage s
     if (tid == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar1, 1);
+        for (int i = 0; i < 2 + LM_RST; ++i) mbar_init(bar_c + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_next = atomicAdd(p.work_ctr, 1);
     }
+    if (tid < 2 * LM_QS) s_qcnt[tid] = 0;
     __syncthreads();
-    int cur = s_next;
-    __syncthreads();
-    uint32_t ph0 = 0, ph1 = 0;
-    int buf = 0;
-    if (tid == 0 && cur < n_items) seg_issue(cur, 0, 0);
+    if (my_n == 0) return;
 
-    while (cur < n_items) {
-        const int2 it = __ldg(&p.items[cur]);
-        const int l = it.x, g = it.y;
-        const int64_t beg = __ldg(p.list_off + l), end = __ldg(p.list_off + l + 1);
-        const int pbeg = __ldg(p.pair_off + l), pend = __ldg(p.pair_off + l + 1);
-        int qid[LM_QS];
-        float thrd[LM_QS];
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j) {
-            const int idx = pbeg + LM_QS * g + j;
-            qid[j] = idx < pend ? __ldg(p.pairq + idx) : -1;
-            thrd[j] = -INFINITY;
-            if (qid[j] >= 0) {
-                const uint32_t u = __ldcg(p.pool_thr + qid[j]);
-                thrd[j] = u ? -ord_to_score(u) : INFINITY;
-            }
-        }
-        int nxt_local = 0;
-        if (tid == 0) nxt_local = atomicAdd(p.work_ctr, 1);
-        if (tid < LM_QS) s_qcnt[tid] = 0;
+    // thread 0 feeds the pipeline: TMA of item i's block and codes; the header it needs is prefetched
+    auto hdr_ptr = [&](int i) { return p.iblk + (size_t)(first + (size_t)i * stride) * blk; };
+    auto issue = [&](int i, const int4& h) {  // h = {list, nvec, vbeg lo, vbeg hi}
+        const long long vbeg = (long long)(((unsigned long long)(uint32_t)h.w << 32) | (uint32_t)h.z);
+        const uint32_t br = bar_r + 8 * (i & (LM_RST - 1)), bc = bar_c + 8 * (i & 1);
+        mbar_expect_tx(br, (uint32_t)blk);
+        bulk_g2s(smem_u32(rbuf + (i & (LM_RST - 1)) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
+        mbar_expect_tx(bc, (uint32_t)h.y * 16u);
+        bulk_g2s(smem_u32(cbuf + (i & 1) * LM_CODE_CAP * 16), p.codes + vbeg * 16, (uint32_t)h.y * 16u, bc);
+    };
+    int4 hnext = make_int4(0, 0, 0, 0);
+    if (tid == 0) {
+        const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr_ptr(0)));
+        issue(0, h0);
+        if (my_n > 1) hnext = __ldg(reinterpret_cast<const int4*>(hdr_ptr(1)));
+    }
 
-        // ---- lookup tables of the (up to) four residual queries: |p|^2 + |r_m|^2 - 2 r_m.p
-        {
-            float cen[SUB];
-#pragma unroll
-            for (int d4 = 0; d4 < SUB / 4; ++d4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(p.centroids + (size_t)l * dim + m * SUB) + d4);
-                cen[4 * d4 + 0] = v.x; cen[4 * d4 + 1] = v.y; cen[4 * d4 + 2] = v.z; cen[4 * d4 + 3] = v.w;
-            }
-            float tt[LM_QS][SUB], rr[LM_QS];
-#pragma unroll
-            for (int j = 0; j < LM_QS; ++j) {
-                rr[j] = 0.f;
-#pragma unroll
-                for (int d4 = 0; d4 < SUB / 4; ++d4) {
-                    float4 v = make_float4(cen[4 * d4], cen[4 * d4 + 1], cen[4 * d4 + 2], cen[4 * d4 + 3]);
-                    if (qid[j] >= 0) v = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)qid[j] * dim + m * SUB) + d4);
-                    const float r0 = v.x - cen[4 * d4], r1 = v.y - cen[4 * d4 + 1], r2 = v.z - cen[4 * d4 + 2], r3 = v.w - cen[4 * d4 + 3];
-                    rr[j] = fmaf(r0, r0, rr[j]); rr[j] = fmaf(r1, r1, rr[j]); rr[j] = fmaf(r2, r2, rr[j]); rr[j] = fmaf(r3, r3, rr[j]);
-                    tt[j][4 * d4 + 0] = -2.f * r0; tt[j][4 * d4 + 1] = -2.f * r1; tt[j][4 * d4 + 2] = -2.f * r2; tt[j][4 * d4 + 3] = -2.f * r3;
-                }
-            }
-            unsigned long long t01[SUB], t23[SUB];
-#pragma unroll
-            for (int d = 0; d < SUB; ++d) { t01[d] = pack2(tt[0][d], tt[1][d]); t23[d] = pack2(tt[2][d], tt[3][d]); }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                unsigned long long a01 = pack2(pn[j] + rr[0], pn[j] + rr[1]);
-                unsigned long long a23 = pack2(pn[j] + rr[2], pn[j] + rr[3]);
-#pragma unroll
-                for (int d = 0; d < SUB; ++d) {
-                    const unsigned long long c2 = pack2(cb[j][d], cb[j][d]);
-                    a01 = ffma2(c2, t01[d], a01);
-                    a23 = ffma2(c2, t23[d], a23);
-                }
-                *reinterpret_cast<ulonglong2*>(lut + (eb + 32 * j) * 256 + m * 16) = make_ulonglong2(a01, a23);
-            }
-        }
-        if (tid == 0) s_next = nxt_local;
-        __syncthreads();  // tables, counters and the next item index are visible
-        const int nxt = s_next;
-
-        const int nseg = (int)((end - beg + LM_CODE_CAP - 1) / LM_CODE_CAP);
-        for (int sg = 0; sg < nseg; ++sg) {
-            if (tid == 0) {  // keep the other buffer in flight: next segment of this list, else the next item
-                if (sg + 1 < nseg) seg_issue(cur, sg + 1, buf ^ 1);
-                else if (nxt < n_items) seg_issue(nxt, 0, buf ^ 1);
-            }
-            const int64_t sbeg = beg + (int64_t)sg * LM_CODE_CAP;
-            const int nvec = (int)min((int64_t)LM_CODE_CAP, end - sbeg);
-            if (sg > 0) {  // make room: a cold (no threshold yet) slot can take every vector of a segment
-#pragma unroll
-                for (int j = 0; j < LM_QS; ++j) {
-                    if (s_qcnt[j] + nvec > LM_QC) {
-                        const int keep = prune_slot(j);
-                        if (keep == p.k) thrd[j] = fminf(thrd[j], -key_score(qkeys[j * LM_QC + p.k - 1]));
-                    }
-                }
-            }
-            if (buf == 0) { mbar_wait(bar0, ph0); ph0 ^= 1; } else { mbar_wait(bar1, ph1); ph1 ^= 1; }
-            const unsigned char* cseg = cbuf + buf * LM_CODE_CAP * 16;
-            for (int v = tid; v < nvec; v += LM_THREADS) {
-                const uint4 cw = *reinterpret_cast<const uint4*>(cseg + v * 16);
-                uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
-                {   // rotate the 16 code bytes left by `rot` positions: new byte t = old byte (t + rot) & 15
-                    const bool r8 = rot & 8, r4 = rot & 4;
-                    uint32_t a0 = r8 ? w[2] : w[0], a1 = r8 ? w[3] : w[1], a2 = r8 ? w[0] : w[2], a3 = r8 ? w[1] : w[3];
-                    uint32_t b0 = r4 ? a1 : a0, b1 = r4 ? a2 : a1, b2 = r4 ? a3 : a2, b3 = r4 ? a0 : a3;
-                    const int sh = (rot & 3) * 8;
-                    w[0] = __funnelshift_r(b0, b1, sh); w[1] = __funnelshift_r(b1, b2, sh);
-                    w[2] = __funnelshift_r(b2, b3, sh); w[3] = __funnelshift_r(b3, b0, sh);
-                }
-                unsigned long long acc01 = 0ull, acc23 = 0ull;
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    // byte0 = table offset, byte1 = code byte: address = code * 256 + table * 16
-                    const uint32_t sel = 0x7600u | (uint32_t)((t & 3) << 4) | (uint32_t)(4 + (t & 1));
-                    const uint32_t a = __byte_perm(w[t >> 2], op[t >> 1], sel);
-                    const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(lut + a);
-                    acc01 = fadd2(acc01, e.x);
-                    acc23 = fadd2(acc23, e.y);
-                }
-                float d0, d1, d2, d3;
-                unpack2(acc01, d0, d1);
-                unpack2(acc23, d2, d3);
-                if ((d0 < thrd[0]) | (d1 < thrd[1]) | (d2 < thrd[2]) | (d3 < thrd[3])) {
-                    const int64_t gpos = sbeg + v;
-                    if (!(p.dead && p.dead[gpos])) {
-                        const float dd[LM_QS] = {d0, d1, d2, d3};
-#pragma unroll
-                        for (int j = 0; j < LM_QS; ++j) {
-                            if (dd[j] < thrd[j]) {
-                                const int pos = atomicAdd(&s_qcnt[j], 1);
-                                if (pos < LM_QC) qkeys[j * LM_QC + pos] = make_key(-dd[j], (uint32_t)gpos);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();  // the segment buffer may be refilled; queue counts are visible
-            buf ^= 1;
-        }
-
-        // ---- hand at most k candidates per slot to the queries' pools
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j)
-            if (s_qcnt[j] > p.k && s_qcnt[j] > 64) prune_slot(j);
-        if (warp < LM_QS) {
-            const int j = warp;
-            const int n = min(s_qcnt[j], LM_QC);
-            const int q = j == 0 ? qid[0] : j == 1 ? qid[1] : j == 2 ? qid[2] : qid[3];
-            if (n > 0 && q >= 0) {
-                const uint64_t* kq = qkeys + j * LM_QC;
-                unsigned long long* dst = p.pool + (size_t)q * p.pool_cap;
+    // one warp per slot: hand at most k of the slot's candidates to the pair's private region of the query's
+    // pool (plain stores: no returning atomics on this path) and tighten the query's threshold
+    auto finalize = [&](int set, const LmHeader* hd, int gitem) {
+        const int j = warp;
+        int* cntp = &s_qcnt[set * LM_QS + j];
+        const int n = *cntp;
+        const int q = hd->qid[j];
+        if (n > 0 && q >= 0) {
+            uint64_t* kq = qkeys + (set * LM_QS + j) * LM_QC;
+            if (n > LM_QC) {  // candidates were dropped: the plain kernel redoes this (query, item)
+                if (lane == 0) p.redo[atomicAdd(p.redo_cnt, 1)] = make_int2(q, gitem * LM_QS + j);
+            } else {
+                const size_t ps = (size_t)q * p.pslots + hd->pslot[j];
+                unsigned long long* dst = p.pool + ps * p.k;
                 uint64_t mink = ~0ull;
                 int kept;
-                if (n > p.k) {  // k < n <= 64: select by rank counting inside the warp
+                if (n > p.k && n <= 64) {  // select by rank counting inside the warp
                     const uint64_t a = lane < n ? kq[lane] : 0ull, b = lane + 32 < n ? kq[lane + 32] : 0ull;
                     int ra = 0, rb = 0;
                     for (int i = 0; i < n; ++i) {
@@ -349,24 +459,24 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     const bool ka = lane < n && ra < p.k, kb = lane + 32 < n && rb < p.k;
                     const unsigned ma = __ballot_sync(0xffffffffu, ka), mb = __ballot_sync(0xffffffffu, kb);
                     kept = __popc(ma) + __popc(mb);
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&p.pool_cnt[q], kept);
-                    base = __shfl_sync(0xffffffffu, base, 0);
                     const unsigned below = (1u << lane) - 1u;
-                    const int ia = base + __popc(ma & below), ib = base + __popc(ma) + __popc(mb & below);
-                    if (ka) { if (ia < p.pool_cap) dst[ia] = a; mink = a; }
-                    if (kb) { if (ib < p.pool_cap) dst[ib] = b; mink = b < mink ? b : mink; }
+                    if (ka) { dst[__popc(ma & below)] = a; mink = a; }
+                    if (kb) { dst[__popc(ma) + __popc(mb & below)] = b; mink = b < mink ? b : mink; }
                 } else {
-                    kept = n;
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&p.pool_cnt[q], kept);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    for (int i = lane; i < n; i += 32) {
+                    if (n > p.k) {  // 64 < n <= QC: warp-level sort, best first
+                        const int P2 = next_pow2(n);
+                        for (int i = n + lane; i < P2; i += 32) kq[i] = 0ull;
+                        __syncwarp();
+                        bitonic_sort_desc<true>(kq, P2, lane, 32);
+                    }
+                    kept = min(n, p.k);
+                    for (int i = lane; i < kept; i += 32) {
                         const uint64_t x = kq[i];
-                        if (base + i < p.pool_cap) dst[base + i] = x;
+                        dst[i] = x;
                         mink = x < mink ? x : mink;
                     }
                 }
+                if (lane == 0) p.pool_cnt[ps] = kept;
                 if (kept >= p.k) {  // this item alone proves k candidates at or above mink
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -377,8 +487,176 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) *cntp = 0;
+    };
+
+#ifdef PYROPE_LM_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    for (int i = 0; i < my_n; ++i) {
+        const int rs = i & (LM_RST - 1), cs = i & 1;
+        LM_T(7);
+        // ---- build the four lookup tables of item i: |p|^2 + |r_m|^2 - 2 r_m.p
+        mbar_wait(bar_r + 8 * rs, (uint32_t)(i / LM_RST) & 1u);
+        LM_T(0);
+        const unsigned char* blkp = rbuf + rs * LM_BLK_MAX;
+        const int4 qv = *reinterpret_cast<const int4*>(reinterpret_cast<const LmHeader*>(blkp)->qid);
+        uint32_t tu[LM_QS];
+        tu[0] = qv.x >= 0 ? __ldcg(p.pool_thr + qv.x) : 0xffffffffu;  // in flight during the build
+        tu[1] = qv.y >= 0 ? __ldcg(p.pool_thr + qv.y) : 0xffffffffu;
+        tu[2] = qv.z >= 0 ? __ldcg(p.pool_thr + qv.z) : 0xffffffffu;
+        tu[3] = qv.w >= 0 ? __ldcg(p.pool_thr + qv.w) : 0xffffffffu;
+        {
+            const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + m;  // slot d*16 + m
+            unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
+#pragma unroll
+            for (int d = 0; d < SUB; ++d) {
+                const ulonglong2 v = rt[d * 16];
+                t01[d] = v.x; t23[d] = v.y;
+                rr01 = ffma2(v.x, v.x, rr01);
+                rr23 = ffma2(v.y, v.y, rr23);
+            }
+            const unsigned long long quarter = pack2(0.25f, 0.25f);  // t = -2 r  =>  |r|^2 = sum t^2 / 4
+            unsigned char* lw = lut + cs * LM_LUT_BYTES + eb * 256 + m * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned long long pj = pack2(pn[j], pn[j]);
+                unsigned long long a01 = ffma2(rr01, quarter, pj), a23 = ffma2(rr23, quarter, pj);
+#pragma unroll
+                for (int d = 0; d < SUB; ++d) {
+                    const unsigned long long c2 = pack2(cb[j][d], cb[j][d]);
+                    a01 = ffma2(c2, t01[d], a01);
+                    a23 = ffma2(c2, t23[d], a23);
+                }
+                *reinterpret_cast<ulonglong2*>(lw + j * (32 * 256)) = make_ulonglong2(a01, a23);
+            }
+        }
+        LM_T(1);
+        asm volatile("bar.sync 1, %0;" ::"n"(LM_THREADS) : "memory");  // tables of item i complete; scan i-1 finished by all
+        LM_T(2);
+        if (tid == 0 && i + 1 < my_n) {
+            issue(i + 1, hnext);
+            if (i + 2 < my_n) hnext = __ldg(reinterpret_cast<const int4*>(hdr_ptr(i + 2)));
+        }
+        if (i > 0 && warp < LM_QS)
+            finalize((i - 1) & 1, reinterpret_cast<const LmHeader*>(rbuf + ((i - 1) & (LM_RST - 1)) * LM_BLK_MAX),
+                     first + (i - 1) * stride);
+
+        LM_T(3);
+        // ---- scan item i
+        float thrd[LM_QS];
+#pragma unroll
+        for (int j = 0; j < LM_QS; ++j)
+            thrd[j] = tu[j] == 0xffffffffu ? -INFINITY : (tu[j] ? -ord_to_score(tu[j]) : INFINITY);
+        const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
+        const int nvec = hd->nvec;
+        const long long vbeg = hd->vbeg;
+        mbar_wait(bar_c + 8 * cs, (uint32_t)(i >> 1) & 1u);
+        LM_T(4);
+        const unsigned char* cseg = cbuf + cs * LM_CODE_CAP * 16;
+        uint32_t opc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            opc[u] = op[u] | ((uint32_t)cs << 16);
+            asm volatile("" : "+r"(opc[u]));  // keep the eight offset words in registers (no rematerialisation in the loop)
+        }
+        for (int c = warp; c * 32 < nvec; c += LM_THREADS / 32) {
+            const int v = c * 32 + lane;
+            if (v < nvec) {
+                const uint4 cw = *reinterpret_cast<const uint4*>(cseg + v * 16);
+                uint32_t w[4];
+                {   // rotate the 16 code bytes: new byte t = old byte (t + rot) & 15
+                    const bool r8 = rot & 8, r4 = rot & 4;
+                    const uint32_t a0 = r8 ? cw.z : cw.x, a1 = r8 ? cw.w : cw.y, a2 = r8 ? cw.x : cw.z, a3 = r8 ? cw.y : cw.w;
+                    const uint32_t b0 = r4 ? a1 : a0, b1 = r4 ? a2 : a1, b2 = r4 ? a3 : a2, b3 = r4 ? a0 : a3;
+                    const int sh = (rot & 3) * 8;
+                    w[0] = __funnelshift_r(b0, b1, sh); w[1] = __funnelshift_r(b1, b2, sh);
+                    w[2] = __funnelshift_r(b2, b3, sh); w[3] = __funnelshift_r(b3, b0, sh);
+                }
+                unsigned long long acc01 = 0ull, acc23 = 0ull;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    // byte0 = table offset, byte1 = code byte: address = code * 256 + table * 16
+                    const uint32_t sel = 0x7600u | (uint32_t)((t & 3) << 4) | (uint32_t)(4 + (t & 1));
+                    const uint32_t a = __byte_perm(w[t >> 2], opc[t >> 1], sel);
+                    const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(lut + a);
+                    acc01 = fadd2(acc01, e.x);
+                    acc23 = fadd2(acc23, e.y);
+                }
+                float d0, d1, d2, d3;
+                unpack2(acc01, d0, d1);
+                unpack2(acc23, d2, d3);
+                if ((d0 < thrd[0]) | (d1 < thrd[1]) | (d2 < thrd[2]) | (d3 < thrd[3])) {
+                    const long long gpos = vbeg + v;
+                    if (!(p.dead && p.dead[gpos])) {
+                        const float dd[LM_QS] = {d0, d1, d2, d3};
+#pragma unroll
+                        for (int j = 0; j < LM_QS; ++j) {
+                            if (dd[j] < thrd[j]) {
+                                const int pos = atomicAdd(&s_qcnt[cs * LM_QS + j], 1);
+                                if (pos < LM_QC) qkeys[(cs * LM_QS + j) * LM_QC + pos] = make_key(-dd[j], (uint32_t)gpos);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        LM_T(5);
+    }
+    LM_T(6);
+#ifdef PYROPE_LM_TIMING
+    if (lane == 0 && p.timing)
+        for (int u = 0; u < 8; ++u) p.timing[((size_t)blockIdx.x * 16 + warp) * 8 + u] = tacc[u];
+#endif
+    asm volatile("bar.sync 1, %0;" ::"n"(LM_THREADS) : "memory");
+    if (warp < LM_QS)
+        finalize((my_n - 1) & 1, reinterpret_cast<const LmHeader*>(rbuf + ((my_n - 1) & (LM_RST - 1)) * LM_BLK_MAX),
+                 first + (my_n - 1) * stride);
+}
+
+// ---- redo: plain scan of one (query, item) whose queue overflowed -------------------------------------------
+struct LmRedo {
+    const float* Q; int dim; const float* centroids; const float* codebook; int ksub;
+    const uint8_t* codes; const uint8_t* dead;
+    const unsigned char* iblk; int blk; const int2* redo; const int32_t* redo_cnt;
+    unsigned long long* pool; int32_t* pool_cnt; int pslots; int k;
+};
+__global__ void __launch_bounds__(256) ivfpq_lm_redo_kernel(LmRedo a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);   // [REDO_QCAP]
+    float* lut = reinterpret_cast<float*>(keys + REDO_QCAP);  // [16*256]
+    float* res = lut + 4096;                                  // [dim]
+    __shared__ int s_cnt;
+    __shared__ uint64_t s_thr;
+    const int tid = threadIdx.x;
+    const int n_redo = *a.redo_cnt;
+    for (int e = blockIdx.x; e < n_redo; e += gridDim.x) {
+        const int2 en = a.redo[e];
+        const LmHeader* hd = reinterpret_cast<const LmHeader*>(a.iblk + (size_t)(en.y / LM_QS) * a.blk);
+        const size_t ps = (size_t)en.x * a.pslots + hd->pslot[en.y % LM_QS];
+        const int l = hd->list, nvec = hd->nvec;
+        const long long vbeg = hd->vbeg;
         __syncthreads();
-        cur = nxt;
+        for (int d = tid; d < a.dim; d += 256) res[d] = a.Q[(size_t)en.x * a.dim + d] - a.centroids[(size_t)l * a.dim + d];
+        CtaQueue Qu{keys, &s_cnt, &s_thr, REDO_QCAP, a.k};
+        Qu.reset(tid);
+        __syncthreads();
+        lut_direct<1>(a.codebook, a.ksub, a.dim / 16, res, a.dim, lut, tid, 256);
+        __syncthreads();
+        for (int c0 = 0; c0 < nvec; c0 += 256) {
+            if (s_cnt + 256 > REDO_QCAP) Qu.prune(tid, 256);  // s_cnt is stable here: every push is behind a barrier
+            const int v = c0 + tid;
+            if (v < nvec && !(a.dead && a.dead[vbeg + v])) {
+                const float d = adc_plain(a.codes + (size_t)(vbeg + v) * 16, lut);
+                Qu.push(make_key(-d, (uint32_t)(vbeg + v)));
+            }
+            __syncthreads();
+        }
+        Qu.prune(tid, 256);
+        const int keep = s_cnt;
+        if (tid == 0) a.pool_cnt[ps] = keep;
+        for (int i = tid; i < keep; i += 256) a.pool[ps * a.k + i] = keys[i];
     }
 }
 
@@ -387,20 +665,31 @@ struct LmFinalParams {
     const float* Q; int dim;
     const float* centroids; const float* codebook; int ksub;
     const uint8_t* codes; const int64_t* list_off; int nlist; const int64_t* labels;
-    const unsigned long long* pool; const int32_t* pool_cnt; int pool_cap; int k;
+    const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k;
     PairOut out;
 };
 
 template <int SUB>
-__global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p, int P2max) {
+__global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [P2max]
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [next_pow2(pool_cap)]
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = min(p.pool_cnt[q], p.pool_cap);
+    __shared__ int s_n;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int sl = tid; sl < p.pslots; sl += blockDim.x) {  // gather the pairs' private regions
+        const size_t ps = (size_t)q * p.pslots + sl;
+        const int c = min(p.pool_cnt[ps], p.k);
+        if (c > 0) {
+            const int base = atomicAdd(&s_n, c);
+            for (int i = 0; i < c; ++i) keys[base + i] = p.pool[ps * p.k + i];
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
     const int P2 = next_pow2(max(n, 2));
-    const unsigned long long* src = p.pool + (size_t)q * p.pool_cap;
-    for (int i = tid; i < P2; i += blockDim.x) keys[i] = i < n ? src[i] : 0ull;
+    for (int i = n + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
     bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
     const int kk = min(n, p.k);
@@ -446,31 +735,40 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p, in
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int lm_maxseg(int64_t max_list_len) { return (int)std::max<int64_t>(1, (max_list_len + LM_CODE_CAP - 1) / LM_CODE_CAP); }
 
 struct LmLayout {
     size_t zero_bytes;  // leading region cleared per search
-    size_t lcnt, lcur, pool_cnt, pool_thr, ctr, loff, nit, ioff, pairq, items, pool, temp, total;
+    size_t lcnt, lcur, pool_cnt, pool_thr, redo_cnt, scanned, loff, nit, ioff, pairq, pairp, redo, iblk, pool, temp, total;
     size_t temp_bytes;
     int64_t max_items;
+    int pool_cap, pslots, blk;
 };
 
-LmLayout lm_layout(int64_t nq, int P, int k, int nlist) {
+LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_list_len) {
     LmLayout L{};
     const int64_t npairs = nq * P;
+    const int maxseg = lm_maxseg(max_list_len);
     size_t o = 0;
     L.lcnt = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.lcur = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
-    L.pool_cnt = o; o += align_up(sizeof(int32_t) * (size_t)nq, 256);
+    L.pool_cnt = o; o += align_up(sizeof(int32_t) * (size_t)nq * P * maxseg, 256);
     L.pool_thr = o; o += align_up(sizeof(uint32_t) * (size_t)nq, 256);
-    L.ctr = o; o += 256;
+    L.redo_cnt = o; o += 256;
+    L.scanned = o; o += 256;
     L.zero_bytes = o;
     L.loff = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.nit = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.ioff = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.pairq = o; o += align_up(sizeof(int32_t) * (size_t)npairs, 256);
-    L.max_items = npairs / LM_QS + std::min<int64_t>(npairs, nlist) + 1;
-    L.items = o; o += align_up(sizeof(int2) * (size_t)L.max_items, 256);
-    L.pool = o; o += align_up(sizeof(unsigned long long) * (size_t)nq * P * k, 256);
+    L.pairp = o; o += align_up(sizeof(int32_t) * (size_t)npairs, 256);
+    L.max_items = (npairs / LM_QS + std::min<int64_t>(npairs, nlist) + 1) * maxseg;
+    L.redo = o; o += align_up(sizeof(int2) * (size_t)L.max_items * LM_QS, 256);
+    L.blk = LM_HDR + dim * 16;
+    L.iblk = o; o += align_up((size_t)L.blk * (size_t)L.max_items, 256);
+    L.pslots = P * maxseg;
+    L.pool_cap = L.pslots * k;
+    L.pool = o; o += align_up(sizeof(unsigned long long) * (size_t)nq * L.pool_cap, 256);
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int32_t*)nullptr, (int32_t*)nullptr, nlist + 1);
     L.temp_bytes = tb + 256;
@@ -483,18 +781,21 @@ template <int SUB>
 cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st) {
     const int P = p.nprobe;
     const int64_t npairs = p.nq * P;
-    const LmLayout L = lm_layout(p.nq, P, p.k, p.nlist);
+    const LmLayout L = lm_layout(p.nq, P, p.k, p.nlist, p.dim, p.max_list_len);
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
     int32_t* lcnt = reinterpret_cast<int32_t*>(base + L.lcnt);
     int32_t* lcur = reinterpret_cast<int32_t*>(base + L.lcur);
     int32_t* pool_cnt = reinterpret_cast<int32_t*>(base + L.pool_cnt);
     uint32_t* pool_thr = reinterpret_cast<uint32_t*>(base + L.pool_thr);
-    int32_t* ctr = reinterpret_cast<int32_t*>(base + L.ctr);
+    int32_t* redo_cnt = reinterpret_cast<int32_t*>(base + L.redo_cnt);
+    unsigned long long* scanned = reinterpret_cast<unsigned long long*>(base + L.scanned);
     int32_t* loff = reinterpret_cast<int32_t*>(base + L.loff);
     int32_t* nit = reinterpret_cast<int32_t*>(base + L.nit);
     int32_t* ioff = reinterpret_cast<int32_t*>(base + L.ioff);
     int32_t* pairq = reinterpret_cast<int32_t*>(base + L.pairq);
-    int2* items = reinterpret_cast<int2*>(base + L.items);
+    int32_t* pairp = reinterpret_cast<int32_t*>(base + L.pairp);
+    int2* redo = reinterpret_cast<int2*>(base + L.redo);
+    unsigned char* iblk = base + L.iblk;
     unsigned long long* pool = reinterpret_cast<unsigned long long*>(base + L.pool);
     void* temp = base + L.temp;
     size_t tb = L.temp_bytes;
@@ -502,52 +803,108 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     cudaError_t e = cudaMemsetAsync(base, 0, L.zero_bytes, st);
     if (e != cudaSuccess) return e;
     const unsigned gb = (unsigned)((npairs + 255) / 256), lb = (unsigned)((p.nlist + 1 + 255) / 256);
-    lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt);
-    lm_items_per_list_kernel<<<lb, 256, 0, st>>>(lcnt, p.nlist + 1, nit);
+    lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt, scanned);
+    lm_items_per_list_kernel<<<lb, 256, 0, st>>>(lcnt, p.list_off, p.nlist, nit);
     e = cub::DeviceScan::ExclusiveSum(temp, tb, lcnt, loff, p.nlist + 1, st);
     if (e != cudaSuccess) return e;
     e = cub::DeviceScan::ExclusiveSum(temp, tb, nit, ioff, p.nlist + 1, st);
     if (e != cudaSuccess) return e;
-    lm_fill_pairs_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, P, p.list_off, loff, lcur, pairq);
-    lm_fill_items_kernel<<<lb, 256, 0, st>>>(nit, ioff, p.nlist, items);
+    lm_fill_pairs_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, P, p.list_off, loff, lcur, pairq, pairp);
+
+    LmPrep pa{};
+    pa.maxseg = lm_maxseg(p.max_list_len); pa.pairp = pairp;
+    pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
+    pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
+    lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
+
+    LmSeed sd{};
+    sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
+    sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
+    sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k);
+    const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
+    e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
+    if (e != cudaSuccess) return e;
+    ivfpq_lm_seed_kernel<<<(unsigned)((p.nq + SEED_NQ - 1) / SEED_NQ), 256, seed_smem, st>>>(sd);
 
     LmParams sp{};
-    sp.Q = p.Q; sp.nq = p.nq; sp.dim = p.dim; sp.centroids = p.centroids; sp.codebook = p.codebook; sp.ksub = p.ksub;
-    sp.codes = p.codes; sp.dead = p.dead; sp.list_off = p.list_off; sp.nlist = p.nlist;
-    sp.items = items; sp.n_items = ioff + p.nlist; sp.pair_off = loff; sp.pairq = pairq;
-    sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pool_cap = P * p.k; sp.k = p.k;
-    sp.work_ctr = ctr;
+#ifdef PYROPE_LM_TIMING
+    static long long* d_timing = nullptr;
+    if (!d_timing) cudaMalloc(&d_timing, sizeof(long long) * 256 * 16 * 8);
+    sp.timing = d_timing;
+#else
+    sp.timing = nullptr;
+#endif
+    sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = p.codebook; sp.codes = p.codes; sp.dead = p.dead;
+    sp.iblk = iblk; sp.n_items = ioff + p.nlist;
+    sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots;
+    sp.redo = redo; sp.redo_cnt = redo_cnt;
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;
     const int64_t grid = std::min<int64_t>(num_sms, L.max_items);
     ivfpq_lm_scan_kernel<SUB><<<(unsigned)grid, LM_THREADS, LM_SMEM, st>>>(sp);
+#ifdef PYROPE_LM_TIMING
+    {
+        cudaStreamSynchronize(st);
+        static long long h[256 * 16 * 8];
+        cudaMemcpy(h, d_timing, sizeof(long long) * (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
+        const char* names[8] = {"wait_blk", "build", "barrier", "issue+finalize", "wait_codes", "scan", "tail", "loop"};
+        for (int w = 0; w < 16; w += 1) {
+            fprintf(stderr, "[lm timing] warp %2d:", w);
+            for (int u = 0; u < 8; ++u) {
+                double sum = 0;
+                for (int b = 0; b < grid; ++b) sum += (double)h[((size_t)b * 16 + w) * 8 + u];
+                fprintf(stderr, " %s=%.0fk", names[u], sum / (double)grid / 1e3);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
+
+    LmRedo rd{};
+    rd.Q = p.Q; rd.dim = p.dim; rd.centroids = p.centroids; rd.codebook = p.codebook; rd.ksub = p.ksub;
+    rd.codes = p.codes; rd.dead = p.dead; rd.iblk = iblk; rd.blk = L.blk; rd.redo = redo; rd.redo_cnt = redo_cnt;
+    rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k;
+    const size_t redo_smem = sizeof(uint64_t) * REDO_QCAP + sizeof(float) * (4096 + (size_t)p.dim);
+    ivfpq_lm_redo_kernel<<<(unsigned)(2 * num_sms), 256, redo_smem, st>>>(rd);
 
     LmFinalParams fp{};
     fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub;
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
-    fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pool_cap = P * p.k; fp.k = p.k; fp.out = p.out;
-    const int P2max = next_pow2(std::max(2, P * p.k));
-    const size_t fsm = sizeof(uint64_t) * (size_t)P2max;
+    fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.out = p.out;
+    const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, L.pool_cap));
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
-    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, 256, fsm, st>>>(fp, P2max);
+    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, 256, fsm, st>>>(fp);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total) {
+bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total, int64_t max_list_len) {
     if (m != 16 || ksub > 256 || ksub < 1) return false;
     const int sub = dim / m;
     if (sub != 4 && sub != 8) return false;
-    if (k < 1 || k > kMaxTopK || (int64_t)nprobe * k > 8192) return false;
-    if (nq * nprobe >= ((int64_t)1 << 31) || list_total >= ((int64_t)1 << 32)) return false;
+    if (k < 1 || k > kMaxTopK || (int64_t)nprobe * k * lm_maxseg(max_list_len) > 16384) return false;
+    if (nq * nprobe >= ((int64_t)1 << 29) || list_total >= ((int64_t)1 << 32)) return false;
     return true;
 }
 
-size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist) { return lm_layout(nq, nprobe, k, nlist).total; }
+size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist, int dim, int64_t max_list_len) {
+    return lm_layout(nq, nprobe, k, nlist, dim, max_list_len).total;
+}
 
-int ivfpq_lm_launches() { return 8; }  // count, items-per-list, 2 scans, pair fill, item fill, scan, final
+// count, items-per-list, 2 scans, pair fill, prepare, seed, scan, redo, final
+int ivfpq_lm_launches() { return 10; }
+
+// codes scored by the most recent list-major search that used `scratch` (sum of probed list lengths)
+cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, int k, int nlist, int dim,
+                                   int64_t max_list_len, unsigned long long* out, cudaStream_t st) {
+    const LmLayout L = lm_layout(nq, nprobe, k, nlist, dim, max_list_len);
+    cudaError_t e = cudaMemcpyAsync(out, reinterpret_cast<const unsigned char*>(scratch) + L.scanned, sizeof(*out),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
 
 cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st) {
     if (p.nq <= 0) return cudaSuccess;
