@@ -463,17 +463,22 @@ int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * k
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
+    // One CTA owns a 128-query tile and streams n-tiles of 256 rows.  Splitting the row range fills idle
+    // SMs when there are few query tiles, but every split starts with no threshold (its first ~2 tiles
+    // are accepted wholesale) and hands k' more candidates per query to the exact re-score, so a split
+    // must keep a long stream: cost model = waves x (tiles per split + a fixed per-split charge).
     const int64_t qtiles = (nq + BM - 1) / BM;
     const int64_t ntiles = std::max<int64_t>(1, (n_scan + BN - 1) / BN);
-    int64_t smax = std::min<int64_t>(std::min<int64_t>(ntiles, 32), std::max<int64_t>(1, 4096 / kprime));
+    const int64_t smax = std::min<int64_t>(std::min<int64_t>(ntiles, 32), std::max<int64_t>(1, 4096 / kprime));
+    const double per_split = 4.0 + kprime / 8.0;  // tiles' worth of selection + re-score work
     int best = 1;
-    double best_eff = -1.0;
+    double best_cost = 1e300;
     for (int64_t s = 1; s <= smax; ++s) {
-        const int64_t units = qtiles * s;
-        const int64_t waves = (units + num_sms - 1) / num_sms;
-        // prefer full waves; among equals prefer fewer splits (longer streams tighten thresholds)
-        const double eff = (double)units / (double)(waves * num_sms) - 1e-4 * (double)s;
-        if (eff > best_eff) { best_eff = eff; best = (int)s; }
+        const int64_t tps = (ntiles + s - 1) / s;
+        if (s > 1 && tps < 16) break;
+        const int64_t waves = (qtiles * s + num_sms - 1) / num_sms;
+        const double cost = (double)waves * ((double)tps + per_split);
+        if (cost < best_cost * 0.97) { best_cost = cost; best = (int)s; }  // prefer fewer splits on near ties
     }
     return best;
 }
