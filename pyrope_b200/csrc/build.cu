@@ -104,8 +104,13 @@ __global__ void __launch_bounds__(256) assign_shortlist_kernel(const float* __re
         }
         if (s > best) { best = s; besti = cand; }
     }
-    const float p0 = __shfl_sync(0xffffffffu, proxy, 0);
-    const float plast = __shfl_sync(0xffffffffu, proxy, max(c - 1, 0));
+    // best and worst proxy score of the (unordered) shortlist
+    float p0 = lane < c ? proxy : -FLT_MAX, plast = lane < c ? proxy : FLT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        p0 = fmaxf(p0, __shfl_xor_sync(0xffffffffu, p0, o));
+        plast = fminf(plast, __shfl_xor_sync(0xffffffffu, plast, o));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         float os = __shfl_xor_sync(0xffffffffu, best, o);

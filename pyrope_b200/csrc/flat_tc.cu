@@ -124,13 +124,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
                const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo, TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // layout: [stage0 | stage1 | barriers | tmem ptr | sbias[2][BN] | sscale[2][BN] | sort staging 4 x cap]
+    // layout: [stage0 | stage1 | barriers | tmem ptr | per epilogue warp: sbias[2][BN], sscale[2][BN]]
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
-    float* sbias = reinterpret_cast<float*>(tmem_ptr_s + 4);
-    float* sscale = sbias + 2 * BN;
-    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(sscale + 2 * BN);
+    float* sterms = reinterpret_cast<float*>(tmem_ptr_s + 4);  // [4 warps][bias 2*BN | scale 2*BN]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
@@ -210,24 +208,61 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         const int64_t gq = qt * BM + et;
         const bool qvalid = gq < p.nq;
         uint64_t* myq = p.queue + ((int64_t)sp * p.nq_pad + (qt * BM + et)) * p.cap;
-        uint64_t* st = sortbuf + (int64_t)ew * p.cap;
+        float* sbias = sterms + ew * (4 * BN);   // private to this warp: the four epilogue warps never wait
+        float* sscale = sbias + 2 * BN;         // for one another, only for the MMA warp (mbarriers)
         int cnt = 0;
         float tau = -INFINITY;
         const int cap = p.cap, kprime = p.kprime;
 
+        // Keep the k' best keys of lane l's queue (in L2), whole warp cooperating, queue held in
+        // registers: a bisection on the 32-bit ordered score finds the k'-th largest score T, keys above
+        // T (and as many keys equal to T as still fit) are compacted back; no sort, no shared memory.
         auto prune_lane = [&](int l) {
             uint64_t* src = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)myq, l));
             const int c = __shfl_sync(0xffffffffu, cnt, l);
-            const int P = next_pow2(max(c, 2));
-            for (int i = lane; i < P; i += 32) st[i] = i < c ? __ldcg(src + i) : 0ull;
-            __syncwarp();
-            bitonic_sort_desc<true>(st, P, lane, 32);
-            const int keep = min(c, kprime);
-            for (int i = lane; i < keep; i += 32) __stcg(src + i, st[i]);
-            __syncwarp();
+            if (c <= kprime) return;  // warp-uniform
+            constexpr int U = 16;     // cap <= 512
+            uint64_t e[U];
+            uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = u * 32 + lane;
+                e[u] = (u * 32 < c && i < c) ? __ldcg(src + i) : 0ull;
+                const uint32_t o = (uint32_t)(e[u] >> 32);
+                if (e[u]) { lo = min(lo, o); hi = max(hi, o); }
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            while (lo < hi) {  // largest T with count(ord >= T) >= k'
+                const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+                int n = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) n += (e[u] != 0ull && (uint32_t)(e[u] >> 32) >= mid);
+                n = __reduce_add_sync(0xffffffffu, n);
+                if (n >= kprime) lo = mid; else hi = mid - 1u;
+            }
+            const uint32_t T = lo;
+            int ngt = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) ngt += (e[u] != 0ull && (uint32_t)(e[u] >> 32) > T);
+            ngt = __reduce_add_sync(0xffffffffu, ngt);
+            int quota = kprime - ngt, out = 0;  // ties at T still admitted
+            const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u * 32 >= c) break;
+                const uint32_t o = (uint32_t)(e[u] >> 32);
+                const bool gt = e[u] != 0ull && o > T, eq = e[u] != 0ull && o == T;
+                const unsigned meq = __ballot_sync(0xffffffffu, eq);
+                const bool take_eq = eq && (int)__popc(meq & below) < quota;
+                quota -= min(quota, (int)__popc(meq));
+                const unsigned mk = __ballot_sync(0xffffffffu, gt || take_eq);
+                if (gt || take_eq) __stcg(src + out + __popc(mk & below), e[u]);
+                out += __popc(mk);
+            }
             if (lane == l) {
-                cnt = keep;
-                tau = (keep == kprime) ? key_score(st[kprime - 1]) : -INFINITY;
+                cnt = out;  // == k'
+                tau = ord_to_score(T);
             }
             __syncwarp();
         };
@@ -235,10 +270,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         for (int ti = 0; ti < ntile; ++ti) {
             const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
             const int64_t n0 = (t_begin + ti) * BN;
-            // stage this tile's per-row scale/bias (2 columns per epilogue thread)
+            // stage this tile's per-row scale/bias (8 columns per lane, private copy per warp)
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int col = et + u * 128;
+            for (int u = 0; u < BN / 32; ++u) {
+                const int col = lane + u * 32;
                 const int64_t pos = n0 + col;
                 float b = -INFINITY, sc = 0.f;
                 if (pos < p.n_scan) {
@@ -248,7 +283,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 sbias[buf * BN + col] = b;
                 sscale[buf * BN + col] = sc;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __syncwarp();
             mbar_wait(tfull0 + 8 * buf, aph);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * BN;
@@ -278,7 +313,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
-        // final: sort every queue, leave the best k' in place, publish the counts
+        // final: leave the best k' (unordered) in place, publish the counts
         for (int l = 0; l < 32; ++l) prune_lane(l);
         p.counts[(int64_t)sp * p.nq_pad + qt * BM + et] = qvalid ? cnt : 0;
     }
@@ -457,9 +492,10 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dim, int box_
 // ---- public launchers ----------------------------------------------------------------------------
 int flat_tc_margin(int k) { return k < 64 ? 16 : 32; }
 bool flat_tc_supported(int dim, int k) { return dim % 4 == 0 && dim >= 8 && k >= 1 && k + flat_tc_margin(k) <= 224; }
-// queue capacity per (split, query): a prune (warp-wide sort) fires when fewer than 32 slots are left and
-// keeps k', so the headroom cap - 32 - k' is the number of accepted candidates between two prunes.
-int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * kprime))); }
+// queue capacity per (split, query): a prune (warp-wide bitonic sort of the whole queue) fires when fewer
+// than 32 slots are left and keeps k'.  The sort is superlinear in the capacity while the number of
+// prunes only falls logarithmically, so the capacity stays close to 2 k'.
+int flat_tc_cap(int kprime) { return std::min(512, std::max(64, next_pow2(2 * kprime + 32))); }
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
@@ -515,7 +551,7 @@ cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
     p.scale = a.scale; p.bias = a.bias; p.queue = a.queue; p.counts = a.counts;
     const int64_t qtiles = (a.nq + BM - 1) / BM;
     p.nq_pad = qtiles * BM;
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 16 * 8 + 16 + 4 * BN * sizeof(float) + 4 * (size_t)a.cap * 8 + 64;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 16 * 8 + 16 + 4 * (4 * BN * sizeof(float)) + 64;
     cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     flat_tc_kernel<<<(unsigned)(qtiles * a.splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
