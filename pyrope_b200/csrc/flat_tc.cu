@@ -222,37 +222,39 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             const int c = __shfl_sync(0xffffffffu, cnt, l);
             if (c <= kprime) return;  // warp-uniform
             constexpr int U = 16;     // cap <= 512
+            const int cu = (c + 31) >> 5;  // occupied registers per lane (warp-uniform)
             uint64_t e[U];
+            uint32_t o[U];                 // ordered scores; empty slots hold 0 (below every valid score)
             uint32_t lo = 0xffffffffu, hi = 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = u * 32 + lane;
-                e[u] = (u * 32 < c && i < c) ? __ldcg(src + i) : 0ull;
-                const uint32_t o = (uint32_t)(e[u] >> 32);
-                if (e[u]) { lo = min(lo, o); hi = max(hi, o); }
+                e[u] = (u < cu && i < c) ? __ldcg(src + i) : 0ull;
+                o[u] = (uint32_t)(e[u] >> 32);
+                if (e[u]) { lo = min(lo, o[u]); hi = max(hi, o[u]); }
             }
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
-            while (lo < hi) {  // largest T with count(ord >= T) >= k'
+            while (lo < hi) {  // largest T with count(ord >= T) >= k'   (mid > lo >= 1: empty slots never count)
                 const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
                 int n = 0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) n += (e[u] != 0ull && (uint32_t)(e[u] >> 32) >= mid);
+                for (int u = 0; u < U; ++u)
+                    if (u < cu) n += (o[u] >= mid);
                 n = __reduce_add_sync(0xffffffffu, n);
                 if (n >= kprime) lo = mid; else hi = mid - 1u;
             }
             const uint32_t T = lo;
             int ngt = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) ngt += (e[u] != 0ull && (uint32_t)(e[u] >> 32) > T);
+            for (int u = 0; u < U; ++u) ngt += (o[u] > T);
             ngt = __reduce_add_sync(0xffffffffu, ngt);
             int quota = kprime - ngt, out = 0;  // ties at T still admitted
             const unsigned below = (1u << lane) - 1u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (u * 32 >= c) break;
-                const uint32_t o = (uint32_t)(e[u] >> 32);
-                const bool gt = e[u] != 0ull && o > T, eq = e[u] != 0ull && o == T;
+                if (u >= cu) break;
+                const bool gt = o[u] > T, eq = e[u] != 0ull && o[u] == T;
                 const unsigned meq = __ballot_sync(0xffffffffu, eq);
                 const bool take_eq = eq && (int)__popc(meq & below) < quota;
                 quota -= min(quota, (int)__popc(meq));
@@ -292,13 +294,21 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 float v[32];
                 tc_ld32(taddr0 + c * 32, v);
                 if (qvalid) {
+                    // common case after warm-up: none of the 32 proxy scores beats the threshold
+                    float mx = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = c * 32 + j;
-                        const float s = fmaf(v[j], sscale[buf * BN + col], sbias[buf * BN + col]);
-                        if (s > tau) {
-                            __stcg(myq + cnt, make_key(s, (uint32_t)(n0 + col)));
-                            ++cnt;
+                        v[j] = fmaf(v[j], sscale[buf * BN + col], sbias[buf * BN + col]);
+                        mx = fmaxf(mx, v[j]);
+                    }
+                    if (mx > tau) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (v[j] > tau) {
+                                __stcg(myq + cnt, make_key(v[j], (uint32_t)(n0 + c * 32 + j)));
+                                ++cnt;
+                            }
                         }
                     }
                 }
@@ -492,10 +502,10 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dim, int box_
 // ---- public launchers ----------------------------------------------------------------------------
 int flat_tc_margin(int k) { return k < 64 ? 16 : 32; }
 bool flat_tc_supported(int dim, int k) { return dim % 4 == 0 && dim >= 8 && k >= 1 && k + flat_tc_margin(k) <= 224; }
-// queue capacity per (split, query): a prune (warp-wide bitonic sort of the whole queue) fires when fewer
-// than 32 slots are left and keeps k'.  The sort is superlinear in the capacity while the number of
-// prunes only falls logarithmically, so the capacity stays close to 2 k'.
-int flat_tc_cap(int kprime) { return std::min(512, std::max(64, next_pow2(2 * kprime + 32))); }
+// queue capacity per (split, query): a prune (register-resident bisection select by the whole warp) fires
+// when fewer than 32 slots are left and keeps k'; the headroom cap - 32 - k' is the number of candidates
+// accepted between two prunes.
+int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * kprime + 32))); }
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
