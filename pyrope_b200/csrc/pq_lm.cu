@@ -45,16 +45,15 @@
 namespace pyrope {
 namespace {
 
-constexpr int LM_THREADS = 512;
+constexpr int LM_THREADS = 256;       // two CTAs per SM
 constexpr int LM_QS = 4;            // query slots per work item
 constexpr int LM_CODE_CAP = 2048;   // codes per item (32 KiB)
 constexpr int LM_QC = 256;          // candidate queue entries per slot
-constexpr int LM_RST = 4;           // item-block stages
 constexpr int LM_HDR = 64;          // item-block header bytes
 constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;
 constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 16;
-constexpr int LM_SMEM = 2 * LM_LUT_BYTES + 2 * LM_CODE_CAP * 16 + LM_RST * LM_BLK_MAX + 2 * LM_QS * LM_QC * 8;
+constexpr int LM_SMEM = LM_LUT_BYTES + LM_CODE_CAP * 16 + 2 * LM_BLK_MAX + LM_QS * LM_QC * 8;
 constexpr int SEED_NQ = 4;          // queries per seed CTA (share the codebook reads)
 constexpr int SEED_CAP = 2048;      // sampled distances per query
 constexpr int REDO_QCAP = 2048;
@@ -124,6 +123,34 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 #else
 #define LM_T(i) do { } while (0)
 #endif
+
+// ---- TMEM as a constant table: the PQ codebook lives in tensor memory for the CTA's lifetime -------------
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[N]) {
+    static_assert(N == 4 || N == 8, "4 or 8 columns");
+    if (N == 8)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4 % N]), "r"(r[5 % N]), "r"(r[6 % N]), "r"(r[7 % N])
+                     : "memory");
+    else
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+                     : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {  // no wait: pair with tmem_ld_wait()
+    if (N == 8)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4 % N]), "=r"(r[5 % N]), "=r"(r[6 % N]), "=r"(r[7 % N])
+                     : "r"(taddr)
+                     : "memory");
+    else
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr)
+                     : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct LmParams {
     long long* timing;  // [grid][16 warps][8] cycle sums per phase (PYROPE_LM_TIMING builds only)
@@ -363,84 +390,106 @@ __global__ void __launch_bounds__(256) ivfpq_lm_seed_kernel(LmSeed a) {
 }
 
 // ---- the scan --------------------------------------------------------------------------------------
+// Two 256-thread CTAs per SM, each a plain build -> scan -> hand-over loop over its own items: while one
+// CTA builds lookup tables (FMA pipe) the other scans (shared-memory crossbar), so the two phases overlap
+// without any intra-CTA software pipelining.
 template <int SUB>
-__global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p) {
+__global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* lut = smem;                                                     // [2][256][16] float4
-    unsigned char* cbuf = lut + 2 * LM_LUT_BYTES;                                   // [2][CODE_CAP] uint4
-    unsigned char* rbuf = cbuf + 2 * LM_CODE_CAP * 16;                              // [RST] item blocks
-    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_RST * LM_BLK_MAX);     // [2][QS][QC]
-    __shared__ __align__(8) uint64_t s_mbar[2 + LM_RST];
-    __shared__ int s_qcnt[2 * LM_QS];
+    unsigned char* lut = smem;                                                     // [256][16] float4
+    unsigned char* cbuf = lut + LM_LUT_BYTES;                                       // [CODE_CAP] uint4
+    unsigned char* rbuf = cbuf + LM_CODE_CAP * 16;                                  // [2] item blocks
+    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + 2 * LM_BLK_MAX);          // [QS][QC]
+    __shared__ __align__(8) uint64_t s_mbar[3];
+    __shared__ int s_qcnt[LM_QS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = p.ksub;
     const int blk = LM_HDR + p.dim * 16;
     const int m = lane & 15;                 // build: this thread's sub-quantiser
-    const int eb = (lane >> 4) + 2 * warp;   // build: its codewords are eb + 32 j, j < 8
+    const int eb = (lane >> 4) + 2 * warp;   // build: its codewords are eb + 16 j, j < 16
     const int n_items = *p.n_items;
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_n = first < n_items ? (n_items - first + stride - 1) / stride : 0;
 
-    // codebook slice in registers for the CTA's lifetime
-    float cb[8][SUB], pn[8];
+    // The PQ codebook (m*k*sub fp32 = 128 KiB at d=128) is parked in TENSOR MEMORY for the CTA's lifetime:
+    // 16 codewords per thread at the thread's own TMEM lane, columns (warp/4)*16*SUB + j*SUB.  Two CTAs per
+    // SM x 256 columns fill the 512-column TMEM exactly; the register file stays free for two resident CTAs.
+    constexpr int EPT = 256 * 16 / LM_THREADS;  // codewords per thread
+    constexpr int TCOLS = (LM_THREADS / 128) * EPT * SUB;  // 256 (SUB = 8) or 128 (SUB = 4)
+    __shared__ uint32_t s_tmem;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tcb = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * EPT * SUB);
+    float pn[EPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int e = eb + 32 * j;
+    for (int j = 0; j < EPT; ++j) {
+        const int e = eb + (LM_THREADS / 16) * j;
         float s = 0.f;
+        uint32_t r[SUB];
 #pragma unroll
         for (int d4 = 0; d4 < SUB / 4; ++d4) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e < K) v = __ldg(reinterpret_cast<const float4*>(p.codebook + ((size_t)m * K + e) * SUB) + d4);
-            cb[j][4 * d4 + 0] = v.x; cb[j][4 * d4 + 1] = v.y; cb[j][4 * d4 + 2] = v.z; cb[j][4 * d4 + 3] = v.w;
+            r[4 * d4 + 0] = __float_as_uint(v.x); r[4 * d4 + 1] = __float_as_uint(v.y);
+            r[4 * d4 + 2] = __float_as_uint(v.z); r[4 * d4 + 3] = __float_as_uint(v.w);
             s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
         }
+        tmem_st<SUB>(tcb + j * SUB, r);
         pn[j] = s;
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     // scan: lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
     uint32_t op[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
         op[i] = (uint32_t)(((lane + 2 * i) & 15) << 4) | ((uint32_t)(((lane + 2 * i + 1) & 15) << 4) << 8);
-    // byte 2 of op[] carries the table buffer (item parity): PRMT drops it into bit 16 of the address
+        asm volatile("" : "+r"(op[i]));  // keep the eight offset words in registers (no rematerialisation in the loop)
+    }
     const int rot = lane & 15;
 
-    const uint32_t bar_c = smem_u32(&s_mbar[0]);  // +8*b: codes buffer b
-    const uint32_t bar_r = smem_u32(&s_mbar[2]);  // +8*s: item-block stage s
+    const uint32_t bar_c = smem_u32(&s_mbar[0]);  // codes
+    const uint32_t bar_r = smem_u32(&s_mbar[1]);  // +8*s: item-block stage s
     if (tid == 0) {
-        for (int i = 0; i < 2 + LM_RST; ++i) mbar_init(bar_c + 8 * i, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(bar_c + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 2 * LM_QS) s_qcnt[tid] = 0;
+    if (tid < LM_QS) s_qcnt[tid] = 0;
     __syncthreads();
-    if (my_n == 0) return;
 
-    // thread 0 feeds the pipeline: TMA of item i's block and codes; the header it needs is prefetched
     auto hdr_ptr = [&](int i) { return p.iblk + (size_t)(first + (size_t)i * stride) * blk; };
-    auto issue = [&](int i, const int4& h) {  // h = {list, nvec, vbeg lo, vbeg hi}
-        const long long vbeg = (long long)(((unsigned long long)(uint32_t)h.w << 32) | (uint32_t)h.z);
-        const uint32_t br = bar_r + 8 * (i & (LM_RST - 1)), bc = bar_c + 8 * (i & 1);
+    auto issue_block = [&](int i) {  // thread 0: TMA of item i's block (header + residual queries)
+        const uint32_t br = bar_r + 8 * (i & 1);
         mbar_expect_tx(br, (uint32_t)blk);
-        bulk_g2s(smem_u32(rbuf + (i & (LM_RST - 1)) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
-        mbar_expect_tx(bc, (uint32_t)h.y * 16u);
-        bulk_g2s(smem_u32(cbuf + (i & 1) * LM_CODE_CAP * 16), p.codes + vbeg * 16, (uint32_t)h.y * 16u, bc);
+        bulk_g2s(smem_u32(rbuf + (i & 1) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
     };
-    int4 hnext = make_int4(0, 0, 0, 0);
-    if (tid == 0) {
-        const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr_ptr(0)));
-        issue(0, h0);
-        if (my_n > 1) hnext = __ldg(reinterpret_cast<const int4*>(hdr_ptr(1)));
+    auto issue_codes = [&](const LmHeader* hd) {  // thread 0: TMA of the item's code segment
+        const uint32_t bytes = (uint32_t)hd->nvec * 16u;
+        mbar_expect_tx(bar_c, bytes);
+        bulk_g2s(smem_u32(cbuf), p.codes + (size_t)hd->vbeg * 16, bytes, bar_c);
+    };
+    if (tid == 0 && my_n > 0) {
+        issue_block(0);
+        const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr_ptr(0)));  // {list, nvec, vbeg lo, vbeg hi}
+        const long long vbeg = (long long)(((unsigned long long)(uint32_t)h0.w << 32) | (uint32_t)h0.z);
+        mbar_expect_tx(bar_c, (uint32_t)h0.y * 16u);
+        bulk_g2s(smem_u32(cbuf), p.codes + (size_t)vbeg * 16, (uint32_t)h0.y * 16u, bar_c);
     }
 
     // one warp per slot: hand at most k of the slot's candidates to the pair's private region of the query's
     // pool (plain stores: no returning atomics on this path) and tighten the query's threshold
-    auto finalize = [&](int set, const LmHeader* hd, int gitem) {
+    auto finalize = [&](const LmHeader* hd, int gitem) {
         const int j = warp;
-        int* cntp = &s_qcnt[set * LM_QS + j];
+        int* cntp = &s_qcnt[j];
         const int n = *cntp;
         const int q = hd->qid[j];
         if (n > 0 && q >= 0) {
-            uint64_t* kq = qkeys + (set * LM_QS + j) * LM_QC;
+            uint64_t* kq = qkeys + j * LM_QC;
             if (n > LM_QC) {  // candidates were dropped: the plain kernel redoes this (query, item)
                 if (lane == 0) p.redo[atomicAdd(p.redo_cnt, 1)] = make_int2(q, gitem * LM_QS + j);
             } else {
@@ -495,13 +544,13 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
     for (int i = 0; i < my_n; ++i) {
-        const int rs = i & (LM_RST - 1), cs = i & 1;
-        LM_T(7);
+        const int rs = i & 1;
         // ---- build the four lookup tables of item i: |p|^2 + |r_m|^2 - 2 r_m.p
-        mbar_wait(bar_r + 8 * rs, (uint32_t)(i / LM_RST) & 1u);
+        mbar_wait(bar_r + 8 * rs, (uint32_t)(i >> 1) & 1u);
         LM_T(0);
         const unsigned char* blkp = rbuf + rs * LM_BLK_MAX;
-        const int4 qv = *reinterpret_cast<const int4*>(reinterpret_cast<const LmHeader*>(blkp)->qid);
+        const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
+        const int4 qv = *reinterpret_cast<const int4*>(hd->qid);
         uint32_t tu[LM_QS];
         tu[0] = qv.x >= 0 ? __ldcg(p.pool_thr + qv.x) : 0xffffffffu;  // in flight during the build
         tu[1] = qv.y >= 0 ? __ldcg(p.pool_thr + qv.y) : 0xffffffffu;
@@ -518,53 +567,44 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 rr23 = ffma2(v.y, v.y, rr23);
             }
             const unsigned long long quarter = pack2(0.25f, 0.25f);  // t = -2 r  =>  |r|^2 = sum t^2 / 4
-            unsigned char* lw = lut + cs * LM_LUT_BYTES + eb * 256 + m * 16;
+            unsigned char* lw = lut + eb * 256 + m * 16;
+            uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
+            tmem_ld<SUB>(tcb, cw[0]);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < EPT; ++j) {
+                if (j + 1 < EPT) tmem_ld<SUB>(tcb + (j + 1) * SUB, cw[(j + 1) & 1]);
                 const unsigned long long pj = pack2(pn[j], pn[j]);
                 unsigned long long a01 = ffma2(rr01, quarter, pj), a23 = ffma2(rr23, quarter, pj);
 #pragma unroll
                 for (int d = 0; d < SUB; ++d) {
-                    const unsigned long long c2 = pack2(cb[j][d], cb[j][d]);
+                    const float c = __uint_as_float(cw[j & 1][d]);
+                    const unsigned long long c2 = pack2(c, c);
                     a01 = ffma2(c2, t01[d], a01);
                     a23 = ffma2(c2, t23[d], a23);
                 }
-                *reinterpret_cast<ulonglong2*>(lw + j * (32 * 256)) = make_ulonglong2(a01, a23);
+                *reinterpret_cast<ulonglong2*>(lw + j * ((LM_THREADS / 16) * 256)) = make_ulonglong2(a01, a23);
+                if (j + 1 < EPT) tmem_ld_wait();
             }
         }
         LM_T(1);
-        asm volatile("bar.sync 1, %0;" ::"n"(LM_THREADS) : "memory");  // tables of item i complete; scan i-1 finished by all
+        __syncthreads();  // tables complete; the previous item's hand-over is done
         LM_T(2);
-        if (tid == 0 && i + 1 < my_n) {
-            issue(i + 1, hnext);
-            if (i + 2 < my_n) hnext = __ldg(reinterpret_cast<const int4*>(hdr_ptr(i + 2)));
-        }
-        if (i > 0 && warp < LM_QS)
-            finalize((i - 1) & 1, reinterpret_cast<const LmHeader*>(rbuf + ((i - 1) & (LM_RST - 1)) * LM_BLK_MAX),
-                     first + (i - 1) * stride);
+        if (tid == 0 && i + 1 < my_n) issue_block(i + 1);
 
-        LM_T(3);
         // ---- scan item i
         float thrd[LM_QS];
 #pragma unroll
         for (int j = 0; j < LM_QS; ++j)
             thrd[j] = tu[j] == 0xffffffffu ? -INFINITY : (tu[j] ? -ord_to_score(tu[j]) : INFINITY);
-        const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
         const int nvec = hd->nvec;
         const long long vbeg = hd->vbeg;
-        mbar_wait(bar_c + 8 * cs, (uint32_t)(i >> 1) & 1u);
-        LM_T(4);
-        const unsigned char* cseg = cbuf + cs * LM_CODE_CAP * 16;
-        uint32_t opc[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            opc[u] = op[u] | ((uint32_t)cs << 16);
-            asm volatile("" : "+r"(opc[u]));  // keep the eight offset words in registers (no rematerialisation in the loop)
-        }
+        mbar_wait(bar_c, (uint32_t)i & 1u);
+        LM_T(3);
         for (int c = warp; c * 32 < nvec; c += LM_THREADS / 32) {
             const int v = c * 32 + lane;
             if (v < nvec) {
-                const uint4 cw = *reinterpret_cast<const uint4*>(cseg + v * 16);
+                const uint4 cw = *reinterpret_cast<const uint4*>(cbuf + v * 16);
                 uint32_t w[4];
                 {   // rotate the 16 code bytes: new byte t = old byte (t + rot) & 15
                     const bool r8 = rot & 8, r4 = rot & 4;
@@ -579,7 +619,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 for (int t = 0; t < 16; ++t) {
                     // byte0 = table offset, byte1 = code byte: address = code * 256 + table * 16
                     const uint32_t sel = 0x7600u | (uint32_t)((t & 3) << 4) | (uint32_t)(4 + (t & 1));
-                    const uint32_t a = __byte_perm(w[t >> 2], opc[t >> 1], sel);
+                    const uint32_t a = __byte_perm(w[t >> 2], op[t >> 1], sel);
                     const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(lut + a);
                     acc01 = fadd2(acc01, e.x);
                     acc23 = fadd2(acc23, e.y);
@@ -594,25 +634,34 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
 #pragma unroll
                         for (int j = 0; j < LM_QS; ++j) {
                             if (dd[j] < thrd[j]) {
-                                const int pos = atomicAdd(&s_qcnt[cs * LM_QS + j], 1);
-                                if (pos < LM_QC) qkeys[(cs * LM_QS + j) * LM_QC + pos] = make_key(-dd[j], (uint32_t)gpos);
+                                const int pos = atomicAdd(&s_qcnt[j], 1);
+                                if (pos < LM_QC) qkeys[j * LM_QC + pos] = make_key(-dd[j], (uint32_t)gpos);
                             }
                         }
                     }
                 }
             }
         }
+        LM_T(4);
+        __syncthreads();  // codes and tables fully consumed, queue counts visible
         LM_T(5);
+        if (tid == 0 && i + 1 < my_n) {  // next item's codes land while its tables are built
+            mbar_wait(bar_r + 8 * ((i + 1) & 1), (uint32_t)((i + 1) >> 1) & 1u);
+            issue_codes(reinterpret_cast<const LmHeader*>(rbuf + ((i + 1) & 1) * LM_BLK_MAX));
+        }
+        if (warp < LM_QS) finalize(hd, first + i * stride);
+        LM_T(6);
     }
-    LM_T(6);
 #ifdef PYROPE_LM_TIMING
     if (lane == 0 && p.timing)
-        for (int u = 0; u < 8; ++u) p.timing[((size_t)blockIdx.x * 16 + warp) * 8 + u] = tacc[u];
+        for (int u = 0; u < 8; ++u) p.timing[((size_t)blockIdx.x * (LM_THREADS / 32) + warp) * 8 + u] = tacc[u];
 #endif
-    asm volatile("bar.sync 1, %0;" ::"n"(LM_THREADS) : "memory");
-    if (warp < LM_QS)
-        finalize((my_n - 1) & 1, reinterpret_cast<const LmHeader*>(rbuf + ((my_n - 1) & (LM_RST - 1)) * LM_BLK_MAX),
-                 first + (my_n - 1) * stride);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TCOLS) : "memory");
+    }
 }
 
 // ---- redo: plain scan of one (query, item) whose queue overflowed -------------------------------------------
@@ -829,7 +878,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmParams sp{};
 #ifdef PYROPE_LM_TIMING
     static long long* d_timing = nullptr;
-    if (!d_timing) cudaMalloc(&d_timing, sizeof(long long) * 256 * 16 * 8);
+    if (!d_timing) cudaMalloc(&d_timing, sizeof(long long) * 512 * 16 * 8);
     sp.timing = d_timing;
 #else
     sp.timing = nullptr;
@@ -840,19 +889,19 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     sp.redo = redo; sp.redo_cnt = redo_cnt;
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;
-    const int64_t grid = std::min<int64_t>(num_sms, L.max_items);
+    const int64_t grid = std::min<int64_t>(2 * num_sms, L.max_items);
     ivfpq_lm_scan_kernel<SUB><<<(unsigned)grid, LM_THREADS, LM_SMEM, st>>>(sp);
 #ifdef PYROPE_LM_TIMING
     {
         cudaStreamSynchronize(st);
-        static long long h[256 * 16 * 8];
-        cudaMemcpy(h, d_timing, sizeof(long long) * (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
-        const char* names[8] = {"wait_blk", "build", "barrier", "issue+finalize", "wait_codes", "scan", "tail", "loop"};
-        for (int w = 0; w < 16; w += 1) {
+        static long long h[512 * 16 * 8];
+        cudaMemcpy(h, d_timing, sizeof(long long) * (size_t)grid * (LM_THREADS / 32) * 8, cudaMemcpyDeviceToHost);
+        const char* names[8] = {"wait_blk", "build", "sync1", "wait_codes", "scan", "sync2", "finalize", "-"};
+        for (int w = 0; w < LM_THREADS / 32; w += 1) {
             fprintf(stderr, "[lm timing] warp %2d:", w);
             for (int u = 0; u < 8; ++u) {
                 double sum = 0;
-                for (int b = 0; b < grid; ++b) sum += (double)h[((size_t)b * 16 + w) * 8 + u];
+                for (int b = 0; b < grid; ++b) sum += (double)h[((size_t)b * (LM_THREADS / 32) + w) * 8 + u];
                 fprintf(stderr, " %s=%.0fk", names[u], sum / (double)grid / 1e3);
             }
             fprintf(stderr, "\n");
