@@ -188,7 +188,18 @@ def make_queries(torch, w: dict):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's loops on the index the GPU built
 # ------------------------------------------------------------------------------------------------
-def oracle_index_from_gpu(ix, w: dict, base_rows=None):
+def base_rows_host(torch, w: dict, n_rows: int) -> np.ndarray:
+    """The first n_rows base vectors, regenerated with the same counter-based generator."""
+    from pyrope_b200 import _lib
+    t = torch.empty(n_rows * w["dim"], dtype=torch.float32, device="cuda")
+    _lib.fill_uniform_device(t.data_ptr(), t.numel(), 42, 0, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return t.view(n_rows, w["dim"]).cpu().numpy()
+
+
+def oracle_index_from_gpu(ix, w: dict, torch=None):
+    """-> (oracle index, rows it holds, note).  IVF_PQ adopts the GPU-built lists (same codebooks, codes);
+    FLAT / IVF_FLAT are rebuilt by the oracle from (a bounded prefix of) the same synthetic rows."""
     from oracle import pyoracle as orc
     metric = {"L2": orc.L2, "IP": orc.IP, "COSINE": orc.COSINE}[w["metric"]]
     if w["kind"] == "IVF_PQ":
@@ -196,25 +207,40 @@ def oracle_index_from_gpu(ix, w: dict, base_rows=None):
         off, rows, codes = ix.lists()
         cb, _ = ix.codebooks()
         o.adopt(ix.centroids(), cb, off, rows, codes)
-        return o
+        return o, w["n"], "the GPU-built index (same codebooks, lists and codes)"
+    if w["kind"] == "FLAT":
+        ns = min(w["n"], max(10_000, (256 << 20) // (w["dim"] * 4)))  # <= 256 MiB of rows on the host
+        o = orc.FlatIndex(w["dim"], metric)
+        o.add_batch(base_rows_host(torch, w, ns))
+        return o, ns, f"the first {ns} of {w['n']} base rows (QPS scaled by {ns}/{w['n']}: the scan is linear in rows)"
+    if w["kind"] == "IVF_FLAT" and w["n"] <= 200_000:
+        o = orc.IvfFlatIndex(w["dim"], metric, nlist=w["nlist"])
+        o.add_batch(base_rows_host(torch, w, w["n"]))
+        o.build()
+        return o, w["n"], "an oracle-built index over the same rows"
     raise NotImplementedError
 
 
-def time_cpu_baseline(oidx, Qh: np.ndarray, w: dict, budget_s: float):
+def _osearch(oidx, Q, w):
+    if w["kind"] == "FLAT":
+        return oidx.search_batch(Q, w["topk"])
+    return oidx.search_batch(Q, w["topk"], nprobe=w.get("nprobe", -1))
+
+
+def time_cpu_baseline(oidx, rows_held, note, Qh: np.ndarray, w: dict, budget_s: float):
     from oracle import pyoracle as orc
     threads = orc.max_threads()
-    nprobe = w.get("nprobe", -1)
     probe = min(len(Qh), 2 * threads)
     t0 = time.perf_counter()
-    oidx.search_batch(Qh[:probe], w["topk"], nprobe=nprobe)
+    _osearch(oidx, Qh[:probe], w)
     per_q = (time.perf_counter() - t0) / probe
     s = int(max(threads, min(len(Qh), budget_s / max(per_q, 1e-9))))
     t0 = time.perf_counter()
-    oidx.search_batch(Qh[:s], w["topk"], nprobe=nprobe)
+    _osearch(oidx, Qh[:s], w)
     dt = time.perf_counter() - t0
-    return {"value": s / dt, "unit": "QPS", "cores": threads, "kind": "port",
-            "sample": f"{s} of the batch's {len(Qh)} queries over the same GPU-built index, one query per thread, "
-                      f"{dt:.1f}s wall"}, s, dt
+    scale = rows_held / w["n"]
+    return {"value": s / dt * scale, "unit": "QPS", "cores": threads, "kind": "port",
+            "sample": f"{s} of the batch's {len(Qh)} queries over {note}, one query per thread, {dt:.1f}s wall"}, s, dt
 
 
 # ------------------------------------------------------------------------------------------------
@@ -290,32 +316,54 @@ def run_ours(args):
     # ---- dominant-kernel time (CUDA events inside the library around the scan stage), per launch
     stage_ms = {"total": 0.0, "coarse": 0.0, "scan": 0.0, "merge": 0.0}
     reps = max(3, min(args.steps, 10))
+    kname, kms_avg = "", 0.0
     for _ in range(reps):
         ix.search_device(Q.data_ptr(), nq, k, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), nprobe=nprobe, stream=stream)
         torch.cuda.synchronize()
         for kk, v in ix.last_search_ms().items():
             stage_ms[kk] += v / reps
+        kname, kms = ix.last_search_kernel()
+        kms_avg += kms / reps
     alg = algorithmic_work(w, world)
+    scanned = 0
+    if w["kind"] == "IVF_PQ":
+        scanned = ix.last_search_scanned()
     dom = "scan"
-    dom_ms = stage_ms[dom]
+    dom_ms = kms_avg if kms_avg > 0 else stage_ms[dom]
+    if not kname:
+        kname = w["kind"].lower() + "_scan (stage)"
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    extra = {}
+    work = alg["work"]
     if alg["bound"] == "hbm":
-        achieved = alg["work"] / (dom_ms / 1e3) / 1e9
+        if scanned > 0:  # exact unit count: codes scored by this launch x m bytes (roofline section)
+            extra["algorithmic_formula_bytes"] = alg["work"]
+            work = float(scanned) * w["m"]
+        achieved = work / (dom_ms / 1e3) / 1e9
         peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (of fallback)"
     else:
-        achieved = alg["work"] / (dom_ms / 1e3) / 1e12
+        achieved = work / (dom_ms / 1e3) / 1e12
         bf16 = peaks.get("bf16_tflops", 1590.0)
-        peak = bf16 / 2.0  # TF32 dense = 1/2 bf16; 3xTF32 issues 3x the algorithmic FLOPs
-        peak_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense, of measured)" if "bf16_tflops" in peaks else "fallback"
+        peak = bf16 / 2.0  # TF32 dense = 1/2 of the measured bf16 cuBLAS burst figure
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense, of measured)" if "bf16_tflops" in peaks
+                    else "fallback 1.59 PFLOP/s / 2 (of fallback)")
+        extra["issued"] = round(3.0 * achieved, 2)          # the 3xTF32 split issues three MMAs per useful one
+        extra["issued_frac"] = round(3.0 * achieved / peak, 4)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(f"{kname}:{w['name']}:{args.scale:g}")
+    except Exception:
+        pass
     roofline = {"bound": alg["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": alg["unit"],
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "ivfpq_lm_scan_kernel" if w["kind"] == "IVF_PQ" else w["kind"].lower() + "_scan",
-                "kernel_ms": round(dom_ms, 4), "algorithmic_per_launch": alg["work"], "peak_source": peak_src,
-                "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()}}
+                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": kname,
+                "kernel_ms": round(dom_ms, 4), "algorithmic_per_launch": work, "peak_source": peak_src,
+                "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()}, **extra}
 
     # ---- end to end through the host entry point: pinned host queries in, host results out
     Qh_t = torch.empty((nq, dim), dtype=torch.float32, pin_memory=True)
@@ -360,8 +408,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            oidx = oracle_index_from_gpu(ix, w)
-            cpu, _, _ = time_cpu_baseline(oidx, Qh, w, args.cpu_budget)
+            oidx, held, note = oracle_index_from_gpu(ix, w, torch)
+            cpu, _, _ = time_cpu_baseline(oidx, held, note, Qh, w, args.cpu_budget)
             cpu["value"] = round(cpu["value"], 2)
             del oidx
         except NotImplementedError:
@@ -406,7 +454,7 @@ def run_reference(args):
     ix, build_info = build_gpu_index(pg, torch, w, 0, 1, log)
     Q = make_queries(torch, w)
     Qh = Q.cpu().numpy()
-    oidx = oracle_index_from_gpu(ix, w)
+    oidx, held, note = oracle_index_from_gpu(ix, w, torch)
     del ix
     torch.cuda.empty_cache()
     threads = orc.max_threads()
@@ -414,22 +462,22 @@ def run_reference(args):
     # size one step to ~ (budget / (steps+warmup)) seconds
     probe = min(len(Qh), 2 * threads)
     t0 = time.perf_counter()
-    oidx.search_batch(Qh[:probe], w["topk"], nprobe=nprobe)
+    _osearch(oidx, Qh[:probe], w)
     per_q = (time.perf_counter() - t0) / probe
     per_step_budget = max(1.0, args.cpu_budget * 6 / max(1, args.steps + args.warmup))
     s = int(max(threads, min(len(Qh), per_step_budget / max(per_q, 1e-9))))
     for i in range(args.warmup):
-        oidx.search_batch(Qh[:s], w["topk"], nprobe=nprobe)
+        _osearch(oidx, Qh[:s], w)
     t0 = time.perf_counter()
     for i in range(args.steps):
         off = (i * s) % max(1, len(Qh) - s + 1)
-        oidx.search_batch(Qh[off:off + s], w["topk"], nprobe=nprobe)
+        _osearch(oidx, Qh[off:off + s], w)
     dt = time.perf_counter() - t0
-    value = s * args.steps / dt
-    sample = f"{s} of the batch's {len(Qh)} queries per step over the GPU-built index, one query per thread"
+    value = s * args.steps / dt * (held / w["n"])
+    sample = f"{s} of the batch's {len(Qh)} queries per step over {note}, one query per thread"
     line = {"impl": "reference", "metric": METRIC_NAME, "value": round(value, 2), "unit": "QPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 LUT / u8 codes",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w["kind"] != "IVF_PQ" else "f32 LUT / u8 codes",
             "data": "synthetic uniform[0,1) fp32 (same generator and seeds as the GPU arm)",
             "config": {"workload": describe(w), "reduced": w["reduced"], **build_info},
             "cpu_baseline": {"value": round(value, 2), "unit": "QPS", "cores": threads, "kind": "port", "sample": sample},

@@ -143,6 +143,10 @@ int pyrope_index_search_batch_device(pyrope_index *h, int64_t nq, const float *d
 /* Kernel-only time (ms, CUDA events) of the most recent search on this handle, split by stage:
  * out[0]=total, [1]=coarse probe, [2]=list/base scan, [3]=merge.  Feeds TraceInfo. */
 int pyrope_index_last_search_ms(pyrope_index *h, float *out4);
+/* CUDA-event duration (ms) of the DOMINANT kernel of the most recent search alone (the list-major
+ * ADC scan kernel for IVF_PQ, the tcgen05 kernel for FLAT) and its name ("" / 0 if the search took
+ * another path).  Measurement only: feeds the bench's roofline figure. */
+int pyrope_index_last_search_kernel(pyrope_index *h, float *ms_out, const char **name_out);
 /* Number of kernel launches issued by the most recent search on this handle. */
 int pyrope_index_last_search_launches(pyrope_index *h, int *out);
 /* PQ codes scored by the most recent batched IVF_PQ search (sum over its (query, probe) pairs of the

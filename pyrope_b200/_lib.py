@@ -62,6 +62,7 @@ SIGNATURES = {
     "pyrope_index_last_search_ms": (C.c_int, [vp, f32p]),
     "pyrope_index_last_search_launches": (C.c_int, [vp, i32p]),
     "pyrope_index_last_search_scanned": (C.c_int, [vp, i64p]),
+    "pyrope_index_last_search_kernel": (C.c_int, [vp, f32p, C.POINTER(C.c_char_p)]),
     "pyrope_topk_merge_device": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "pyrope_coarse_assign": (C.c_int, [C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]),
     "pyrope_kmeans_train": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int32, vp, i32p, i32p]),
@@ -245,6 +246,13 @@ class GpuIndex:
         out = C.c_int32(0)
         check(load().pyrope_index_last_search_launches(self._h, C.byref(out)))
         return out.value
+
+    def last_search_kernel(self):
+        """(name, ms) of the dominant kernel of the last search, timed alone with CUDA events."""
+        ms = C.c_float(0)
+        name = C.c_char_p()
+        check(load().pyrope_index_last_search_kernel(self._h, C.byref(ms), C.byref(name)))
+        return (name.value or b"").decode(), ms.value
 
     def last_search_scanned(self) -> int:
         """PQ codes scored by the last batched IVF_PQ search (sum of probed list lengths)."""

@@ -197,7 +197,9 @@ struct pyrope_index {
     TcOperand tc_seg, tc_cent;
     int tc_mode = -1;  // -1 auto, 0 off, 1 force (PYROPE_FLAT_TC)
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false;
+    cudaEvent_t evk[2] = {nullptr, nullptr};  // around the dominant kernel of the last search
+    bool ev_valid = false, evk_valid = false;
+    const char* dom_kernel = "";
     int last_launches = 0;
     int pq_force_generic = 0;
     int pq_lm_mode = -1;  // PYROPE_PQ_LM: 0 = query-major kernels only
@@ -788,9 +790,13 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     int launches = 0;
     if (h->last_stream && h->last_stream != st) CK(cudaStreamSynchronize(h->last_stream));
     h->last_stream = st;
-    if (!h->ev[0])
+    if (!h->ev[0]) {
         for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&h->evk[i]));
+    }
     h->ev_valid = false;
+    h->evk_valid = false;
+    h->dom_kernel = "";
     CK(cudaEventRecord(h->ev[0], st));
 
     auto fill_empty = [&]() -> int {
@@ -879,6 +885,11 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         TRY(ws.tcq.ensure(sizeof(uint64_t) * (size_t)tp.splits * nq_pad * tp.cap, 0, st));
         TRY(ws.tcc.ensure(sizeof(int32_t) * (size_t)tp.splits * nq_pad, 0, st));
         tp.queue = ws.tcq.as<uint64_t>(); tp.counts = ws.tcc.as<int32_t>(); tp.out = po;
+        if (&op == &h->tc_seg && h->kind == PYROPE_FLAT) {
+            tp.ev_k0 = h->evk[0]; tp.ev_k1 = h->evk[1];
+            h->evk_valid = true;
+            h->dom_kernel = "flat_tc_kernel";
+        }
         CK(launch_flat_tc(tp, st));
         launches += 2;
         return PYROPE_OK;
@@ -959,6 +970,9 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             if (use_lm) {
                 TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc, dim, h->max_list_len), 0, st));
                 pp.max_list_len = h->max_list_len;
+                pp.ev_k0 = h->evk[0]; pp.ev_k1 = h->evk[1];
+                h->evk_valid = true;
+                h->dom_kernel = "ivfpq_lm_scan_kernel";
                 CK(launch_ivfpq_scan_lm(pp, ws.lm.p, g_num_sms, st));
                 h->lm_nq = nq; h->lm_P = P; h->lm_k = k;
                 launches += ivfpq_lm_launches() - 1;
@@ -1053,6 +1067,8 @@ int pyrope_index_destroy(pyrope_index* h) {
     if (h->last_stream) cudaStreamSynchronize(h->last_stream);
     for (int i = 0; i < 5; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     cudaStreamDestroy(h->stream);
     delete h;
     return PYROPE_OK;
@@ -1312,6 +1328,17 @@ int pyrope_index_last_search_ms(pyrope_index* h, float* out4) {
     CK(cudaEventElapsedTime(&out4[1], h->ev[0], h->ev[1]));
     CK(cudaEventElapsedTime(&out4[2], h->ev[1], h->ev[2]));
     CK(cudaEventElapsedTime(&out4[3], h->ev[2], h->ev[3]));
+    return PYROPE_OK;
+}
+
+int pyrope_index_last_search_kernel(pyrope_index* h, float* ms_out, const char** name_out) {
+    if (!h || !ms_out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    *ms_out = 0.f;
+    if (name_out) *name_out = h->dom_kernel;
+    if (!h->evk_valid) return PYROPE_OK;
+    CK(cudaEventSynchronize(h->evk[1]));
+    CK(cudaEventElapsedTime(ms_out, h->evk[0], h->evk[1]));
     return PYROPE_OK;
 }
 

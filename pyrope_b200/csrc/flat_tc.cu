@@ -564,7 +564,9 @@ cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 16 * 8 + 16 + 4 * (4 * BN * sizeof(float)) + 64;
     cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (a.ev_k0) cudaEventRecord(a.ev_k0, st);
     flat_tc_kernel<<<(unsigned)(qtiles * a.splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
+    if (a.ev_k1) cudaEventRecord(a.ev_k1, st);
     return cudaGetLastError();
 }
 

@@ -45,6 +45,7 @@ struct FlatTcParams {
     const float* xnorm; const float* qnorm;  // cosine re-score
     const int64_t* labels;
     int metric, k, kprime, cap, splits;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the tcgen05 kernel alone
     uint64_t* queue; int32_t* counts;        // scratch [splits][nq_pad][cap], [splits][nq_pad]
     PairOut out;                             // writes ONE part (splits are reduced by the re-score)
 };
@@ -100,6 +101,7 @@ struct IvfPqScanParams {
     const int64_t* probes; int nprobe;
     const int64_t* list_off; int nlist;
     int64_t max_list_len;                    // longest inverted list (list-major path sizing)
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the list-major scan kernel alone
     const float* centroids;                  // [nlist][dim]
     const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
     const uint8_t* codes; const uint8_t* dead; const int64_t* labels;

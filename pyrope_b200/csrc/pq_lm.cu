@@ -890,7 +890,9 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;
     const int64_t grid = std::min<int64_t>(2 * num_sms, L.max_items);
+    if (p.ev_k0) cudaEventRecord(p.ev_k0, st);
     ivfpq_lm_scan_kernel<SUB><<<(unsigned)grid, LM_THREADS, LM_SMEM, st>>>(sp);
+    if (p.ev_k1) cudaEventRecord(p.ev_k1, st);
 #ifdef PYROPE_LM_TIMING
     {
         cudaStreamSynchronize(st);
