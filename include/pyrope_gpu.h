@@ -140,6 +140,17 @@ int pyrope_index_search_batch(pyrope_index *h, int64_t nq, const float *Q, int t
 int pyrope_index_search_batch_device(pyrope_index *h, int64_t nq, const float *dQ, int topk,
                                      int64_t max_scans, int nprobe, float *d_scores,
                                      int64_t *d_rows, int32_t *d_counts, void *stream);
+/* Multi-GPU split of a batched IVF search: the coarse ranking of IvfFlatVectorIndex.cs:186-198 /
+ * IvfPqVectorIndex.cs:141-150 depends only on the replicated centroids, so each rank ranks centroids for
+ * ITS slice of the batch (coarse_probe), the probe lists are all-gathered (nq x nprobe int64, list ids in
+ * rank order, -1 = none; nprobe must be the effective value, >= 1), and every rank scans its list shard
+ * for ALL queries with the gathered probes (search_batch_probed).  Device pointers. */
+int pyrope_index_coarse_probe_device(pyrope_index *h, int64_t nq, const float *dQ, int nprobe,
+                                     int64_t *d_probes_out, void *stream);
+int pyrope_index_search_batch_probed_device(pyrope_index *h, int64_t nq, const float *dQ, int topk,
+                                            int64_t max_scans, int nprobe, const int64_t *d_probes,
+                                            float *d_scores, int64_t *d_rows, int32_t *d_counts,
+                                            void *stream);
 /* Kernel-only time (ms, CUDA events) of the most recent search on this handle, split by stage:
  * out[0]=total, [1]=coarse probe, [2]=list/base scan, [3]=merge.  Feeds TraceInfo. */
 int pyrope_index_last_search_ms(pyrope_index *h, float *out4);

@@ -59,6 +59,8 @@ SIGNATURES = {
     "pyrope_index_stats": (C.c_int, [vp, i64p, i64p, i32p, i32p]),
     "pyrope_index_search_batch": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
     "pyrope_index_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp]),
+    "pyrope_index_coarse_probe_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, vp, vp]),
+    "pyrope_index_search_batch_probed_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp]),
     "pyrope_index_last_search_ms": (C.c_int, [vp, f32p]),
     "pyrope_index_last_search_launches": (C.c_int, [vp, i32p]),
     "pyrope_index_last_search_scanned": (C.c_int, [vp, i64p]),
@@ -236,6 +238,16 @@ class GpuIndex:
                       max_scans: int = -1, nprobe: int = -1, stream: int | None = None):
         check(load().pyrope_index_search_batch_device(self._h, nq, vp(q_ptr), topk, max_scans, nprobe, vp(scores_ptr),
                                                       vp(rows_ptr), vp(counts_ptr), vp(stream) if stream else None))
+
+    def coarse_probe_device(self, q_ptr: int, nq: int, nprobe: int, probes_ptr: int, stream: int | None = None):
+        check(load().pyrope_index_coarse_probe_device(self._h, nq, vp(q_ptr), nprobe, vp(probes_ptr),
+                                                      vp(stream) if stream else None))
+
+    def search_probed_device(self, q_ptr: int, nq: int, topk: int, nprobe: int, probes_ptr: int, scores_ptr: int,
+                             rows_ptr: int, counts_ptr: int, max_scans: int = -1, stream: int | None = None):
+        check(load().pyrope_index_search_batch_probed_device(self._h, nq, vp(q_ptr), topk, max_scans, nprobe,
+                                                             vp(probes_ptr), vp(scores_ptr), vp(rows_ptr),
+                                                             vp(counts_ptr), vp(stream) if stream else None))
 
     def last_search_ms(self):
         out = (C.c_float * 4)()

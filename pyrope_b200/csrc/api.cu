@@ -783,8 +783,12 @@ __global__ void fill_empty_kernel(float* s, int64_t* l, int32_t* c, int64_t nq, 
     if (c && i < nq) c[i] = 0;
 }
 
+// ext_probes: probe lists computed elsewhere ([nq][P] list ids in rank order, -1 = none) — the coarse stage is
+// skipped.  probes_only_out: run ONLY the coarse stage and write [nq][P] there (multi-GPU: every rank
+// ranks centroids for its slice of the batch, the lists are all-gathered, then every rank scans its shard).
 int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_scans, int nprobe, float* d_scores,
-                  int64_t* d_rows, int32_t* d_counts, cudaStream_t st) {
+                  int64_t* d_rows, int32_t* d_counts, cudaStream_t st, const int64_t* ext_probes = nullptr,
+                  int64_t* probes_only_out = nullptr) {
     Workspace& ws = h->ws;
     const int dim = h->dim, k = topk;
     int launches = 0;
@@ -811,7 +815,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     Segment& seg = h->seg;
     const bool ivf = h->kind != PYROPE_FLAT;
     const int64_t seg_scan = (h->kind == PYROPE_IVF_PQ) ? seg.nslots : segment_cutoff(seg, max_scans);
-    const bool scan_seg = seg_scan > 0 && seg.live > 0;
+    const bool scan_seg = seg_scan > 0 && seg.live > 0 && !probes_only_out;
     int64_t seg_live_scanned = 0;
     if (scan_seg) seg_live_scanned = (max_scans >= 0 && h->kind != PYROPE_IVF_PQ) ? std::min<int64_t>(max_scans, seg.live) : seg.live;
 
@@ -824,7 +828,8 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         if (h->kind == PYROPE_IVF_FLAT && max_scans >= 0 && seg_live_scanned >= max_scans) scan_lists = false;
     }
     if (P > kMaxTopK) return fail(PYROPE_ERR_UNSUPPORTED, "nprobe %d exceeds the supported maximum %d", P, kMaxTopK);
-    if (k <= 0 || (!scan_seg && !scan_lists)) {
+    if (probes_only_out && !scan_lists) return fail(PYROPE_ERR_INVALID_STATE, "index has no inverted lists to probe");
+    if (!probes_only_out && (k <= 0 || (!scan_seg && !scan_lists))) {
         TRY(fill_empty());
         CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); CK(cudaEventRecord(h->ev[3], st));
         h->ev_valid = true;
@@ -845,7 +850,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     if (groups > max_parts - (scan_seg ? 1 : 0)) groups = std::max(1, max_parts - (scan_seg ? 1 : 0));
     const bool use_tc_seg = scan_seg && h->tc_mode != 0 && flat_tc_supported(dim, k) &&
                             (h->tc_mode == 1 || seg_scan >= 8192);
-    const bool use_tc_coarse = scan_lists && h->tc_mode != 0 && flat_tc_supported(dim, P) &&
+    const bool use_tc_coarse = scan_lists && !ext_probes && h->tc_mode != 0 && flat_tc_supported(dim, P) &&
                                (h->tc_mode == 1 || h->nc >= 2048);
     int seg_splits = 0;
     if (scan_seg) seg_splits = use_tc_seg ? 1 : flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
@@ -896,7 +901,14 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     };
 
     // ---- coarse probe: exact FLAT top-P over the centroids
-    if (scan_lists && use_tc_coarse) {
+    const int64_t* probes_dev = ext_probes;
+    if (scan_lists && !ext_probes) {
+        TRY(ws.probes.ensure(sizeof(int64_t) * (size_t)nq * P, 0, st));
+        probes_dev = ws.probes.as<int64_t>();
+    }
+    if (ext_probes) {
+        // supplied by the caller
+    } else if (scan_lists && use_tc_coarse) {
         TRY(ws.probes.ensure(sizeof(int64_t) * (size_t)nq * P, 0, st));
         TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * P, 0, st));
         TRY(run_tc(h->tc_cent, h->centroids.as<float>(), h->nc, h->nc, nullptr, h->cnorms.as<float>(), nullptr, P,
@@ -920,6 +932,13 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         launches += 2;
     }
     CK(cudaEventRecord(h->ev[1], st));
+    if (probes_only_out) {
+        CK(cudaMemcpyAsync(probes_only_out, probes_dev, sizeof(int64_t) * (size_t)nq * P, cudaMemcpyDeviceToDevice, st));
+        CK(cudaEventRecord(h->ev[2], st)); CK(cudaEventRecord(h->ev[3], st));
+        h->ev_valid = true;
+        h->last_launches = launches;
+        return PYROPE_OK;
+    }
 
     // ---- buffer / base scan
     if (scan_seg && use_tc_seg) {
@@ -947,13 +966,13 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             const int32_t* allow = nullptr;
             if (max_scans >= 0) {
                 TRY(ws.allow.ensure(sizeof(int32_t) * (size_t)nq * P, 0, st));
-                CK(launch_probe_allow(ws.probes.as<int64_t>(), nq, P, h->list_off.as<int64_t>(),
+                CK(launch_probe_allow(probes_dev, nq, P, h->list_off.as<int64_t>(),
                                       max_scans - seg_live_scanned, ws.allow.as<int32_t>(), st));
                 ++launches;
                 allow = ws.allow.as<int32_t>();
             }
             IvfFlatScanParams ip{};
-            ip.Q = dQ; ip.nq = nq; ip.dim = dim; ip.probes = ws.probes.as<int64_t>(); ip.nprobe = P; ip.allow = allow;
+            ip.Q = dQ; ip.nq = nq; ip.dim = dim; ip.probes = probes_dev; ip.nprobe = P; ip.allow = allow;
             ip.list_off = h->list_off.as<int64_t>(); ip.vecs = h->list_vecs.as<float>(); ip.dead = ldead;
             ip.norms = h->list_norms.as<float>(); ip.labels = h->list_labels.as<int64_t>(); ip.qnorm = qnorm;
             ip.metric = h->metric; ip.k = k; ip.groups = groups;
@@ -961,7 +980,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             CK(launch_ivfflat_scan(ip, st));
         } else {
             IvfPqScanParams pp{};
-            pp.Q = dQ; pp.nq = nq; pp.dim = dim; pp.probes = ws.probes.as<int64_t>(); pp.nprobe = P;
+            pp.Q = dQ; pp.nq = nq; pp.dim = dim; pp.probes = probes_dev; pp.nprobe = P;
             pp.list_off = h->list_off.as<int64_t>(); pp.nlist = h->nc; pp.centroids = h->centroids.as<float>();
             pp.codebook = h->codebook.as<float>(); pp.m = h->m; pp.ksub = h->k;
             pp.codes = h->list_codes.as<uint8_t>(); pp.dead = ldead; pp.labels = h->list_labels.as<int64_t>();
@@ -1288,6 +1307,34 @@ int pyrope_index_search_batch_device(pyrope_index* h, int64_t nq, const float* d
     if (h->kind == PYROPE_IVF_FLAT && max_scans >= 0 && h->list_ndead > 0) TRY(compact_lists(h));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     TRY(search_device(h, nq, dQ, topk, max_scans, nprobe, d_scores, d_rows, d_counts, st));
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_index_coarse_probe_device(pyrope_index* h, int64_t nq, const float* dQ, int nprobe, int64_t* d_probes_out,
+                                     void* stream) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (nq < 0 || (nq > 0 && (!dQ || !d_probes_out))) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    if (h->kind == PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "FLAT has no coarse stage");
+    if (nq == 0) return PYROPE_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    TRY(search_device(h, nq, dQ, 1, -1, nprobe, nullptr, nullptr, nullptr, st, nullptr, d_probes_out));
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_index_search_batch_probed_device(pyrope_index* h, int64_t nq, const float* dQ, int topk, int64_t max_scans,
+                                            int nprobe, const int64_t* d_probes, float* d_scores, int64_t* d_rows,
+                                            int32_t* d_counts, void* stream) {
+    TRY(validate_search(h, nq, dQ, topk));
+    if (h->kind == PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "FLAT has no coarse stage");
+    if (!d_probes) return fail(PYROPE_ERR_INVALID_ARG, "probes is null");
+    if (nq == 0) return PYROPE_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->kind == PYROPE_IVF_FLAT && max_scans >= 0 && h->list_ndead > 0) TRY(compact_lists(h));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    TRY(search_device(h, nq, dQ, topk, max_scans, nprobe, d_scores, d_rows, d_counts, st, d_probes, nullptr));
     if (!stream) CK(cudaStreamSynchronize(st));
     return PYROPE_OK;
 }
