@@ -149,6 +149,7 @@ struct Segment {
 struct Workspace {
     DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probe_scores, probe_cnt, allow, qnorm,
         qhi, qlo, tcq, tcc,  // tensor-core path: split queries, candidate queues, counts
+        tcg, tct,            // two-pass threshold: group maxima, per-query tau
         hq, hs, hl, hc,      // h*: staging for the host-pointer entry point
         lm;                  // list-major IVF_PQ scan scratch
 };
@@ -885,7 +886,15 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         tp.X = X; tp.Xhi = op.hi.as<float>(); tp.Xlo = op.lo.as<float>(); tp.n_rows = n_rows; tp.n_scan = n_scan_rows;
         tp.scale = op.scale.as<float>(); tp.bias = op.bias.as<float>(); tp.xnorm = xnorm; tp.qnorm = qnorm; tp.labels = labels;
         tp.metric = h->metric; tp.k = kk; tp.kprime = kk + flat_tc_margin(kk); tp.cap = flat_tc_cap(tp.kprime);
-        tp.splits = flat_tc_pick_splits(nq, n_scan_rows, tp.kprime, g_num_sms);
+        const bool twopass = flat_tc_twopass(dim, n_scan_rows, tp.kprime);
+        tp.splits = twopass ? flat_tc_pick_splits_seeded(nq, n_scan_rows, tp.kprime, g_num_sms)
+                            : flat_tc_pick_splits(nq, n_scan_rows, tp.kprime, g_num_sms);
+        if (twopass) {
+            TRY(ws.tcg.ensure(sizeof(float) * flat_tc_gmax_floats(nq, n_scan_rows), 0, st));
+            TRY(ws.tct.ensure(sizeof(float) * (size_t)flat_tc_nq_pad(nq), 0, st));
+            tp.gmax_ws = ws.tcg.as<float>(); tp.tau_ws = ws.tct.as<float>();
+            launches += 2;
+        }
         const int64_t nq_pad = flat_tc_nq_pad(nq);
         TRY(ws.tcq.ensure(sizeof(uint64_t) * (size_t)tp.splits * nq_pad * tp.cap, 0, st));
         TRY(ws.tcc.ensure(sizeof(int32_t) * (size_t)tp.splits * nq_pad, 0, st));

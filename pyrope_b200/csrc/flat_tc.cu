@@ -118,6 +118,11 @@ struct TcParams {
     uint64_t* queue;     // [splits][nq_pad][cap]
     int32_t* counts;     // [splits][nq_pad]
     int64_t nq_pad;
+    // two-pass threshold (epilogue-bound shapes): pass A (gmax != null) only records, per query, the
+    // maximum proxy score of every 32-row group; pass B starts every query at tau_init instead of -inf
+    float* gmax;         // [nq_pad][gstride]
+    int64_t gstride;     // groups per query = ntiles * 8
+    const float* tau_init;  // [nq_pad] nullable
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -211,7 +216,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         float* sbias = sterms + ew * (4 * BN);   // private to this warp: the four epilogue warps never wait
         float* sscale = sbias + 2 * BN;         // for one another, only for the MMA warp (mbarriers)
         int cnt = 0;
-        float tau = -INFINITY;
+        const bool gmode = p.gmax != nullptr;
+        float tau = (!gmode && p.tau_init && qvalid) ? __ldg(p.tau_init + gq) : -INFINITY;
         const int cap = p.cap, kprime = p.kprime;
 
         // Keep the k' best keys of lane l's queue (in L2), whole warp cooperating, queue held in
@@ -293,7 +299,15 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             for (int c = 0; c < BN / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr0 + c * 32, v);
-                if (qvalid) {
+                if (qvalid && gmode) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        mx = fmaxf(mx, fmaf(v[j], sscale[buf * BN + col], sbias[buf * BN + col]));
+                    }
+                    p.gmax[gq * p.gstride + (t_begin + ti) * (BN / 32) + c] = mx;
+                } else if (qvalid) {
                     // common case after warm-up: none of the 32 proxy scores beats the threshold
                     float mx = -INFINITY;
 #pragma unroll
@@ -312,7 +326,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                         }
                     }
                 }
-                unsigned full = __ballot_sync(0xffffffffu, cnt > cap - 32);
+                unsigned full = gmode ? 0u : __ballot_sync(0xffffffffu, cnt > cap - 32);
                 while (full) {
                     const int l = __ffs(full) - 1;
                     full &= full - 1;
@@ -324,8 +338,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
         // final: leave the best k' (unordered) in place, publish the counts
-        for (int l = 0; l < 32; ++l) prune_lane(l);
-        p.counts[(int64_t)sp * p.nq_pad + qt * BM + et] = qvalid ? cnt : 0;
+        if (!gmode) {
+            for (int l = 0; l < 32; ++l) prune_lane(l);
+            p.counts[(int64_t)sp * p.nq_pad + qt * BM + et] = qvalid ? cnt : 0;
+        }
     }
 
     tc_fence_before();
@@ -334,6 +350,36 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// ---- two-pass threshold: the k'-th largest group maximum bounds the k'-th best score from below -------
+// (each of the k' best groups holds at least one row scoring >= its maximum).  One warp per query.
+__global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __restrict__ gmax, int64_t gstride, int ngroups,
+                                                            int64_t nq, int kprime, float* tau_out) {
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float* g = gmax + q * gstride;
+    float tau = -INFINITY;
+    if (ngroups > kprime) {
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (int i = lane; i < ngroups; i += 32) {
+            const uint32_t o = score_to_ord(__ldg(g + i));
+            lo = min(lo, o);
+            hi = max(hi, o);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        while (lo < hi) {  // largest T with count(ord >= T) >= k'
+            const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+            int n = 0;
+            for (int i = lane; i < ngroups; i += 32) n += score_to_ord(__ldg(g + i)) >= mid;
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (n >= kprime) lo = mid; else hi = mid - 1u;
+        }
+        tau = lo > 1u ? ord_to_score(lo - 1u) : -INFINITY;  // pass B accepts s > tau, i.e. s >= value(T)
+    }
+    if (lane == 0) tau_out[q] = tau;
 }
 
 // ---- exact fp32 re-score of the survivors + final ordering -------------------------------------
@@ -508,7 +554,38 @@ bool flat_tc_supported(int dim, int k) { return dim % 4 == 0 && dim >= 8 && k >=
 int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * kprime + 32))); }
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
+bool flat_tc_twopass(int dim, int64_t n_scan, int kprime) {
+    // epilogue-bound regime only: short K (few MMAs per tile), a long stream and a wide k'
+    return dim <= 256 && n_scan >= 16384 && kprime >= 32 && !getenv("PYROPE_TC_ONEPASS");
+}
+size_t flat_tc_gmax_floats(int64_t nq, int64_t n_scan) {
+    return (size_t)flat_tc_nq_pad(nq) * (size_t)((n_scan + BN - 1) / BN) * (BN / 32);
+}
+
+// splits when every query already has a threshold (two-pass) or no per-split state at all (pass A): only
+// wave quantisation and a small fixed cost per CTA matter
+static int pick_splits_seeded(int64_t nq, int64_t n_scan, int num_sms, int64_t smax_extra) {
+    const int64_t qtiles = (nq + BM - 1) / BM;
+    const int64_t ntiles = std::max<int64_t>(1, (n_scan + BN - 1) / BN);
+    const int64_t smax = std::min<int64_t>(std::min<int64_t>(ntiles, 32), smax_extra);
+    int best = 1;
+    double best_cost = 1e300;
+    for (int64_t s = 1; s <= smax; ++s) {
+        const int64_t tps = (ntiles + s - 1) / s;
+        if (s > 1 && tps < 8) break;
+        const int64_t waves = (qtiles * s + num_sms - 1) / num_sms;
+        const double cost = (double)waves * ((double)tps + 2.0);
+        if (cost < best_cost * 0.98) { best_cost = cost; best = (int)s; }
+    }
+    return best;
+}
+
+int flat_tc_pick_splits_seeded(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
+    return pick_splits_seeded(nq, n_scan, num_sms, std::max<int64_t>(1, 4096 / kprime));
+}
+
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
+
     // One CTA owns a 128-query tile and streams n-tiles of 256 rows.  Splitting the row range fills idle
     // SMs when there are few query tiles, but every split starts with no threshold (its first ~2 tiles
     // are accepted wholesale) and hands k' more candidates per query to the exact re-score, so a split
@@ -548,25 +625,43 @@ cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, c
     return cudaGetLastError();
 }
 
+static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st);
+
 cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
+    if (a.gmax_ws && a.tau_ws) {  // two-pass threshold
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = launch_flat_tc_pass(a, pick_splits_seeded(a.nq, a.n_scan, sms, 32), a.gmax_ws, nullptr, st);
+        if (e != cudaSuccess) return e;
+        const int64_t ntiles = (a.n_scan + BN - 1) / BN;
+        tc_gmax_select_kernel<<<(unsigned)((a.nq + 3) / 4), 128, 0, st>>>(a.gmax_ws, ntiles * (BN / 32), (int)(ntiles * (BN / 32)),
+                                                                           a.nq, a.kprime, a.tau_ws);
+        return launch_flat_tc_pass(a, a.splits, nullptr, a.tau_ws, st);
+    }
+    return launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st);
+}
+
+static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st) {
     CUtensorMap mqh, mql, mxh, mxl;
     if (!make_map(&mqh, a.Qhi, a.nq, a.dim, BM) || !make_map(&mql, a.Qlo, a.nq, a.dim, BM) ||
         !make_map(&mxh, a.Xhi, a.n_rows, a.dim, BN) || !make_map(&mxl, a.Xlo, a.n_rows, a.dim, BN))
         return cudaErrorInvalidValue;
     TcParams p{};
-    p.nq = a.nq; p.n_scan = a.n_scan; p.dim = a.dim; p.kprime = a.kprime; p.cap = a.cap; p.splits = a.splits;
+    p.nq = a.nq; p.n_scan = a.n_scan; p.dim = a.dim; p.kprime = a.kprime; p.cap = a.cap; p.splits = splits;
     p.ntiles = (a.n_scan + BN - 1) / BN;
-    p.tiles_per_split = (p.ntiles + a.splits - 1) / a.splits;
+    p.tiles_per_split = (p.ntiles + splits - 1) / splits;
+    p.gmax = gmax; p.gstride = p.ntiles * (BN / 32); p.tau_init = tau_init;
     p.scale = a.scale; p.bias = a.bias; p.queue = a.queue; p.counts = a.counts;
     const int64_t qtiles = (a.nq + BM - 1) / BM;
     p.nq_pad = qtiles * BM;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 16 * 8 + 16 + 4 * (4 * BN * sizeof(float)) + 64;
     cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (a.ev_k0) cudaEventRecord(a.ev_k0, st);
-    flat_tc_kernel<<<(unsigned)(qtiles * a.splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
-    if (a.ev_k1) cudaEventRecord(a.ev_k1, st);
+    if (a.ev_k0 && !gmax) cudaEventRecord(a.ev_k0, st);
+    flat_tc_kernel<<<(unsigned)(qtiles * splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
+    if (a.ev_k1 && !gmax) cudaEventRecord(a.ev_k1, st);
     return cudaGetLastError();
 }
 

@@ -47,8 +47,15 @@ struct FlatTcParams {
     int metric, k, kprime, cap, splits;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the tcgen05 kernel alone
     uint64_t* queue; int32_t* counts;        // scratch [splits][nq_pad][cap], [splits][nq_pad]
+    float* gmax_ws = nullptr;                // optional two-pass threshold scratch: flat_tc_gmax_floats() floats
+    float* tau_ws = nullptr;                 //   and flat_tc_nq_pad() floats (both set => two passes)
     PairOut out;                             // writes ONE part (splits are reduced by the re-score)
 };
+// two-pass threshold (group maxima -> per-query tau -> filtered pass): worth it only when the tile is
+// epilogue-bound (small dim) and the stream is long
+bool flat_tc_twopass(int dim, int64_t n_scan, int kprime);
+size_t flat_tc_gmax_floats(int64_t nq, int64_t n_scan);
+int flat_tc_pick_splits_seeded(int64_t nq, int64_t n_scan, int kprime, int num_sms);
 bool flat_tc_supported(int dim, int k);
 int flat_tc_margin(int k);
 int flat_tc_cap(int kprime);

@@ -138,3 +138,26 @@ def test_tc_agrees_with_cuda_core_path(gpu, monkeypatch):
     rb = _s(b, q, 10)
     assert_batch_equivalent(ra, rb, ctx="tc vs cuda-core")
     assert recall_at_k(ra[0], rb[0], 10) > 0.999
+
+
+def test_two_pass_threshold_matches_oracle_and_one_pass(gpu, force_tc, monkeypatch):
+    """n >= 16384, d <= 256, k' >= 32: group-maxima pass -> per-query threshold -> filtered pass."""
+    rng = np.random.default_rng(17)
+    base = rng.random((20_000, 128), dtype=np.float32)
+    base[5000:5040] = base[100]          # 41 identical rows: more ties than k' at the threshold
+    q = rng.random((150, 128), dtype=np.float32)
+    q[0] = base[100]
+    for metric in (orc.L2, orc.IP, orc.COSINE):
+        ref = orc.FlatIndex(128, metric)
+        ref.add_batch(base)
+        want = ref.search_batch(q, 20)
+        ix = gpu.GpuIndex(gpu.FLAT, 128, metric)
+        ix.add(base)
+        got = _s(ix, q, 20)
+        assert ix.last_search_launches() >= 6   # split, operand prep, pass A, select, pass B, re-score, merge
+        assert_batch_equivalent(want, got, ctx=f"two-pass metric={metric}")
+        monkeypatch.setenv("PYROPE_TC_ONEPASS", "1")
+        one = gpu.GpuIndex(gpu.FLAT, 128, metric)
+        one.add(base)
+        assert_batch_equivalent(_s(one, q, 20), got, ctx=f"one-pass vs two-pass metric={metric}")
+        monkeypatch.delenv("PYROPE_TC_ONEPASS")
