@@ -362,18 +362,35 @@ __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __rest
     const float* g = gmax + q * gstride;
     float tau = -INFINITY;
     if (ngroups > kprime) {
+        constexpr int R = 64;  // register-resident up to 2048 groups, re-read from L1/L2 beyond
+        const bool in_regs = ngroups <= R * 32;
+        uint32_t o[R];
         uint32_t lo = 0xffffffffu, hi = 0u;
-        for (int i = lane; i < ngroups; i += 32) {
-            const uint32_t o = score_to_ord(__ldg(g + i));
-            lo = min(lo, o);
-            hi = max(hi, o);
+        if (in_regs) {
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int i = u * 32 + lane;
+                o[u] = i < ngroups ? score_to_ord(__ldg(g + i)) : 0u;
+                if (i < ngroups) { lo = min(lo, o[u]); hi = max(hi, o[u]); }
+            }
+        } else {
+            for (int i = lane; i < ngroups; i += 32) {
+                const uint32_t v = score_to_ord(__ldg(g + i));
+                lo = min(lo, v);
+                hi = max(hi, v);
+            }
         }
         lo = __reduce_min_sync(0xffffffffu, lo);
         hi = __reduce_max_sync(0xffffffffu, hi);
-        while (lo < hi) {  // largest T with count(ord >= T) >= k'
+        while (lo < hi) {  // largest T with count(ord >= T) >= k'   (mid > lo >= 1: padding zeros never count)
             const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
             int n = 0;
-            for (int i = lane; i < ngroups; i += 32) n += score_to_ord(__ldg(g + i)) >= mid;
+            if (in_regs) {
+#pragma unroll
+                for (int u = 0; u < R; ++u) n += o[u] >= mid;
+            } else {
+                for (int i = lane; i < ngroups; i += 32) n += score_to_ord(__ldg(g + i)) >= mid;
+            }
             n = __reduce_add_sync(0xffffffffu, n);
             if (n >= kprime) lo = mid; else hi = mid - 1u;
         }
@@ -408,6 +425,7 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int 
     }
     __syncthreads();
     const int total = s_total;
+    P = min(P, next_pow2(max(total, 2)));  // sort only as much as there is (block-uniform)
     for (int i = total + tid; i < P; i += blockDim.x) keys[i] = 0ull;
     const float* qv = p.Q + q * p.dim;
     const bool vec_ok = (p.dim % 4 == 0);
