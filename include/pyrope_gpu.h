@@ -165,6 +165,20 @@ int pyrope_index_last_search_launches(pyrope_index *h, int *out);
  * the unit count behind the bench's algorithmic HBM bytes (m bytes per scored code). */
 int pyrope_index_last_search_scanned(pyrope_index *h, int64_t *codes_out);
 
+/* ---- host micro-batcher: the reference calls IVectorIndex.Search with ONE query per Garnet session thread
+ *      (VectorCommandSet.cs:458, under the read lock of BruteForceVectorIndex.cs:282).  The shim's Search calls
+ *      pyrope_batcher_search instead, which blocks while a dispatcher thread gathers the queries that arrive
+ *      within max_wait_us (or max_batch of them), issues one pyrope_index_search_batch per group of equal
+ *      (topK, MaxScans, NProbe) and returns each caller its own result.  Thread-safe; results are written into
+ *      the caller's buffers (topk entries each); errors carry pyrope_batcher_last_error(). */
+typedef struct pyrope_batcher pyrope_batcher;
+int pyrope_batcher_create(pyrope_index *h, int max_batch, int max_wait_us, pyrope_batcher **out);
+int pyrope_batcher_destroy(pyrope_batcher *b);
+int pyrope_batcher_search(pyrope_batcher *b, const float *query, int topk, int64_t max_scans, int nprobe,
+                          float *scores_out, int64_t *rows_out, int32_t *count_out);
+int pyrope_batcher_stats(pyrope_batcher *b, int64_t *batches_out, int64_t *queries_out);
+const char *pyrope_batcher_last_error(void);
+
 /* ---- cross-shard merge (the step after ncclAllGather; semantics of DeltaVectorIndex.cs:95-121
  *      without the id-dedupe, which sharding makes unnecessary): parts x nq x k_in candidate lists
  *      -> nq x k_out, best first, ties to the lower part index.  rows < 0 mark empty slots. */

@@ -65,6 +65,11 @@ SIGNATURES = {
     "pyrope_index_last_search_launches": (C.c_int, [vp, i32p]),
     "pyrope_index_last_search_scanned": (C.c_int, [vp, i64p]),
     "pyrope_index_last_search_kernel": (C.c_int, [vp, f32p, C.POINTER(C.c_char_p)]),
+    "pyrope_batcher_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "pyrope_batcher_destroy": (C.c_int, [vp]),
+    "pyrope_batcher_search": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int, vp, vp, i32p]),
+    "pyrope_batcher_stats": (C.c_int, [vp, i64p, i64p]),
+    "pyrope_batcher_last_error": (C.c_char_p, []),
     "pyrope_topk_merge_device": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "pyrope_coarse_assign": (C.c_int, [C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]),
     "pyrope_kmeans_train": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int32, vp, i32p, i32p]),
@@ -271,6 +276,37 @@ class GpuIndex:
         out = C.c_int64(0)
         check(load().pyrope_index_last_search_scanned(self._h, C.byref(out)))
         return out.value
+
+
+class Batcher:
+    """Host micro-batcher (csrc/batcher.cu): search() blocks like IVectorIndex.Search does; concurrent callers
+    share one batched launch.  ctypes drops the GIL during the call, so Python threads batch for real."""
+
+    def __init__(self, index: GpuIndex, max_batch: int = 256, max_wait_us: int = 200):
+        b = vp()
+        check(load().pyrope_batcher_create(index._h, max_batch, max_wait_us, C.byref(b)))
+        self._b, self._index = b, index
+
+    def search(self, q, topk: int, max_scans: int = -1, nprobe: int = -1):
+        q = _np(q, np.float32).reshape(-1)
+        kk = max(topk, 1)
+        scores, rows, cnt = np.zeros(kk, np.float32), np.full(kk, -1, np.int64), C.c_int32(0)
+        rc = load().pyrope_batcher_search(self._b, _p(q), topk, max_scans, nprobe, _p(scores), _p(rows), C.byref(cnt))
+        if rc:
+            raise PyropeGpuError(rc, (load().pyrope_batcher_last_error() or b"").decode())
+        return scores[:cnt.value], rows[:cnt.value]
+
+    def stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(load().pyrope_batcher_stats(self._b, C.byref(a), C.byref(b)))
+        return {"batches": a.value, "queries": b.value}
+
+    def close(self):
+        if getattr(self, "_b", None):
+            load().pyrope_batcher_destroy(self._b)
+            self._b = None
+
+    __del__ = close
 
 
 # ---- building blocks ---------------------------------------------------------------------------

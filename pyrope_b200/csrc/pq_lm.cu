@@ -269,11 +269,18 @@ __device__ __forceinline__ void lut_direct(const float* __restrict__ codebook, i
 #pragma unroll
             for (int j = 0; j < NQ; ++j) a[j] = 0.f;
             if (e < K) {
-                const float* cw = codebook + ((size_t)mi * K + e) * sub;
-                for (int d = 0; d < sub; ++d) {
-                    const float c = __ldg(cw + d);
+                const float4* cw = reinterpret_cast<const float4*>(codebook + ((size_t)mi * K + e) * sub);
+                for (int d4 = 0; d4 < sub / 4; ++d4) {  // sub is 4 or 8 on this path
+                    const float4 c = __ldg(cw + d4);
+                    const float cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-                    for (int j = 0; j < NQ; ++j) { const float df = res[j * dim + mi * sub + d] - c; a[j] = fmaf(df, df, a[j]); }
+                    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) {
+                            const float df = res[j * dim + mi * sub + d4 * 4 + u] - cc[u];
+                            a[j] = fmaf(df, df, a[j]);
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -714,6 +721,7 @@ struct LmFinalParams {
     const float* Q; int dim;
     const float* centroids; const float* codebook; int ksub;
     const uint8_t* codes; const int64_t* list_off; int nlist; const int64_t* labels;
+    const int64_t* probes; int P;
     const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k;
     PairOut out;
 };
@@ -745,10 +753,12 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order
     for (int i = warp; i < kk; i += blockDim.x / 32) {
         const uint32_t pos = key_pos(keys[i]);
-        int lo = 0, hi = p.nlist;  // list with list_off[l] <= pos < list_off[l+1]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(p.list_off + mid) <= (int64_t)pos) lo = mid; else hi = mid;
+        int lo = 0;  // the list holding pos is one of this query's probed lists: test them in parallel
+        for (int p0 = 0; p0 < p.P; p0 += 32) {
+            const int64_t l = p0 + lane < p.P ? __ldg(p.probes + q * p.P + p0 + lane) : -1;
+            const bool hit = l >= 0 && __ldg(p.list_off + l) <= (int64_t)pos && (int64_t)pos < __ldg(p.list_off + l + 1);
+            const unsigned mh = __ballot_sync(0xffffffffu, hit);
+            if (mh) { lo = (int)__shfl_sync(0xffffffffu, l, __ffs(mh) - 1); break; }
         }
         float dm = 0.f;
         if (lane < 16) {
@@ -921,6 +931,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmFinalParams fp{};
     fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub;
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
+    fp.probes = p.probes; fp.P = P;
     fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.out = p.out;
     const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, L.pool_cap));
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
