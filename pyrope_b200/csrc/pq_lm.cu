@@ -4,35 +4,37 @@
 // and the ADC loop of IvfPqVectorIndex.Search (IvfPqVectorIndex.cs:152-199).  The reference walks
 // query -> probed list -> code; a batch of 10^4 queries x 64 probes hits every inverted list ~10 times,
 // so this path inverts the loop: (query, probe) pairs are grouped BY LIST and one work item is one
-// list segment (<= 2048 codes) x up to four of the queries that probe it.
+// inverted list x up to four of the queries that probe it.
 //
 // Pipeline (all on one stream, no host synchronisation):
 //   lm_count / scans / lm_fill_pairs   group the pairs by list (counting sort on device);
 //   lm_prepare_kernel                  one warp per item writes the item block: header (list, code range,
-//                                      four query ids) + the four residual queries -2(q - c) interleaved
-//                                      as float4 per dimension (slot d*16 + m: conflict-free reads);
+//                                      four query ids, their pool slots) + the four residual queries
+//                                      -2(q - c) interleaved as float4 per dimension (slot d*16 + m);
 //   ivfpq_lm_seed_kernel               per query, an upper bound of its k-th best ADC distance from (a
 //                                      sample of) its nearest list, so no item starts without a threshold;
-//   ivfpq_lm_scan_kernel               persistent CTAs, static item striding.  Per item:
-//       - item block and code segment arrive by TMA bulk copies (cp.async.bulk + mbarrier), issued one
-//         item ahead; codes double buffered, item blocks four deep;
-//       - the PQ codebook (m*k*sub fp32 = 128 KiB at d=128) stays in REGISTERS for the CTA's lifetime
-//         (8 codewords per thread); the four lookup tables are built with packed FFMA2 as
-//         |p|^2 + |r_m|^2 - 2 r_m.p and stored interleaved, LUT[e][m] = {q0,q1,q2,q3} at byte
-//         e*256 + m*16, double buffered so fast warps build item i+1 while slow warps still scan item i;
-//       - scan: lane l reads table (l+t) mod 16 at step t, so the eight lanes of every quarter warp
-//         touch eight distinct 16-byte bank groups whatever the code bytes are (conflict-free by
-//         construction); the 16 code bytes are rotated once per lane so step t uses a compile-time
-//         byte and the address (code<<8 | table<<4) is one PRMT; one LDS.128 = four (query, code) lookups;
-//       - candidates below the query's global threshold go to a small per-slot queue; after the item,
-//         one warp per slot hands at most k of them to the query's pool in HBM and tightens the
+//   ivfpq_lm_scan_kernel               two 256-thread persistent CTAs per SM, static item striding.  Per item:
+//       - the item block arrives by a TMA bulk copy (cp.async.bulk + mbarrier), one item ahead;
+//       - the PQ codebook (m*k*sub fp32 = 128 KiB at d=128) is parked in TENSOR MEMORY for the CTA's lifetime
+//         (tcgen05.st once, tcgen05.ld per build; 2 CTAs x 256 columns = the whole TMEM), which leaves the
+//         register file free for two resident CTAs: one builds tables (FMA pipe) while the other scans
+//         (shared-memory crossbar);
+//       - the four lookup tables are built with packed FFMA2 as |p|^2 + |r_m|^2 - 2 r_m.p and stored
+//         interleaved, LUT[e][m] = {q0,q1,q2,q3} at byte e*256 + m*16;
+//       - scan: codes stream from L2/HBM as one coalesced 16-byte row per lane, prefetched a chunk ahead;
+//         lane l reads table (l+t) mod 16 at step t, so the eight lanes of every quarter warp touch eight
+//         distinct 16-byte bank groups whatever the code bytes are (conflict-free by construction); the 16
+//         code bytes are rotated once per lane so step t uses a compile-time byte and the address
+//         (code<<8 | table<<4) is one PRMT; one LDS.128 = four (query, code) lookups, summed with FADD2;
+//       - candidates below the query's global threshold go to a small per-slot queue; after the item, one
+//         warp per slot hands at most k of them to the pair's private pool region in HBM and tightens the
 //         threshold (atomicMax).  A queue that overflows sends the (query, item) to the redo list;
 //   ivfpq_lm_redo_kernel               plain per-(query, item) scan for the rare overflows;
 //   ivfpq_lm_final_kernel              best k of the pool, RE-SCORED in the reference's exact fp32 order
 //                                      (L2SquaredUnsafe per sub-vector, sequential sum over m), so
 //                                      reported distances never come from the fused-multiply-add path.
-// HBM traffic is one pass over the probed lists' codes (shared by the batch) instead of one pass per
-// (query, probe); the scan is bound by the 128 B/clk/SM shared-memory crossbar (ncu: 4 wavefronts per
+// HBM traffic is one pass over the probed lists' codes (shared by the batch through L2) instead of one pass
+// per (query, probe); the scan is bound by the 128 B/clk/SM shared-memory crossbar (ncu: 4 wavefronts per
 // LDS.128, zero excess).
 #include <cub/cub.cuh>
 
@@ -47,13 +49,12 @@ namespace {
 
 constexpr int LM_THREADS = 256;       // two CTAs per SM
 constexpr int LM_QS = 4;            // query slots per work item
-constexpr int LM_CODE_CAP = 2048;   // codes per item (32 KiB)
 constexpr int LM_QC = 256;          // candidate queue entries per slot
 constexpr int LM_HDR = 64;          // item-block header bytes
 constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;
 constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 16;
-constexpr int LM_SMEM = LM_LUT_BYTES + LM_CODE_CAP * 16 + 2 * LM_BLK_MAX + LM_QS * LM_QC * 8;
+constexpr int LM_SMEM = LM_LUT_BYTES + 2 * LM_BLK_MAX + LM_QS * LM_QC * 8;
 constexpr int SEED_NQ = 4;          // queries per seed CTA (share the codebook reads)
 constexpr int SEED_CAP = 2048;      // sampled distances per query
 constexpr int REDO_QCAP = 2048;
@@ -183,8 +184,7 @@ __global__ void lm_items_per_list_kernel(const int32_t* __restrict__ lcnt, const
     if (i > nlist) return;
     int v = 0;
     if (i < nlist) {
-        const int64_t len = list_off[i + 1] - list_off[i];
-        v = ((lcnt[i] + LM_QS - 1) / LM_QS) * (int)((len + LM_CODE_CAP - 1) / LM_CODE_CAP);
+        v = (lcnt[i] + LM_QS - 1) / LM_QS;
     }
     nit[i] = v;
 }
@@ -218,22 +218,21 @@ __global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
     }
     const int l = lo, rel = w - a.ioff[l];
     const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
-    const int nseg = (int)((len + LM_CODE_CAP - 1) / LM_CODE_CAP);
-    const int g = rel / nseg, sg = rel - g * nseg;
+    const int g = rel;
     const int pbeg = a.loff[l], pend = a.loff[l + 1];
     int qid[LM_QS], psl[LM_QS];
 #pragma unroll
     for (int j = 0; j < LM_QS; ++j) {
         const int idx = pbeg + LM_QS * g + j;
         qid[j] = idx < pend ? a.pairq[idx] : -1;
-        psl[j] = idx < pend ? a.pairp[idx] * a.maxseg + sg : 0;
+        psl[j] = idx < pend ? a.pairp[idx] : 0;
     }
     unsigned char* blkp = a.iblk + (size_t)w * a.blk;
     if (lane == 0) {
         LmHeader h{};
         h.list = l;
-        h.vbeg = beg + (int64_t)sg * LM_CODE_CAP;
-        h.nvec = (int)min((int64_t)LM_CODE_CAP, len - (int64_t)sg * LM_CODE_CAP);
+        h.vbeg = beg;
+        h.nvec = (int)len;
 #pragma unroll
         for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = psl[j]; }
         *reinterpret_cast<LmHeader*>(blkp) = h;
@@ -404,10 +403,9 @@ template <int SUB>
 __global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* lut = smem;                                                     // [256][16] float4
-    unsigned char* cbuf = lut + LM_LUT_BYTES;                                       // [CODE_CAP] uint4
-    unsigned char* rbuf = cbuf + LM_CODE_CAP * 16;                                  // [2] item blocks
+    unsigned char* rbuf = lut + LM_LUT_BYTES;                                       // [2] item blocks
     uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + 2 * LM_BLK_MAX);          // [QS][QC]
-    __shared__ __align__(8) uint64_t s_mbar[3];
+    __shared__ __align__(8) uint64_t s_mbar[2];
     __shared__ int s_qcnt[LM_QS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -460,10 +458,9 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p
     }
     const int rot = lane & 15;
 
-    const uint32_t bar_c = smem_u32(&s_mbar[0]);  // codes
-    const uint32_t bar_r = smem_u32(&s_mbar[1]);  // +8*s: item-block stage s
+    const uint32_t bar_r = smem_u32(&s_mbar[0]);  // +8*s: item-block stage s
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(bar_c + 8 * i, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(bar_r + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < LM_QS) s_qcnt[tid] = 0;
@@ -475,18 +472,7 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p
         mbar_expect_tx(br, (uint32_t)blk);
         bulk_g2s(smem_u32(rbuf + (i & 1) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
     };
-    auto issue_codes = [&](const LmHeader* hd) {  // thread 0: TMA of the item's code segment
-        const uint32_t bytes = (uint32_t)hd->nvec * 16u;
-        mbar_expect_tx(bar_c, bytes);
-        bulk_g2s(smem_u32(cbuf), p.codes + (size_t)hd->vbeg * 16, bytes, bar_c);
-    };
-    if (tid == 0 && my_n > 0) {
-        issue_block(0);
-        const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr_ptr(0)));  // {list, nvec, vbeg lo, vbeg hi}
-        const long long vbeg = (long long)(((unsigned long long)(uint32_t)h0.w << 32) | (uint32_t)h0.z);
-        mbar_expect_tx(bar_c, (uint32_t)h0.y * 16u);
-        bulk_g2s(smem_u32(cbuf), p.codes + (size_t)vbeg * 16, (uint32_t)h0.y * 16u, bar_c);
-    }
+    if (tid == 0 && my_n > 0) issue_block(0);
 
     // one warp per slot: hand at most k of the slot's candidates to the pair's private region of the query's
     // pool (plain stores: no returning atomics on this path) and tighten the query's threshold
@@ -558,6 +544,13 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p
         const unsigned char* blkp = rbuf + rs * LM_BLK_MAX;
         const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
         const int4 qv = *reinterpret_cast<const int4*>(hd->qid);
+        const int nvec = hd->nvec;
+        const long long vbeg = hd->vbeg;
+        // codes stream straight from L2/HBM, one coalesced 16-byte row per lane, one chunk ahead; the first
+        // chunk's load is in flight during the table build
+        const uint4* cp = reinterpret_cast<const uint4*>(p.codes) + vbeg;
+        uint4 cnext = make_uint4(0u, 0u, 0u, 0u);
+        if (warp * 32 + lane < nvec) cnext = __ldg(cp + warp * 32 + lane);
         uint32_t tu[LM_QS];
         tu[0] = qv.x >= 0 ? __ldcg(p.pool_thr + qv.x) : 0xffffffffu;  // in flight during the build
         tu[1] = qv.y >= 0 ? __ldcg(p.pool_thr + qv.y) : 0xffffffffu;
@@ -604,14 +597,12 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p
 #pragma unroll
         for (int j = 0; j < LM_QS; ++j)
             thrd[j] = tu[j] == 0xffffffffu ? -INFINITY : (tu[j] ? -ord_to_score(tu[j]) : INFINITY);
-        const int nvec = hd->nvec;
-        const long long vbeg = hd->vbeg;
-        mbar_wait(bar_c, (uint32_t)i & 1u);
         LM_T(3);
         for (int c = warp; c * 32 < nvec; c += LM_THREADS / 32) {
             const int v = c * 32 + lane;
+            const uint4 cw = cnext;
+            if (v + LM_THREADS < nvec) cnext = __ldg(cp + v + LM_THREADS);
             if (v < nvec) {
-                const uint4 cw = *reinterpret_cast<const uint4*>(cbuf + v * 16);
                 uint32_t w[4];
                 {   // rotate the 16 code bytes: new byte t = old byte (t + rot) & 15
                     const bool r8 = rot & 8, r4 = rot & 4;
@@ -650,12 +641,8 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p
             }
         }
         LM_T(4);
-        __syncthreads();  // codes and tables fully consumed, queue counts visible
+        __syncthreads();  // tables fully consumed, queue counts visible
         LM_T(5);
-        if (tid == 0 && i + 1 < my_n) {  // next item's codes land while its tables are built
-            mbar_wait(bar_r + 8 * ((i + 1) & 1), (uint32_t)((i + 1) >> 1) & 1u);
-            issue_codes(reinterpret_cast<const LmHeader*>(rbuf + ((i + 1) & 1) * LM_BLK_MAX));
-        }
         if (warp < LM_QS) finalize(hd, first + i * stride);
         LM_T(6);
     }
@@ -794,7 +781,7 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-inline int lm_maxseg(int64_t max_list_len) { return (int)std::max<int64_t>(1, (max_list_len + LM_CODE_CAP - 1) / LM_CODE_CAP); }
+inline int lm_maxseg(int64_t) { return 1; }  // one item covers a whole list (codes stream from L2/HBM, no staging buffer)
 
 struct LmLayout {
     size_t zero_bytes;  // leading region cleared per search
@@ -859,8 +846,14 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     void* temp = base + L.temp;
     size_t tb = L.temp_bytes;
 
+    // PYROPE_LM_STAGES=1: print the duration of every kernel of this pipeline (debug aid, synchronises)
+    static const bool stage_dbg = getenv("PYROPE_LM_STAGES") != nullptr;
+    cudaEvent_t sev[8];
+    int nsev = 0;
+    auto mark = [&]() { if (stage_dbg && nsev < 8) { cudaEventCreate(&sev[nsev]); cudaEventRecord(sev[nsev], st); ++nsev; } };
     cudaError_t e = cudaMemsetAsync(base, 0, L.zero_bytes, st);
     if (e != cudaSuccess) return e;
+    mark();
     const unsigned gb = (unsigned)((npairs + 255) / 256), lb = (unsigned)((p.nlist + 1 + 255) / 256);
     lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt, scanned);
     lm_items_per_list_kernel<<<lb, 256, 0, st>>>(lcnt, p.list_off, p.nlist, nit);
@@ -874,7 +867,9 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     pa.maxseg = lm_maxseg(p.max_list_len); pa.pairp = pairp;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
     pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
+    mark();
     lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
+    mark();
 
     LmSeed sd{};
     sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
@@ -884,6 +879,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
     if (e != cudaSuccess) return e;
     ivfpq_lm_seed_kernel<<<(unsigned)((p.nq + SEED_NQ - 1) / SEED_NQ), 256, seed_smem, st>>>(sd);
+    mark();
 
     LmParams sp{};
 #ifdef PYROPE_LM_TIMING
@@ -926,7 +922,9 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     rd.codes = p.codes; rd.dead = p.dead; rd.iblk = iblk; rd.blk = L.blk; rd.redo = redo; rd.redo_cnt = redo_cnt;
     rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k;
     const size_t redo_smem = sizeof(uint64_t) * REDO_QCAP + sizeof(float) * (4096 + (size_t)p.dim);
+    mark();
     ivfpq_lm_redo_kernel<<<(unsigned)(2 * num_sms), 256, redo_smem, st>>>(rd);
+    mark();
 
     LmFinalParams fp{};
     fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub;
@@ -937,6 +935,23 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
     ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, 256, fsm, st>>>(fp);
+    mark();
+    if (stage_dbg && nsev == 7) {
+        cudaEventSynchronize(sev[6]);
+        const char* names[6] = {"group", "prepare", "seed", "scan", "redo", "final"};
+        fprintf(stderr, "[lm stages]");
+        for (int i = 0; i < 6; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, sev[i], sev[i + 1]);
+            fprintf(stderr, " %s=%.3fms", names[i], ms);
+        }
+        int nredo = 0;
+        cudaMemcpy(&nredo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost);
+        int nit = 0;
+        cudaMemcpy(&nit, ioff + p.nlist, sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, " items=%d redo=%d\n", nit, nredo);
+        for (int i = 0; i < nsev; ++i) cudaEventDestroy(sev[i]);
+    }
     return cudaGetLastError();
 }
 
