@@ -375,7 +375,7 @@ def run_ours(args):
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get(f"{kname}:{w['name']}:{args.scale:g}")
+        traffic = tr.get(f"{kname}:{w['name']}:{args.scale:g}") if world == 1 else None
     except Exception:
         pass
     roofline = {"bound": alg["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": alg["unit"],

@@ -156,7 +156,7 @@ struct Workspace {
 
 // tf32 hi/lo split + per-row proxy terms of one operand table (base rows or centroids)
 struct TcOperand {
-    DevBuf hi, lo, scale, bias;
+    DevBuf hi, lo, scale, bias, amax;
     int64_t rows_valid = 0;
     bool dirty = true;
     void invalidate() { dirty = true; }
@@ -770,9 +770,16 @@ int ensure_tc_operand(TcOperand& op, const float* X, int64_t n, int dim, int met
     TRY(op.lo.ensure(sizeof(float) * (size_t)n * dim, keep_e, st));
     TRY(op.scale.ensure(sizeof(float) * (size_t)n, keep_r, st));
     TRY(op.bias.ensure(sizeof(float) * (size_t)n, keep_r, st));
-    if (op.rows_valid < n)
+    if (!op.amax.p) {
+        TRY(op.amax.ensure(sizeof(float), 0, st, true));
+        op.rows_valid = 0;
+    }
+    if (op.rows_valid == 0) CK(cudaMemsetAsync(op.amax.p, 0, sizeof(float), st));
+    if (op.rows_valid < n) {
         CK(launch_tc_prepare(X, n, dim, metric, dead, op.hi.as<float>(), op.lo.as<float>(), op.scale.as<float>(),
                              op.bias.as<float>(), op.rows_valid, st));
+        CK(launch_tc_amax(X, n, dim, op.scale.as<float>(), op.amax.as<float>(), op.rows_valid, st));
+    }
     op.rows_valid = n;
     op.dirty = false;
     return PYROPE_OK;
@@ -893,6 +900,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             TRY(ws.tcg.ensure(sizeof(float) * flat_tc_gmax_floats(nq, n_scan_rows), 0, st));
             TRY(ws.tct.ensure(sizeof(float) * (size_t)flat_tc_nq_pad(nq), 0, st));
             tp.gmax_ws = ws.tcg.as<float>(); tp.tau_ws = ws.tct.as<float>();
+            if (!getenv("PYROPE_TC_PASSA_3X")) tp.amax = op.amax.as<float>();
             launches += 2;
         }
         const int64_t nq_pad = flat_tc_nq_pad(nq);

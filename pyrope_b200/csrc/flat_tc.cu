@@ -120,6 +120,9 @@ struct TcParams {
     int64_t nq_pad;
     // two-pass threshold (epilogue-bound shapes): pass A (gmax != null) only records, per query, the
     // maximum proxy score of every 32-row group; pass B starts every query at tau_init instead of -inf
+    float uscale;        // metric with one scale for every row (L2: 2, IP: 1): skip the per-row scale loads
+    int has_uscale;
+    int one_term;        // pass A only: D = Qhi.Xhi (1xTF32, hi tiles only); the select step covers the error
     float* gmax;         // [nq_pad][gstride]
     int64_t gstride;     // groups per query = ntiles * 8
     const float* tau_init;  // [nq_pad] nullable
@@ -170,11 +173,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const uint32_t sb = smem_u32(stage_base + s * STAGE_BYTES);
-                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                    mbar_expect_tx(full0 + 8 * s, p.one_term ? QH_BYTES + XH_BYTES : STAGE_BYTES);
                     tma_load_2d(sb, &map_qhi, full0 + 8 * s, kc * BK, (int)(qt * BM));
-                    tma_load_2d(sb + QH_BYTES, &map_qlo, full0 + 8 * s, kc * BK, (int)(qt * BM));
                     tma_load_2d(sb + 2 * QH_BYTES, &map_xhi, full0 + 8 * s, kc * BK, n0);
-                    tma_load_2d(sb + 2 * QH_BYTES + XH_BYTES, &map_xlo, full0 + 8 * s, kc * BK, n0);
+                    if (!p.one_term) {
+                        tma_load_2d(sb + QH_BYTES, &map_qlo, full0 + 8 * s, kc * BK, (int)(qt * BM));
+                        tma_load_2d(sb + 2 * QH_BYTES + XH_BYTES, &map_xlo, full0 + 8 * s, kc * BK, n0);
+                    }
                 }
             }
         }
@@ -197,9 +202,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
 #pragma unroll
                     for (int k4 = 0; k4 < BK / 8; ++k4) {
                         const uint64_t adv = (uint64_t)(k4 * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                        tc_mma_tf32(d_tmem, qlo + adv, xhi + adv, kInstrDesc, (kc | k4) != 0);
-                        tc_mma_tf32(d_tmem, qhi + adv, xlo + adv, kInstrDesc, 1);
-                        tc_mma_tf32(d_tmem, qhi + adv, xhi + adv, kInstrDesc, 1);
+                        if (p.one_term) {
+                            tc_mma_tf32(d_tmem, qhi + adv, xhi + adv, kInstrDesc, (kc | k4) != 0);
+                        } else {
+                            tc_mma_tf32(d_tmem, qlo + adv, xhi + adv, kInstrDesc, (kc | k4) != 0);
+                            tc_mma_tf32(d_tmem, qhi + adv, xlo + adv, kInstrDesc, 1);
+                            tc_mma_tf32(d_tmem, qhi + adv, xhi + adv, kInstrDesc, 1);
+                        }
                     }
                     tc_commit(empty0 + 8 * s);  // frees the shared-memory stage when these MMAs retire
                 }
@@ -299,29 +308,44 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             for (int c = 0; c < BN / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr0 + c * 32, v);
+                if (qvalid) {  // proxy scores, in place: v = D * scale + bias (row terms read 4 columns at a time)
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + buf * BN + c * 32);
+                    const float4* s4 = reinterpret_cast<const float4*>(sscale + buf * BN + c * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bb = b4[j4];
+                        float4 ss = make_float4(p.uscale, p.uscale, p.uscale, p.uscale);
+                        if (!p.has_uscale) ss = s4[j4];
+                        v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], ss.x, bb.x);
+                        v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], ss.y, bb.y);
+                        v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], ss.z, bb.z);
+                        v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], ss.w, bb.w);
+                    }
+                }
                 if (qvalid && gmode) {
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        mx = fmaxf(mx, fmaf(v[j], sscale[buf * BN + col], sbias[buf * BN + col]));
-                    }
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
                     p.gmax[gq * p.gstride + (t_begin + ti) * (BN / 32) + c] = mx;
                 } else if (qvalid) {
-                    // common case after warm-up: none of the 32 proxy scores beats the threshold
-                    float mx = -INFINITY;
+                    // common case after warm-up: no proxy score of an 8-column group beats the threshold; the
+                    // element-wise test (divergent: lanes are different queries) runs only for groups with a hit
+                    float gm[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        v[j] = fmaf(v[j], sscale[buf * BN + col], sbias[buf * BN + col]);
-                        mx = fmaxf(mx, v[j]);
+                    for (int g = 0; g < 4; ++g) {
+                        gm[g] = -INFINITY;
+#pragma unroll
+                        for (int j = g * 8; j < g * 8 + 8; ++j) gm[g] = fmaxf(gm[g], v[j]);
                     }
-                    if (mx > tau) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (v[j] > tau) {
-                                __stcg(myq + cnt, make_key(v[j], (uint32_t)(n0 + c * 32 + j)));
-                                ++cnt;
+                    for (int g = 0; g < 4; ++g) {
+                        if (gm[g] > tau) {
+#pragma unroll
+                            for (int j = g * 8; j < g * 8 + 8; ++j) {
+                                if (v[j] > tau) {
+                                    __stcg(myq + cnt, make_key(v[j], (uint32_t)(n0 + c * 32 + j)));
+                                    ++cnt;
+                                }
                             }
                         }
                     }
@@ -354,8 +378,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
 
 // ---- two-pass threshold: the k'-th largest group maximum bounds the k'-th best score from below -------
 // (each of the k' best groups holds at least one row scoring >= its maximum).  One warp per query.
+// When pass A ran with ONE tf32 product (hi.hi only) its scores differ from the 3-term proxy by at most
+// eps_q = 2^-10 (1 + 2^-7) |q| max_r(|scale_r| |x_r|)  (each operand rounded to 11 significant bits, Cauchy-
+// Schwarz), so tau is lowered by eps_q (+ the same again for the 3-term side's own rounding, generously).
 __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __restrict__ gmax, int64_t gstride, int ngroups,
-                                                            int64_t nq, int kprime, float* tau_out) {
+                                                            int64_t nq, int kprime, float* tau_out,
+                                                            const float* __restrict__ Q, int dim,
+                                                            const float* __restrict__ amax) {
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
@@ -395,6 +424,13 @@ __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __rest
             if (n >= kprime) lo = mid; else hi = mid - 1u;
         }
         tau = lo > 1u ? ord_to_score(lo - 1u) : -INFINITY;  // pass B accepts s > tau, i.e. s >= value(T)
+        if (amax) {
+            float qq = 0.f;
+            for (int d = lane; d < dim; d += 32) { const float v = __ldg(Q + q * dim + d); qq = fmaf(v, v, qq); }
+            qq = warp_sum(qq);
+            const float eps = 2.f * 9.85e-4f * sqrtf(qq) * __ldg(amax);  // 2 x 2^-10 (1 + 2^-7) |q| A
+            tau -= eps + 1e-6f * fabsf(tau);
+        }
     }
     if (lane == 0) tau_out[q] = tau;
 }
@@ -430,15 +466,23 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int 
     const float* qv = p.Q + q * p.dim;
     const bool vec_ok = (p.dim % 4 == 0);
     const float qn = p.metric == kCosine ? p.qnorm[q] : 0.f;
+    // gather every split's survivors first (independent loads), then score them in one flat loop
     for (int s = 0; s < p.splits; ++s) {
-        const int c = p.counts[(int64_t)s * p.nq_pad + q];
+        const int c = (s + 1 < p.splits ? s_off[s + 1] : total) - s_off[s];
         const uint64_t* src = p.queue + ((int64_t)s * p.nq_pad + q) * p.cap;
-        for (int i = warp; i < c; i += 8) {
-            const uint32_t pos = key_pos(__ldcg(src + i));
-            const float* x = p.X + (int64_t)pos * p.dim;
-            float a = 0.f;
+        for (int i = tid; i < c; i += blockDim.x) keys[s_off[s] + i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    const int hl = lane & 15, half = lane >> 4;  // two candidates per warp, 16 lanes each
+    for (int i0 = warp * 2; i0 < total; i0 += 16) {
+        const int i = i0 + half;
+        const bool on = i < total;
+        const uint32_t pos = on ? key_pos(keys[i]) : 0u;
+        const float* x = p.X + (int64_t)pos * p.dim;
+        float a = 0.f;
+        if (on) {
             if (vec_ok) {
-                for (int d = lane * 4; d < p.dim; d += 128) {
+                for (int d = hl * 4; d < p.dim; d += 64) {
                     float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
                     float4 qq = __ldg(reinterpret_cast<const float4*>(qv + d));
                     if (p.metric == kL2) {
@@ -449,23 +493,24 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int 
                     }
                 }
             } else {
-                for (int d = lane; d < p.dim; d += 32) {
+                for (int d = hl; d < p.dim; d += 16) {
                     float xv = __ldg(x + d), qq = __ldg(qv + d);
                     if (p.metric == kL2) { float df = qq - xv; a = fmaf(df, df, a); }
                     else a = fmaf(qq, xv, a);
                 }
             }
-            a = warp_sum(a);
-            if (lane == 0) {
-                float score;
-                if (p.metric == kL2) score = -a;
-                else if (p.metric == kIP) score = a;
-                else {
-                    float xn = p.xnorm[pos];
-                    score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : a / (qn * xn);
-                }
-                keys[s_off[s] + i] = make_key(score, pos);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);  // within each half warp
+        if (on && hl == 0) {
+            float score;
+            if (p.metric == kL2) score = -a;
+            else if (p.metric == kIP) score = a;
+            else {
+                float xn = p.xnorm[pos];
+                score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : a / (qn * xn);
             }
+            keys[i] = make_key(score, pos);
         }
     }
     __syncthreads();
@@ -530,6 +575,17 @@ __global__ void tc_rowterms_kernel(const float* __restrict__ X, int64_t n, int d
         scale[r] = sc;
         bias[r] = b;
     }
+}
+
+// A = max over rows of |scale_r| * |x_r|  (float bits are order-preserving for non-negative values)
+__global__ void tc_amax_kernel(const float* __restrict__ X, int64_t n, int dim, const float* __restrict__ scale, float* amax) {
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    float a = 0.f;
+    for (int d = lane; d < dim; d += 32) { float v = __ldg(X + r * dim + d); a = fmaf(v, v, a); }
+    a = warp_sum(a);
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(fabsf(scale ? scale[r] : 1.f) * sqrtf(a)));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -636,6 +692,15 @@ cudaError_t launch_tc_prepare(const float* X, int64_t n, int dim, int metric, co
     return cudaGetLastError();
 }
 
+cudaError_t launch_tc_amax(const float* X, int64_t n, int dim, const float* scale, float* amax, int64_t from_row,
+                           cudaStream_t st) {
+    if (n <= from_row) return cudaSuccess;
+    const int64_t rows = n - from_row;
+    tc_amax_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(X + from_row * dim, rows, dim,
+                                                                        scale ? scale + from_row : nullptr, amax);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* scale, float* bias,
                                cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
@@ -655,7 +720,7 @@ cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (a.n_scan + BN - 1) / BN;
         tc_gmax_select_kernel<<<(unsigned)((a.nq + 3) / 4), 128, 0, st>>>(a.gmax_ws, ntiles * (BN / 32), (int)(ntiles * (BN / 32)),
-                                                                           a.nq, a.kprime, a.tau_ws);
+                                                                           a.nq, a.kprime, a.tau_ws, a.Q, a.dim, a.amax);
         return launch_flat_tc_pass(a, a.splits, nullptr, a.tau_ws, st);
     }
     return launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st);
@@ -671,6 +736,9 @@ static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float*
     p.ntiles = (a.n_scan + BN - 1) / BN;
     p.tiles_per_split = (p.ntiles + splits - 1) / splits;
     p.gmax = gmax; p.gstride = p.ntiles * (BN / 32); p.tau_init = tau_init;
+    p.one_term = (gmax && a.amax) ? 1 : 0;
+    p.has_uscale = (a.metric == kL2 || a.metric == kIP || !a.scale) ? 1 : 0;
+    p.uscale = a.metric == kL2 && a.scale ? 2.f : 1.f;
     p.scale = a.scale; p.bias = a.bias; p.queue = a.queue; p.counts = a.counts;
     const int64_t qtiles = (a.nq + BM - 1) / BM;
     p.nq_pad = qtiles * BM;

@@ -47,6 +47,7 @@ struct FlatTcParams {
     int metric, k, kprime, cap, splits;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the tcgen05 kernel alone
     uint64_t* queue; int32_t* counts;        // scratch [splits][nq_pad][cap], [splits][nq_pad]
+    const float* amax = nullptr;             // optional: max_r |scale_r||x_r| of the operand => pass A runs 1xTF32
     float* gmax_ws = nullptr;                // optional two-pass threshold scratch: flat_tc_gmax_floats() floats
     float* tau_ws = nullptr;                 //   and flat_tc_nq_pad() floats (both set => two passes)
     PairOut out;                             // writes ONE part (splits are reduced by the re-score)
@@ -66,6 +67,9 @@ cudaError_t launch_tc_prepare(const float* X, int64_t n, int dim, int metric, co
                               float* lo, float* scale, float* bias, int64_t from_row, cudaStream_t st);
 cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, const uint8_t* dead, float* scale,
                                float* bias, cudaStream_t st);
+// amax (device float, zero-initialised) = max(amax, max over rows [from_row, n) of |scale_r| * |x_r|)
+cudaError_t launch_tc_amax(const float* X, int64_t n, int dim, const float* scale, float* amax, int64_t from_row,
+                           cudaStream_t st);
 cudaError_t launch_flat_tc(const FlatTcParams& p, cudaStream_t st);
 // selection only: leaves the k' best proxy candidates per (split, query) sorted in queue/counts
 cudaError_t launch_flat_tc_select(const FlatTcParams& p, cudaStream_t st);

@@ -49,7 +49,7 @@ namespace {
 
 constexpr int LM_THREADS = 256;       // two CTAs per SM
 constexpr int LM_QS = 4;            // query slots per work item
-constexpr int LM_QC = 256;          // candidate queue entries per slot
+constexpr int LM_QC = 512;          // candidate queue entries per slot
 constexpr int LM_HDR = 64;          // item-block header bytes
 constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;
@@ -263,6 +263,7 @@ template <int NQ>
 __device__ __forceinline__ void lut_direct(const float* __restrict__ codebook, int K, int sub, const float* res, int dim,
                                            float* lut, int tid, int nthr) {
     for (int e = tid; e < 256; e += nthr) {
+#pragma unroll 4
         for (int mi = 0; mi < 16; ++mi) {
             float a[NQ];
 #pragma unroll
