@@ -284,23 +284,34 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             __syncwarp();
         };
 
+        // per-row scale/bias of a tile (8 columns per lane, private copy per warp), fetched ONE TILE AHEAD so
+        // the L2 round trip hides behind the current tile's epilogue
+        float nb[BN / 32], ns[BN / 32];
+        auto load_terms = [&](int ti) {
+            const int64_t n0 = (t_begin + ti) * BN;
+#pragma unroll
+            for (int u = 0; u < BN / 32; ++u) {
+                const int64_t pos = n0 + lane + u * 32;
+                nb[u] = -INFINITY; ns[u] = 0.f;
+                if (pos < p.n_scan) {
+                    nb[u] = p.bias ? __ldg(p.bias + pos) : 0.f;
+                    ns[u] = (p.scale && !p.has_uscale) ? __ldg(p.scale + pos) : 1.f;
+                }
+            }
+        };
+        auto store_terms = [&](uint32_t buf) {
+#pragma unroll
+            for (int u = 0; u < BN / 32; ++u) {
+                sbias[buf * BN + lane + u * 32] = nb[u];
+                sscale[buf * BN + lane + u * 32] = ns[u];
+            }
+            __syncwarp();
+        };
+        if (ntile > 0) { load_terms(0); store_terms(0); }
         for (int ti = 0; ti < ntile; ++ti) {
             const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
             const int64_t n0 = (t_begin + ti) * BN;
-            // stage this tile's per-row scale/bias (8 columns per lane, private copy per warp)
-#pragma unroll
-            for (int u = 0; u < BN / 32; ++u) {
-                const int col = lane + u * 32;
-                const int64_t pos = n0 + col;
-                float b = -INFINITY, sc = 0.f;
-                if (pos < p.n_scan) {
-                    b = p.bias ? __ldg(p.bias + pos) : 0.f;
-                    sc = p.scale ? __ldg(p.scale + pos) : 1.f;
-                }
-                sbias[buf * BN + col] = b;
-                sscale[buf * BN + col] = sc;
-            }
-            __syncwarp();
+            if (ti + 1 < ntile) load_terms(ti + 1);  // consumed after this tile
             mbar_wait(tfull0 + 8 * buf, aph);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * BN;
@@ -360,6 +371,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            if (ti + 1 < ntile) store_terms(buf ^ 1);
         }
         // final: leave the best k' (unordered) in place, publish the counts
         if (!gmode) {
