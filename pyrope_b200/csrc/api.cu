@@ -199,6 +199,8 @@ struct pyrope_index {
     int tc_mode = -1;  // -1 auto, 0 off, 1 force (PYROPE_FLAT_TC)
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evk[2] = {nullptr, nullptr};  // around the dominant kernel of the last search
+    cudaStream_t aux = nullptr;               // side stream of the list-major path (threshold seed)
+    cudaEvent_t evf[2] = {nullptr, nullptr};  // fork / join
     bool ev_valid = false, evk_valid = false;
     const char* dom_kernel = "";
     int last_launches = 0;
@@ -805,6 +807,8 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     if (!h->ev[0]) {
         for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&h->ev[i]));
         for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&h->evk[i]));
+        for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->evf[i], cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     }
     h->ev_valid = false;
     h->evk_valid = false;
@@ -1007,6 +1011,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                 TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc, dim, h->max_list_len), 0, st));
                 pp.max_list_len = h->max_list_len;
                 pp.ev_k0 = h->evk[0]; pp.ev_k1 = h->evk[1];
+                pp.aux_stream = h->aux; pp.ev_fork = h->evf[0]; pp.ev_join = h->evf[1];
                 h->evk_valid = true;
                 h->dom_kernel = "ivfpq_lm_scan_kernel";
                 CK(launch_ivfpq_scan_lm(pp, ws.lm.p, g_num_sms, st));
@@ -1105,6 +1110,9 @@ int pyrope_index_destroy(pyrope_index* h) {
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; ++i)
         if (h->evk[i]) cudaEventDestroy(h->evk[i]);
+    for (int i = 0; i < 2; ++i)
+        if (h->evf[i]) cudaEventDestroy(h->evf[i]);
+    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
     cudaStreamDestroy(h->stream);
     delete h;
     return PYROPE_OK;

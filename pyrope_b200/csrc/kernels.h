@@ -113,6 +113,8 @@ struct IvfPqScanParams {
     const int64_t* list_off; int nlist;
     int64_t max_list_len;                    // longest inverted list (list-major path sizing)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the list-major scan kernel alone
+    cudaStream_t aux_stream = nullptr;             // optional side stream (+ fork/join events): the threshold seed
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // kernel overlaps the grouping / item-block kernels
     const float* centroids;                  // [nlist][dim]
     const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
     const uint8_t* codes; const uint8_t* dead; const int64_t* labels;

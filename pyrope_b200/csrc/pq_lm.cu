@@ -201,9 +201,18 @@ __global__ void lm_fill_pairs_kernel(const int64_t* __restrict__ probes, int64_t
     }
 }
 
+// item -> list map: thread per list writes its (few) items
+__global__ void lm_fill_items_kernel(const int32_t* __restrict__ nit, const int32_t* __restrict__ ioff, int nlist, int32_t* item_list) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlist) return;
+    const int n = nit[l], o = ioff[l];
+    for (int g = 0; g < n; ++g) item_list[o + g] = l;
+}
+
 // one warp per item: header + the four residual queries t = -2 (q - c), interleaved per dimension
 struct LmPrep {
-    const int32_t* ioff; const int32_t* loff; const int32_t* pairq; const int32_t* pairp; const int64_t* list_off; int nlist;
+    const int32_t* ioff; const int32_t* item_list; const int32_t* loff; const int32_t* pairq; const int32_t* pairp;
+    const int64_t* list_off; int nlist;
     int maxseg;
     const float* Q; const float* centroids; int dim;
     unsigned char* iblk; int blk;
@@ -211,12 +220,7 @@ struct LmPrep {
 __global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
     const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= a.ioff[a.nlist]) return;
-    int lo = 0, hi = a.nlist;  // last list with ioff[l] <= w
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(a.ioff + mid) <= w) lo = mid; else hi = mid;
-    }
-    const int l = lo, rel = w - a.ioff[l];
+    const int l = a.item_list[w], rel = w - a.ioff[l];
     const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
     const int g = rel;
     const int pbeg = a.loff[l], pend = a.loff[l + 1];
@@ -733,11 +737,13 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     }
     __syncthreads();
     const int n = s_n;
-    const int P2 = next_pow2(max(n, 2));
-    for (int i = n + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
-    __syncthreads();
-    bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
     const int kk = min(n, p.k);
+    if (n > kk) {
+        const int P2 = next_pow2(max(n, 2));
+        for (int i = n + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
+    }
     // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order
     for (int i = warp; i < kk; i += blockDim.x / 32) {
         const uint32_t pos = key_pos(keys[i]);
@@ -786,7 +792,7 @@ inline int lm_maxseg(int64_t) { return 1; }  // one item covers a whole list (co
 
 struct LmLayout {
     size_t zero_bytes;  // leading region cleared per search
-    size_t lcnt, lcur, pool_cnt, pool_thr, redo_cnt, scanned, loff, nit, ioff, pairq, pairp, redo, iblk, pool, temp, total;
+    size_t lcnt, lcur, pool_cnt, pool_thr, redo_cnt, scanned, loff, nit, ioff, pairq, pairp, item_list, redo, iblk, pool, temp, total;
     size_t temp_bytes;
     int64_t max_items;
     int pool_cap, pslots, blk;
@@ -810,6 +816,7 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.pairq = o; o += align_up(sizeof(int32_t) * (size_t)npairs, 256);
     L.pairp = o; o += align_up(sizeof(int32_t) * (size_t)npairs, 256);
     L.max_items = (npairs / LM_QS + std::min<int64_t>(npairs, nlist) + 1) * maxseg;
+    L.item_list = o; o += align_up(sizeof(int32_t) * (size_t)L.max_items, 256);
     L.redo = o; o += align_up(sizeof(int2) * (size_t)L.max_items * LM_QS, 256);
     L.blk = LM_HDR + dim * 16;
     L.iblk = o; o += align_up((size_t)L.blk * (size_t)L.max_items, 256);
@@ -841,6 +848,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     int32_t* ioff = reinterpret_cast<int32_t*>(base + L.ioff);
     int32_t* pairq = reinterpret_cast<int32_t*>(base + L.pairq);
     int32_t* pairp = reinterpret_cast<int32_t*>(base + L.pairp);
+    int32_t* item_list = reinterpret_cast<int32_t*>(base + L.item_list);
     int2* redo = reinterpret_cast<int2*>(base + L.redo);
     unsigned char* iblk = base + L.iblk;
     unsigned long long* pool = reinterpret_cast<unsigned long long*>(base + L.pool);
@@ -855,6 +863,23 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     cudaError_t e = cudaMemsetAsync(base, 0, L.zero_bytes, st);
     if (e != cudaSuccess) return e;
     mark();
+    // the seed kernel only needs the probe lists: it runs on the caller-provided side stream while the
+    // pairs are grouped and the item blocks are written
+    const bool fork = p.aux_stream && p.ev_fork && p.ev_join && !stage_dbg;
+    cudaStream_t sst = fork ? p.aux_stream : st;
+    if (fork) {
+        cudaEventRecord(p.ev_fork, st);
+        cudaStreamWaitEvent(p.aux_stream, p.ev_fork, 0);
+        LmSeed sd{};
+        sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
+        sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
+        sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k);
+        const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
+        e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
+        if (e != cudaSuccess) return e;
+        ivfpq_lm_seed_kernel<<<(unsigned)((p.nq + SEED_NQ - 1) / SEED_NQ), 256, seed_smem, sst>>>(sd);
+        cudaEventRecord(p.ev_join, p.aux_stream);
+    }
     const unsigned gb = (unsigned)((npairs + 255) / 256), lb = (unsigned)((p.nlist + 1 + 255) / 256);
     lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt, scanned);
     lm_items_per_list_kernel<<<lb, 256, 0, st>>>(lcnt, p.list_off, p.nlist, nit);
@@ -866,20 +891,26 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
 
     LmPrep pa{};
     pa.maxseg = lm_maxseg(p.max_list_len); pa.pairp = pairp;
+    lm_fill_items_kernel<<<lb, 256, 0, st>>>(nit, ioff, p.nlist, item_list);
+    pa.item_list = item_list;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
     pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
     mark();
     lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
     mark();
 
-    LmSeed sd{};
-    sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
-    sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
-    sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k);
-    const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
-    e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
-    if (e != cudaSuccess) return e;
-    ivfpq_lm_seed_kernel<<<(unsigned)((p.nq + SEED_NQ - 1) / SEED_NQ), 256, seed_smem, st>>>(sd);
+    if (!fork) {
+        LmSeed sd{};
+        sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
+        sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
+        sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k);
+        const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
+        e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
+        if (e != cudaSuccess) return e;
+        ivfpq_lm_seed_kernel<<<(unsigned)((p.nq + SEED_NQ - 1) / SEED_NQ), 256, seed_smem, st>>>(sd);
+    } else {
+        cudaStreamWaitEvent(st, p.ev_join, 0);
+    }
     mark();
 
     LmParams sp{};
