@@ -42,6 +42,10 @@ def workload(name: str, scale: float) -> dict:
         w["n"] = max(4096, int(round(w["n"] * scale)))
     elif name == "c1":
         w = dict(kind="FLAT", metric="L2", dim=128, n=10_000, nq=100, topk=10)
+    elif name == "c2x":  # IVF_FLAT at a size where the list scan is HBM/L2-bound (not a BASELINE config; roofline of K4)
+        w = dict(kind="IVF_FLAT", metric="L2", dim=128, n=10_000_000, nq=10_000, topk=10, nlist=4096, nprobe=16)
+        w["n"] = max(4096, int(round(w["n"] * scale)))
+        w["nlist"] = max(64, int(round(w["nlist"] * scale)))
     elif name == "c2":
         w = dict(kind="IVF_FLAT", metric="L2", dim=128, n=10_000, nq=100, topk=10, nlist=100, nprobe=3)
     elif name == "c3":
@@ -49,7 +53,7 @@ def workload(name: str, scale: float) -> dict:
     else:
         raise SystemExit(f"unknown workload {name}")
     w["name"] = name
-    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5"))
+    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5", "c2x"))
     return w
 
 
