@@ -147,7 +147,7 @@ struct Segment {
 };
 
 struct Workspace {
-    DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probe_scores, probe_cnt, allow, qnorm,
+    DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probes_raw, probe_scores, probe_cnt, allow, qnorm,
         qhi, qlo, tcq, tcc,  // tensor-core path: split queries, candidate queues, counts
         tcg, tct,            // two-pass threshold: group maxima, per-query tau
         hq, hs, hl, hc,      // h*: staging for the host-pointer entry point
@@ -856,13 +856,17 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     }
     const bool use_lm = scan_lists && h->kind == PYROPE_IVF_PQ && !h->pq_force_generic && h->pq_lm_mode != 0 &&
                         ivfpq_lm_supported(dim, h->m, h->k, P, k, nq, h->list_total, h->max_list_len);
-    if (use_lm) groups = 1;
+    const bool use_flm = scan_lists && h->kind == PYROPE_IVF_FLAT && h->pq_lm_mode != 0 && nq >= 64 &&
+                         ivfflat_lm_supported(dim, h->metric, P, k, nq, h->list_total, max_scans >= 0);
+    if (use_lm || use_flm) groups = 1;
     int max_parts = kMergeMaxCandidates / k;
     if (max_parts < 1) max_parts = 1;
     if (groups > max_parts - (scan_seg ? 1 : 0)) groups = std::max(1, max_parts - (scan_seg ? 1 : 0));
     const bool use_tc_seg = scan_seg && h->tc_mode != 0 && flat_tc_supported(dim, k) &&
                             (h->tc_mode == 1 || seg_scan >= 8192);
-    const bool use_tc_coarse = scan_lists && !ext_probes && h->tc_mode != 0 && flat_tc_supported(dim, P) &&
+    // the fast coarse stage ranks Pc >= P candidate lists; they are re-ranked in the reference's arithmetic
+    const int Pc = std::min(h->nc, std::min(P + 8, kMaxTopK));
+    const bool use_tc_coarse = scan_lists && !ext_probes && h->tc_mode != 0 && flat_tc_supported(dim, Pc) &&
                                (h->tc_mode == 1 || h->nc >= 2048);
     int seg_splits = 0;
     if (scan_seg) seg_splits = use_tc_seg ? 1 : flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
@@ -929,28 +933,32 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     }
     if (ext_probes) {
         // supplied by the caller
-    } else if (scan_lists && use_tc_coarse) {
-        TRY(ws.probes.ensure(sizeof(int64_t) * (size_t)nq * P, 0, st));
-        TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * P, 0, st));
-        TRY(run_tc(h->tc_cent, h->centroids.as<float>(), h->nc, h->nc, nullptr, h->cnorms.as<float>(), nullptr, P,
-                   PairOut{ws.probe_scores.as<float>(), ws.probes.as<int64_t>(), 1, 0}));
     } else if (scan_lists) {
-        int csplits = flat_scan_pick_splits(nq, h->nc, P, g_num_sms, 0);
-        int ccap = flat_scan_cap(P);
-        TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)csplits * nq * ccap, 0, st));
-        TRY(ws.cpairs_s.ensure(sizeof(float) * (size_t)nq * csplits * P, 0, st));
-        TRY(ws.cpairs_l.ensure(sizeof(int64_t) * (size_t)nq * csplits * P, 0, st));
-        TRY(ws.probes.ensure(sizeof(int64_t) * (size_t)nq * P, 0, st));
-        TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * P, 0, st));
-        FlatScanParams cp{};
-        cp.Q = dQ; cp.nq = nq; cp.dim = dim; cp.X = h->centroids.as<float>(); cp.n_scan = h->nc;
-        cp.dead = nullptr; cp.xnorm = h->cnorms.as<float>(); cp.qnorm = qnorm; cp.labels = nullptr;
-        cp.metric = h->metric; cp.k = P; cp.splits = csplits; cp.queue = ws.queue.as<uint64_t>(); cp.cap = ccap;
-        cp.out = PairOut{ws.cpairs_s.as<float>(), ws.cpairs_l.as<int64_t>(), csplits, 0};
-        CK(launch_flat_scan(cp, st));
-        CK(launch_merge_pairs(nq, csplits, P, P, ws.cpairs_s.as<float>(), ws.cpairs_l.as<int64_t>(), P, (int64_t)csplits * P,
-                              ws.probe_scores.as<float>(), ws.probes.as<int64_t>(), nullptr, st));
-        launches += 2;
+        TRY(ws.probes_raw.ensure(sizeof(int64_t) * (size_t)nq * Pc, 0, st));
+        TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * Pc, 0, st));
+        if (use_tc_coarse) {
+            TRY(run_tc(h->tc_cent, h->centroids.as<float>(), h->nc, h->nc, nullptr, h->cnorms.as<float>(), nullptr, Pc,
+                       PairOut{ws.probe_scores.as<float>(), ws.probes_raw.as<int64_t>(), 1, 0}));
+        } else {
+            int csplits = flat_scan_pick_splits(nq, h->nc, Pc, g_num_sms, 0);
+            int ccap = flat_scan_cap(Pc);
+            TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)csplits * nq * ccap, 0, st));
+            TRY(ws.cpairs_s.ensure(sizeof(float) * (size_t)nq * csplits * Pc, 0, st));
+            TRY(ws.cpairs_l.ensure(sizeof(int64_t) * (size_t)nq * csplits * Pc, 0, st));
+            FlatScanParams cp{};
+            cp.Q = dQ; cp.nq = nq; cp.dim = dim; cp.X = h->centroids.as<float>(); cp.n_scan = h->nc;
+            cp.dead = nullptr; cp.xnorm = h->cnorms.as<float>(); cp.qnorm = qnorm; cp.labels = nullptr;
+            cp.metric = h->metric; cp.k = Pc; cp.splits = csplits; cp.queue = ws.queue.as<uint64_t>(); cp.cap = ccap;
+            cp.out = PairOut{ws.cpairs_s.as<float>(), ws.cpairs_l.as<int64_t>(), csplits, 0};
+            CK(launch_flat_scan(cp, st));
+            CK(launch_merge_pairs(nq, csplits, Pc, Pc, ws.cpairs_s.as<float>(), ws.cpairs_l.as<int64_t>(), Pc, (int64_t)csplits * Pc,
+                                  ws.probe_scores.as<float>(), ws.probes_raw.as<int64_t>(), nullptr, st));
+            launches += 2;
+        }
+        // IvfFlatVectorIndex.cs:186-198 / IvfPqVectorIndex.cs:141-150: rank by the reference's own arithmetic
+        CK(launch_coarse_rerank_exact(h->metric, dim, nq, dQ, h->centroids.as<float>(), h->cnorms.as<float>(),
+                                      ws.probes_raw.as<int64_t>(), Pc, ws.probes.as<int64_t>(), nullptr, P, st));
+        ++launches;
     }
     CK(cudaEventRecord(h->ev[1], st));
     if (probes_only_out) {
@@ -998,7 +1006,17 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             ip.norms = h->list_norms.as<float>(); ip.labels = h->list_labels.as<int64_t>(); ip.qnorm = qnorm;
             ip.metric = h->metric; ip.k = k; ip.groups = groups;
             ip.out = out; ip.out.part_base = seg_splits;
-            CK(launch_ivfflat_scan(ip, st));
+            if (use_flm) {
+                TRY(ws.lm.ensure(ivfflat_lm_scratch_bytes(nq, P, k, h->nc), 0, st));
+                ip.ev_k0 = h->evk[0]; ip.ev_k1 = h->evk[1];
+                h->evk_valid = true;
+                h->dom_kernel = "ivf_lm_scan_kernel";
+                CK(launch_ivfflat_scan_lm(ip, h->nc, ws.lm.p, g_num_sms, st));
+                h->lm_nq = nq; h->lm_P = P; h->lm_k = k;
+                launches += ivfflat_lm_launches() - 1;
+            } else {
+                CK(launch_ivfflat_scan(ip, st));
+            }
         } else {
             IvfPqScanParams pp{};
             pp.Q = dQ; pp.nq = nq; pp.dim = dim; pp.probes = probes_dev; pp.nprobe = P;
@@ -1426,8 +1444,11 @@ int pyrope_index_last_search_scanned(pyrope_index* h, int64_t* codes_out) {
     *codes_out = 0;
     if (h->lm_nq <= 0 || !h->ws.lm.p) return PYROPE_OK;
     unsigned long long v = 0;
-    CK(ivfpq_lm_scanned_codes(h->ws.lm.p, h->lm_nq, h->lm_P, h->lm_k, h->nc, h->dim, h->max_list_len, &v,
-                              h->last_stream ? h->last_stream : h->stream));
+    if (h->kind == PYROPE_IVF_FLAT)
+        CK(ivfflat_lm_scanned_rows(h->ws.lm.p, h->lm_nq, h->lm_P, h->lm_k, h->nc, &v, h->last_stream ? h->last_stream : h->stream));
+    else
+        CK(ivfpq_lm_scanned_codes(h->ws.lm.p, h->lm_nq, h->lm_P, h->lm_k, h->nc, h->dim, h->max_list_len, &v,
+                                  h->last_stream ? h->last_stream : h->stream));
     *codes_out = (int64_t)v;
     return PYROPE_OK;
 }

@@ -130,6 +130,53 @@ __global__ void scatter_i32_kernel(const int32_t* src, const int64_t* idx, int64
     if (i < n) dst[idx[i]] = src[i];
 }
 
+// Coarse ranking in the reference's arithmetic: the fast coarse stage hands P_in >= P_out candidate lists per
+// query; their scores are recomputed exactly as IvfFlatVectorIndex.cs:186-193 / IvfPqVectorIndex.cs:141-147 do
+// (VectorMath.L2Squared / DotProduct / Cosine, single 8-lane accumulator) and the best P_out are emitted in
+// descending order (ties to the lower list index), so the probed set equals the oracle's even when two
+// centroids score within a rounding error of each other.  One CTA per query.
+template <int METRIC>
+__global__ void __launch_bounds__(128) coarse_rerank_kernel(const float* __restrict__ Q, int dim,
+                                                            const float* __restrict__ C, const float* __restrict__ cnorms,
+                                                            const int64_t* __restrict__ pin, int P_in,
+                                                            int64_t* pout, float* sout, int P_out, int Psort) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);   // [Psort]
+    float* qs = reinterpret_cast<float*>(keys + Psort);       // [dim]
+    __shared__ float s_qn;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int d = tid; d < dim; d += blockDim.x) qs[d] = Q[q * dim + d];
+    __syncthreads();
+    if (METRIC == 2 && tid == 0) s_qn = norm_eval(qs, dim);
+    __syncthreads();
+    for (int i = tid; i < Psort; i += blockDim.x) {
+        uint64_t key = 0ull;
+        if (i < P_in) {
+            const int64_t l = pin[q * P_in + i];
+            if (l >= 0) {
+                const float* cv = C + l * dim;
+                float s;
+                if (METRIC == 0) s = -a2_eval<0>(qs, cv, dim);
+                else if (METRIC == 1) s = a2_eval<1>(qs, cv, dim);
+                else {
+                    const float cn = cnorms[l];
+                    s = (s_qn < 1e-6f || cn < 1e-6f) ? 0.f : __fdiv_rn(a2_eval<1>(qs, cv, dim), __fmul_rn(s_qn, cn));
+                }
+                key = make_key(s, (uint32_t)l);
+            }
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_desc<false>(keys, Psort, tid, blockDim.x);
+    for (int i = tid; i < P_out; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        pout[q * P_out + i] = key ? (int64_t)key_pos(key) : -1;
+        if (sout) sout[q * P_out + i] = key ? key_score(key) : 0.f;
+    }
+}
+
 __global__ void row_norms_kernel(const float* X, int64_t n, int dim, int64_t ldx, float* out) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -256,6 +303,21 @@ cudaError_t launch_assign_from_shortlist(int metric, int dim, int64_t n, const f
 cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n, int32_t* dst, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     scatter_i32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, idx, n, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_coarse_rerank_exact(int metric, int dim, int64_t nq, const float* Q, const float* centroids,
+                                       const float* cnorms, const int64_t* probes_in, int P_in, int64_t* probes_out,
+                                       float* scores_out, int P_out, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    const int Psort = next_pow2(P_in < 2 ? 2 : P_in);
+    const size_t smem = sizeof(uint64_t) * (size_t)Psort + sizeof(float) * (size_t)dim;
+    if (metric == kL2)
+        coarse_rerank_kernel<0><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, P_in, probes_out, scores_out, P_out, Psort);
+    else if (metric == kIP)
+        coarse_rerank_kernel<1><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, P_in, probes_out, scores_out, P_out, Psort);
+    else
+        coarse_rerank_kernel<2><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, P_in, probes_out, scores_out, P_out, Psort);
     return cudaGetLastError();
 }
 

@@ -101,9 +101,18 @@ struct IvfFlatScanParams {
     const float* vecs; const uint8_t* dead; const float* norms; const int64_t* labels;
     const float* qnorm;
     int metric; int k; int groups;           // grid.y: probe groups (parts)
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the list-major scan kernel alone
     PairOut out;
 };
 cudaError_t launch_ivfflat_scan(const IvfFlatScanParams& p, cudaStream_t st);
+// List-major variant (ivf_lm.cu): pairs grouped by list, 16 queries share one pass over a list's rows; writes
+// ONE part.  L2 / inner product, dim % 4 == 0 and dim <= 128, no MaxScans budget.
+bool ivfflat_lm_supported(int dim, int metric, int nprobe, int k, int64_t nq, int64_t list_total, bool has_budget);
+size_t ivfflat_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist);
+int ivfflat_lm_launches();
+cudaError_t launch_ivfflat_scan_lm(const IvfFlatScanParams& p, int nlist, void* scratch, int num_sms, cudaStream_t st);
+cudaError_t ivfflat_lm_scanned_rows(const void* scratch, int64_t nq, int nprobe, int k, int nlist, unsigned long long* out,
+                                    cudaStream_t st);
 
 // ---- K5: IVF_PQ LUT build + ADC scan ----------------------------------------------------------
 // Replaces ProductQuantizer.ComputeDistanceTable:98-120 + IvfPqVectorIndex.Search:152-199.
@@ -145,6 +154,10 @@ cudaError_t launch_probe_allow(const int64_t* probes, int64_t nq, int nprobe,
 cudaError_t launch_assign_exact(int metric, int dim, int64_t n, const float* X, int64_t ldx,
                                 int nc, const float* centroids, const float* cnorms,
                                 int32_t* assign, cudaStream_t st);
+// exact-order re-ranking of the coarse stage's candidate lists (P_in >= P_out), best first, ties to the lower index
+cudaError_t launch_coarse_rerank_exact(int metric, int dim, int64_t nq, const float* Q, const float* centroids,
+                                       const float* cnorms, const int64_t* probes_in, int P_in, int64_t* probes_out,
+                                       float* scores_out, int P_out, cudaStream_t st);
 // ComputeNorm:72-100 in the reference's order, one row per thread group
 cudaError_t launch_row_norms_exact(const float* X, int64_t n, int dim, int64_t ldx, float* out,
                                    cudaStream_t st);
