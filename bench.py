@@ -348,7 +348,7 @@ def run_ours(args):
         kms_avg += kms / reps
     alg = algorithmic_work(w, world)
     scanned = 0
-    if w["kind"] == "IVF_PQ":
+    if w["kind"] in ("IVF_PQ", "IVF_FLAT"):
         scanned = ix.last_search_scanned()
     dom = "scan"
     dom_ms = kms_avg if kms_avg > 0 else stage_ms[dom]
@@ -364,7 +364,7 @@ def run_ours(args):
     if alg["bound"] == "hbm":
         if scanned > 0:  # exact unit count: codes scored by this launch x m bytes (roofline section)
             extra["algorithmic_formula_bytes"] = alg["work"]
-            work = float(scanned) * w["m"]
+            work = float(scanned) * (w["m"] if w["kind"] == "IVF_PQ" else w["dim"] * 4)
         achieved = work / (dom_ms / 1e3) / 1e9
         peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (of fallback)"

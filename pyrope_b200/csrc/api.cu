@@ -957,7 +957,8 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         }
         // IvfFlatVectorIndex.cs:186-198 / IvfPqVectorIndex.cs:141-150: rank by the reference's own arithmetic
         CK(launch_coarse_rerank_exact(h->metric, dim, nq, dQ, h->centroids.as<float>(), h->cnorms.as<float>(),
-                                      ws.probes_raw.as<int64_t>(), Pc, ws.probes.as<int64_t>(), nullptr, P, st));
+                                      ws.probes_raw.as<int64_t>(), ws.probe_scores.as<float>(), Pc, ws.probes.as<int64_t>(),
+                                      nullptr, P, (h->kind == PYROPE_IVF_FLAT && max_scans >= 0) ? 1 : 0, st));
         ++launches;
     }
     CK(cudaEventRecord(h->ev[1], st));

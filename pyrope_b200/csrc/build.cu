@@ -138,14 +138,29 @@ __global__ void scatter_i32_kernel(const int32_t* src, const int64_t* idx, int64
 template <int METRIC>
 __global__ void __launch_bounds__(128) coarse_rerank_kernel(const float* __restrict__ Q, int dim,
                                                             const float* __restrict__ C, const float* __restrict__ cnorms,
-                                                            const int64_t* __restrict__ pin, int P_in,
-                                                            int64_t* pout, float* sout, int P_out, int Psort) {
+                                                            const int64_t* __restrict__ pin,
+                                                            const float* __restrict__ sin, int P_in,
+                                                            int64_t* pout, float* sout, int P_out, int Psort, int need_order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);   // [Psort]
     float* qs = reinterpret_cast<float*>(keys + Psort);       // [dim]
     __shared__ float s_qn;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
+    // Fast path: the stage-one scores (fp32, accurate to ~1e-6 relative, sorted descending) already separate the
+    // P_out-th from the (P_out+1)-th candidate by far more than their rounding error, so the probed SET is
+    // settled; unless the caller needs the exact order too (MaxScans budgets walk lists in rank order), copy.
+    if (!need_order && sin && !sout) {
+        bool settled = P_in <= P_out;
+        if (!settled) {
+            const float a = sin[q * P_in + P_out - 1], b = sin[q * P_in + P_out];
+            settled = pin[q * P_in + P_out] < 0 || (a - b) > 2e-5f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
+        }
+        if (settled) {  // block-uniform
+            for (int i = tid; i < P_out; i += blockDim.x) pout[q * P_out + i] = i < P_in ? pin[q * P_in + i] : -1;
+            return;
+        }
+    }
     for (int d = tid; d < dim; d += blockDim.x) qs[d] = Q[q * dim + d];
     __syncthreads();
     if (METRIC == 2 && tid == 0) s_qn = norm_eval(qs, dim);
@@ -307,17 +322,17 @@ cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n
 }
 
 cudaError_t launch_coarse_rerank_exact(int metric, int dim, int64_t nq, const float* Q, const float* centroids,
-                                       const float* cnorms, const int64_t* probes_in, int P_in, int64_t* probes_out,
-                                       float* scores_out, int P_out, cudaStream_t st) {
+                                       const float* cnorms, const int64_t* probes_in, const float* scores_in, int P_in,
+                                       int64_t* probes_out, float* scores_out, int P_out, int need_order, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     const int Psort = next_pow2(P_in < 2 ? 2 : P_in);
     const size_t smem = sizeof(uint64_t) * (size_t)Psort + sizeof(float) * (size_t)dim;
     if (metric == kL2)
-        coarse_rerank_kernel<0><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, P_in, probes_out, scores_out, P_out, Psort);
+        coarse_rerank_kernel<0><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, scores_in, P_in, probes_out, scores_out, P_out, Psort, need_order);
     else if (metric == kIP)
-        coarse_rerank_kernel<1><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, P_in, probes_out, scores_out, P_out, Psort);
+        coarse_rerank_kernel<1><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, scores_in, P_in, probes_out, scores_out, P_out, Psort, need_order);
     else
-        coarse_rerank_kernel<2><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, P_in, probes_out, scores_out, P_out, Psort);
+        coarse_rerank_kernel<2><<<(unsigned)nq, 128, smem, st>>>(Q, dim, centroids, cnorms, probes_in, scores_in, P_in, probes_out, scores_out, P_out, Psort, need_order);
     return cudaGetLastError();
 }
 

@@ -34,8 +34,8 @@ namespace {
 
 constexpr int FG = 16;         // queries per work item
 constexpr int FT = 256;        // threads (8 warps)
-constexpr int FQC = 128;       // candidate queue entries per slot
-constexpr int FSEED = 256;     // rows sampled per query for the starting threshold
+constexpr int FQC = 256;       // candidate queue entries per slot
+constexpr int FSEED = 512;     // rows sampled per query for the starting threshold
 constexpr int FREDO_QCAP = 2048;
 
 __device__ __forceinline__ unsigned long long pack2(float a, float b) {

@@ -154,10 +154,12 @@ cudaError_t launch_probe_allow(const int64_t* probes, int64_t nq, int nprobe,
 cudaError_t launch_assign_exact(int metric, int dim, int64_t n, const float* X, int64_t ldx,
                                 int nc, const float* centroids, const float* cnorms,
                                 int32_t* assign, cudaStream_t st);
-// exact-order re-ranking of the coarse stage's candidate lists (P_in >= P_out), best first, ties to the lower index
+// exact-order re-ranking of the coarse stage's candidate lists (P_in >= P_out), best first, ties to the lower index;
+// scores_in (stage-one scores, sorted descending) lets queries whose probed set is already settled skip it
+// unless need_order is set
 cudaError_t launch_coarse_rerank_exact(int metric, int dim, int64_t nq, const float* Q, const float* centroids,
-                                       const float* cnorms, const int64_t* probes_in, int P_in, int64_t* probes_out,
-                                       float* scores_out, int P_out, cudaStream_t st);
+                                       const float* cnorms, const int64_t* probes_in, const float* scores_in, int P_in,
+                                       int64_t* probes_out, float* scores_out, int P_out, int need_order, cudaStream_t st);
 // ComputeNorm:72-100 in the reference's order, one row per thread group
 cudaError_t launch_row_norms_exact(const float* X, int64_t n, int dim, int64_t ldx, float* out,
                                    cudaStream_t st);
