@@ -139,8 +139,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     float* sterms = reinterpret_cast<float*>(tmem_ptr_s + 4);  // [4 warps][bias 2*BN | scale 2*BN]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
-    const uint32_t tfull0 = smem_u32(&bars[4]), tempty0 = smem_u32(&bars[6]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
 
     const int64_t qtiles = (p.nq + BM - 1) / BM;
     const int64_t qt = blockIdx.x % qtiles, sp = blockIdx.x / qtiles;
