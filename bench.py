@@ -452,7 +452,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * args.steps),
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -505,10 +505,28 @@ def run_reference(args):
             "config": {"workload": describe(w), "reduced": w["reduced"], **build_info},
             "cpu_baseline": {"value": round(value, 2), "unit": "QPS", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 2), "unit": "QPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything libraries print (NCCL's version banner, ...) was
+    redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process (native libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -348,6 +348,7 @@ struct FlRedo {
     const int2* items; const int32_t* pair_off; const int32_t* pairp;
     const int2* redo; const int32_t* redo_cnt;
     unsigned long long* pool; int32_t* pool_cnt; int pslots; int k;
+    const uint32_t* pool_thr;  // the query's current threshold: a valid bound, so the redo queue starts warm
 };
 template <int METRIC>
 __global__ void __launch_bounds__(256) ivf_lm_redo_kernel(FlRedo a) {
@@ -366,6 +367,8 @@ __global__ void __launch_bounds__(256) ivf_lm_redo_kernel(FlRedo a) {
         __syncthreads();
         CtaQueue Qu{keys, &s_cnt, &s_thr, FREDO_QCAP, a.k};
         Qu.reset(tid);
+        __syncthreads();
+        if (tid == 0) s_thr = (uint64_t)__ldcg(a.pool_thr + en.x) << 32;  // keys at or below it cannot be in the top k
         __syncthreads();
         float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane * 4 < a.dim) qv = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)en.x * a.dim) + lane);
@@ -533,7 +536,7 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
     FlRedo rd{};
     rd.Q = p.Q; rd.dim = p.dim; rd.vecs = p.vecs; rd.dead = p.dead; rd.list_off = p.list_off; rd.items = items;
     rd.pair_off = loff; rd.pairp = pairp; rd.redo = redo; rd.redo_cnt = redo_cnt; rd.pool = pool; rd.pool_cnt = pool_cnt;
-    rd.pslots = P; rd.k = p.k;
+    rd.pslots = P; rd.k = p.k; rd.pool_thr = pool_thr;
     ivf_lm_redo_kernel<METRIC><<<(unsigned)(2 * num_sms), 256, sizeof(uint64_t) * FREDO_QCAP, st>>>(rd);
 
     FlFinal fp{};

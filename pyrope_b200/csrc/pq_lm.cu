@@ -669,6 +669,7 @@ struct LmRedo {
     const uint8_t* codes; const uint8_t* dead;
     const unsigned char* iblk; int blk; const int2* redo; const int32_t* redo_cnt;
     unsigned long long* pool; int32_t* pool_cnt; int pslots; int k;
+    const uint32_t* pool_thr;  // the query's current threshold: a valid bound, so the redo queue starts warm
 };
 __global__ void __launch_bounds__(256) ivfpq_lm_redo_kernel(LmRedo a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -689,6 +690,8 @@ __global__ void __launch_bounds__(256) ivfpq_lm_redo_kernel(LmRedo a) {
         for (int d = tid; d < a.dim; d += 256) res[d] = a.Q[(size_t)en.x * a.dim + d] - a.centroids[(size_t)l * a.dim + d];
         CtaQueue Qu{keys, &s_cnt, &s_thr, REDO_QCAP, a.k};
         Qu.reset(tid);
+        __syncthreads();
+        if (tid == 0) s_thr = (uint64_t)__ldcg(a.pool_thr + en.x) << 32;  // keys at or below it cannot be in the top k
         __syncthreads();
         lut_direct<1>(a.codebook, a.ksub, a.dim / 16, res, a.dim, lut, tid, 256);
         __syncthreads();
@@ -952,7 +955,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmRedo rd{};
     rd.Q = p.Q; rd.dim = p.dim; rd.centroids = p.centroids; rd.codebook = p.codebook; rd.ksub = p.ksub;
     rd.codes = p.codes; rd.dead = p.dead; rd.iblk = iblk; rd.blk = L.blk; rd.redo = redo; rd.redo_cnt = redo_cnt;
-    rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k;
+    rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k; rd.pool_thr = pool_thr;
     const size_t redo_smem = sizeof(uint64_t) * REDO_QCAP + sizeof(float) * (4096 + (size_t)p.dim);
     mark();
     ivfpq_lm_redo_kernel<<<(unsigned)(2 * num_sms), 256, redo_smem, st>>>(rd);
