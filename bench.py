@@ -190,6 +190,60 @@ def make_queries(torch, w: dict):
     return q.view(w["nq"], w["dim"])
 
 
+def recall_at_10(pg, torch, w: dict, ix, Q, nq_eval: int, log) -> dict:
+    """recall@10 of the configured index against exact FLAT top-10 (the reference never computes
+    recall; the metric is quoted 'at fixed recall@10', i.e. at the recall this (nlist, nprobe, m) gives).
+    Exact answers: the base is regenerated chunk by chunk into a FLAT index on the CUDA-core path (no split
+    copies), per-chunk top-10 lists are merged with pyrope_topk_merge_device.  Setup work, untimed."""
+    from pyrope_b200 import _lib
+    k = 10
+    nq_eval = min(nq_eval, w["nq"])
+    metric = {"L2": pg.L2, "IP": pg.INNER_PRODUCT, "COSINE": pg.COSINE}[w["metric"]]
+    dim, n = w["dim"], w["n"]
+    q = Q[:nq_eval].contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+    chunk = min(n, 10_000_000)
+    nchunks = (n + chunk - 1) // chunk
+    S = torch.zeros((nchunks, nq_eval, k), dtype=torch.float32, device="cuda")
+    R = torch.full((nchunks, nq_eval, k), -1, dtype=torch.int64, device="cuda")
+    cnt = torch.empty((nq_eval,), dtype=torch.int32, device="cuda")
+    stage = torch.empty(chunk * dim, dtype=torch.float32, device="cuda")
+    labels = torch.empty(chunk, dtype=torch.int64, device="cuda")
+    old = os.environ.get("PYROPE_FLAT_TC")
+    os.environ["PYROPE_FLAT_TC"] = "0"
+    try:
+        for c in range(nchunks):
+            r0 = c * chunk
+            rows = min(chunk, n - r0)
+            _lib.fill_uniform_device(stage.data_ptr(), rows * dim, 42, r0 * dim, stream=stream)
+            labels[:rows] = torch.arange(r0, r0 + rows, device="cuda")
+            torch.cuda.synchronize()
+            fx = pg.GpuIndex(pg.FLAT, dim, metric)
+            fx.add_device(stage.data_ptr(), rows, labels.data_ptr())
+            fx.search_device(q.data_ptr(), nq_eval, k, S[c].data_ptr(), R[c].data_ptr(), cnt.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            fx.close()
+    finally:
+        if old is None:
+            os.environ.pop("PYROPE_FLAT_TC", None)
+        else:
+            os.environ["PYROPE_FLAT_TC"] = old
+    ms = torch.empty((nq_eval, k), dtype=torch.float32, device="cuda")
+    mr = torch.empty((nq_eval, k), dtype=torch.int64, device="cuda")
+    _lib.topk_merge_device(nq_eval, nchunks, k, k, S.data_ptr(), R.data_ptr(), ms.data_ptr(), mr.data_ptr(), cnt.data_ptr(),
+                           stream=stream)
+    gs = torch.empty((nq_eval, k), dtype=torch.float32, device="cuda")
+    gr = torch.empty((nq_eval, k), dtype=torch.int64, device="cuda")
+    ix.search_device(q.data_ptr(), nq_eval, k, gs.data_ptr(), gr.data_ptr(), cnt.data_ptr(), nprobe=w.get("nprobe", -1), stream=stream)
+    torch.cuda.synchronize()
+    truth, got = mr.cpu().numpy(), gr.cpu().numpy()
+    hit = sum(len(set(t.tolist()) & set(g.tolist()) - {-1}) for t, g in zip(truth, got))
+    del stage, labels, S, R
+    torch.cuda.empty_cache()
+    return {"recall_at_10": round(hit / (nq_eval * k), 4), "recall_queries": nq_eval,
+            "recall_truth": "exact FLAT top-10 over the full base (GPU CUDA-core path, chunked)"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's loops on the index the GPU built
 # ------------------------------------------------------------------------------------------------
@@ -426,6 +480,14 @@ def run_ours(args):
     e2e = {"value": round(nq * args.steps / e2e_s, 1), "unit": "QPS", "h2d_bytes_per_step": nq * dim * 4,
            "d2h_bytes_per_step": nq * k * 12 + nq * 4}
 
+    # ---- recall@10 of this configuration (N=1, IVF workloads): what "at fixed recall@10" refers to
+    recall = {}
+    if world == 1 and w["kind"] != "FLAT" and args.recall_queries > 0:
+        try:
+            recall = recall_at_10(pg, torch, w, ix, Q, args.recall_queries, log)
+        except Exception as ex:  # never lose the bench line over the quality read-out
+            recall = {"recall_at_10": None, "recall_error": str(ex)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -447,7 +509,7 @@ def run_ours(args):
             "config": {"workload": describe(w), "reduced": w["reduced"], "l2_policy": "inputs larger than L2 (index "
                        f"{w['n'] * w.get('m', w['dim'] * 4) / 1e6:.0f} MB scanned region vs 126 MB L2)",
                        "parallelism": f"lists sharded list_id % {world}" if w["kind"] != "FLAT" else f"rows sharded in {world} blocks",
-                       "exchange": ("nccl all_gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
+                       **recall, "exchange": ("nccl all_gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
                                    ("nccl all_gather of per-rank top-k + on-device merge" if world > 1 else "none"), **build_info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * args.steps),
             "roofline": roofline, "cpu_baseline": cpu,
@@ -536,6 +598,7 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("PYROPE_BENCH_SCALE", "1.0")))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--recall-queries", type=int, default=200, help="queries used for the recall@10 read-out (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
