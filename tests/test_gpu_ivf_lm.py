@@ -86,3 +86,17 @@ def test_ivfflat_lm_deletes_buffer_and_query_major_agree(gpu, monkeypatch):
     assert qm.last_search_launches() < 10
     assert_batch_equivalent(other, got, ctx="query-major vs list-major")
     assert recall_at_k(other[0], got[0], 10) > 0.999
+
+
+def test_ivfflat_lm_edge_shapes(gpu):
+    rng = np.random.default_rng(10)
+    centers = rng.random((3, 64), dtype=np.float32)
+    base = np.concatenate([c + np.float32(1e-3) * rng.standard_normal((150, 64)).astype(np.float32) for c in centers])
+    q = np.concatenate([base[:40] + np.float32(1e-3), rng.random((40, 64), dtype=np.float32)]).astype(np.float32)
+    ref, ix = _pair(gpu, base, 64, 8, orc.L2, gpu.L2)
+    for k, nprobe in ((10, 1), (10, 64), (400, 2), (1000, 8)):
+        got = _s(ix, q, k, nprobe=nprobe)
+        assert_batch_equivalent(ref.search_batch(q, k, nprobe=nprobe), got, ctx=f"ivf lm edge k={k} nprobe={nprobe}")
+    for nq, k, nprobe in ((80, 10, 3), (64, 50, 2), (80, 10, 3)):   # scratch re-initialised between searches
+        assert_batch_equivalent(ref.search_batch(q[:nq], k, nprobe=nprobe), _s(ix, q[:nq], k, nprobe=nprobe),
+                                ctx=f"ivf lm repeat nq={nq} k={k}")

@@ -161,3 +161,29 @@ def test_tc_shortlist_kmeans_matches_exact_path(gpu, monkeypatch):
     c2, it2 = gpu.kmeans_train(X, 2500, gpu.L2, 3, 42)
     assert it1 == it2
     np.testing.assert_array_equal(c1, c2)
+
+
+def test_lm_edge_shapes_empty_lists_and_short_results(gpu):
+    """nprobe > nlist, lists left empty by k-means, k larger than everything the probes hold, and a batch that
+    mixes all of it: result counts and contents must follow the reference (count = min(k, scored))."""
+    rng = np.random.default_rng(9)
+    # 3 tight blobs, nlist = 8: several centroids collapse onto the same points -> empty lists after assignment
+    centers = rng.random((3, 128), dtype=np.float32)
+    base = np.concatenate([c + np.float32(1e-3) * rng.standard_normal((150, 128)).astype(np.float32) for c in centers])
+    q = np.concatenate([base[:40] + np.float32(1e-3), rng.random((40, 128), dtype=np.float32)]).astype(np.float32)
+    ref, ix = _pair(gpu, base, 128, 8)
+    sizes = np.diff(ix.lists()[0])
+    for k, nprobe in ((10, 1), (10, 64), (500, 2), (1000, 8)):
+        rid, rsc, rcn = ref.search_batch(q, k, nprobe=nprobe)
+        got = _s(ix, q, k, nprobe=nprobe)
+        assert_batch_equivalent((rid, rsc, rcn), got, ctx=f"lm edge k={k} nprobe={nprobe} sizes={sizes.tolist()}")
+        assert (got[2] <= min(k, len(base))).all()
+
+
+def test_lm_repeated_searches_reuse_scratch(gpu, mid):
+    """Different batch sizes / k / nprobe back to back on one handle: per-search scratch (pools, thresholds,
+    item blocks) must be re-initialised every time."""
+    base, q, ref, ix = mid
+    for nq, k, nprobe in ((300, 10, 8), (64, 100, 2), (200, 1, 16), (300, 10, 8)):
+        assert_batch_equivalent(ref.search_batch(q[:nq], k, nprobe=nprobe), _s(ix, q[:nq], k, nprobe=nprobe),
+                                ctx=f"lm repeat nq={nq} k={k} nprobe={nprobe}")
