@@ -119,6 +119,15 @@ int pyrope_index_get_codebooks(pyrope_index *h, float *codebooks_out, int32_t *k
 int pyrope_index_get_lists(pyrope_index *h, int64_t *offsets_out, int64_t *rows_out,
                            uint8_t *codes_out, int64_t *total_out);
 
+/* ---- snapshot / load: replace IVectorIndex.Snapshot / Load (BruteForceVectorIndex.cs:58-107,
+ *      IvfFlatVectorIndex.cs:233-298; IVF_PQ's are no-ops in the reference, IvfPqVectorIndex.cs:228-229).
+ *      One binary file per index, written to path + ".tmp" and moved into place like DeltaVectorIndex.cs:160-212
+ *      does.  load() requires an index created with the same kind / dim / metric / m / k and replaces its whole
+ *      state (rows, tombstones, trained codebooks, inverted lists).  Missing file -> NOT_FOUND
+ *      (FileNotFoundException in the shim), foreign file -> INVALID_ARG. */
+int pyrope_index_snapshot(pyrope_index *h, const char *path);
+int pyrope_index_load(pyrope_index *h, const char *path);
+
 /* ---- stats: replaces IVectorIndex.GetStats (O(1), host-side, never a device sync;
  *      BruteForceVectorIndex.cs:119-131, IvfFlatVectorIndex.cs:300-312).  live_rows counts every
  *      searchable row; the shim reproduces IvfPqVectorIndex.cs:230's hard-coded 0 itself. */

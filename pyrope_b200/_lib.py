@@ -56,6 +56,8 @@ SIGNATURES = {
     "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
     "pyrope_index_get_lists": (C.c_int, [vp, vp, vp, vp, i64p]),
+    "pyrope_index_snapshot": (C.c_int, [vp, C.c_char_p]),
+    "pyrope_index_load": (C.c_int, [vp, C.c_char_p]),
     "pyrope_index_stats": (C.c_int, [vp, i64p, i64p, i32p, i32p]),
     "pyrope_index_search_batch": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
     "pyrope_index_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp]),
@@ -216,6 +218,12 @@ class GpuIndex:
         codes = np.zeros((max(tot.value, 1), self.m), np.uint8) if self.kind == IVF_PQ else None
         check(load().pyrope_index_get_lists(self._h, _p(off), _p(rows), _p(codes), C.byref(tot)))
         return off, rows[:tot.value], (codes[:tot.value] if codes is not None else None)
+
+    def snapshot(self, path: str):
+        check(load().pyrope_index_snapshot(self._h, str(path).encode()))
+
+    def load(self, path: str):
+        check(load().pyrope_index_load(self._h, str(path).encode()))
 
     def stats(self):
         live, buf = C.c_int64(0), C.c_int64(0)

@@ -1334,6 +1334,186 @@ int pyrope_index_get_lists(pyrope_index* h, int64_t* offsets_out, int64_t* rows_
     return PYROPE_OK;
 }
 
+// ---- snapshot / load (IVectorIndex.Snapshot / Load; DeltaVectorIndex.cs:160-212 writes tmp-then-move) -------
+// Binary, little-endian, self-describing enough to refuse a mismatched index.  The reference's formats are JSON
+// (BruteForce / IVF_FLAT) or a no-op (IVF_PQ, IvfPqVectorIndex.cs:228-229); a drop-in only has to round-trip
+// its own state, which this does for all three kinds, trained codebooks and inverted lists included.
+}  // extern "C"
+namespace {
+struct SnapIO {
+    FILE* f = nullptr;
+    bool ok = true;
+    std::vector<unsigned char> stage;
+    void w(const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
+    void r(void* p, size_t n) { if (ok && n && fread(p, 1, n, f) != n) ok = false; }
+    template <typename T> void wv(T v) { w(&v, sizeof v); }
+    template <typename T> T rv() { T v{}; r(&v, sizeof v); return v; }
+    template <typename T> void wvec(const std::vector<T>& v) { wv<uint64_t>(v.size()); w(v.data(), sizeof(T) * v.size()); }
+    template <typename T> void rvec(std::vector<T>& v) {
+        uint64_t n = rv<uint64_t>();
+        if (!ok || n > ((uint64_t)1 << 40)) { ok = false; return; }
+        v.resize((size_t)n);
+        r(v.data(), sizeof(T) * v.size());
+    }
+    // device array <-> file through a 64 MiB host stage
+    int wdev(const void* d, size_t bytes) {
+        wv<uint64_t>(bytes);
+        stage.resize(std::min<size_t>(bytes, (size_t)64 << 20));
+        for (size_t o = 0; o < bytes; o += stage.size()) {
+            size_t n = std::min(stage.size(), bytes - o);
+            CK(cudaMemcpy(stage.data(), (const char*)d + o, n, cudaMemcpyDeviceToHost));
+            w(stage.data(), n);
+        }
+        return PYROPE_OK;
+    }
+    int rdev(DevBuf& b, cudaStream_t st) {
+        uint64_t bytes = rv<uint64_t>();
+        if (!ok || bytes > ((uint64_t)1 << 42)) { ok = false; return PYROPE_OK; }
+        if (bytes == 0) return PYROPE_OK;
+        TRY(b.ensure((size_t)bytes, 0, st, true));
+        stage.resize(std::min<size_t>((size_t)bytes, (size_t)64 << 20));
+        for (size_t o = 0; o < bytes; o += stage.size()) {
+            size_t n = std::min(stage.size(), (size_t)bytes - o);
+            r(stage.data(), n);
+            if (!ok) return PYROPE_OK;
+            CK(cudaMemcpy((char*)b.p + o, stage.data(), n, cudaMemcpyHostToDevice));
+        }
+        return PYROPE_OK;
+    }
+};
+constexpr char kSnapMagic[8] = {'P', 'Y', 'R', 'G', 'P', 'U', '0', '1'};
+}  // namespace
+extern "C" {
+
+int pyrope_index_snapshot(pyrope_index* h, const char* path) {
+    if (!h || !path || !*path) return fail(PYROPE_ERR_INVALID_ARG, "Path cannot be empty");
+    std::lock_guard<std::mutex> g(h->mu);
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->last_stream) CK(cudaStreamSynchronize(h->last_stream));
+    const std::string tmp = std::string(path) + ".tmp";
+    SnapIO io;
+    io.f = fopen(tmp.c_str(), "wb");
+    if (!io.f) return fail(PYROPE_ERR_INVALID_ARG, "cannot open %s for writing", tmp.c_str());
+    int rc = PYROPE_OK;
+    auto body = [&]() -> int {
+        io.w(kSnapMagic, 8);
+        io.wv<int32_t>(h->kind); io.wv<int32_t>(h->dim); io.wv<int32_t>(h->metric); io.wv<int32_t>(h->nlist);
+        io.wv<int32_t>(h->m); io.wv<int32_t>(h->k); io.wv<int64_t>(h->next_row);
+        const Segment& s = h->seg;
+        io.wv<int64_t>(s.nslots); io.wv<int64_t>(s.live); io.wv<int64_t>(s.ndead);
+        TRY(io.wdev(s.X.p, sizeof(float) * (size_t)s.nslots * h->dim));
+        TRY(io.wdev(s.labels.p, sizeof(int64_t) * (size_t)s.nslots));
+        io.wvec(s.dead_h); io.wvec(s.slot_row); io.wvec(s.free_stack);
+        io.wv<int32_t>(h->built ? 1 : 0); io.wv<int32_t>(h->frozen ? 1 : 0); io.wv<int32_t>(h->nc);
+        io.wv<int32_t>(h->shard_rank); io.wv<int32_t>(h->shard_world);
+        const bool have_cent = h->nc > 0 && h->centroids.p;
+        TRY(io.wdev(h->centroids.p, have_cent ? sizeof(float) * (size_t)h->nc * h->dim : 0));
+        const bool have_cb = h->kind == PYROPE_IVF_PQ && h->codebook.p && !h->ksub.empty();
+        TRY(io.wdev(h->codebook.p, have_cb ? sizeof(float) * (size_t)h->m * h->k * h->sub : 0));
+        io.wvec(h->ksub);
+        io.wv<int64_t>(h->built ? h->list_total : 0);
+        if (h->built) {
+            io.wvec(h->list_off_h);
+            TRY(io.wdev(h->list_rows.p, sizeof(int64_t) * (size_t)h->list_total));
+            TRY(io.wdev(h->list_labels.p, sizeof(int64_t) * (size_t)h->list_total));
+            if (h->kind == PYROPE_IVF_FLAT) TRY(io.wdev(h->list_vecs.p, sizeof(float) * (size_t)h->list_total * h->dim));
+            else TRY(io.wdev(h->list_codes.p, (size_t)h->list_total * h->m));
+            io.wvec(h->list_dead_h);
+        }
+        return PYROPE_OK;
+    };
+    rc = body();
+    const bool ok = io.ok && fclose(io.f) == 0;
+    if (rc != PYROPE_OK) { remove(tmp.c_str()); return rc; }
+    if (!ok) { remove(tmp.c_str()); return fail(PYROPE_ERR_INVALID_STATE, "short write to %s", tmp.c_str()); }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(PYROPE_ERR_INVALID_STATE, "cannot move %s into place", tmp.c_str()); }
+    return PYROPE_OK;
+}
+
+int pyrope_index_load(pyrope_index* h, const char* path) {
+    if (!h || !path || !*path) return fail(PYROPE_ERR_INVALID_ARG, "Path cannot be empty");
+    std::lock_guard<std::mutex> g(h->mu);
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->last_stream) CK(cudaStreamSynchronize(h->last_stream));
+    SnapIO io;
+    io.f = fopen(path, "rb");
+    if (!io.f) return fail(PYROPE_ERR_NOT_FOUND, "Snapshot file not found: %s", path);  // FileNotFoundException
+    cudaStream_t st = h->stream;
+    auto body = [&]() -> int {
+        char magic[8];
+        io.r(magic, 8);
+        if (!io.ok || memcmp(magic, kSnapMagic, 8) != 0) return fail(PYROPE_ERR_INVALID_ARG, "%s is not a pyrope_gpu snapshot", path);
+        const int kind = io.rv<int32_t>(), dim = io.rv<int32_t>(), metric = io.rv<int32_t>(), nlist = io.rv<int32_t>();
+        const int m = io.rv<int32_t>(), k = io.rv<int32_t>();
+        if (kind != h->kind || metric != h->metric || m != h->m || k != h->k) return fail(PYROPE_ERR_INVALID_ARG, "snapshot is of a different index type");
+        if (dim != h->dim) return fail(PYROPE_ERR_DIMENSION, "Vector dimension mismatch");
+        h->nlist = nlist;
+        h->next_row = io.rv<int64_t>();
+        Segment& s = h->seg;
+        s.clear();
+        const int64_t nslots = io.rv<int64_t>();
+        s.live = io.rv<int64_t>(); s.ndead = io.rv<int64_t>();
+        if (!io.ok || nslots < 0) return fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
+        TRY(s.reserve(std::max<int64_t>(nslots, 1), st, true));
+        s.nslots = nslots;
+        { DevBuf t; TRY(io.rdev(t, st)); if (t.p) CK(cudaMemcpy(s.X.p, t.p, sizeof(float) * (size_t)nslots * dim, cudaMemcpyDeviceToDevice)); }
+        { DevBuf t; TRY(io.rdev(t, st)); if (t.p) CK(cudaMemcpy(s.labels.p, t.p, sizeof(int64_t) * (size_t)nslots, cudaMemcpyDeviceToDevice)); }
+        io.rvec(s.dead_h); io.rvec(s.slot_row); io.rvec(s.free_stack);
+        if (!io.ok || (int64_t)s.dead_h.size() != nslots) return fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
+        if (nslots) CK(cudaMemcpy(s.dead.p, s.dead_h.data(), (size_t)nslots, cudaMemcpyHostToDevice));
+        if (s.cosine && nslots) CK(launch_row_norms_exact(s.X.as<float>(), nslots, dim, dim, s.norms.as<float>(), st));
+        s.tc_dirty = true;
+        h->tc_seg.invalidate();
+        h->built = io.rv<int32_t>() != 0; h->frozen = io.rv<int32_t>() != 0; h->nc = io.rv<int32_t>();
+        h->shard_rank = io.rv<int32_t>(); h->shard_world = io.rv<int32_t>();
+        TRY(io.rdev(h->centroids, st));
+        TRY(io.rdev(h->codebook, st));
+        io.rvec(h->ksub);
+        if (h->kind == PYROPE_IVF_PQ && !h->ksub.empty()) {
+            TRY(h->ksub_d.ensure(sizeof(int32_t) * h->ksub.size(), 0, st, true));
+            CK(cudaMemcpy(h->ksub_d.p, h->ksub.data(), sizeof(int32_t) * h->ksub.size(), cudaMemcpyHostToDevice));
+        }
+        h->list_total = io.rv<int64_t>();
+        h->list_ndead = 0;
+        h->list_dead_h.clear();
+        h->list_dead.release();
+        h->max_list_len = 0;
+        if (h->built) {
+            io.rvec(h->list_off_h);
+            if (!io.ok || (int)h->list_off_h.size() != h->nc + 1) return fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
+            TRY(h->list_off.ensure(sizeof(int64_t) * h->list_off_h.size(), 0, st, true));
+            CK(cudaMemcpy(h->list_off.p, h->list_off_h.data(), sizeof(int64_t) * h->list_off_h.size(), cudaMemcpyHostToDevice));
+            for (int c = 0; c < h->nc; ++c) h->max_list_len = std::max(h->max_list_len, h->list_off_h[(size_t)c + 1] - h->list_off_h[(size_t)c]);
+            TRY(io.rdev(h->list_rows, st));
+            TRY(io.rdev(h->list_labels, st));
+            if (h->kind == PYROPE_IVF_FLAT) TRY(io.rdev(h->list_vecs, st)); else TRY(io.rdev(h->list_codes, st));
+            std::vector<uint8_t> ld;
+            io.rvec(ld);
+            if (!ld.empty()) {
+                TRY(ensure_list_dead(h));
+                h->list_dead_h = ld;
+                for (uint8_t b : ld) h->list_ndead += b ? 1 : 0;
+                CK(cudaMemcpy(h->list_dead.p, ld.data(), ld.size(), cudaMemcpyHostToDevice));
+            }
+            TRY(h->cnorms.ensure(sizeof(float) * (size_t)std::max(h->nc, 1), 0, st, true));
+            if (h->metric == kCosine) {
+                CK(launch_row_norms_exact(h->centroids.as<float>(), h->nc, dim, dim, h->cnorms.as<float>(), st));
+                if (h->kind == PYROPE_IVF_FLAT && h->list_total) {
+                    TRY(h->list_norms.ensure(sizeof(float) * (size_t)h->list_total, 0, st, true));
+                    CK(launch_row_norms_exact(h->list_vecs.as<float>(), h->list_total, dim, dim, h->list_norms.as<float>(), st));
+                }
+            }
+        }
+        h->tc_cent.invalidate();
+        if (h->kind != PYROPE_FLAT) { h->row_loc.assign((size_t)h->next_row, -1); h->lists_loc_valid = false; }
+        CK(cudaStreamSynchronize(st));
+        return io.ok ? PYROPE_OK : fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
+    };
+    const int rc = body();
+    fclose(io.f);
+    return rc;
+}
+
 int pyrope_index_stats(pyrope_index* h, int64_t* live_rows, int64_t* buffer_rows, int* dim, int* metric) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     if (live_rows) *live_rows = h->seg.live + (h->built ? h->list_total - h->list_ndead : 0);
