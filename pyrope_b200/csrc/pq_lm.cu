@@ -55,8 +55,8 @@ constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;
 constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 16;
 constexpr int LM_SMEM = LM_LUT_BYTES + 2 * LM_BLK_MAX + LM_QS * LM_QC * 8;
-constexpr int SEED_NQ = 4;          // queries per seed CTA (share the codebook reads)
-constexpr int SEED_CAP = 2048;      // sampled distances per query
+constexpr int SEED_NQ = 2;          // queries per seed CTA (share the codebook reads; small tables -> 5 CTAs/SM)
+constexpr int SEED_CAP = 1024;      // sampled distances per query
 constexpr int REDO_QCAP = 2048;
 
 struct __align__(16) LmHeader {
@@ -339,7 +339,10 @@ __global__ void __launch_bounds__(256) ivfpq_lm_seed_kernel(LmSeed a) {
         }
         if (tid == 0) s_more = 0;
         __syncthreads();
-        if (s_list[0] < 0 && s_list[1] < 0 && s_list[2] < 0 && s_list[3] < 0) break;
+        bool any_list = false;
+#pragma unroll
+        for (int j = 0; j < SEED_NQ; ++j) any_list |= s_list[j] >= 0;
+        if (!any_list) break;
         for (int i = tid; i < SEED_NQ * dim; i += 256) {
             const int j = i / dim, d = i - j * dim;
             const int64_t l = s_list[j];
@@ -969,7 +972,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, L.pool_cap));
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
-    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, 256, fsm, st>>>(fp);
+    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, (P * p.k <= 1024 ? 128 : 256), fsm, st>>>(fp);
     mark();
     if (stage_dbg && nsev == 7) {
         cudaEventSynchronize(sev[6]);
