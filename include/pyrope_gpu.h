@@ -90,6 +90,10 @@ int pyrope_index_delete_row(pyrope_index *h, int64_t row);
  * (the seenIds skip at IvfFlatVectorIndex.cs:210, IvfPqVectorIndex.cs:170). */
 int pyrope_index_shadow_row(pyrope_index *h, int64_t row, int shadowed);
 
+/* Replace the label of every row: labels_by_row[r] for row ordinal r, n_rows >= rows ever added.  Used after
+ * pyrope_index_load by a shim whose labels are process-local id ordinals. */
+int pyrope_index_set_labels(pyrope_index *h, int64_t n_rows, const int64_t *labels_by_row);
+
 /* ---- build: replaces IVectorIndex.Build (IvfFlatVectorIndex.cs:85-145, IvfPqVectorIndex.cs:55-116;
  *      FLAT is a no-op, BruteForceVectorIndex.cs:56).  Training follows KMeansUtils.Train
  *      (KMeansUtils.cs:10-68: System.Random init seed 42 / 123 / 42+m, <=10 Lloyd iterations,
@@ -194,6 +198,67 @@ const char *pyrope_batcher_last_error(void);
 int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float *d_scores,
                              const int64_t *d_rows, float *d_scores_out, int64_t *d_rows_out,
                              int32_t *d_counts_out, void *stream);
+
+/* ---- Head+Tail on device: replaces DeltaVectorIndex (Vector/DeltaVectorIndex.cs) when BOTH sides are GPU
+ *      indexes — a small mutable FLAT head and an IVF_FLAT / IVF_PQ / FLAT tail (VectorIndexRegistry.cs:110-111).
+ *      Identity across the two sides is the row LABEL: the shim passes its id ordinal (Dictionary<string,long>) as
+ *      the label of every row it adds to either side, so "same id" == "same label".  The delta object borrows the
+ *      two handles (destroying it leaves them alive); writes keep going to the handles directly
+ *      (Add/Upsert -> head, Delete -> both, DeltaVectorIndex.cs:26-74). */
+typedef struct pyrope_delta pyrope_delta;
+/* DeltaVectorIndex..ctor :18-28: dimension / metric mismatch -> INVALID_ARG (ArgumentException). */
+int pyrope_delta_create(pyrope_index *head, pyrope_index *tail, pyrope_delta **out);
+int pyrope_delta_destroy(pyrope_delta *d);
+/* DeltaVectorIndex.Search :76-122 for nq queries: head top-k and tail top-k with the SAME options (:85,88),
+ * merged on the device — the head's copy of a label replaces the tail's, descending score, first topk.
+ * One H2D of the queries, one D2H of the results, no host round trip between the stages.
+ * topk <= 0 -> OUT_OF_RANGE (the FLAT head throws first, BruteForceVectorIndex.cs:278). */
+int pyrope_delta_search_batch(pyrope_delta *d, int64_t nq, const float *Q, int topk, int64_t max_scans,
+                              int nprobe, float *scores_out, int64_t *labels_out, int32_t *counts_out);
+int pyrope_delta_search_batch_device(pyrope_delta *d, int64_t nq, const float *dQ, int topk,
+                                     int64_t max_scans, int nprobe, float *d_scores, int64_t *d_labels,
+                                     int32_t *d_counts, void *stream);
+/* DeltaVectorIndex.Build :124-158 (compaction) without the per-vector Scan() -> Add loop: the head's live rows
+ * move device-to-device, in scan order, into the tail's write buffer (a label the tail already buffers is
+ * overwritten in place, one that sits in an inverted list is shadowed — Dictionary semantics of
+ * IvfFlatVectorIndex.cs:47), every head row is tombstoned, then the tail is built.  moved_out = rows moved;
+ * tail_rows_out (nullable, one entry per moved row in head scan order) = the tail row ordinal now holding it. */
+int pyrope_delta_compact(pyrope_delta *d, int64_t *moved_out, int64_t *tail_rows_out);
+/* DeltaVectorIndex.GetStats :224-239: head count + tail count (duplicates counted twice, as there). */
+int pyrope_delta_stats(pyrope_delta *d, int64_t *count_out);
+/* DeltaVectorIndex.Snapshot / Load :160-222: path + ".head", path + ".tail" and a manifest at path. */
+int pyrope_delta_snapshot(pyrope_delta *d, const char *path);
+int pyrope_delta_load(pyrope_delta *d, const char *path);
+
+/* ---- the reference's index classes with their STRING ids (csrc/vindex.cu): the host half of the drop-in.
+ *      One pyrope_vindex is a BruteForceVectorIndex / IvfFlatVectorIndex / IvfPqVectorIndex (kind) or a
+ *      DeltaVectorIndex over two of them; it keeps the id dictionaries those classes keep and maps their
+ *      Add / Upsert / Delete / Build / Search semantics onto the row-ordinal entry points above, so the C# class
+ *      behind IVectorIndex is a one-line forwarder per method.  Search returns id ORDINALS (process-wide, the
+ *      row labels); pyrope_vindex_id turns one into its UTF-8 string.  Errors: pyrope_vindex_last_error().
+ *      Status codes map to the exceptions the reference throws: INVALID_ARG -> ArgumentException ("Id cannot be
+ *      empty."), DIMENSION -> ArgumentException("Vector dimension mismatch"), OUT_OF_RANGE ->
+ *      ArgumentOutOfRangeException (FLAT topK <= 0), INVALID_STATE -> InvalidOperationException (FLAT duplicate
+ *      Add, BruteForceVectorIndex.cs:141-144), NOT_FOUND -> FileNotFoundException (Load). */
+typedef struct pyrope_vindex pyrope_vindex;
+int pyrope_vindex_create(int kind, int dim, int metric, int nlist, int pq_m, int pq_k, pyrope_vindex **out);
+/* DeltaVectorIndex(head, tail) :18-28; head must be FLAT.  Borrows both (destroy the delta first). */
+int pyrope_vindex_create_delta(pyrope_vindex *head, pyrope_vindex *tail, pyrope_vindex **out);
+int pyrope_vindex_destroy(pyrope_vindex *v);
+int pyrope_vindex_native(pyrope_vindex *v, pyrope_index **out); /* row-ordinal handle (NULL for a delta) */
+int pyrope_vindex_add(pyrope_vindex *v, const char *id, const float *vec, int len);
+int pyrope_vindex_upsert(pyrope_vindex *v, const char *id, const float *vec, int len);
+int pyrope_vindex_delete(pyrope_vindex *v, const char *id, int *removed_out);
+int pyrope_vindex_build(pyrope_vindex *v); /* a delta compacts: DeltaVectorIndex.Build :124-158 */
+/* nq queries of `len` floats each (len != Dimension -> DIMENSION). */
+int pyrope_vindex_search(pyrope_vindex *v, int64_t nq, const float *Q, int len, int topk, int64_t max_scans,
+                         int nprobe, float *scores_out, int64_t *id_ordinals_out, int32_t *counts_out);
+int pyrope_vindex_id(int64_t id_ordinal, char *buf, int cap, int *len_out);
+int pyrope_vindex_stats(pyrope_vindex *v, int64_t *count_out, int *dim_out, int *metric_out);
+int pyrope_vindex_get_centroids(pyrope_vindex *v, float *centroids_out, int *n_out); /* n_out 0 == null */
+int pyrope_vindex_snapshot(pyrope_vindex *v, const char *path); /* index file(s) + "<file>.ids" id tables */
+int pyrope_vindex_load(pyrope_vindex *v, const char *path);
+const char *pyrope_vindex_last_error(void);
 
 /* ---- building blocks exposed for parity tests and for "next" rows --------------- */
 /* KMeansUtils.FindNearestCentroid (KMeansUtils.cs:70-93), bit-exact: assign_out[i] = first index

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pyrope_index_update_row": (C.c_int, [vp, C.c_int64, vp]),
     "pyrope_index_delete_row": (C.c_int, [vp, C.c_int64]),
     "pyrope_index_shadow_row": (C.c_int, [vp, C.c_int64, C.c_int]),
+    "pyrope_index_set_labels": (C.c_int, [vp, C.c_int64, vp]),
     "pyrope_index_build": (C.c_int, [vp]),
     "pyrope_index_set_train_params": (C.c_int, [vp, C.c_int64, C.c_int]),
     "pyrope_index_set_codebooks": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -73,6 +74,29 @@ SIGNATURES = {
     "pyrope_batcher_stats": (C.c_int, [vp, i64p, i64p]),
     "pyrope_batcher_last_error": (C.c_char_p, []),
     "pyrope_topk_merge_device": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "pyrope_delta_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "pyrope_delta_destroy": (C.c_int, [vp]),
+    "pyrope_delta_search_batch": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
+    "pyrope_delta_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp]),
+    "pyrope_delta_compact": (C.c_int, [vp, i64p, vp]),
+    "pyrope_delta_stats": (C.c_int, [vp, i64p]),
+    "pyrope_delta_snapshot": (C.c_int, [vp, C.c_char_p]),
+    "pyrope_delta_load": (C.c_int, [vp, C.c_char_p]),
+    "pyrope_vindex_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "pyrope_vindex_create_delta": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "pyrope_vindex_destroy": (C.c_int, [vp]),
+    "pyrope_vindex_native": (C.c_int, [vp, C.POINTER(vp)]),
+    "pyrope_vindex_add": (C.c_int, [vp, C.c_char_p, vp, C.c_int]),
+    "pyrope_vindex_upsert": (C.c_int, [vp, C.c_char_p, vp, C.c_int]),
+    "pyrope_vindex_delete": (C.c_int, [vp, C.c_char_p, i32p]),
+    "pyrope_vindex_build": (C.c_int, [vp]),
+    "pyrope_vindex_search": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
+    "pyrope_vindex_id": (C.c_int, [C.c_int64, C.c_char_p, C.c_int, i32p]),
+    "pyrope_vindex_stats": (C.c_int, [vp, i64p, i32p, i32p]),
+    "pyrope_vindex_get_centroids": (C.c_int, [vp, vp, i32p]),
+    "pyrope_vindex_snapshot": (C.c_int, [vp, C.c_char_p]),
+    "pyrope_vindex_load": (C.c_int, [vp, C.c_char_p]),
+    "pyrope_vindex_last_error": (C.c_char_p, []),
     "pyrope_coarse_assign": (C.c_int, [C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]),
     "pyrope_kmeans_train": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int32, vp, i32p, i32p]),
     "pyrope_pq_encode": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp, vp]),

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include <unordered_map>
 #include "../../include/pyrope_gpu.h"
 #include "common.cuh"
 #include "dotnet_random.h"
@@ -181,6 +182,9 @@ struct pyrope_index {
     std::vector<int64_t> list_off_h;
     std::vector<uint8_t> list_dead_h;
     int64_t list_total = 0, list_ndead = 0, max_list_len = 0;
+    // compacted view of the lists for MaxScans-budgeted IVF_FLAT searches (compact_lists)
+    DevBuf bv_vecs, bv_labels, bv_norms, bv_off;
+    uint64_t lists_version = 1, bv_version = 0;  // lists_version moves whenever lists or their dead flags change
     // shape of the most recent list-major IVF_PQ search (for pyrope_index_last_search_scanned)
     int64_t lm_nq = 0; int lm_P = 0, lm_k = 0;
     std::vector<int32_t> ksub;
@@ -480,18 +484,59 @@ int gather_build_data(Index* h, bool include_lists, BuildData& bd) {
     cudaStream_t st = h->stream;
     Segment& s = h->seg;
     const int dim = h->dim;
+    // uniqueData (IvfFlatVectorIndex.cs:91-108) is a Dictionary filled from the lists first, then from the buffer:
+    // an indexed id that was re-added through the buffer KEEPS its list position and takes the buffer's vector.
+    // A shadowed list entry (flag 2) is matched to the live buffer slot carrying the same label; callers that do
+    // not pass labels get the buffer row appended at the end instead (their labels differ by construction).
+    std::unordered_map<int64_t, int64_t> repl_at;  // list position -> buffer slot that replaces it
+    std::vector<uint8_t> slot_used;
+    if (include_lists && h->built && !h->list_dead_h.empty() && s.live > 0) {
+        std::vector<int64_t> sh;
+        for (int64_t i = 0; i < h->list_total; ++i)
+            if (h->list_dead_h[(size_t)i] == 2) sh.push_back(i);
+        if (!sh.empty()) {
+            DevBuf di, dl;
+            TRY(di.ensure(sizeof(int64_t) * sh.size(), 0, st, true));
+            TRY(dl.ensure(sizeof(int64_t) * sh.size(), 0, st, true));
+            CK(cudaMemcpyAsync(di.p, sh.data(), sizeof(int64_t) * sh.size(), cudaMemcpyHostToDevice, st));
+            CK(launch_gather_rows(h->list_labels.p, 8, di.as<int64_t>(), (int64_t)sh.size(), dl.p, st));
+            std::vector<int64_t> shl(sh.size()), bl((size_t)s.nslots);
+            CK(cudaMemcpyAsync(shl.data(), dl.p, sizeof(int64_t) * sh.size(), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(bl.data(), s.labels.p, sizeof(int64_t) * (size_t)s.nslots, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::unordered_map<int64_t, int64_t> slot_of;
+            for (int64_t i = 0; i < s.nslots; ++i)
+                if (!s.dead_h[(size_t)i]) slot_of[bl[(size_t)i]] = i;
+            slot_used.assign((size_t)s.nslots, 0);
+            for (size_t j = 0; j < sh.size(); ++j) {
+                auto it = slot_of.find(shl[j]);
+                if (it == slot_of.end() || slot_used[(size_t)it->second]) continue;
+                repl_at[sh[j]] = it->second;
+                slot_used[(size_t)it->second] = 1;
+            }
+        }
+    }
     std::vector<int64_t> list_pos;
+    std::vector<int64_t> repl_out, repl_slot;  // output index <- buffer slot
     if (include_lists && h->built) {
         list_pos.reserve((size_t)h->list_total);
-        for (int64_t i = 0; i < h->list_total; ++i)
+        for (int64_t i = 0; i < h->list_total; ++i) {
             if (h->list_dead_h.empty() || !h->list_dead_h[(size_t)i]) list_pos.push_back(i);
+            else if (!repl_at.empty()) {
+                auto it = repl_at.find(i);
+                if (it == repl_at.end()) continue;
+                repl_out.push_back((int64_t)list_pos.size());
+                repl_slot.push_back(it->second);
+                list_pos.push_back(i);
+            }
+        }
     }
     std::vector<int64_t> slots;
-    const bool dense_buffer = (s.ndead == 0);
+    const bool dense_buffer = (s.ndead == 0) && repl_out.empty();
     if (!dense_buffer) {
         slots.reserve((size_t)s.live);
         for (int64_t i = 0; i < s.nslots; ++i)
-            if (!s.dead_h[(size_t)i]) slots.push_back(i);
+            if (!s.dead_h[(size_t)i] && (slot_used.empty() || !slot_used[(size_t)i])) slots.push_back(i);
     }
     const int64_t nb = dense_buffer ? s.nslots : (int64_t)slots.size();
     const int64_t nl = (int64_t)list_pos.size();
@@ -516,6 +561,23 @@ int gather_build_data(Index* h, bool include_lists, BuildData& bd) {
         CK(launch_gather_rows(h->list_vecs.p, (int64_t)dim * 4, idx.as<int64_t>(), nl, bd.Xown.p, st));
         CK(launch_gather_rows(h->list_rows.p, 8, idx.as<int64_t>(), nl, bd.rows.p, st));
         CK(launch_gather_rows(h->list_labels.p, 8, idx.as<int64_t>(), nl, bd.labels.p, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (!repl_out.empty()) {  // replaced entries: the buffer's vector and row ordinal at the list entry's place
+        const int64_t nr = (int64_t)repl_out.size();
+        DevBuf a, b, tx, tr;
+        TRY(a.ensure(sizeof(int64_t) * (size_t)nr, 0, st, true));
+        TRY(b.ensure(sizeof(int64_t) * (size_t)nr, 0, st, true));
+        TRY(tx.ensure(sizeof(float) * (size_t)nr * dim, 0, st, true));
+        TRY(tr.ensure(sizeof(int64_t) * (size_t)nr, 0, st, true));
+        std::vector<int64_t> rrow((size_t)nr);
+        for (int64_t i = 0; i < nr; ++i) rrow[(size_t)i] = s.slot_row[(size_t)repl_slot[(size_t)i]];
+        CK(cudaMemcpyAsync(a.p, repl_slot.data(), sizeof(int64_t) * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b.p, repl_out.data(), sizeof(int64_t) * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(tr.p, rrow.data(), sizeof(int64_t) * (size_t)nr, cudaMemcpyHostToDevice, st));
+        CK(launch_gather_rows(s.X.p, (int64_t)dim * 4, a.as<int64_t>(), nr, tx.p, st));
+        CK(launch_scatter_rows(tx.p, (int64_t)dim * 4, b.as<int64_t>(), nr, bd.Xown.p, st));
+        CK(launch_scatter_rows(tr.p, 8, b.as<int64_t>(), nr, bd.rows.p, st));
         CK(cudaStreamSynchronize(st));
     }
     if (nb) {
@@ -571,6 +633,7 @@ int finish_lists(Index* h, const BuildData& bd, int32_t* d_assign, int nc, SortS
     h->list_dead_h.clear();
     h->list_dead.release();
     h->list_ndead = 0;
+    h->lists_version++;
     h->nc = nc;
     h->built = true;
     h->tc_cent.invalidate();
@@ -704,9 +767,12 @@ int build_ivfpq(Index* h) {
     return PYROPE_OK;
 }
 
-// physically drop dead/shadowed list entries (IVF_FLAT; needed before a MaxScans-limited search)
+// A MaxScans budget walks the probed lists entry by entry and never counts a deleted or shadowed entry
+// (IvfFlatVectorIndex.cs:209-212), so a budgeted IVF_FLAT search over lists that hold such entries scans a
+// compacted VIEW of them (dead entries squeezed out, offsets recomputed).  The lists themselves are left alone:
+// a shadowed entry's position still decides where its replacement lands at the next Build (:91-108).
 int compact_lists(Index* h) {
-    if (h->list_ndead == 0) return PYROPE_OK;
+    if (h->list_ndead == 0 || h->bv_version == h->lists_version) return PYROPE_OK;
     cudaStream_t st = h->stream;
     std::vector<int64_t> keep;
     keep.reserve((size_t)h->list_total);
@@ -717,33 +783,22 @@ int compact_lists(Index* h) {
         noff[(size_t)c + 1] = (int64_t)keep.size();
     }
     const int64_t n = (int64_t)keep.size();
-    DevBuf idx, nv, nr, nl, nn;
-    TRY(idx.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
+    const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+    DevBuf idx;
+    TRY(idx.ensure(sizeof(int64_t) * n1, 0, st, true));
     CK(cudaMemcpyAsync(idx.p, keep.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-    TRY(nv.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1) * h->dim, 0, st, true));
-    TRY(nr.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
-    TRY(nl.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
-    CK(launch_gather_rows(h->list_vecs.p, (int64_t)h->dim * 4, idx.as<int64_t>(), n, nv.p, st));
-    CK(launch_gather_rows(h->list_rows.p, 8, idx.as<int64_t>(), n, nr.p, st));
-    CK(launch_gather_rows(h->list_labels.p, 8, idx.as<int64_t>(), n, nl.p, st));
+    TRY(h->bv_vecs.ensure(sizeof(float) * n1 * h->dim, 0, st));
+    TRY(h->bv_labels.ensure(sizeof(int64_t) * n1, 0, st));
+    TRY(h->bv_off.ensure(sizeof(int64_t) * noff.size(), 0, st));
+    CK(launch_gather_rows(h->list_vecs.p, (int64_t)h->dim * 4, idx.as<int64_t>(), n, h->bv_vecs.p, st));
+    CK(launch_gather_rows(h->list_labels.p, 8, idx.as<int64_t>(), n, h->bv_labels.p, st));
     if (h->metric == kCosine) {
-        TRY(nn.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1), 0, st, true));
-        CK(launch_gather_rows(h->list_norms.p, 4, idx.as<int64_t>(), n, nn.p, st));
+        TRY(h->bv_norms.ensure(sizeof(float) * n1, 0, st));
+        CK(launch_gather_rows(h->list_norms.p, 4, idx.as<int64_t>(), n, h->bv_norms.p, st));
     }
-    CK(cudaMemcpyAsync(h->list_off.p, noff.data(), sizeof(int64_t) * noff.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->bv_off.p, noff.data(), sizeof(int64_t) * noff.size(), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    std::swap(h->list_vecs.p, nv.p); std::swap(h->list_vecs.bytes, nv.bytes);
-    std::swap(h->list_rows.p, nr.p); std::swap(h->list_rows.bytes, nr.bytes);
-    std::swap(h->list_labels.p, nl.p); std::swap(h->list_labels.bytes, nl.bytes);
-    if (h->metric == kCosine) { std::swap(h->list_norms.p, nn.p); std::swap(h->list_norms.bytes, nn.bytes); }
-    h->list_off_h = noff;
-    h->max_list_len = 0;
-    for (int c = 0; c < h->nc; ++c) h->max_list_len = std::max(h->max_list_len, noff[(size_t)c + 1] - noff[(size_t)c]);
-    h->list_total = n;
-    h->list_dead_h.clear();
-    h->list_dead.release();
-    h->list_ndead = 0;
-    h->lists_loc_valid = false;
+    h->bv_version = h->lists_version;
     return PYROPE_OK;
 }
 
@@ -994,9 +1049,12 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         const uint8_t* ldead = h->list_ndead > 0 ? h->list_dead.as<uint8_t>() : nullptr;
         if (h->kind == PYROPE_IVF_FLAT) {
             const int32_t* allow = nullptr;
+            const bool budget_view = max_scans >= 0 && h->list_ndead > 0;
+            if (budget_view && h->bv_version != h->lists_version)
+                return fail(PYROPE_ERR_INVALID_STATE, "budgeted IVF_FLAT search without a compacted list view");
             if (max_scans >= 0) {
                 TRY(ws.allow.ensure(sizeof(int32_t) * (size_t)nq * P, 0, st));
-                CK(launch_probe_allow(probes_dev, nq, P, h->list_off.as<int64_t>(),
+                CK(launch_probe_allow(probes_dev, nq, P, (budget_view ? h->bv_off : h->list_off).as<int64_t>(),
                                       max_scans - seg_live_scanned, ws.allow.as<int32_t>(), st));
                 ++launches;
                 allow = ws.allow.as<int32_t>();
@@ -1005,6 +1063,10 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             ip.Q = dQ; ip.nq = nq; ip.dim = dim; ip.probes = probes_dev; ip.nprobe = P; ip.allow = allow;
             ip.list_off = h->list_off.as<int64_t>(); ip.vecs = h->list_vecs.as<float>(); ip.dead = ldead;
             ip.norms = h->list_norms.as<float>(); ip.labels = h->list_labels.as<int64_t>(); ip.qnorm = qnorm;
+            if (budget_view) {
+                ip.list_off = h->bv_off.as<int64_t>(); ip.vecs = h->bv_vecs.as<float>(); ip.dead = nullptr;
+                ip.norms = h->bv_norms.as<float>(); ip.labels = h->bv_labels.as<int64_t>();
+            }
             ip.metric = h->metric; ip.k = k; ip.groups = groups;
             ip.out = out; ip.out.part_base = seg_splits;
             if (use_flm) {
@@ -1217,6 +1279,7 @@ int pyrope_index_delete_row(pyrope_index* h, int64_t row) {
         TRY(ensure_list_dead(h));
         if (!(h->list_dead_h[(size_t)pos])) h->list_ndead++;
         h->list_dead_h[(size_t)pos] |= 1;
+        h->lists_version++;
         CK(cudaMemcpyAsync(h->list_dead.as<uint8_t>() + pos, &h->list_dead_h[(size_t)pos], 1, cudaMemcpyHostToDevice, st));
         h->row_loc[(size_t)row] = -1;
     }
@@ -1239,8 +1302,35 @@ int pyrope_index_shadow_row(pyrope_index* h, int64_t row, int shadowed) {
     if (!old && nv) h->list_ndead++;
     if (old && !nv) h->list_ndead--;
     h->list_dead_h[(size_t)pos] = nv;
+    h->lists_version++;
     CK(cudaMemcpyAsync(h->list_dead.as<uint8_t>() + pos, &h->list_dead_h[(size_t)pos], 1, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return PYROPE_OK;
+}
+
+int pyrope_index_set_labels(pyrope_index* h, int64_t n_rows, const int64_t* labels_by_row) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (n_rows < h->next_row || (n_rows > 0 && !labels_by_row))
+        return fail(PYROPE_ERR_INVALID_ARG, "labels for %lld rows needed, %lld given", (long long)h->next_row, (long long)n_rows);
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaStream_t st = h->stream;
+    Segment& s = h->seg;
+    if (s.nslots > 0) {
+        std::vector<int64_t> L((size_t)s.nslots);
+        for (int64_t i = 0; i < s.nslots; ++i) {
+            const int64_t row = h->kind == PYROPE_FLAT ? i : s.slot_row[(size_t)i];
+            L[(size_t)i] = row >= 0 ? labels_by_row[(size_t)row] : -1;
+        }
+        CK(cudaMemcpyAsync(s.labels.p, L.data(), sizeof(int64_t) * L.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (h->kind != PYROPE_FLAT && h->list_total > 0) {
+        DevBuf dl;
+        TRY(dl.ensure(sizeof(int64_t) * (size_t)n_rows, 0, st, true));
+        CK(cudaMemcpyAsync(dl.p, labels_by_row, sizeof(int64_t) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+        CK(launch_gather_rows(dl.p, 8, h->list_rows.as<int64_t>(), h->list_total, h->list_labels.p, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return PYROPE_OK;
 }
 
@@ -1474,6 +1564,7 @@ int pyrope_index_load(pyrope_index* h, const char* path) {
             CK(cudaMemcpy(h->ksub_d.p, h->ksub.data(), sizeof(int32_t) * h->ksub.size(), cudaMemcpyHostToDevice));
         }
         h->list_total = io.rv<int64_t>();
+        h->lists_version++;
         h->list_ndead = 0;
         h->list_dead_h.clear();
         h->list_dead.release();
@@ -1642,6 +1733,295 @@ int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const f
     CK(launch_merge_pairs(nq, parts, k_in, k_out, d_scores, d_rows, nq * (int64_t)k_in, k_in, d_scores_out, d_rows_out,
                           d_counts_out, (cudaStream_t)stream));
     if (!stream) CK(cudaStreamSynchronize(nullptr));
+    return PYROPE_OK;
+}
+
+// ---- Head+Tail on device (DeltaVectorIndex.cs) ------------------------------------------------------
+}  // extern "C"
+
+struct pyrope_delta {
+    pyrope_index* head = nullptr;
+    pyrope_index* tail = nullptr;
+    std::mutex mu;
+    DevBuf ps, pl, pc, q, os, ol, oc;  // partial (head | tail) results, staged queries, merged outputs
+};
+
+namespace {
+
+// DeltaVectorIndex.Search:76-122 for nq queries: head top-k, tail top-k (same options, :85,88), merge by id with
+// the head's copy winning, descending, Take(topK) — one stream, no host round trip between the three stages.
+int delta_search_device(pyrope_delta* d, int64_t nq, const float* dQ, int topk, int64_t max_scans, int nprobe,
+                        float* d_scores, int64_t* d_labels, int32_t* d_counts, cudaStream_t st) {
+    Index* hd = d->head;
+    Index* tl = d->tail;
+    const size_t per = (size_t)nq * topk;
+    TRY(d->ps.ensure(sizeof(float) * 2 * per, 0, st));
+    TRY(d->pl.ensure(sizeof(int64_t) * 2 * per, 0, st));
+    TRY(d->pc.ensure(sizeof(int32_t) * 2 * (size_t)nq, 0, st));
+    {
+        std::lock_guard<std::mutex> g(hd->mu);
+        TRY(search_device(hd, nq, dQ, topk, max_scans, nprobe, d->ps.as<float>(), d->pl.as<int64_t>(),
+                          d->pc.as<int32_t>(), st));
+    }
+    {
+        std::lock_guard<std::mutex> g(tl->mu);
+        if (tl->kind == PYROPE_IVF_FLAT && max_scans >= 0 && tl->list_ndead > 0) TRY(compact_lists(tl));
+        TRY(search_device(tl, nq, dQ, topk, max_scans, nprobe, d->ps.as<float>() + per, d->pl.as<int64_t>() + per,
+                          d->pc.as<int32_t>() + nq, st));
+    }
+    CK(launch_merge_pairs(nq, 2, topk, topk, d->ps.as<float>(), d->pl.as<int64_t>(), (int64_t)per, topk, d_scores,
+                          d_labels, d_counts, st, /*dedupe=*/true));
+    return PYROPE_OK;
+}
+
+int delta_validate(pyrope_delta* d, int64_t nq, const float* Q, int topk) {
+    if (!d) return fail(PYROPE_ERR_INVALID_ARG, "delta handle is null");
+    if (nq < 0 || (nq > 0 && !Q)) return fail(PYROPE_ERR_INVALID_ARG, "query is null");
+    if (topk <= 0) return fail(PYROPE_ERR_OUT_OF_RANGE, "topK must be positive.");  // the FLAT head throws first
+    if (2 * topk > kMergeMaxCandidates || topk > kMaxTopK)
+        return fail(PYROPE_ERR_UNSUPPORTED, "topK %d exceeds the supported maximum %d", topk, kMaxTopK);
+    return PYROPE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pyrope_delta_create(pyrope_index* head, pyrope_index* tail, pyrope_delta** out) {
+    if (!out) return fail(PYROPE_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    if (!head || !tail) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (head == tail) return fail(PYROPE_ERR_INVALID_ARG, "Head and Tail must be different indexes");
+    if (head->dim != tail->dim) return fail(PYROPE_ERR_INVALID_ARG, "Head and Tail dimensions must match");
+    if (head->metric != tail->metric) return fail(PYROPE_ERR_INVALID_ARG, "Head and Tail metrics must match");
+    if (head->kind != PYROPE_FLAT) return fail(PYROPE_ERR_UNSUPPORTED, "the head must be a FLAT index");
+    pyrope_delta* d = new (std::nothrow) pyrope_delta();
+    if (!d) return fail(PYROPE_ERR_OOM, "out of host memory");
+    d->head = head;
+    d->tail = tail;
+    *out = d;
+    return PYROPE_OK;
+}
+
+int pyrope_delta_destroy(pyrope_delta* d) {
+    if (!d) return PYROPE_OK;
+    cudaStreamSynchronize(d->head->stream);
+    delete d;
+    return PYROPE_OK;
+}
+
+int pyrope_delta_search_batch_device(pyrope_delta* d, int64_t nq, const float* dQ, int topk, int64_t max_scans,
+                                     int nprobe, float* d_scores, int64_t* d_labels, int32_t* d_counts, void* stream) {
+    TRY(delta_validate(d, nq, dQ, topk));
+    if (nq == 0) return PYROPE_OK;
+    if (!d_scores || !d_labels) return fail(PYROPE_ERR_INVALID_ARG, "output buffer is null");
+    std::lock_guard<std::mutex> g(d->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->head->stream;
+    TRY(delta_search_device(d, nq, dQ, topk, max_scans, nprobe, d_scores, d_labels, d_counts, st));
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_delta_search_batch(pyrope_delta* d, int64_t nq, const float* Q, int topk, int64_t max_scans, int nprobe,
+                              float* scores_out, int64_t* labels_out, int32_t* counts_out) {
+    TRY(delta_validate(d, nq, Q, topk));
+    if (nq == 0) return PYROPE_OK;
+    if (!scores_out || !labels_out || !counts_out) return fail(PYROPE_ERR_INVALID_ARG, "output buffer is null");
+    std::lock_guard<std::mutex> g(d->mu);
+    cudaStream_t st = d->head->stream;
+    const int dim = d->head->dim;
+    TRY(d->q.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
+    TRY(d->os.ensure(sizeof(float) * (size_t)nq * topk, 0, st));
+    TRY(d->ol.ensure(sizeof(int64_t) * (size_t)nq * topk, 0, st));
+    TRY(d->oc.ensure(sizeof(int32_t) * (size_t)nq, 0, st));
+    CK(cudaMemcpyAsync(d->q.p, Q, sizeof(float) * (size_t)nq * dim, cudaMemcpyHostToDevice, st));
+    TRY(delta_search_device(d, nq, d->q.as<float>(), topk, max_scans, nprobe, d->os.as<float>(), d->ol.as<int64_t>(),
+                            d->oc.as<int32_t>(), st));
+    CK(cudaMemcpyAsync(scores_out, d->os.p, sizeof(float) * (size_t)nq * topk, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(labels_out, d->ol.p, sizeof(int64_t) * (size_t)nq * topk, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(counts_out, d->oc.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
+int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows_out) {
+    if (!d) return fail(PYROPE_ERR_INVALID_ARG, "delta handle is null");
+    if (moved_out) *moved_out = 0;
+    std::lock_guard<std::mutex> g(d->mu);
+    Index* hd = d->head;
+    Index* tl = d->tail;
+    std::lock_guard<std::mutex> gh(hd->mu);
+    std::lock_guard<std::mutex> gt(tl->mu);
+    if (hd->last_stream) CK(cudaStreamSynchronize(hd->last_stream));
+    if (tl->last_stream) CK(cudaStreamSynchronize(tl->last_stream));
+    cudaStream_t st = tl->stream;
+    Segment& hs = hd->seg;
+    const int dim = hd->dim;
+    const int64_t n = hs.live;
+    if (n > 0) {
+        // 1. the head's live rows in scan order (bfHead.Scan(), DeltaVectorIndex.cs:133)
+        std::vector<int64_t> slots;
+        slots.reserve((size_t)n);
+        for (int64_t i = 0; i < hs.nslots; ++i)
+            if (!hs.dead_h[(size_t)i]) slots.push_back(i);
+        DevBuf idx, mx, ml;
+        TRY(idx.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+        TRY(mx.ensure(sizeof(float) * (size_t)n * dim, 0, st, true));
+        TRY(ml.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+        CK(cudaStreamSynchronize(hd->stream));
+        CK(cudaMemcpyAsync(idx.p, slots.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(launch_gather_rows(hs.X.p, (int64_t)dim * 4, idx.as<int64_t>(), n, mx.p, st));
+        CK(launch_gather_rows(hs.labels.p, 8, idx.as<int64_t>(), n, ml.p, st));
+        std::vector<int64_t> mlab((size_t)n);
+        CK(cudaMemcpyAsync(mlab.data(), ml.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        // 2. _tail.Add(id, vec) per row (:146): an id the tail already buffers is overwritten in place
+        //    (Dictionary semantics, IvfFlatVectorIndex.cs:47 / IvfPqVectorIndex.cs:42); an id that sits in an
+        //    inverted list is shadowed by the new buffer row until the Build below folds it in.
+        std::vector<int64_t> order((size_t)n);  // moved rows sorted by label
+        for (int64_t i = 0; i < n; ++i) order[(size_t)i] = i;
+        std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return mlab[(size_t)a] < mlab[(size_t)b]; });
+        std::vector<int64_t> sorted((size_t)n);
+        for (int64_t i = 0; i < n; ++i) sorted[(size_t)i] = mlab[(size_t)order[(size_t)i]];
+        std::vector<int64_t> target((size_t)n, -1);  // moved row -> tail buffer slot it overwrites
+        DevBuf dsorted, where;
+        Segment& ts = tl->seg;
+        const bool lists_matter = tl->built && tl->kind == PYROPE_IVF_FLAT && tl->list_total > 0;
+        if (ts.live > 0 || lists_matter) {
+            TRY(dsorted.ensure(sizeof(int64_t) * (size_t)n, 0, st, true));
+            CK(cudaMemcpyAsync(dsorted.p, sorted.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
+        if (ts.live > 0) {
+            TRY(where.ensure(sizeof(int64_t) * (size_t)ts.nslots, 0, st, true));
+            CK(launch_find_labels(ts.labels.as<int64_t>(), ts.dead.as<uint8_t>(), ts.nslots, dsorted.as<int64_t>(), n,
+                                  where.as<int64_t>(), st));
+            std::vector<int64_t> wh((size_t)ts.nslots);
+            CK(cudaMemcpyAsync(wh.data(), where.p, sizeof(int64_t) * wh.size(), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int64_t s = 0; s < ts.nslots; ++s)
+                if (wh[(size_t)s] >= 0) target[(size_t)order[(size_t)wh[(size_t)s]]] = s;
+        }
+        if (lists_matter) {
+            TRY(ensure_list_dead(tl));
+            TRY(where.ensure(sizeof(int64_t) * (size_t)tl->list_total, 0, st, true));
+            CK(launch_find_labels(tl->list_labels.as<int64_t>(), tl->list_dead.as<uint8_t>(), tl->list_total,
+                                  dsorted.as<int64_t>(), n, where.as<int64_t>(), st));
+            std::vector<int64_t> wh((size_t)tl->list_total);
+            CK(cudaMemcpyAsync(wh.data(), where.p, sizeof(int64_t) * wh.size(), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            bool any = false;
+            for (int64_t i = 0; i < tl->list_total; ++i)
+                if (wh[(size_t)i] >= 0) {
+                    if (!tl->list_dead_h[(size_t)i]) tl->list_ndead++;
+                    tl->lists_version++;
+                    tl->list_dead_h[(size_t)i] |= 2;
+                    any = true;
+                }
+            if (any)
+                CK(cudaMemcpyAsync(tl->list_dead.p, tl->list_dead_h.data(), (size_t)tl->list_total, cudaMemcpyHostToDevice, st));
+        }
+        std::vector<int64_t> over_src, over_dst, app_src;
+        for (int64_t i = 0; i < n; ++i) {
+            if (target[(size_t)i] >= 0) { over_src.push_back(i); over_dst.push_back(target[(size_t)i]); }
+            else app_src.push_back(i);
+        }
+        if (!over_src.empty()) {
+            const int64_t no = (int64_t)over_src.size();
+            DevBuf a, b, tmp;
+            TRY(a.ensure(sizeof(int64_t) * (size_t)no, 0, st, true));
+            TRY(b.ensure(sizeof(int64_t) * (size_t)no, 0, st, true));
+            TRY(tmp.ensure(sizeof(float) * (size_t)no * dim, 0, st, true));
+            CK(cudaMemcpyAsync(a.p, over_src.data(), sizeof(int64_t) * (size_t)no, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(b.p, over_dst.data(), sizeof(int64_t) * (size_t)no, cudaMemcpyHostToDevice, st));
+            CK(launch_gather_rows(mx.p, (int64_t)dim * 4, a.as<int64_t>(), no, tmp.p, st));
+            CK(launch_scatter_rows(tmp.p, (int64_t)dim * 4, b.as<int64_t>(), no, ts.X.p, st));
+            if (ts.cosine)
+                for (int64_t i = 0; i < no; ++i)
+                    CK(launch_row_norms_exact(ts.X.as<float>() + over_dst[(size_t)i] * dim, 1, dim, dim,
+                                              ts.norms.as<float>() + over_dst[(size_t)i], st));
+            ts.tc_dirty = true;
+            CK(cudaStreamSynchronize(st));
+            if (tail_rows_out)
+                for (int64_t i = 0; i < no; ++i)
+                    tail_rows_out[over_src[(size_t)i]] =
+                        tl->kind == PYROPE_FLAT ? over_dst[(size_t)i] : ts.slot_row[(size_t)over_dst[(size_t)i]];
+        }
+        if (!app_src.empty()) {
+            const int64_t na = (int64_t)app_src.size();
+            const float* ax = mx.as<float>();
+            const int64_t* al = ml.as<int64_t>();
+            DevBuf a, tx, tlab;
+            if (na != n) {
+                TRY(a.ensure(sizeof(int64_t) * (size_t)na, 0, st, true));
+                TRY(tx.ensure(sizeof(float) * (size_t)na * dim, 0, st, true));
+                TRY(tlab.ensure(sizeof(int64_t) * (size_t)na, 0, st, true));
+                CK(cudaMemcpyAsync(a.p, app_src.data(), sizeof(int64_t) * (size_t)na, cudaMemcpyHostToDevice, st));
+                CK(launch_gather_rows(mx.p, (int64_t)dim * 4, a.as<int64_t>(), na, tx.p, st));
+                CK(launch_gather_rows(ml.p, 8, a.as<int64_t>(), na, tlab.p, st));
+                CK(cudaStreamSynchronize(st));
+                ax = tx.as<float>();
+                al = tlab.as<int64_t>();
+            }
+            const int64_t first = tl->next_row;
+            if (tl->kind != PYROPE_FLAT) tl->row_loc.resize((size_t)(first + na), -1);
+            tl->next_row += na;
+            int r = seg_append(tl, na, ax, true, al, true, first);
+            if (r != PYROPE_OK) { tl->next_row = first; return r; }
+            if (tail_rows_out)
+                for (int64_t i = 0; i < na; ++i) tail_rows_out[app_src[(size_t)i]] = first + i;
+        }
+        // 3. _head.Delete(id) per row (:147): tombstones, slots stay (BruteForceVectorIndex.cs:231-254)
+        CK(cudaMemsetAsync(hs.dead.p, 1, (size_t)hs.nslots, hd->stream));
+        std::fill(hs.dead_h.begin(), hs.dead_h.end(), (uint8_t)1);
+        hs.ndead = hs.nslots;
+        hs.live = 0;
+        hs.tc_dirty = true;
+        CK(cudaStreamSynchronize(hd->stream));
+        if (moved_out) *moved_out = n;
+    }
+    // 4. _head.Build() is a no-op for FLAT; _tail.Build() (:151-152)
+    if (tl->kind == PYROPE_IVF_FLAT) return build_ivfflat(tl);
+    if (tl->kind == PYROPE_IVF_PQ) return build_ivfpq(tl);
+    return PYROPE_OK;
+}
+
+int pyrope_delta_stats(pyrope_delta* d, int64_t* count_out) {
+    if (!d || !count_out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    // DeltaVectorIndex.cs:232-236: plain sum of both sides (duplicates counted twice, as in the reference)
+    Index* hd = d->head;
+    Index* tl = d->tail;
+    *count_out = hd->seg.live + tl->seg.live + (tl->built ? tl->list_total - tl->list_ndead : 0);
+    return PYROPE_OK;
+}
+
+int pyrope_delta_snapshot(pyrope_delta* d, const char* path) {
+    if (!d) return fail(PYROPE_ERR_INVALID_ARG, "delta handle is null");
+    if (!path || !*path) return fail(PYROPE_ERR_INVALID_ARG, "Path cannot be empty.");
+    const std::string base(path);
+    TRY(pyrope_index_snapshot(d->head, (base + ".head").c_str()));
+    TRY(pyrope_index_snapshot(d->tail, (base + ".tail").c_str()));
+    const std::string tmp = base + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(PYROPE_ERR_INVALID_ARG, "cannot open %s for writing", tmp.c_str());
+    const char* manifest = "{\"Type\": \"Delta\", \"Head\": \".head\", \"Tail\": \".tail\"}";  // DeltaVectorIndex.cs:183
+    const bool ok = fwrite(manifest, 1, strlen(manifest), f) == strlen(manifest);
+    if (fclose(f) != 0 || !ok) { remove(tmp.c_str()); return fail(PYROPE_ERR_INVALID_ARG, "short write to %s", tmp.c_str()); }
+    if (rename(tmp.c_str(), base.c_str()) != 0) { remove(tmp.c_str()); return fail(PYROPE_ERR_INVALID_ARG, "cannot move %s into place", tmp.c_str()); }
+    return PYROPE_OK;
+}
+
+int pyrope_delta_load(pyrope_delta* d, const char* path) {
+    if (!d) return fail(PYROPE_ERR_INVALID_ARG, "delta handle is null");
+    if (!path || !*path) return fail(PYROPE_ERR_INVALID_ARG, "Path cannot be empty.");
+    const std::string base(path);
+    // DeltaVectorIndex.cs:200-216: each side is loaded only if its file exists
+    for (int side = 0; side < 2; ++side) {
+        const std::string p = base + (side == 0 ? ".head" : ".tail");
+        FILE* f = fopen(p.c_str(), "rb");
+        if (!f) continue;
+        fclose(f);
+        TRY(pyrope_index_load(side == 0 ? d->head : d->tail, p.c_str()));
+    }
     return PYROPE_OK;
 }
 

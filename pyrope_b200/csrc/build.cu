@@ -258,6 +258,42 @@ __global__ void gather_rows_kernel(const uint8_t* X, int64_t row_bytes, const in
     }
 }
 
+// scatter rows: out[idx[r]] = X[r]
+__global__ void scatter_rows_kernel(const uint8_t* X, int64_t row_bytes, const int64_t* idx, int64_t n,
+                                    uint8_t* out) {
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const uint8_t* src = X + r * row_bytes;
+    uint8_t* dst = out + idx[r] * row_bytes;
+    if ((row_bytes & 15) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int64_t i = lane; i < row_bytes / 16; i += 32) d4[i] = s4[i];
+    } else {
+        for (int64_t i = lane; i < row_bytes; i += 32) dst[i] = src[i];
+    }
+}
+
+// where[i] = position in the ascending array `sorted` (ns entries) holding labels[i], or -1; entries whose
+// skip byte is non-zero are not looked up.  Compaction uses it to find the tail rows a moved head id replaces.
+__global__ void find_labels_kernel(const int64_t* __restrict__ labels, const uint8_t* __restrict__ skip, int64_t n,
+                                   const int64_t* __restrict__ sorted, int64_t ns, int64_t* __restrict__ where) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t hit = -1;
+    if (!skip || !skip[i]) {
+        const int64_t v = labels[i];
+        int64_t lo = 0, hi = ns;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (sorted[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        if (lo < ns && sorted[lo] == v) hit = lo;
+    }
+    where[i] = hit;
+}
+
 __global__ void iota64_kernel(int64_t* out, int64_t n, int64_t base) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = base + i;
@@ -374,6 +410,21 @@ cudaError_t launch_gather_rows(const void* X, int64_t row_bytes, const int64_t* 
     if (n <= 0) return cudaSuccess;
     gather_rows_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>((const uint8_t*)X, row_bytes, idx, n,
                                                                (uint8_t*)out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_rows(const void* X, int64_t row_bytes, const int64_t* idx, int64_t n, void* out,
+                                cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    scatter_rows_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>((const uint8_t*)X, row_bytes, idx, n,
+                                                                (uint8_t*)out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_find_labels(const int64_t* labels, const uint8_t* skip, int64_t n, const int64_t* sorted,
+                               int64_t ns, int64_t* where, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    find_labels_kernel<<<blocks_for(n, 256), 256, 0, st>>>(labels, skip, n, sorted, ns, where);
     return cudaGetLastError();
 }
 

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) merge_pairs_kernel(int64_t nq, int parts,
                                                           const int64_t* __restrict__ in_l,
                                                           int64_t part_stride, int64_t q_stride,
                                                           float* out_s, int64_t* out_l,
-                                                          int32_t* out_c, int P) {
+                                                          int32_t* out_c, int P, int dedupe) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ int s_count;
@@ -220,7 +220,18 @@ __global__ void __launch_bounds__(256) merge_pairs_kernel(int64_t nq, int parts,
         if (i < total) {
             int part = i / k_in, j = i - part * k_in;
             int64_t a = part * part_stride + q * q_stride + j;
-            if (in_l[a] >= 0) key = make_key(in_s[a], (uint32_t)i);
+            const int64_t lab = in_l[a];
+            if (lab >= 0) {
+                bool dup = false;
+                if (dedupe) {  // the same id in a lower part (the head) wins
+                    for (int pp = 0; pp < part && !dup; ++pp) {
+                        const int64_t b = pp * part_stride + q * q_stride;
+                        for (int jj = 0; jj < k_in; ++jj)
+                            if (in_l[b + jj] == lab) { dup = true; break; }
+                    }
+                }
+                if (!dup) key = make_key(in_s[a], (uint32_t)i);
+            }
         }
         keys[i] = key;
     }
@@ -288,14 +299,14 @@ cudaError_t launch_flat_scan(const FlatScanParams& p, cudaStream_t st) {
 cudaError_t launch_merge_pairs(int64_t nq, int parts, int k_in, int k_out, const float* in_scores,
                                const int64_t* in_labels, int64_t part_stride, int64_t q_stride,
                                float* out_scores, int64_t* out_labels, int32_t* out_counts,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool dedupe) {
     if (nq <= 0) return cudaSuccess;
     int total = parts * k_in;
     if (total > kMergeMaxCandidates) return cudaErrorInvalidValue;
     int P = next_pow2(total < 2 ? 2 : total);
     merge_pairs_kernel<<<(unsigned)nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(
         nq, parts, k_in, k_out, in_scores, in_labels, part_stride, q_stride, out_scores, out_labels,
-        out_counts, P);
+        out_counts, P, dedupe ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -85,10 +85,12 @@ cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n
 
 // ---- K6: merge ------------------------------------------------------------------------------
 // in: candidate (score,label) at address part*part_stride + q*q_stride + j, j < k_in.
+// dedupe: a candidate whose label already occurs in a LOWER part is dropped (DeltaVectorIndex.cs:98-110: the
+// head's copy of an id replaces the tail's).
 cudaError_t launch_merge_pairs(int64_t nq, int parts, int k_in, int k_out, const float* in_scores,
                                const int64_t* in_labels, int64_t part_stride, int64_t q_stride,
                                float* out_scores, int64_t* out_labels, int32_t* out_counts,
-                               cudaStream_t st);
+                               cudaStream_t st, bool dedupe = false);
 constexpr int kMergeMaxCandidates = 4096;
 
 // ---- K4: IVF_FLAT inverted-list scan ----------------------------------------------------------
@@ -178,6 +180,12 @@ cudaError_t launch_kmeans_update(const float* X, int64_t ldx, int dim, int nc,
 // gather rows: out[i] = X[idx[i]]  (rows of `width` elements of `elem` bytes)
 cudaError_t launch_gather_rows(const void* X, int64_t row_bytes, const int64_t* idx, int64_t n,
                                void* out, cudaStream_t st);
+// scatter rows: out[idx[i]] = X[i]
+cudaError_t launch_scatter_rows(const void* X, int64_t row_bytes, const int64_t* idx, int64_t n,
+                                void* out, cudaStream_t st);
+// where[i] = index of labels[i] in the ascending array sorted[ns], or -1 (also -1 where skip[i] != 0)
+cudaError_t launch_find_labels(const int64_t* labels, const uint8_t* skip, int64_t n, const int64_t* sorted,
+                               int64_t ns, int64_t* where, cudaStream_t st);
 cudaError_t launch_iota64(int64_t* out, int64_t n, int64_t base, cudaStream_t st);
 cudaError_t launch_fill_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset,
                                 cudaStream_t st);
