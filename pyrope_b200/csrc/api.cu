@@ -1806,6 +1806,8 @@ int pyrope_delta_create(pyrope_index* head, pyrope_index* tail, pyrope_delta** o
 int pyrope_delta_destroy(pyrope_delta* d) {
     if (!d) return PYROPE_OK;
     cudaStreamSynchronize(d->head->stream);
+    // the tail's last search ran on the head's stream: do not leave it a handle the head may destroy first
+    if (d->tail->last_stream == d->head->stream) d->tail->last_stream = nullptr;
     delete d;
     return PYROPE_OK;
 }
@@ -1818,7 +1820,10 @@ int pyrope_delta_search_batch_device(pyrope_delta* d, int64_t nq, const float* d
     std::lock_guard<std::mutex> g(d->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : d->head->stream;
     TRY(delta_search_device(d, nq, dQ, topk, max_scans, nprobe, d_scores, d_labels, d_counts, st));
-    if (!stream) CK(cudaStreamSynchronize(st));
+    if (!stream) {
+        CK(cudaStreamSynchronize(st));
+        if (d->tail->last_stream == st) d->tail->last_stream = nullptr;
+    }
     return PYROPE_OK;
 }
 
@@ -1841,6 +1846,7 @@ int pyrope_delta_search_batch(pyrope_delta* d, int64_t nq, const float* Q, int t
     CK(cudaMemcpyAsync(labels_out, d->ol.p, sizeof(int64_t) * (size_t)nq * topk, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(counts_out, d->oc.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (d->tail->last_stream == st) d->tail->last_stream = nullptr;
     return PYROPE_OK;
 }
 

@@ -186,6 +186,15 @@ class _VectorIndex:
             pass
 
 
+class _BorrowedGpuIndex(_lib.GpuIndex):
+    """Row-ordinal view of a handle the vindex owns: never destroys it."""
+
+    def close(self):
+        self._h = None
+
+    __del__ = close
+
+
 class _Leaf(_VectorIndex):
     def _create(self, kind, dimension, metric, nlist=100, m=4, k=256):
         v = vp()
@@ -196,10 +205,10 @@ class _Leaf(_VectorIndex):
         """Row-ordinal view of the same index (borrowed handle) for bit-exact parity reads."""
         h = vp()
         _ck(_lib.load().pyrope_vindex_native(self._v, C.byref(h)))
-        g = _lib.GpuIndex.__new__(_lib.GpuIndex)
+        g = _BorrowedGpuIndex.__new__(_BorrowedGpuIndex)
         g._h, g.kind, g.dim, g.metric = h, self._kind, self._dim, int(self._metric)
         g.nlist, g.m, g.k = self._nlist, self._m, self._k
-        g.close = lambda: None  # the vindex owns it
+        g._owner = self  # keep the owning index alive while the view is in use
         return g
 
 
