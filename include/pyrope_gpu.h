@@ -260,6 +260,25 @@ int pyrope_vindex_snapshot(pyrope_vindex *v, const char *path); /* index file(s)
 int pyrope_vindex_load(pyrope_vindex *v, const char *path);
 const char *pyrope_vindex_last_error(void);
 
+/* ---- data formats either side of the path (csrc/formats.cu; host only).  Errors: pyrope_formats_last_error().
+ *      pyrope_parse_vector = VectorParsing.ParseVector (Utils/VectorParsing.cs:10-35): a VEC.ADD / VEC.SEARCH payload
+ *      is tried as a JSON array, then as ',' / ' ' separated text, then taken as raw little-endian float32 (length a
+ *      multiple of 4) — the binary form is what the benchmark client sends (VectorEncoding.ToLittleEndianBytes,
+ *      Benchmarks/Encoding/VectorEncoding.cs:8-16 = pyrope_encode_vector).  Empty payload -> INVALID_ARG
+ *      (ArgumentException), nothing matches -> INVALID_ARG "Unsupported vector format." (FormatException).
+ *      n_out = element count; at most cap floats are written (call with out = NULL to size the buffer). */
+int pyrope_parse_vector(const uint8_t *data, int64_t len, float *out, int64_t cap, int64_t *n_out);
+int pyrope_encode_vector(const float *vec, int64_t n, uint8_t *out, int64_t cap_bytes);
+/* FvecsReader.Read (Benchmarks/Datasets/FvecsReader.cs:14-60): records of int32 d + d float32.  limit < 0 = all
+ * (null), 0 = none; skip = records to pass over first.  dimension <= 0 -> INVALID_ARG "Invalid vector dimension",
+ * short record -> INVALID_ARG "Truncated fvecs record.", a torn 4-byte header at the end of the file ends the read.
+ * out may be NULL to query count / dimension. */
+int pyrope_fvecs_read(const char *path, int64_t limit, int64_t skip, float *out, int64_t cap_floats,
+                      int64_t *count_out, int *dim_out);
+/* The same records streamed into an index's device storage in 64 MiB batches (labels = row ordinals). */
+int pyrope_index_add_fvecs(pyrope_index *h, const char *path, int64_t limit, int64_t *added_out);
+const char *pyrope_formats_last_error(void);
+
 /* ---- building blocks exposed for parity tests and for "next" rows --------------- */
 /* KMeansUtils.FindNearestCentroid (KMeansUtils.cs:70-93), bit-exact: assign_out[i] = first index
  * of the best score.  Host pointers. */

@@ -97,6 +97,11 @@ SIGNATURES = {
     "pyrope_vindex_snapshot": (C.c_int, [vp, C.c_char_p]),
     "pyrope_vindex_load": (C.c_int, [vp, C.c_char_p]),
     "pyrope_vindex_last_error": (C.c_char_p, []),
+    "pyrope_parse_vector": (C.c_int, [vp, C.c_int64, vp, C.c_int64, i64p]),
+    "pyrope_encode_vector": (C.c_int, [vp, C.c_int64, vp, C.c_int64]),
+    "pyrope_fvecs_read": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, vp, C.c_int64, i64p, i32p]),
+    "pyrope_index_add_fvecs": (C.c_int, [vp, C.c_char_p, C.c_int64, i64p]),
+    "pyrope_formats_last_error": (C.c_char_p, []),
     "pyrope_coarse_assign": (C.c_int, [C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]),
     "pyrope_kmeans_train": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int32, vp, i32p, i32p]),
     "pyrope_pq_encode": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp, vp]),

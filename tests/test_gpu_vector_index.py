@@ -402,3 +402,29 @@ def test_delta_snapshot_load_roundtrip(vi, tmp_path):  # DeltaVectorIndex.cs:160
         assert [r.Score for r in a] == [r.Score for r in b]
     assert e.GetStats() == d.GetStats()
     assert e.Delete("v7") and not e.Delete("v7")
+
+
+def test_fvecs_streams_into_an_index(vi, tmp_path):  # FvecsReader.cs -> pyrope_index_add_fvecs
+    import struct
+
+    import pyrope_b200 as pg
+    from pyrope_b200 import formats as fm
+    rng = np.random.default_rng(21)
+    X = rng.random((3000, 32), dtype=np.float32)
+    p = tmp_path / "base.fvecs"
+    with open(p, "wb") as f:
+        for r in X:
+            f.write(struct.pack("<i", 32))
+            f.write(r.tobytes())
+    ix = pg.GpuIndex(pg.FLAT, 32, pg.L2)
+    assert fm.AddFvecs(ix, str(p), limit=2500) == 2500
+    ref = orc.FlatIndex(32, orc.L2)
+    ref.add_batch(fm.ReadFvecs(str(p), limit=2500))
+    Q = rng.random((8, 32), dtype=np.float32)
+    sc, rows, cnt = ix.search(Q, 10)
+    rid, rsc, rcn = ref.search_batch(Q, 10)
+    for i in range(8):
+        assert_topk_equivalent(rid[i], rsc[i], rows[i], sc[i], ctx="fvecs")
+    bad = pg.GpuIndex(pg.FLAT, 16, pg.L2)
+    with pytest.raises(ValueError, match="dimension"):
+        fm.AddFvecs(bad, str(p))
