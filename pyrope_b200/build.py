@@ -14,6 +14,7 @@ SOURCES = ["api.cu", "flat.cu", "ivf.cu", "pq.cu", "pq_lm.cu", "ivf_lm.cu", "bui
 HEADERS = ["common.cuh", "kernels.h", "exact_arith.cuh", "dotnet_random.h", "../../include/pyrope_gpu.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+EXTRA = os.environ.get("PYROPE_NVCC_EXTRA", "").split()  # e.g. -DPYROPE_LM_TIMING for the per-phase cycle counters
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
@@ -36,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + hdrs + [os.path.abspath(__file__)]):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):

@@ -47,14 +47,26 @@
 namespace pyrope {
 namespace {
 
-constexpr int LM_THREADS = 256;       // two CTAs per SM
-constexpr int LM_QS = 4;            // query slots per work item
-constexpr int LM_QC = 512;          // candidate queue entries per slot
-constexpr int LM_HDR = 64;          // item-block header bytes
+constexpr int LM_SCAN_WARPS = 8;    // warps 0-7 scan (one per query slot at hand-over)
+constexpr int LM_BUILD_WARPS = 8;   // warps 8-15 build the next item's tables
+constexpr int LM_THREADS = 32 * (LM_SCAN_WARPS + LM_BUILD_WARPS);  // one persistent CTA per SM
+constexpr int LM_BLK_STAGES = 3;    // item blocks in flight: being scanned, being built from, arriving
+constexpr int LM_QS = 8;            // query slots per work item (two halves of four)
+constexpr int LM_QC = 256;          // candidate queue entries per slot (two sets: items alternate)
+constexpr int LM_PF = 4;            // code chunks (256 rows each) a scan warp keeps in flight (even: two per iteration)
+constexpr int LM_HDR = 96;          // item-block header bytes
 constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
-constexpr int LM_LUT_BYTES = 256 * 256;
-constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 16;
-constexpr int LM_SMEM = LM_LUT_BYTES + 2 * LM_BLK_MAX + LM_QS * LM_QC * 8;
+constexpr int LM_LUT_BYTES = 256 * 256;  // [256 codes][16 tables][8 queries] u16
+constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 32;
+constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + 2 * LM_QS * LM_QC * 8;
+// Fixed-point lookup tables: entry = round(T * s) with s = LM_QMAX / B, B >= every table value of that (query,
+// item); 16 entries sum to < 2^15, so two queries share one 32-bit add and bit 15 is free for the threshold test.
+constexpr float LM_QMAX = 2046.f;
+// |sum of 16 rounded entries - s * sum of the fp32 entries| <= 16 * 0.5 (+ the product's own rounding)
+constexpr float LM_QERR = 8.25f;
+// Threshold tightening: every query keeps a histogram of its candidates' distances over [thr0/2, thr0] (thr0 = the
+// seed bound); the upper edge of the bucket where the running count reaches k bounds the k-th best distance.
+constexpr int LM_HB = 64;
 constexpr int SEED_NQ = 2;          // queries per seed CTA (share the codebook reads; small tables -> 5 CTAs/SM)
 constexpr int SEED_CAP = 1024;      // sampled distances per query
 constexpr int REDO_QCAP = 2048;
@@ -63,9 +75,10 @@ struct __align__(16) LmHeader {
     int list, nvec;
     long long vbeg;
     int qid[LM_QS];
-    int pslot[LM_QS];  // (probe rank * maxseg + segment): the pair's private slot in the query's pool
-    int pad[4];
+    short pslot[LM_QS];  // (probe rank * maxseg + segment): the pair's private slot in the query's pool
+    float s[LM_QS];      // fixed-point scale of the slot's lookup tables (0: slot unused)
 };
+static_assert(LM_SCAN_WARPS == LM_QS, "one scan warp per query slot");
 static_assert(sizeof(LmHeader) == LM_HDR, "header size");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -93,6 +106,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 28)) __trap();  // a broken pipeline must fault, not hang the GPU
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// ask L2 to fetch a byte range from HBM (no destination, no completion: SASS UBLKPF)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// barrier among the scan warps only (named barrier 1; the builders never join it)
+__device__ __forceinline__ void scan_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LM_SCAN_WARPS * 32) : "memory"); }
 // TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -119,11 +141,7 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 }
 
 
-#ifdef PYROPE_LM_TIMING
-#define LM_T(i) do { long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } while (0)
-#else
 #define LM_T(i) do { } while (0)
-#endif
 
 // ---- TMEM as a constant table: the PQ codebook lives in tensor memory for the CTA's lifetime -------------
 template <int N>
@@ -154,11 +172,14 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {  // 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct LmParams {
-    long long* timing;  // [grid][16 warps][8] cycle sums per phase (PYROPE_LM_TIMING builds only)
     int dim, ksub, k;
     const float* codebook; const uint8_t* codes; const uint8_t* dead;
     const unsigned char* iblk; const int32_t* n_items;
-    unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots;  // pool [nq][pslots][k], counts [nq][pslots]
+    unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots;  // pool [nq][pslots][kc], counts [nq][pslots]
+    int kc;              // pool entries per (query, probe) pair: k plus room for candidates tied within the rounding band
+    uint32_t* hist;            // [nq][LM_HB] candidates per distance bucket (zero-initialised)
+    const float* thr0;         // [nq] seed bound the buckets are laid over (0: query was not seeded)
+    const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits)
     int2* redo; int32_t* redo_cnt;
 };
 
@@ -216,7 +237,25 @@ struct LmPrep {
     int maxseg;
     const float* Q; const float* centroids; int dim;
     unsigned char* iblk; int blk;
+    const float* cmax;     // [16] max codeword norm per sub-quantiser
+    uint32_t* sinv_max;    // [nq] max over the query's items of 1 / scale, as float bits (zero-initialised)
 };
+// max_e |codeword(m, e)| per sub-quantiser (slightly rounded up): the table bound of lm_prepare_kernel
+__global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ codebook, int K, int sub, float* cmax) {
+    __shared__ uint32_t s_mx[16];
+    const int e = threadIdx.x;
+    if (e < 16) s_mx[e] = 0u;
+    __syncthreads();
+    if (e < K) {
+        for (int mi = 0; mi < 16; ++mi) {
+            float a = 0.f;
+            for (int d = 0; d < sub; ++d) { const float c = codebook[((size_t)mi * K + e) * sub + d]; a = fmaf(c, c, a); }
+            atomicMax(&s_mx[mi], __float_as_uint(sqrtf(a) * 1.000001f));  // non-negative floats order like their bits
+        }
+    }
+    __syncthreads();
+    if (e < 16) cmax[e] = __uint_as_float(s_mx[e]);
+}
 __global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
     const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= a.ioff[a.nlist]) return;
@@ -232,32 +271,54 @@ __global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
         psl[j] = idx < pend ? a.pairp[idx] : 0;
     }
     unsigned char* blkp = a.iblk + (size_t)w * a.blk;
+    const int sub = a.dim >> 4, D0 = lane * 4;
+    const bool on = lane * 4 < a.dim;
+    const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;  // the lane's four dimensions lie in one sub-vector
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
+    float scale[LM_QS];
+#pragma unroll
+    for (int h = 0; h < LM_QS / 4; ++h) {  // queries 4h .. 4h+3 form one float4-interleaved half
+        float4 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 q = c;
+            if (on && qid[4 * h + j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[4 * h + j] * a.dim) + lane);
+            t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
+            // fixed-point scale: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
+            float r2 = 0.25f * (t[j].x * t[j].x + t[j].y * t[j].y + t[j].z * t[j].z + t[j].w * t[j].w);
+            if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
+            float b = on ? sqrtf(r2) * 1.000001f + cm : 0.f;
+            b *= b;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+            scale[4 * h + j] = qid[4 * h + j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
+        }
+        if (on) {
+            // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
+            // table build read 256 contiguous bytes per d (no bank conflicts)
+            float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR + (size_t)h * a.dim * 16);
+            dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+            dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+            dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+            dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+        }
+    }
     if (lane == 0) {
         LmHeader h{};
         h.list = l;
         h.vbeg = beg;
         h.nvec = (int)len;
 #pragma unroll
-        for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = psl[j]; }
+        for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = (short)psl[j]; h.s[j] = scale[j]; }
         *reinterpret_cast<LmHeader*>(blkp) = h;
     }
-    if (lane * 4 < a.dim) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
-        float4 t[LM_QS];
+    if (lane < LM_QS) {
+        float mys = 0.f;
+        int myq = -1;
 #pragma unroll
-        for (int j = 0; j < LM_QS; ++j) {
-            float4 q = c;
-            if (qid[j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[j] * a.dim) + lane);
-            t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
-        }
-        // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
-        // table build read 256 contiguous bytes per d (no bank conflicts)
-        float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR);
-        const int sub = a.dim >> 4, D0 = lane * 4;
-        dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
-        dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
-        dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
-        dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+        for (int j = 0; j < LM_QS; ++j) { mys = lane == j ? scale[j] : mys; myq = lane == j ? qid[j] : myq; }
+        if (myq >= 0) atomicMax(a.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
     }
 }
 
@@ -307,6 +368,7 @@ struct LmSeed {
     const float* centroids; const float* codebook; int ksub;
     const uint8_t* codes; const uint8_t* dead; const int64_t* list_off;
     uint32_t* pool_thr; int k; int sample;
+    float* thr0;  // [nq] out: the bound as a distance (histogram range of the scan's threshold tightening)
 };
 __global__ void __launch_bounds__(256) ivfpq_lm_seed_kernel(LmSeed a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -398,269 +460,377 @@ __global__ void __launch_bounds__(256) ivfpq_lm_seed_kernel(LmSeed a) {
                 // the scan kernel evaluates the same distances in |p|^2+|r|^2-2r.p form: cover its rounding
                 const float tp = t + 2e-5f * t + 1e-5f * s_rr[warp] + 1e-12f;
                 a.pool_thr[q0 + warp] = score_to_ord(-tp) - 1u;  // accept iff dist <= tp
+                a.thr0[q0 + warp] = tp;
             }
         }
     }
 }
 
 // ---- the scan --------------------------------------------------------------------------------------
-// Two 256-thread CTAs per SM, each a plain build -> scan -> hand-over loop over its own items: while one
-// CTA builds lookup tables (FMA pipe) the other scans (shared-memory crossbar), so the two phases overlap
-// without any intra-CTA software pipelining.
+// One 512-thread persistent CTA per SM, warp-specialised: warps 8-15 BUILD the lookup tables of item i+1 (FMA pipe,
+// codewords from tensor memory) into one half of a double-buffered table while warps 0-7 SCAN item i from the
+// other half (shared-memory crossbar).  Hand-over is by mbarriers only: block-arrived (TMA), table-full (builders
+// -> scanners), item-done (scanners -> builders); the two groups never meet at a CTA-wide barrier inside the loop.
+//
+// Tables are FIXED POINT: the fp32 value T = |p|^2 + |r_m|^2 - 2 r_m.p of (query j, table m, code e) is stored as
+// the 16-bit integer round(T * s_j), s_j = LM_QMAX / B_j with B_j = max_m (|r_j,m| + max_e |p_m,e|)^2 >= T (triangle
+// inequality; lm_prepare_kernel puts s_j in the item header), so one LDS.128 serves EIGHT queries and a (code, query)
+// sum is an exact integer below 2^15: two queries share one 32-bit IADD, and `(0x8000 | threshold) - sum` keeps bit 15
+// set exactly when sum <= threshold.  The integer sum differs from s_j x (the fp32 sum) by at most LM_QERR, which
+// every threshold below allows for; reported distances never come from this path (the final kernel re-scores in
+// the reference's order).
 template <int SUB>
-__global__ void __launch_bounds__(LM_THREADS, 2) ivfpq_lm_scan_kernel(LmParams p) {
+__global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* lut = smem;                                                     // [256][16] float4
-    unsigned char* rbuf = lut + LM_LUT_BYTES;                                       // [2] item blocks
-    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + 2 * LM_BLK_MAX);          // [QS][QC]
-    __shared__ __align__(8) uint64_t s_mbar[2];
-    __shared__ int s_qcnt[LM_QS];
+    unsigned char* lut0 = smem;                                                    // [2][256][16] x 8 u16
+    unsigned char* rbuf = lut0 + 2 * LM_LUT_BYTES;                                  // [3] item blocks
+    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_BLK_STAGES * LM_BLK_MAX);  // [2][QS][QC]
+    __shared__ __align__(8) uint64_t s_mbar[LM_BLK_STAGES + 4];
+    __shared__ int s_qcnt[2 * LM_QS];
+    __shared__ int s_ti[LM_SCAN_WARPS * LM_QS];     // per scan warp: integer thresholds of its current item (-1: slot unused)
+    __shared__ float s_inv[LM_SCAN_WARPS * LM_QS];  // per scan warp: 1 / s_j
+    __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool builder = warp >= LM_SCAN_WARPS;
     const int K = p.ksub;
-    const int blk = LM_HDR + p.dim * 16;
-    const int m = lane & 15;                 // build: this thread's sub-quantiser
-    const int eb = (lane >> 4) + 2 * warp;   // build: its codewords are eb + 16 j, j < 16
+    const int blk = LM_HDR + p.dim * 32;
     const int n_items = *p.n_items;
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_n = first < n_items ? (n_items - first + stride - 1) / stride : 0;
 
+    const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: item block stage s arrived (TMA)
+    const uint32_t bar_full = smem_u32(&s_mbar[LM_BLK_STAGES]);         // +8*b: table half b built
+    const uint32_t bar_done = smem_u32(&s_mbar[LM_BLK_STAGES + 2]);     // +8*b: item in half b scanned and handed over
+    if (tid == 0) {
+        for (int i = 0; i < LM_BLK_STAGES; ++i) mbar_init(bar_blk + 8 * i, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, LM_BUILD_WARPS); mbar_init(bar_done + 8 * i, LM_SCAN_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 2 * LM_QS) s_qcnt[tid] = 0;
+
     // The PQ codebook (m*k*sub fp32 = 128 KiB at d=128) is parked in TENSOR MEMORY for the CTA's lifetime:
-    // 16 codewords per thread at the thread's own TMEM lane, columns (warp/4)*16*SUB + j*SUB.  Two CTAs per
-    // SM x 256 columns fill the 512-column TMEM exactly; the register file stays free for two resident CTAs.
-    constexpr int EPT = 256 * 16 / LM_THREADS;  // codewords per thread
-    constexpr int TCOLS = (LM_THREADS / 128) * EPT * SUB;  // 256 (SUB = 8) or 128 (SUB = 4)
-    __shared__ uint32_t s_tmem;
-    if (warp == 0) {
+    // 16 codewords per builder thread at the thread's own TMEM lane, columns (bw/4)*16*SUB + j*SUB.
+    constexpr int BT = LM_BUILD_WARPS * 32;     // builder threads
+    constexpr int EPT = 256 * 16 / BT;          // codewords per builder thread
+    constexpr int TCOLS = (BT / 128) * EPT * SUB;  // 256 (SUB = 8) or 128 (SUB = 4)
+    if (warp == LM_SCAN_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tcb = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * EPT * SUB);
-    float pn[EPT];
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int e = eb + (LM_THREADS / 16) * j;
-        float s = 0.f;
-        uint32_t r[SUB];
-#pragma unroll
-        for (int d4 = 0; d4 < SUB / 4; ++d4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < K) v = __ldg(reinterpret_cast<const float4*>(p.codebook + ((size_t)m * K + e) * SUB) + d4);
-            r[4 * d4 + 0] = __float_as_uint(v.x); r[4 * d4 + 1] = __float_as_uint(v.y);
-            r[4 * d4 + 2] = __float_as_uint(v.z); r[4 * d4 + 3] = __float_as_uint(v.w);
-            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
-        }
-        tmem_st<SUB>(tcb + j * SUB, r);
-        pn[j] = s;
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    // scan: lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
-    uint32_t op[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        op[i] = (uint32_t)(((lane + 2 * i) & 15) << 4) | ((uint32_t)(((lane + 2 * i + 1) & 15) << 4) << 8);
-        asm volatile("" : "+r"(op[i]));  // keep the eight offset words in registers (no rematerialisation in the loop)
-    }
-    const int rot = lane & 15;
-
-    const uint32_t bar_r = smem_u32(&s_mbar[0]);  // +8*s: item-block stage s
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(bar_r + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (tid < LM_QS) s_qcnt[tid] = 0;
-    __syncthreads();
 
     auto hdr_ptr = [&](int i) { return p.iblk + (size_t)(first + (size_t)i * stride) * blk; };
-    auto issue_block = [&](int i) {  // thread 0: TMA of item i's block (header + residual queries)
-        const uint32_t br = bar_r + 8 * (i & 1);
+    auto issue_block = [&](int i) {  // one thread: TMA of item i's block (header + residual queries)
+        const uint32_t br = bar_blk + 8 * (i % LM_BLK_STAGES);
         mbar_expect_tx(br, (uint32_t)blk);
-        bulk_g2s(smem_u32(rbuf + (i & 1) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
+        bulk_g2s(smem_u32(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
     };
-    if (tid == 0 && my_n > 0) issue_block(0);
 
-    // one warp per slot: hand at most k of the slot's candidates to the pair's private region of the query's
-    // pool (plain stores: no returning atomics on this path) and tighten the query's threshold
-    auto finalize = [&](const LmHeader* hd, int gitem) {
-        const int j = warp;
-        int* cntp = &s_qcnt[j];
-        const int n = *cntp;
-        const int q = hd->qid[j];
-        if (n > 0 && q >= 0) {
-            uint64_t* kq = qkeys + j * LM_QC;
-            if (n > LM_QC) {  // candidates were dropped: the plain kernel redoes this (query, item)
-                if (lane == 0) p.redo[atomicAdd(p.redo_cnt, 1)] = make_int2(q, gitem * LM_QS + j);
-            } else {
-                const size_t ps = (size_t)q * p.pslots + hd->pslot[j];
-                unsigned long long* dst = p.pool + ps * p.k;
-                uint64_t mink = ~0ull;
-                int kept;
-                if (n > p.k && n <= 64) {  // select by rank counting inside the warp
-                    const uint64_t a = lane < n ? kq[lane] : 0ull, b = lane + 32 < n ? kq[lane + 32] : 0ull;
-                    int ra = 0, rb = 0;
-                    for (int i = 0; i < n; ++i) {
-                        const uint64_t x = kq[i];
-                        ra += x > a;
-                        rb += x > b;
+    if (builder) {
+        // =================================== table builders ===================================
+        const int bw = warp - LM_SCAN_WARPS;
+        const int m = lane & 15;                 // this thread's sub-quantiser
+        const int eb = (lane >> 4) + 2 * bw;     // its codewords are eb + 16 j, j < 16
+        const uint32_t tcb = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((bw >> 2) * EPT * SUB);
+        float pn[EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int e = eb + (BT / 16) * j;
+            float s = 0.f;
+            uint32_t r[SUB];
+#pragma unroll
+            for (int d4 = 0; d4 < SUB / 4; ++d4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < K) v = __ldg(reinterpret_cast<const float4*>(p.codebook + ((size_t)m * K + e) * SUB) + d4);
+                r[4 * d4 + 0] = __float_as_uint(v.x); r[4 * d4 + 1] = __float_as_uint(v.y);
+                r[4 * d4 + 2] = __float_as_uint(v.z); r[4 * d4 + 3] = __float_as_uint(v.w);
+                s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            }
+            tmem_st<SUB>(tcb + j * SUB, r);
+            pn[j] = s;
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (tid == LM_SCAN_WARPS * 32 && my_n > 0) issue_block(0);
+        const unsigned long long magic2 = pack2(8388608.f, 8388608.f);  // 2^23: the sum's low mantissa bits are the integer
+        const unsigned long long quarter = pack2(0.25f, 0.25f);          // t = -2 r  =>  |r|^2 = sum t^2 / 4
+        for (int i = 0; i < my_n; ++i) {
+            const int b = i & 1;
+            mbar_wait(bar_done + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);  // item i-2 has left this half (and its block stage)
+            if (tid == LM_SCAN_WARPS * 32 && i + 1 < my_n) issue_block(i + 1);
+            mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
+            const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
+            const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
+            // the builders run one item ahead of the scanners: pull this item's codes from HBM into L2 now, so the
+            // scanners' loads (a few hundred rows ahead at most) find them there
+            if (tid == LM_SCAN_WARPS * 32 && hd->nvec > 0)
+                bulk_prefetch_l2(p.codes + (size_t)hd->vbeg * 16, (uint32_t)hd->nvec * 16u);
+            unsigned char* lut = lut0 + b * LM_LUT_BYTES;
+            // four queries at a time: |p|^2 + |r_m|^2 - 2 r_m.p, x s_j, rounded
+#pragma unroll 1
+            for (int h = 0; h < LM_QS / 4; ++h) {
+                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + h * p.dim + m;  // slot d*16 + m
+                unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
+#pragma unroll
+                for (int d = 0; d < SUB; ++d) {
+                    const ulonglong2 v = rt[d * 16];
+                    t01[d] = v.x; t23[d] = v.y;
+                    rr01 = ffma2(v.x, v.x, rr01);
+                    rr23 = ffma2(v.y, v.y, rr23);
+                }
+                const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
+                const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
+                unsigned char* lw = lut + eb * 256 + m * 16 + h * 8;
+                uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
+                tmem_ld<SUB>(tcb, cw[0]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    if (j + 1 < EPT) tmem_ld<SUB>(tcb + (j + 1) * SUB, cw[(j + 1) & 1]);
+                    const unsigned long long pj = pack2(pn[j], pn[j]);
+                    unsigned long long a01 = ffma2(rr01, quarter, pj), a23 = ffma2(rr23, quarter, pj);
+#pragma unroll
+                    for (int d = 0; d < SUB; ++d) {
+                        const float c = __uint_as_float(cw[j & 1][d]);
+                        const unsigned long long c2 = pack2(c, c);
+                        a01 = ffma2(c2, t01[d], a01);
+                        a23 = ffma2(c2, t23[d], a23);
                     }
-                    const bool ka = lane < n && ra < p.k, kb = lane + 32 < n && rb < p.k;
-                    const unsigned ma = __ballot_sync(0xffffffffu, ka), mb = __ballot_sync(0xffffffffu, kb);
-                    kept = __popc(ma) + __popc(mb);
-                    const unsigned below = (1u << lane) - 1u;
-                    if (ka) { dst[__popc(ma & below)] = a; mink = a; }
-                    if (kb) { dst[__popc(ma) + __popc(mb & below)] = b; mink = b < mink ? b : mink; }
-                } else {
-                    if (n > p.k) {  // 64 < n <= QC: warp-level sort, best first
+                    a01 = ffma2(a01, s01, magic2);
+                    a23 = ffma2(a23, s23, magic2);
+                    const uint32_t w0 = __byte_perm((uint32_t)a01, (uint32_t)(a01 >> 32), 0x5410);
+                    const uint32_t w1 = __byte_perm((uint32_t)a23, (uint32_t)(a23 >> 32), 0x5410);
+                    *reinterpret_cast<uint2*>(lw + j * ((BT / 16) * 256)) = make_uint2(w0, w1);
+                    if (j + 1 < EPT) tmem_ld_wait();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * b);  // release: this warp's table stores are visible to the waiters
+        }
+    } else {
+        // =================================== scanners ===================================
+        // lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
+        uint32_t op[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            op[i] = (uint32_t)(((lane + 2 * i) & 15) << 4) | ((uint32_t)(((lane + 2 * i + 1) & 15) << 4) << 8);
+            asm volatile("" : "+r"(op[i]));  // keep the eight offset words in registers (no rematerialisation in the loop)
+        }
+        const int rot = lane & 15;
+
+        // one warp per slot: hand the slot's candidates to the pair's private region of the query's pool (plain
+        // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
+        // approximate (fixed point), so beyond the k best the region also keeps whatever lies within twice the
+        // rounding bound of the k-th: one of those may be the better one once re-scored.
+        auto finalize = [&](const LmHeader* hd, int gitem, uint64_t* qk, int* qcnt, float inv_s) {
+            const int j = warp;
+            int* cntp = &qcnt[j];
+            const int n = *cntp;
+            const int q = hd->qid[j];
+            if (n > 0 && q >= 0) {
+                uint64_t* kq = qk + j * LM_QC;
+                bool redo = n > LM_QC;  // candidates were dropped: the plain kernel redoes this (query, item)
+                if (!redo) {
+                    const size_t ps = (size_t)q * p.pslots + hd->pslot[j];
+                    unsigned long long* dst = p.pool + ps * p.kc;
+                    const float err = LM_QERR * inv_s;
+                    int kept = n;
+                    float dk = 0.f;  // k-th best approximate distance of this pair
+                    if (n > p.k) {   // warp-level sort, best first
                         const int P2 = next_pow2(n);
                         for (int i = n + lane; i < P2; i += 32) kq[i] = 0ull;
                         __syncwarp();
                         bitonic_sort_desc<true>(kq, P2, lane, 32);
-                    }
-                    kept = min(n, p.k);
-                    for (int i = lane; i < kept; i += 32) {
-                        const uint64_t x = kq[i];
-                        dst[i] = x;
-                        mink = x < mink ? x : mink;
-                    }
-                }
-                if (lane == 0) p.pool_cnt[ps] = kept;
-                if (kept >= p.k) {  // this item alone proves k candidates at or above mink
+                        dk = -key_score(kq[p.k - 1]);
+                        const float lim = dk + 2.f * err;
+                        int extra = 0;
+                        for (int i = p.k + lane; i < n; i += 32) extra += (-key_score(kq[i]) <= lim);
+                        extra = __reduce_add_sync(0xffffffffu, extra);  // sorted: the band is a prefix of the tail
+                        kept = p.k + extra;
+                        if (kept > p.kc) redo = true;
+                    } else if (n == p.k) {
+                        float mx = 0.f;
+                        for (int i = lane; i < n; i += 32) mx = fmaxf(mx, -key_score(kq[i]));
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const uint64_t x = __shfl_xor_sync(0xffffffffu, mink, o);
-                        mink = x < mink ? x : mink;
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        dk = mx;
                     }
-                    if (lane == 0) atomicMax(p.pool_thr + q, (uint32_t)(mink >> 32));
+                    if (!redo) {
+                        for (int i = lane; i < kept; i += 32) dst[i] = kq[i];
+                        if (lane == 0) {
+                            p.pool_cnt[ps] = kept;
+                            // k candidates whose true distance is at most dk + err each: a bound of the k-th best
+                            if (n >= p.k) atomicMax(p.pool_thr + q, score_to_ord(-(dk + err)) - 1u);
+                        }
+                        // Across pairs: count the candidates per distance bucket; once the running count reaches k
+                        // the bucket's upper edge (+ the rounding bound) is a bound of the query's k-th best.
+                        // Counts read here may lag other CTAs' additions: a lagging count only loosens the bound.
+                        const float t0 = __ldg(p.thr0 + q);
+                        if (t0 > 0.f) {
+                            uint32_t* hq = p.hist + (size_t)q * LM_HB;
+                            const float lo = 0.5f * t0, wid = t0 * (0.5f / LM_HB);
+                            for (int i = lane; i < kept; i += 32) {
+                                const int bk = (int)fminf(fmaxf((-key_score(kq[i]) - lo) / wid, 0.f), (float)(LM_HB - 1));
+                                atomicAdd(hq + bk, 1u);
+                            }
+                            __syncwarp();
+                            const uint2 cc = __ldcg(reinterpret_cast<const uint2*>(hq) + lane);  // LM_HB = 64: two buckets per lane
+                            uint32_t cum = cc.x + cc.y;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t up = __shfl_up_sync(0xffffffffu, cum, o);
+                                if (lane >= o) cum += up;
+                            }
+                            const unsigned reach = __ballot_sync(0xffffffffu, cum >= (uint32_t)p.k);
+                            if (reach) {
+                                const int fl = __ffs(reach) - 1;
+                                if (lane == fl) {
+                                    const int bk = 2 * lane + ((cum - cc.y >= (uint32_t)p.k) ? 0 : 1);
+                                    // a bucket holds distances up to its upper edge (and anything clamped into bucket 0 / the last
+                                    // one is counted as if at that bucket's edge: bucket 0 is conservative, the last is never tighter
+                                    // than the seed bound)
+                                    const float edge = bk == LM_HB - 1 ? t0 * 1.01f + 2.f * err : lo + wid * (float)(bk + 1);
+                                    const float errq = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
+                                    atomicMax(p.pool_thr + q, score_to_ord(-(edge * 1.00001f + errq)) - 1u);
+                                }
+                            }
+                        }
+                    }
                 }
+                if (redo && lane == 0) p.redo[atomicAdd(p.redo_cnt, 1)] = make_int2(q, gitem * LM_QS + j);
             }
-        }
-        __syncwarp();
-        if (lane == 0) *cntp = 0;
-    };
+            __syncwarp();
+            if (lane == 0) *cntp = 0;
+        };
 
-#ifdef PYROPE_LM_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
-#endif
-    for (int i = 0; i < my_n; ++i) {
-        const int rs = i & 1;
-        // ---- build the four lookup tables of item i: |p|^2 + |r_m|^2 - 2 r_m.p
-        mbar_wait(bar_r + 8 * rs, (uint32_t)(i >> 1) & 1u);
-        LM_T(0);
-        const unsigned char* blkp = rbuf + rs * LM_BLK_MAX;
-        const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
-        const int4 qv = *reinterpret_cast<const int4*>(hd->qid);
-        const int nvec = hd->nvec;
-        const long long vbeg = hd->vbeg;
-        // codes stream straight from L2/HBM, one coalesced 16-byte row per lane, one chunk ahead; the first
-        // chunk's load is in flight during the table build
-        const uint4* cp = reinterpret_cast<const uint4*>(p.codes) + vbeg;
-        uint4 cnext = make_uint4(0u, 0u, 0u, 0u);
-        if (warp * 32 + lane < nvec) cnext = __ldg(cp + warp * 32 + lane);
-        uint32_t tu[LM_QS];
-        tu[0] = qv.x >= 0 ? __ldcg(p.pool_thr + qv.x) : 0xffffffffu;  // in flight during the build
-        tu[1] = qv.y >= 0 ? __ldcg(p.pool_thr + qv.y) : 0xffffffffu;
-        tu[2] = qv.z >= 0 ? __ldcg(p.pool_thr + qv.z) : 0xffffffffu;
-        tu[3] = qv.w >= 0 ? __ldcg(p.pool_thr + qv.w) : 0xffffffffu;
-        {
-            const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + m;  // slot d*16 + m
-            unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
+        // codes stream straight from L2/HBM, one coalesced 16-byte row per lane, LM_PF chunks of 256 rows ahead; the
+        // first chunks of item i+1 are requested before item i is handed over, so they arrive behind the barrier
+        uint4 cq[LM_PF];
+        auto prefetch_item = [&](int i) {
+            mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
+            const LmHeader* h = reinterpret_cast<const LmHeader*>(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX);
+            const int nv = h->nvec;
+            const uint4* cp = reinterpret_cast<const uint4*>(p.codes) + h->vbeg;
 #pragma unroll
-            for (int d = 0; d < SUB; ++d) {
-                const ulonglong2 v = rt[d * 16];
-                t01[d] = v.x; t23[d] = v.y;
-                rr01 = ffma2(v.x, v.x, rr01);
-                rr23 = ffma2(v.y, v.y, rr23);
+            for (int u = 0; u < LM_PF; ++u) {
+                const int v = (warp + u * LM_SCAN_WARPS) * 32 + lane;
+                cq[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (v < nv) cq[u] = __ldg(cp + v);
             }
-            const unsigned long long quarter = pack2(0.25f, 0.25f);  // t = -2 r  =>  |r|^2 = sum t^2 / 4
-            unsigned char* lw = lut + eb * 256 + m * 16;
-            uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
-            tmem_ld<SUB>(tcb, cw[0]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                if (j + 1 < EPT) tmem_ld<SUB>(tcb + (j + 1) * SUB, cw[(j + 1) & 1]);
-                const unsigned long long pj = pack2(pn[j], pn[j]);
-                unsigned long long a01 = ffma2(rr01, quarter, pj), a23 = ffma2(rr23, quarter, pj);
-#pragma unroll
-                for (int d = 0; d < SUB; ++d) {
-                    const float c = __uint_as_float(cw[j & 1][d]);
-                    const unsigned long long c2 = pack2(c, c);
-                    a01 = ffma2(c2, t01[d], a01);
-                    a23 = ffma2(c2, t23[d], a23);
+        };
+        if (my_n > 0) prefetch_item(0);
+        for (int i = 0; i < my_n; ++i) {
+            const int b = i & 1;
+            const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;  // arrived: prefetch_item(i) waited for it
+            const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
+            const int nvec = hd->nvec;
+            const long long vbeg = hd->vbeg;
+            const uint4* cp = reinterpret_cast<const uint4*>(p.codes) + vbeg;
+            uint64_t* qk = qkeys + b * (LM_QS * LM_QC);  // queues and counters alternate with the item parity, so this
+            int* qcnt = s_qcnt + b * LM_QS;              // item's pushes never meet the previous item's hand-over
+            // every warp keeps its own copy of the slots' scalars (lanes 0-7 compute one slot each): the current
+            // threshold becomes an integer bound, accept sum <= floor(s * tau) + QERR (rounded up)
+            int* ti_w = s_ti + warp * LM_QS;
+            float* inv_w = s_inv + warp * LM_QS;
+            {
+                int ti = -1;
+                float inv = 0.f;
+                if (lane < LM_QS) {
+                    const int myq = hd->qid[lane];
+                    if (myq >= 0) {
+                        const float mys = hd->s[lane];
+                        const uint32_t mytu = __ldcg(p.pool_thr + myq);
+                        const float tau = mytu ? -ord_to_score(mytu) : INFINITY;
+                        ti = (int)fminf(fmaxf(tau, 0.f) * mys + (LM_QERR + 1.f), 32767.f);
+                        inv = 1.f / mys;
+                    }
+                    ti_w[lane] = ti;
+                    inv_w[lane] = inv;
                 }
-                *reinterpret_cast<ulonglong2*>(lw + j * ((LM_THREADS / 16) * 256)) = make_ulonglong2(a01, a23);
-                if (j + 1 < EPT) tmem_ld_wait();
+                __syncwarp();
             }
-        }
-        LM_T(1);
-        __syncthreads();  // tables complete; the previous item's hand-over is done
-        LM_T(2);
-        if (tid == 0 && i + 1 < my_n) issue_block(i + 1);
-
-        // ---- scan item i
-        float thrd[LM_QS];
+            uint32_t th[LM_QS / 2];  // per query pair: (0x8000 | threshold) halves; an unused slot never passes (0x7fff, no guard bit)
 #pragma unroll
-        for (int j = 0; j < LM_QS; ++j)
-            thrd[j] = tu[j] == 0xffffffffu ? -INFINITY : (tu[j] ? -ord_to_score(tu[j]) : INFINITY);
-        LM_T(3);
-        for (int c = warp; c * 32 < nvec; c += LM_THREADS / 32) {
-            const int v = c * 32 + lane;
-            const uint4 cw = cnext;
-            if (v + LM_THREADS < nvec) cnext = __ldg(cp + v + LM_THREADS);
-            if (v < nvec) {
-                uint32_t w[4];
+            for (int u = 0; u < LM_QS / 2; ++u) {
+                const int t0 = ti_w[2 * u], t1 = ti_w[2 * u + 1];
+                th[u] = (t0 >= 0 ? (0x8000u | (uint32_t)t0) : 0x7fffu) | ((t1 >= 0 ? (0x8000u | (uint32_t)t1) : 0x7fffu) << 16);
+            }
+            mbar_wait(bar_full + 8 * b, (uint32_t)(i >> 1) & 1u);  // acquire: the builders' table stores
+            const unsigned char* lut = lut0 + b * LM_LUT_BYTES;
+            // two chunks (rows v0 and v1 = v0 + 256) per iteration: 32 independent table reads in flight per lane
+            for (int c = warp; c * 32 < nvec; c += 2 * LM_SCAN_WARPS) {
+                const int v0 = c * 32 + lane, v1 = v0 + LM_SCAN_WARPS * 32;
+                const uint4 cw0 = cq[0], cw1 = cq[1];
+#pragma unroll
+                for (int u = 0; u + 2 < LM_PF; ++u) cq[u] = cq[u + 2];
+                if (v0 + LM_PF * LM_SCAN_WARPS * 32 < nvec) cq[LM_PF - 2] = __ldg(cp + v0 + LM_PF * LM_SCAN_WARPS * 32);
+                if (v1 + LM_PF * LM_SCAN_WARPS * 32 < nvec) cq[LM_PF - 1] = __ldg(cp + v1 + LM_PF * LM_SCAN_WARPS * 32);
+                uint32_t wa[4], wb[4];
                 {   // rotate the 16 code bytes: new byte t = old byte (t + rot) & 15
                     const bool r8 = rot & 8, r4 = rot & 4;
-                    const uint32_t a0 = r8 ? cw.z : cw.x, a1 = r8 ? cw.w : cw.y, a2 = r8 ? cw.x : cw.z, a3 = r8 ? cw.y : cw.w;
-                    const uint32_t b0 = r4 ? a1 : a0, b1 = r4 ? a2 : a1, b2 = r4 ? a3 : a2, b3 = r4 ? a0 : a3;
                     const int sh = (rot & 3) * 8;
-                    w[0] = __funnelshift_r(b0, b1, sh); w[1] = __funnelshift_r(b1, b2, sh);
-                    w[2] = __funnelshift_r(b2, b3, sh); w[3] = __funnelshift_r(b3, b0, sh);
+                    {
+                        const uint32_t a0 = r8 ? cw0.z : cw0.x, a1 = r8 ? cw0.w : cw0.y, a2 = r8 ? cw0.x : cw0.z, a3 = r8 ? cw0.y : cw0.w;
+                        const uint32_t b0 = r4 ? a1 : a0, b1 = r4 ? a2 : a1, b2 = r4 ? a3 : a2, b3 = r4 ? a0 : a3;
+                        wa[0] = __funnelshift_r(b0, b1, sh); wa[1] = __funnelshift_r(b1, b2, sh);
+                        wa[2] = __funnelshift_r(b2, b3, sh); wa[3] = __funnelshift_r(b3, b0, sh);
+                    }
+                    {
+                        const uint32_t a0 = r8 ? cw1.z : cw1.x, a1 = r8 ? cw1.w : cw1.y, a2 = r8 ? cw1.x : cw1.z, a3 = r8 ? cw1.y : cw1.w;
+                        const uint32_t b0 = r4 ? a1 : a0, b1 = r4 ? a2 : a1, b2 = r4 ? a3 : a2, b3 = r4 ? a0 : a3;
+                        wb[0] = __funnelshift_r(b0, b1, sh); wb[1] = __funnelshift_r(b1, b2, sh);
+                        wb[2] = __funnelshift_r(b2, b3, sh); wb[3] = __funnelshift_r(b3, b0, sh);
+                    }
                 }
-                unsigned long long acc01 = 0ull, acc23 = 0ull;
+                // rows past the end read table entries of code 0 (their code words are zero) and are discarded below
+                uint32_t A0 = 0u, A1 = 0u, A2 = 0u, A3 = 0u, B0 = 0u, B1 = 0u, B2 = 0u, B3 = 0u;
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
                     // byte0 = table offset, byte1 = code byte: address = code * 256 + table * 16
                     const uint32_t sel = 0x7600u | (uint32_t)((t & 3) << 4) | (uint32_t)(4 + (t & 1));
-                    const uint32_t a = __byte_perm(w[t >> 2], op[t >> 1], sel);
-                    const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(lut + a);
-                    acc01 = fadd2(acc01, e.x);
-                    acc23 = fadd2(acc23, e.y);
+                    const uint32_t aa = __byte_perm(wa[t >> 2], op[t >> 1], sel);
+                    const uint32_t ab = __byte_perm(wb[t >> 2], op[t >> 1], sel);
+                    const uint4 ea = *reinterpret_cast<const uint4*>(lut + aa);
+                    const uint4 eb = *reinterpret_cast<const uint4*>(lut + ab);
+                    A0 += ea.x; A1 += ea.y; A2 += ea.z; A3 += ea.w;
+                    B0 += eb.x; B1 += eb.y; B2 += eb.z; B3 += eb.w;
                 }
-                float d0, d1, d2, d3;
-                unpack2(acc01, d0, d1);
-                unpack2(acc23, d2, d3);
-                if ((d0 < thrd[0]) | (d1 < thrd[1]) | (d2 < thrd[2]) | (d3 < thrd[3])) {
-                    const long long gpos = vbeg + v;
-                    if (!(p.dead && p.dead[gpos])) {
-                        const float dd[LM_QS] = {d0, d1, d2, d3};
+                // bit 15 / 31 of (guarded threshold - sum) survives exactly where sum <= threshold
+                const uint32_t hita = v0 < nvec ? ((th[0] - A0) | (th[1] - A1) | (th[2] - A2) | (th[3] - A3)) & 0x80008000u : 0u;
+                const uint32_t hitb = v1 < nvec ? ((th[0] - B0) | (th[1] - B1) | (th[2] - B2) | (th[3] - B3)) & 0x80008000u : 0u;
+                if (hita | hitb) {
 #pragma unroll
-                        for (int j = 0; j < LM_QS; ++j) {
-                            if (dd[j] < thrd[j]) {
-                                const int pos = atomicAdd(&s_qcnt[j], 1);
-                                if (pos < LM_QC) qkeys[j * LM_QC + pos] = make_key(-dd[j], (uint32_t)gpos);
+                    for (int r = 0; r < 2; ++r) {
+                        if (r ? hitb : hita) {
+                            const long long gpos = vbeg + (r ? v1 : v0);
+                            if (!(p.dead && p.dead[gpos])) {
+                                const uint32_t acc[4] = {r ? B0 : A0, r ? B1 : A1, r ? B2 : A2, r ? B3 : A3};
+#pragma unroll
+                                for (int j = 0; j < LM_QS; ++j) {
+                                    const int sum = (int)((acc[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                                    if (sum <= ti_w[j]) {
+                                        const int pos = atomicAdd(&qcnt[j], 1);
+                                        if (pos < LM_QC) qk[j * LM_QC + pos] = make_key(-((float)sum * inv_w[j]), (uint32_t)gpos);
+                                    }
+                                }
                             }
                         }
                     }
                 }
             }
+            if (i + 1 < my_n) prefetch_item(i + 1);
+            scan_bar_sync();  // queue counts complete (the only barrier among the scan warps per item)
+            finalize(hd, first + i * stride, qk, qcnt, inv_w[warp]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_done + 8 * b);  // this warp no longer needs table half b or the item's block
         }
-        LM_T(4);
-        __syncthreads();  // tables fully consumed, queue counts visible
-        LM_T(5);
-        if (warp < LM_QS) finalize(hd, first + i * stride);
-        LM_T(6);
     }
-#ifdef PYROPE_LM_TIMING
-    if (lane == 0 && p.timing)
-        for (int u = 0; u < 8; ++u) p.timing[((size_t)blockIdx.x * (LM_THREADS / 32) + warp) * 8 + u] = tacc[u];
-#endif
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (warp == LM_SCAN_WARPS) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TCOLS) : "memory");
     }
@@ -671,7 +841,7 @@ struct LmRedo {
     const float* Q; int dim; const float* centroids; const float* codebook; int ksub;
     const uint8_t* codes; const uint8_t* dead;
     const unsigned char* iblk; int blk; const int2* redo; const int32_t* redo_cnt;
-    unsigned long long* pool; int32_t* pool_cnt; int pslots; int k;
+    unsigned long long* pool; int32_t* pool_cnt; int pslots; int k; int kc;
     const uint32_t* pool_thr;  // the query's current threshold: a valid bound, so the redo queue starts warm
 };
 __global__ void __launch_bounds__(256) ivfpq_lm_redo_kernel(LmRedo a) {
@@ -710,17 +880,18 @@ __global__ void __launch_bounds__(256) ivfpq_lm_redo_kernel(LmRedo a) {
         Qu.prune(tid, 256);
         const int keep = s_cnt;
         if (tid == 0) a.pool_cnt[ps] = keep;
-        for (int i = tid; i < keep; i += 256) a.pool[ps * a.k + i] = keys[i];
+        for (int i = tid; i < keep; i += 256) a.pool[ps * a.kc + i] = keys[i];
     }
 }
 
-// ---- pool -> best k, exact re-score, final order ----------------------------------------------------
+// ---- pool -> candidates within the rounding band of the k-th, exact re-score, final order -----------------
 struct LmFinalParams {
     const float* Q; int dim;
     const float* centroids; const float* codebook; int ksub;
     const uint8_t* codes; const int64_t* list_off; int nlist; const int64_t* labels;
     const int64_t* probes; int P;
-    const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k;
+    const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k; int kc;
+    const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits): bounds every pool entry's error
     PairOut out;
 };
 
@@ -730,28 +901,39 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [next_pow2(pool_cap)]
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ int s_n;
-    if (tid == 0) s_n = 0;
+    __shared__ int s_n, s_m;
+    if (tid == 0) { s_n = 0; s_m = 0; }
     __syncthreads();
     for (int sl = tid; sl < p.pslots; sl += blockDim.x) {  // gather the pairs' private regions
         const size_t ps = (size_t)q * p.pslots + sl;
-        const int c = min(p.pool_cnt[ps], p.k);
+        const int c = min(p.pool_cnt[ps], p.kc);
         if (c > 0) {
             const int base = atomicAdd(&s_n, c);
-            for (int i = 0; i < c; ++i) keys[base + i] = p.pool[ps * p.k + i];
+            for (int i = 0; i < c; ++i) keys[base + i] = p.pool[ps * p.kc + i];
         }
     }
     __syncthreads();
     const int n = s_n;
     const int kk = min(n, p.k);
+    // Pool distances are approximate (fixed-point tables): |d - true| <= err.  Everything within 2 err of the k-th
+    // best approximate distance can still belong to the true top k, so all of it is re-scored.
+    int nres = n;
     if (n > kk) {
         const int P2 = next_pow2(max(n, 2));
         for (int i = n + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
         __syncthreads();
         bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
+        const float err = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
+        const float dk = -key_score(keys[kk - 1]);
+        const float lim = dk + 2.f * err + 1e-5f * dk;
+        int mine = 0;
+        for (int i = kk + tid; i < n; i += blockDim.x) mine += (-key_score(keys[i]) <= lim);
+        if (mine) atomicAdd(&s_m, mine);  // sorted: the band is a prefix of the tail
+        __syncthreads();
+        nres = kk + s_m;
     }
     // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order
-    for (int i = warp; i < kk; i += blockDim.x / 32) {
+    for (int i = warp; i < nres; i += blockDim.x / 32) {
         const uint32_t pos = key_pos(keys[i]);
         int lo = 0;  // the list holding pos is one of this query's probed lists: test them in parallel
         for (int p0 = 0; p0 < p.P; p0 += 32) {
@@ -776,8 +958,8 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
         if (lane == 0) keys[i] = make_key(-dist, pos);
     }
     __syncthreads();
-    const int P3 = next_pow2(max(kk, 2));
-    for (int i = kk + tid; i < P3; i += blockDim.x) keys[i] = 0ull;
+    const int P3 = next_pow2(max(nres, 2));
+    for (int i = nres + tid; i < P3; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
     bitonic_sort_desc<false>(keys, P3, tid, blockDim.x);
     const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
@@ -798,11 +980,13 @@ inline int lm_maxseg(int64_t) { return 1; }  // one item covers a whole list (co
 
 struct LmLayout {
     size_t zero_bytes;  // leading region cleared per search
-    size_t lcnt, lcur, pool_cnt, pool_thr, redo_cnt, scanned, loff, nit, ioff, pairq, pairp, item_list, redo, iblk, pool, temp, total;
+    size_t lcnt, lcur, pool_cnt, pool_thr, sinv_max, hist, thr0, redo_cnt, scanned, cmax, loff, nit, ioff, pairq, pairp, item_list, redo, iblk, pool, temp, total;
     size_t temp_bytes;
     int64_t max_items;
-    int pool_cap, pslots, blk;
+    int pool_cap, pslots, blk, kc;
 };
+// pool entries per (query, probe) pair: the k best plus room for candidates within the rounding band of the k-th
+inline int lm_kc(int k) { return k + 6 + k / 8; }
 
 LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_list_len) {
     LmLayout L{};
@@ -813,9 +997,13 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.lcur = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.pool_cnt = o; o += align_up(sizeof(int32_t) * (size_t)nq * P * maxseg, 256);
     L.pool_thr = o; o += align_up(sizeof(uint32_t) * (size_t)nq, 256);
+    L.sinv_max = o; o += align_up(sizeof(uint32_t) * (size_t)nq, 256);
+    L.hist = o; o += align_up(sizeof(uint32_t) * (size_t)nq * LM_HB, 256);
+    L.thr0 = o; o += align_up(sizeof(float) * (size_t)nq, 256);
     L.redo_cnt = o; o += 256;
     L.scanned = o; o += 256;
     L.zero_bytes = o;
+    L.cmax = o; o += 256;
     L.loff = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.nit = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.ioff = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
@@ -824,10 +1012,11 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.max_items = (npairs / LM_QS + std::min<int64_t>(npairs, nlist) + 1) * maxseg;
     L.item_list = o; o += align_up(sizeof(int32_t) * (size_t)L.max_items, 256);
     L.redo = o; o += align_up(sizeof(int2) * (size_t)L.max_items * LM_QS, 256);
-    L.blk = LM_HDR + dim * 16;
+    L.blk = LM_HDR + dim * 32;
     L.iblk = o; o += align_up((size_t)L.blk * (size_t)L.max_items, 256);
     L.pslots = P * maxseg;
-    L.pool_cap = L.pslots * k;
+    L.kc = lm_kc(k);
+    L.pool_cap = L.pslots * L.kc;
     L.pool = o; o += align_up(sizeof(unsigned long long) * (size_t)nq * L.pool_cap, 256);
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int32_t*)nullptr, (int32_t*)nullptr, nlist + 1);
@@ -847,6 +1036,10 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     int32_t* lcur = reinterpret_cast<int32_t*>(base + L.lcur);
     int32_t* pool_cnt = reinterpret_cast<int32_t*>(base + L.pool_cnt);
     uint32_t* pool_thr = reinterpret_cast<uint32_t*>(base + L.pool_thr);
+    uint32_t* sinv_max = reinterpret_cast<uint32_t*>(base + L.sinv_max);
+    float* cmax = reinterpret_cast<float*>(base + L.cmax);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(base + L.hist);
+    float* thr0 = reinterpret_cast<float*>(base + L.thr0);
     int32_t* redo_cnt = reinterpret_cast<int32_t*>(base + L.redo_cnt);
     unsigned long long* scanned = reinterpret_cast<unsigned long long*>(base + L.scanned);
     int32_t* loff = reinterpret_cast<int32_t*>(base + L.loff);
@@ -879,7 +1072,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
         LmSeed sd{};
         sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
         sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
-        sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k);
+        sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k); sd.thr0 = thr0;
         const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
         e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
         if (e != cudaSuccess) return e;
@@ -887,6 +1080,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
         cudaEventRecord(p.ev_join, p.aux_stream);
     }
     const unsigned gb = (unsigned)((npairs + 255) / 256), lb = (unsigned)((p.nlist + 1 + 255) / 256);
+    lm_cmax_kernel<<<1, 256, 0, st>>>(p.codebook, p.ksub, p.dim / 16, cmax);
     lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt, scanned);
     lm_items_per_list_kernel<<<lb, 256, 0, st>>>(lcnt, p.list_off, p.nlist, nit);
     e = cub::DeviceScan::ExclusiveSum(temp, tb, lcnt, loff, p.nlist + 1, st);
@@ -901,6 +1095,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     pa.item_list = item_list;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
     pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
+    pa.cmax = cmax; pa.sinv_max = sinv_max;
     mark();
     lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
     mark();
@@ -909,7 +1104,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
         LmSeed sd{};
         sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
         sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
-        sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k);
+        sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k); sd.thr0 = thr0;
         const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
         e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
         if (e != cudaSuccess) return e;
@@ -920,45 +1115,22 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     mark();
 
     LmParams sp{};
-#ifdef PYROPE_LM_TIMING
-    static long long* d_timing = nullptr;
-    if (!d_timing) cudaMalloc(&d_timing, sizeof(long long) * 512 * 16 * 8);
-    sp.timing = d_timing;
-#else
-    sp.timing = nullptr;
-#endif
     sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = p.codebook; sp.codes = p.codes; sp.dead = p.dead;
     sp.iblk = iblk; sp.n_items = ioff + p.nlist;
-    sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots;
+    sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
+    sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
     sp.redo = redo; sp.redo_cnt = redo_cnt;
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;
-    const int64_t grid = std::min<int64_t>(2 * num_sms, L.max_items);
+    const int64_t grid = std::min<int64_t>(num_sms, L.max_items);
     if (p.ev_k0) cudaEventRecord(p.ev_k0, st);
     ivfpq_lm_scan_kernel<SUB><<<(unsigned)grid, LM_THREADS, LM_SMEM, st>>>(sp);
     if (p.ev_k1) cudaEventRecord(p.ev_k1, st);
-#ifdef PYROPE_LM_TIMING
-    {
-        cudaStreamSynchronize(st);
-        static long long h[512 * 16 * 8];
-        cudaMemcpy(h, d_timing, sizeof(long long) * (size_t)grid * (LM_THREADS / 32) * 8, cudaMemcpyDeviceToHost);
-        const char* names[8] = {"wait_blk", "build", "sync1", "wait_codes", "scan", "sync2", "finalize", "-"};
-        for (int w = 0; w < LM_THREADS / 32; w += 1) {
-            fprintf(stderr, "[lm timing] warp %2d:", w);
-            for (int u = 0; u < 8; ++u) {
-                double sum = 0;
-                for (int b = 0; b < grid; ++b) sum += (double)h[((size_t)b * (LM_THREADS / 32) + w) * 8 + u];
-                fprintf(stderr, " %s=%.0fk", names[u], sum / (double)grid / 1e3);
-            }
-            fprintf(stderr, "\n");
-        }
-    }
-#endif
 
     LmRedo rd{};
     rd.Q = p.Q; rd.dim = p.dim; rd.centroids = p.centroids; rd.codebook = p.codebook; rd.ksub = p.ksub;
     rd.codes = p.codes; rd.dead = p.dead; rd.iblk = iblk; rd.blk = L.blk; rd.redo = redo; rd.redo_cnt = redo_cnt;
-    rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k; rd.pool_thr = pool_thr;
+    rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k; rd.kc = L.kc; rd.pool_thr = pool_thr;
     const size_t redo_smem = sizeof(uint64_t) * REDO_QCAP + sizeof(float) * (4096 + (size_t)p.dim);
     mark();
     ivfpq_lm_redo_kernel<<<(unsigned)(2 * num_sms), 256, redo_smem, st>>>(rd);
@@ -968,11 +1140,11 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub;
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
     fp.probes = p.probes; fp.P = P;
-    fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.out = p.out;
+    fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out;
     const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, L.pool_cap));
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
-    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, (P * p.k <= 1024 ? 128 : 256), fsm, st>>>(fp);
+    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, (L.pool_cap <= 2048 ? 128 : 256), fsm, st>>>(fp);
     mark();
     if (stage_dbg && nsev == 7) {
         cudaEventSynchronize(sev[6]);
@@ -999,7 +1171,7 @@ bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq,
     if (m != 16 || ksub > 256 || ksub < 1) return false;
     const int sub = dim / m;
     if (sub != 4 && sub != 8) return false;
-    if (k < 1 || k > kMaxTopK || (int64_t)nprobe * k * lm_maxseg(max_list_len) > 16384) return false;
+    if (k < 1 || k > kMaxTopK || (int64_t)nprobe * lm_kc(k) * lm_maxseg(max_list_len) > 16384 || nprobe > 32767) return false;
     if (nq * nprobe >= ((int64_t)1 << 29) || list_total >= ((int64_t)1 << 32)) return false;
     return true;
 }
@@ -1008,8 +1180,8 @@ size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist, int dim,
     return lm_layout(nq, nprobe, k, nlist, dim, max_list_len).total;
 }
 
-// count, items-per-list, 2 scans, pair fill, prepare, seed, scan, redo, final
-int ivfpq_lm_launches() { return 10; }
+// codeword bound, count, items-per-list, 2 scans, pair fill, item fill, prepare, seed, scan, redo, final
+int ivfpq_lm_launches() { return 12; }
 
 // codes scored by the most recent list-major search that used `scratch` (sum of probed list lengths)
 cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, int k, int nlist, int dim,
