@@ -47,10 +47,10 @@
 namespace pyrope {
 namespace {
 
-constexpr int LM_SCAN_WARPS = 8;    // warps 0-7 scan (one per query slot at hand-over)
-constexpr int LM_BUILD_WARPS = 8;   // warps 8-15 build the next item's tables
+constexpr int LM_SCAN_WARPS = 8;    // warps 0-7 scan
+constexpr int LM_BUILD_WARPS = 8;   // the last 8 warps build the next item's tables and hand finished items over (one per query slot)
 constexpr int LM_THREADS = 32 * (LM_SCAN_WARPS + LM_BUILD_WARPS);  // one persistent CTA per SM
-constexpr int LM_BLK_STAGES = 3;    // item blocks in flight: being scanned, being built from, arriving
+constexpr int LM_BLK_STAGES = 5;    // item blocks in flight: arriving, being built from, being scanned, two awaiting hand-over
 constexpr int LM_QS = 8;            // query slots per work item (two halves of four)
 constexpr int LM_QC = 256;          // candidate queue entries per slot (two sets: items alternate)
 constexpr int LM_PF = 4;            // code chunks (256 rows each) a scan warp keeps in flight (even: two per iteration)
@@ -78,7 +78,7 @@ struct __align__(16) LmHeader {
     short pslot[LM_QS];  // (probe rank * maxseg + segment): the pair's private slot in the query's pool
     float s[LM_QS];      // fixed-point scale of the slot's lookup tables (0: slot unused)
 };
-static_assert(LM_SCAN_WARPS == LM_QS, "one scan warp per query slot");
+static_assert(LM_BUILD_WARPS == LM_QS && LM_SCAN_WARPS % 4 == 0, "one builder warp per query slot; builders start a TMEM lane quadrant");
 static_assert(sizeof(LmHeader) == LM_HDR, "header size");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -113,8 +113,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// barrier among the scan warps only (named barrier 1; the builders never join it)
-__device__ __forceinline__ void scan_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LM_SCAN_WARPS * 32) : "memory"); }
 // TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -501,13 +499,14 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
 
     const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: item block stage s arrived (TMA)
     const uint32_t bar_full = smem_u32(&s_mbar[LM_BLK_STAGES]);         // +8*b: table half b built
-    const uint32_t bar_done = smem_u32(&s_mbar[LM_BLK_STAGES + 2]);     // +8*b: item in half b scanned and handed over
+    const uint32_t bar_done = smem_u32(&s_mbar[LM_BLK_STAGES + 2]);     // +8*b: every scan warp has left the item in half b
     if (tid == 0) {
         for (int i = 0; i < LM_BLK_STAGES; ++i) mbar_init(bar_blk + 8 * i, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, LM_BUILD_WARPS); mbar_init(bar_done + 8 * i, LM_SCAN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 2 * LM_QS) s_qcnt[tid] = 0;
+    for (int i = tid; i < 2 * LM_LUT_BYTES / 16; i += LM_THREADS) reinterpret_cast<uint4*>(lut0)[i] = make_uint4(0u, 0u, 0u, 0u);
 
     // The PQ codebook (m*k*sub fp32 = 128 KiB at d=128) is parked in TENSOR MEMORY for the CTA's lifetime:
     // 16 codewords per builder thread at the thread's own TMEM lane, columns (bw/4)*16*SUB + j*SUB.
@@ -554,78 +553,13 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         if (tid == LM_SCAN_WARPS * 32 && my_n > 0) issue_block(0);
-        const unsigned long long magic2 = pack2(8388608.f, 8388608.f);  // 2^23: the sum's low mantissa bits are the integer
-        const unsigned long long quarter = pack2(0.25f, 0.25f);          // t = -2 r  =>  |r|^2 = sum t^2 / 4
-        for (int i = 0; i < my_n; ++i) {
-            const int b = i & 1;
-            mbar_wait(bar_done + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);  // item i-2 has left this half (and its block stage)
-            if (tid == LM_SCAN_WARPS * 32 && i + 1 < my_n) issue_block(i + 1);
-            mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
-            const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
-            const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
-            // the builders run one item ahead of the scanners: pull this item's codes from HBM into L2 now, so the
-            // scanners' loads (a few hundred rows ahead at most) find them there
-            if (tid == LM_SCAN_WARPS * 32 && hd->nvec > 0)
-                bulk_prefetch_l2(p.codes + (size_t)hd->vbeg * 16, (uint32_t)hd->nvec * 16u);
-            unsigned char* lut = lut0 + b * LM_LUT_BYTES;
-            // four queries at a time: |p|^2 + |r_m|^2 - 2 r_m.p, x s_j, rounded
-#pragma unroll 1
-            for (int h = 0; h < LM_QS / 4; ++h) {
-                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + h * p.dim + m;  // slot d*16 + m
-                unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
-#pragma unroll
-                for (int d = 0; d < SUB; ++d) {
-                    const ulonglong2 v = rt[d * 16];
-                    t01[d] = v.x; t23[d] = v.y;
-                    rr01 = ffma2(v.x, v.x, rr01);
-                    rr23 = ffma2(v.y, v.y, rr23);
-                }
-                const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
-                const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
-                unsigned char* lw = lut + eb * 256 + m * 16 + h * 8;
-                uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
-                tmem_ld<SUB>(tcb, cw[0]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < EPT; ++j) {
-                    if (j + 1 < EPT) tmem_ld<SUB>(tcb + (j + 1) * SUB, cw[(j + 1) & 1]);
-                    const unsigned long long pj = pack2(pn[j], pn[j]);
-                    unsigned long long a01 = ffma2(rr01, quarter, pj), a23 = ffma2(rr23, quarter, pj);
-#pragma unroll
-                    for (int d = 0; d < SUB; ++d) {
-                        const float c = __uint_as_float(cw[j & 1][d]);
-                        const unsigned long long c2 = pack2(c, c);
-                        a01 = ffma2(c2, t01[d], a01);
-                        a23 = ffma2(c2, t23[d], a23);
-                    }
-                    a01 = ffma2(a01, s01, magic2);
-                    a23 = ffma2(a23, s23, magic2);
-                    const uint32_t w0 = __byte_perm((uint32_t)a01, (uint32_t)(a01 >> 32), 0x5410);
-                    const uint32_t w1 = __byte_perm((uint32_t)a23, (uint32_t)(a23 >> 32), 0x5410);
-                    *reinterpret_cast<uint2*>(lw + j * ((BT / 16) * 256)) = make_uint2(w0, w1);
-                    if (j + 1 < EPT) tmem_ld_wait();
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * b);  // release: this warp's table stores are visible to the waiters
-        }
-    } else {
-        // =================================== scanners ===================================
-        // lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
-        uint32_t op[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            op[i] = (uint32_t)(((lane + 2 * i) & 15) << 4) | ((uint32_t)(((lane + 2 * i + 1) & 15) << 4) << 8);
-            asm volatile("" : "+r"(op[i]));  // keep the eight offset words in registers (no rematerialisation in the loop)
-        }
-        const int rot = lane & 15;
-
-        // one warp per slot: hand the slot's candidates to the pair's private region of the query's pool (plain
+        // Hand-over runs on the BUILDER warps (they have the slack), one warp per slot, two items behind the build:
+        // hand the slot's candidates to the pair's private region of the query's pool (plain
         // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
         // approximate (fixed point), so beyond the k best the region also keeps whatever lies within twice the
         // rounding bound of the k-th: one of those may be the better one once re-scored.
-        auto finalize = [&](const LmHeader* hd, int gitem, uint64_t* qk, int* qcnt, float inv_s) {
-            const int j = warp;
+        auto finalize = [&](const LmHeader* hd, int gitem, uint64_t* qk, int* qcnt) {
+            const int j = bw;
             int* cntp = &qcnt[j];
             const int n = *cntp;
             const int q = hd->qid[j];
@@ -635,7 +569,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 if (!redo) {
                     const size_t ps = (size_t)q * p.pslots + hd->pslot[j];
                     unsigned long long* dst = p.pool + ps * p.kc;
-                    const float err = LM_QERR * inv_s;
+                    const float err = LM_QERR / hd->s[j];
                     int kept = n;
                     float dk = 0.f;  // k-th best approximate distance of this pair
                     if (n > p.k) {   // warp-level sort, best first
@@ -704,6 +638,83 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             __syncwarp();
             if (lane == 0) *cntp = 0;
         };
+
+        auto hand_over = [&](int i) {  // item i: wait until every scan warp has left it, then empty its queues
+            const int b = i & 1;
+            mbar_wait(bar_done + 8 * b, (uint32_t)(i >> 1) & 1u);
+            finalize(reinterpret_cast<const LmHeader*>(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), first + i * stride,
+                     qkeys + b * (LM_QS * LM_QC), s_qcnt + b * LM_QS);
+        };
+        const unsigned long long magic2 = pack2(8388608.f, 8388608.f);  // 2^23: the sum's low mantissa bits are the integer
+        const unsigned long long quarter = pack2(0.25f, 0.25f);          // t = -2 r  =>  |r|^2 = sum t^2 / 4
+        for (int i = 0; i < my_n; ++i) {
+            const int b = i & 1;
+            if (i >= 2) hand_over(i - 2);  // frees table half b and queue set b (the scanners wait for bar_full before reusing them)
+            if (tid == LM_SCAN_WARPS * 32 && i + 1 < my_n) issue_block(i + 1);
+            mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
+            const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
+            const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
+            // the builders run one item ahead of the scanners: pull this item's codes from HBM into L2 now, so the
+            // scanners' loads (a few hundred rows ahead at most) find them there
+            if (tid == LM_SCAN_WARPS * 32 && hd->nvec > 0)
+                bulk_prefetch_l2(p.codes + (size_t)hd->vbeg * 16, (uint32_t)hd->nvec * 16u);
+            unsigned char* lut = lut0 + b * LM_LUT_BYTES;
+            // four queries at a time: |p|^2 + |r_m|^2 - 2 r_m.p, x s_j, rounded
+#pragma unroll 1
+            for (int h = 0; h < LM_QS / 4; ++h) {
+                // slots fill in order: a half whose first slot is unused has no query at all.  Its table entries keep
+                // whatever an earlier item left there (or the initial zeros): at most LM_QMAX each, so the sums of the
+                // unused lanes stay below 2^15 and never disturb their neighbours
+                if (hd->qid[4 * h] < 0) continue;
+                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + h * p.dim + m;  // slot d*16 + m
+                unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
+#pragma unroll
+                for (int d = 0; d < SUB; ++d) {
+                    const ulonglong2 v = rt[d * 16];
+                    t01[d] = v.x; t23[d] = v.y;
+                    rr01 = ffma2(v.x, v.x, rr01);
+                    rr23 = ffma2(v.y, v.y, rr23);
+                }
+                const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
+                const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
+                unsigned char* lw = lut + eb * 256 + m * 16 + h * 8;
+                uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
+                tmem_ld<SUB>(tcb, cw[0]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    if (j + 1 < EPT) tmem_ld<SUB>(tcb + (j + 1) * SUB, cw[(j + 1) & 1]);
+                    const unsigned long long pj = pack2(pn[j], pn[j]);
+                    unsigned long long a01 = ffma2(rr01, quarter, pj), a23 = ffma2(rr23, quarter, pj);
+#pragma unroll
+                    for (int d = 0; d < SUB; ++d) {
+                        const float c = __uint_as_float(cw[j & 1][d]);
+                        const unsigned long long c2 = pack2(c, c);
+                        a01 = ffma2(c2, t01[d], a01);
+                        a23 = ffma2(c2, t23[d], a23);
+                    }
+                    a01 = ffma2(a01, s01, magic2);
+                    a23 = ffma2(a23, s23, magic2);
+                    const uint32_t w0 = __byte_perm((uint32_t)a01, (uint32_t)(a01 >> 32), 0x5410);
+                    const uint32_t w1 = __byte_perm((uint32_t)a23, (uint32_t)(a23 >> 32), 0x5410);
+                    *reinterpret_cast<uint2*>(lw + j * ((BT / 16) * 256)) = make_uint2(w0, w1);
+                    if (j + 1 < EPT) tmem_ld_wait();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * b);  // release: this warp's table stores are visible to the waiters
+        }
+        for (int i = max(my_n - 2, 0); i < my_n; ++i) hand_over(i);
+    } else {
+        // =================================== scanners ===================================
+        // lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
+        uint32_t op[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            op[i] = (uint32_t)(((lane + 2 * i) & 15) << 4) | ((uint32_t)(((lane + 2 * i + 1) & 15) << 4) << 8);
+            asm volatile("" : "+r"(op[i]));  // keep the eight offset words in registers (no rematerialisation in the loop)
+        }
+        const int rot = lane & 15;
 
         // codes stream straight from L2/HBM, one coalesced 16-byte row per lane, LM_PF chunks of 256 rows ahead; the
         // first chunks of item i+1 are requested before item i is handed over, so they arrive behind the barrier
@@ -821,10 +832,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 }
             }
             if (i + 1 < my_n) prefetch_item(i + 1);
-            scan_bar_sync();  // queue counts complete (the only barrier among the scan warps per item)
-            finalize(hd, first + i * stride, qk, qcnt, inv_w[warp]);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_done + 8 * b);  // this warp no longer needs table half b or the item's block
+            if (lane == 0) mbar_arrive(bar_done + 8 * b);  // release: this warp's pushes; it no longer reads table half b
         }
     }
 
