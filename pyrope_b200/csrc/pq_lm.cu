@@ -4,38 +4,38 @@
 // and the ADC loop of IvfPqVectorIndex.Search (IvfPqVectorIndex.cs:152-199).  The reference walks
 // query -> probed list -> code; a batch of 10^4 queries x 64 probes hits every inverted list ~10 times,
 // so this path inverts the loop: (query, probe) pairs are grouped BY LIST and one work item is one
-// inverted list x up to four of the queries that probe it.
+// inverted list x up to EIGHT of the queries that probe it.
 //
 // Pipeline (all on one stream, no host synchronisation):
+//   lm_cmax_kernel                     max codeword norm per sub-quantiser (bound of every table value);
 //   lm_count / scans / lm_fill_pairs   group the pairs by list (counting sort on device);
 //   lm_prepare_kernel                  one warp per item writes the item block: header (list, code range,
-//                                      four query ids, their pool slots) + the four residual queries
-//                                      -2(q - c) interleaved as float4 per dimension (slot d*16 + m);
+//                                      eight query ids, their pool slots, their fixed-point scales) + the eight
+//                                      residual queries -2(q - c), two float4-interleaved halves (slot d*16 + m);
 //   ivfpq_lm_seed_kernel               per query, an upper bound of its k-th best ADC distance from (a
 //                                      sample of) its nearest list, so no item starts without a threshold;
-//   ivfpq_lm_scan_kernel               two 256-thread persistent CTAs per SM, static item striding.  Per item:
-//       - the item block arrives by a TMA bulk copy (cp.async.bulk + mbarrier), one item ahead;
-//       - the PQ codebook (m*k*sub fp32 = 128 KiB at d=128) is parked in TENSOR MEMORY for the CTA's lifetime
-//         (tcgen05.st once, tcgen05.ld per build; 2 CTAs x 256 columns = the whole TMEM), which leaves the
-//         register file free for two resident CTAs: one builds tables (FMA pipe) while the other scans
-//         (shared-memory crossbar);
-//       - the four lookup tables are built with packed FFMA2 as |p|^2 + |r_m|^2 - 2 r_m.p and stored
-//         interleaved, LUT[e][m] = {q0,q1,q2,q3} at byte e*256 + m*16;
-//       - scan: codes stream from L2/HBM as one coalesced 16-byte row per lane, prefetched a chunk ahead;
-//         lane l reads table (l+t) mod 16 at step t, so the eight lanes of every quarter warp touch eight
-//         distinct 16-byte bank groups whatever the code bytes are (conflict-free by construction); the 16
-//         code bytes are rotated once per lane so step t uses a compile-time byte and the address
-//         (code<<8 | table<<4) is one PRMT; one LDS.128 = four (query, code) lookups, summed with FADD2;
-//       - candidates below the query's global threshold go to a small per-slot queue; after the item, one
-//         warp per slot hands at most k of them to the pair's private pool region in HBM and tightens the
-//         threshold (atomicMax).  A queue that overflows sends the (query, item) to the redo list;
+//   ivfpq_lm_scan_kernel               one 512-thread persistent CTA per SM, warp-specialised (see the kernel):
+//       - builder warps: item block by TMA bulk copy (cp.async.bulk + mbarrier), the item's codes pulled into L2
+//         by a bulk prefetch, PQ codebook parked in TENSOR MEMORY (tcgen05.st once, tcgen05.ld per build), tables
+//         |p|^2 + |r_m|^2 - 2 r_m.p built with packed FFMA2 and stored as 16-bit fixed point, eight queries per
+//         16 bytes: LUT[e][m] = {q0..q7} at byte e*256 + m*16, double buffered;
+//       - scan warps: codes stream from L2 as one coalesced 16-byte row per lane, four chunks in flight; lane l
+//         reads table (l+t) mod 16 at step t, so the eight lanes of every quarter warp touch eight distinct
+//         16-byte bank groups whatever the code bytes are (conflict-free by construction); the 16 code bytes are
+//         rotated once per lane so step t uses a compile-time byte and the address (code<<8 | table<<4) is one
+//         PRMT; one LDS.128 = eight (query, code) lookups, summed as exact integers, two queries per IADD;
+//       - candidates within the query's threshold go to a per-slot queue; the builder warps hand each finished
+//         item's queues to the pairs' private pool regions in HBM and tighten the thresholds (per pair, and
+//         across pairs through a per-query histogram of candidate distances).  A queue or region that overflows
+//         sends the (query, item) to the redo list;
 //   ivfpq_lm_redo_kernel               plain per-(query, item) scan for the rare overflows;
-//   ivfpq_lm_final_kernel              best k of the pool, RE-SCORED in the reference's exact fp32 order
-//                                      (L2SquaredUnsafe per sub-vector, sequential sum over m), so
-//                                      reported distances never come from the fused-multiply-add path.
+//   ivfpq_lm_final_kernel              everything in the pool within the rounding band of the k-th best is
+//                                      RE-SCORED in the reference's exact fp32 order (L2SquaredUnsafe per
+//                                      sub-vector, sequential sum over m), then the best k are taken: reported
+//                                      distances never come from the fixed-point path.
 // HBM traffic is one pass over the probed lists' codes (shared by the batch through L2) instead of one pass
-// per (query, probe); the scan is bound by the 128 B/clk/SM shared-memory crossbar (ncu: 4 wavefronts per
-// LDS.128, zero excess).
+// per (query, probe); the scan itself is bound by the 128 B/clk/SM shared-memory crossbar (4 wavefronts per
+// LDS.128, zero excess) and the builders by the FMA pipe.
 #include <cub/cub.cuh>
 
 #include <cstdio>
