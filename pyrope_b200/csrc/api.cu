@@ -961,14 +961,15 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                             : flat_tc_pick_splits(nq, n_scan_rows, tp.kprime, g_num_sms);
         if (twopass) {
             TRY(ws.tcg.ensure(sizeof(float) * flat_tc_gmax_floats(nq, n_scan_rows), 0, st));
-            TRY(ws.tct.ensure(sizeof(float) * (size_t)flat_tc_nq_pad(nq), 0, st));
+            TRY(ws.tct.ensure(sizeof(float) * (2 * (size_t)flat_tc_nq_pad(nq) + 16), 0, st));  // tau | band | overflow flag
             tp.gmax_ws = ws.tcg.as<float>(); tp.tau_ws = ws.tct.as<float>();
             if (!getenv("PYROPE_TC_PASSA_3X")) tp.amax = op.amax.as<float>();
-            launches += 2;
+            launches += 3;
         }
         const int64_t nq_pad = flat_tc_nq_pad(nq);
-        TRY(ws.tcq.ensure(sizeof(uint64_t) * (size_t)tp.splits * nq_pad * tp.cap, 0, st));
-        TRY(ws.tcc.ensure(sizeof(int32_t) * (size_t)tp.splits * nq_pad, 0, st));
+        const size_t tparts = (size_t)tp.splits * flat_tc_parts_per_split(tp);
+        TRY(ws.tcq.ensure(sizeof(uint64_t) * tparts * nq_pad * tp.cap, 0, st));
+        TRY(ws.tcc.ensure(sizeof(int32_t) * tparts * nq_pad, 0, st));
         tp.queue = ws.tcq.as<uint64_t>(); tp.counts = ws.tcc.as<int32_t>(); tp.out = po;
         if (&op == &h->tc_seg && h->kind == PYROPE_FLAT) {
             tp.ev_k0 = h->evk[0]; tp.ev_k1 = h->evk[1];

@@ -28,7 +28,7 @@ namespace pyrope {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;  // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps (+ 4 more when the columns are halved)
 constexpr int QH_BYTES = BM * BK * 4, XH_BYTES = BN * BK * 4;
 constexpr int STAGE_BYTES = 2 * QH_BYTES + 2 * XH_BYTES;  // 96 KiB
 constexpr int TMEM_COLS = 512;
@@ -126,11 +126,21 @@ struct TcParams {
     float* gmax;         // [nq_pad][gstride]
     int64_t gstride;     // groups per query = ntiles * 8
     const float* tau_init;  // [nq_pad] nullable
+    // pass B with ONE tf32 product: scores are off by at most band/2 from the exact proxy, so pruning keeps
+    // everything within `band` of the k'-th best and the threshold trails it by `band`; a queue that cannot be
+    // pruned below its capacity raises *overflow and the three-term kernel (run_if = overflow) redoes the batch
+    const float* band;   // [nq_pad] nullable (null: three-term scores, exact pruning)
+    int* overflow;       // nullable
+    const int* run_if;   // nullable: the whole grid exits at once unless *run_if != 0
+    // epilogue-bound shapes: 2 = eight epilogue warps, warps 8-11 take the upper half of every tile's columns and keep
+    // their own queues (part index = split * halves + half); 1 = four epilogue warps (warps 8-11 idle)
+    int halves;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
                const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo, TcParams p) {
+    if (p.run_if && *p.run_if == 0) return;  // fallback pass of the one-term path: nothing overflowed
     extern __shared__ __align__(1024) uint8_t smem[];
     // layout: [stage0 | stage1 | barriers | tmem ptr | per epilogue warp: sbias[2][BN], sscale[2][BN]]
     uint8_t* stage_base = smem;
@@ -151,7 +161,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4 * p.halves); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -215,18 +225,23 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 tc_commit(tfull0 + 8 * buf);    // accumulator tile complete
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue: thread <-> query =================
-        const int ew = warp - 4;                       // TMEM lane quarter
+    } else if (warp >= 4 && warp < 4 + 4 * p.halves) {
+        // ================= epilogue: thread <-> query (x column half) =================
+        const int ew = (warp - 4) & 3;                 // TMEM lane quarter
+        const int hf = (warp - 4) >> 2;                // column half of every tile this warp reads
+        const int HN = BN / p.halves;                  // columns per epilogue warp and tile
+        const int CH = HN / 32;                        // 32-column chunks of them
         const int et = ew * 32 + lane;                 // 0..127
         const int64_t gq = qt * BM + et;
         const bool qvalid = gq < p.nq;
-        uint64_t* myq = p.queue + ((int64_t)sp * p.nq_pad + (qt * BM + et)) * p.cap;
-        float* sbias = sterms + ew * (4 * BN);   // private to this warp: the four epilogue warps never wait
-        float* sscale = sbias + 2 * BN;         // for one another, only for the MMA warp (mbarriers)
+        const int64_t part = sp * p.halves + hf;
+        uint64_t* myq = p.queue + (part * p.nq_pad + (qt * BM + et)) * p.cap;
+        float* sbias = sterms + (warp - 4) * (4 * HN);   // private to this warp: the epilogue warps never wait
+        float* sscale = sbias + 2 * HN;                 // for one another, only for the MMA warp (mbarriers)
         int cnt = 0;
         const bool gmode = p.gmax != nullptr;
         float tau = (!gmode && p.tau_init && qvalid) ? __ldg(p.tau_init + gq) : -INFINITY;
+        const float band = (!gmode && p.band && qvalid) ? __ldg(p.band + gq) : 0.f;
         const int cap = p.cap, kprime = p.kprime;
 
         // Keep the k' best keys of lane l's queue (in L2), whole warp cooperating, queue held in
@@ -259,12 +274,35 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 n = __reduce_add_sync(0xffffffffu, n);
                 if (n >= kprime) lo = mid; else hi = mid - 1u;
             }
-            const uint32_t T = lo;
-            int ngt = 0;
+            uint32_t T = lo;
+            const float bl = __shfl_sync(0xffffffffu, band, l);
+            int quota, out = 0;
+            if (bl > 0.f) {
+                // approximate scores: everything within the band below the k'-th best may still beat it once
+                // re-scored, so it all stays (ties included: no quota)
+                T = score_to_ord(ord_to_score(lo) - bl);
+                int nk = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) ngt += (o[u] > T);
-            ngt = __reduce_add_sync(0xffffffffu, ngt);
-            int quota = kprime - ngt, out = 0;  // ties at T still admitted
+                for (int u = 0; u < U; ++u) nk += (e[u] != 0ull && o[u] >= T);
+                nk = __reduce_add_sync(0xffffffffu, nk);
+                if (nk > cap - 64) {  // cannot shrink: flag the batch for the exact fallback, keep going with exactly k'
+                    if (lane == 0 && p.overflow) atomicExch(p.overflow, 1);
+                    T = lo;
+                    quota = -1;
+                } else {
+                    T = T > 0u ? T - 1u : 0u;  // keep o >= threshold  <=>  o > T
+                    quota = 0;
+                }
+            } else {
+                quota = -1;
+            }
+            if (quota < 0) {
+                int ngt = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) ngt += (o[u] > T);
+                ngt = __reduce_add_sync(0xffffffffu, ngt);
+                quota = kprime - ngt;  // ties at T still admitted
+            }
             const unsigned below = (1u << lane) - 1u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -278,7 +316,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 out += __popc(mk);
             }
             if (lane == l) {
-                cnt = out;  // == k'
+                cnt = out;  // == k' (more with a band)
                 tau = ord_to_score(T);
             }
             __syncwarp();
@@ -288,9 +326,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         // the L2 round trip hides behind the current tile's epilogue
         float nb[BN / 32], ns[BN / 32];
         auto load_terms = [&](int ti) {
-            const int64_t n0 = (t_begin + ti) * BN;
+            const int64_t n0 = (t_begin + ti) * BN + hf * HN;
 #pragma unroll
             for (int u = 0; u < BN / 32; ++u) {
+                if (u >= CH) break;
                 const int64_t pos = n0 + lane + u * 32;
                 nb[u] = -INFINITY; ns[u] = 0.f;
                 if (pos < p.n_scan) {
@@ -302,8 +341,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         auto store_terms = [&](uint32_t buf) {
 #pragma unroll
             for (int u = 0; u < BN / 32; ++u) {
-                sbias[buf * BN + lane + u * 32] = nb[u];
-                sscale[buf * BN + lane + u * 32] = ns[u];
+                if (u >= CH) break;
+                sbias[buf * HN + lane + u * 32] = nb[u];
+                sscale[buf * HN + lane + u * 32] = ns[u];
             }
             __syncwarp();
         };
@@ -316,12 +356,12 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = hf * CH; c < hf * CH + CH; ++c) {
                 float v[32];
                 tc_ld32(taddr0 + c * 32, v);
                 if (qvalid) {  // proxy scores, in place: v = D * scale + bias (row terms read 4 columns at a time)
-                    const float4* b4 = reinterpret_cast<const float4*>(sbias + buf * BN + c * 32);
-                    const float4* s4 = reinterpret_cast<const float4*>(sscale + buf * BN + c * 32);
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + buf * HN + (c - hf * CH) * 32);
+                    const float4* s4 = reinterpret_cast<const float4*>(sscale + buf * HN + (c - hf * CH) * 32);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 bb = b4[j4];
@@ -376,7 +416,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         // final: leave the best k' (unordered) in place, publish the counts
         if (!gmode) {
             for (int l = 0; l < 32; ++l) prune_lane(l);
-            p.counts[(int64_t)sp * p.nq_pad + qt * BM + et] = qvalid ? cnt : 0;
+            p.counts[part * p.nq_pad + qt * BM + et] = qvalid ? cnt : 0;
         }
     }
 
@@ -396,10 +436,12 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
 __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __restrict__ gmax, int64_t gstride, int ngroups,
                                                             int64_t nq, int kprime, float* tau_out,
                                                             const float* __restrict__ Q, int dim,
-                                                            const float* __restrict__ amax) {
+                                                            const float* __restrict__ amax, float* band_out, int* overflow) {
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && overflow) *overflow = 0;
     if (q >= nq) return;
+    float band = 0.f;
     const float* g = gmax + q * gstride;
     float tau = -INFINITY;
     if (ngroups > kprime) {
@@ -442,9 +484,15 @@ __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __rest
             qq = warp_sum(qq);
             const float eps = 2.f * 9.85e-4f * sqrtf(qq) * __ldg(amax);  // 2 x 2^-10 (1 + 2^-7) |q| A
             tau -= eps + 1e-6f * fabsf(tau);
+            // a one-term pass B sees the same scores as pass A: a row of the true top k' scores at least
+            // (k'-th group maximum) - eps there, which is this tau; its pruning band is the same 2 x eps_q
+            band = eps + 1e-6f * fabsf(tau);
         }
     }
-    if (lane == 0) tau_out[q] = tau;
+    if (lane == 0) {
+        tau_out[q] = tau;
+        if (band_out) band_out[q] = band;
+    }
 }
 
 // ---- exact fp32 re-score of the survivors + final ordering -------------------------------------
@@ -637,6 +685,7 @@ bool flat_tc_supported(int dim, int k) { return dim % 4 == 0 && dim >= 8 && k >=
 // queue capacity per (split, query): a prune (register-resident bisection select by the whole warp) fires
 // when fewer than 32 slots are left and keeps k'; the headroom cap - 32 - k' is the number of candidates
 // accepted between two prunes.
+int flat_tc_parts_per_split(const FlatTcParams& a) { return (a.gmax_ws && a.tau_ws) ? 2 : 1; }
 int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * kprime + 32))); }
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
@@ -667,7 +716,9 @@ static int pick_splits_seeded(int64_t nq, int64_t n_scan, int num_sms, int64_t s
 }
 
 int flat_tc_pick_splits_seeded(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
-    return pick_splits_seeded(nq, n_scan, num_sms, std::max<int64_t>(1, 4096 / kprime));
+    // two column halves per split, up to cap entries each within the band: the re-score holds them all in shared
+    // memory (16,384 keys = 128 KiB), so at most 16 splits
+    return pick_splits_seeded(nq, n_scan, num_sms, std::min<int64_t>(16, std::max<int64_t>(1, 4096 / kprime)));
 }
 
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms) {
@@ -720,7 +771,14 @@ cudaError_t launch_tc_rowterms(const float* X, int64_t n, int dim, int metric, c
     return cudaGetLastError();
 }
 
-static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st);
+// mode: 0 = three-term scores; 1 = one-term pass B (band pruning, raises the overflow flag); 2 = three-term fallback that
+// runs only if the flag was raised
+static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st,
+                                       int mode = 0);
+// the two-pass path is the epilogue-bound regime: eight epilogue warps, two column halves per tile, each with its own
+// queues, so a (split, query) pair owns flat_tc_parts_per_split() parts of queue / counts
+// one-term pass B: tau_ws holds [tau | band | overflow flag]
+static bool one_term_b(const FlatTcParams& a) { return a.gmax_ws && a.tau_ws && a.amax && !getenv("PYROPE_TC_PASSB_3X"); }
 
 cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
@@ -731,14 +789,22 @@ cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
         cudaError_t e = launch_flat_tc_pass(a, pick_splits_seeded(a.nq, a.n_scan, sms, 32), a.gmax_ws, nullptr, st);
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (a.n_scan + BN - 1) / BN;
+        const int64_t nq_pad = flat_tc_nq_pad(a.nq);
+        const bool ot = one_term_b(a);
         tc_gmax_select_kernel<<<(unsigned)((a.nq + 3) / 4), 128, 0, st>>>(a.gmax_ws, ntiles * (BN / 32), (int)(ntiles * (BN / 32)),
-                                                                           a.nq, a.kprime, a.tau_ws, a.Q, a.dim, a.amax);
-        return launch_flat_tc_pass(a, a.splits, nullptr, a.tau_ws, st);
+                                                                           a.nq, a.kprime, a.tau_ws, a.Q, a.dim, a.amax,
+                                                                           ot ? a.tau_ws + nq_pad : nullptr,
+                                                                           ot ? reinterpret_cast<int*>(a.tau_ws + 2 * nq_pad) : nullptr);
+        if (!ot) return launch_flat_tc_pass(a, a.splits, nullptr, a.tau_ws, st);
+        e = launch_flat_tc_pass(a, a.splits, nullptr, a.tau_ws, st, 1);
+        if (e != cudaSuccess) return e;
+        return launch_flat_tc_pass(a, a.splits, nullptr, a.tau_ws, st, 2);
     }
     return launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st);
 }
 
-static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st) {
+static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st,
+                                       int mode) {
     CUtensorMap mqh, mql, mxh, mxl;
     if (!make_map(&mqh, a.Qhi, a.nq, a.dim, BM) || !make_map(&mql, a.Qlo, a.nq, a.dim, BM) ||
         !make_map(&mxh, a.Xhi, a.n_rows, a.dim, BN) || !make_map(&mxl, a.Xlo, a.n_rows, a.dim, BN))
@@ -748,7 +814,11 @@ static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float*
     p.ntiles = (a.n_scan + BN - 1) / BN;
     p.tiles_per_split = (p.ntiles + splits - 1) / splits;
     p.gmax = gmax; p.gstride = p.ntiles * (BN / 32); p.tau_init = tau_init;
-    p.one_term = (gmax && a.amax) ? 1 : 0;
+    p.halves = flat_tc_parts_per_split(a);
+    p.one_term = ((gmax && a.amax) || mode == 1) ? 1 : 0;
+    const int64_t nq_pad_f = flat_tc_nq_pad(a.nq);
+    if (mode == 1) { p.band = a.tau_ws + nq_pad_f; p.overflow = reinterpret_cast<int*>(a.tau_ws + 2 * nq_pad_f); }
+    if (mode == 2) p.run_if = reinterpret_cast<const int*>(a.tau_ws + 2 * nq_pad_f);
     p.has_uscale = (a.metric == kL2 || a.metric == kIP || !a.scale) ? 1 : 0;
     p.uscale = a.metric == kL2 && a.scale ? 2.f : 1.f;
     p.scale = a.scale; p.bias = a.bias; p.queue = a.queue; p.counts = a.counts;
@@ -757,9 +827,9 @@ static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float*
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 16 * 8 + 16 + 4 * (4 * BN * sizeof(float)) + 64;
     cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (a.ev_k0 && !gmax) cudaEventRecord(a.ev_k0, st);
+    if (a.ev_k0 && !gmax && mode != 2) cudaEventRecord(a.ev_k0, st);
     flat_tc_kernel<<<(unsigned)(qtiles * splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
-    if (a.ev_k1 && !gmax) cudaEventRecord(a.ev_k1, st);
+    if (a.ev_k1 && !gmax && mode != 2) cudaEventRecord(a.ev_k1, st);
     return cudaGetLastError();
 }
 
@@ -769,9 +839,14 @@ cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     RescoreParams r{};
     r.Q = a.Q; r.nq = a.nq; r.dim = a.dim; r.X = a.X; r.xnorm = a.xnorm; r.qnorm = a.qnorm; r.labels = a.labels;
-    r.metric = a.metric; r.k = a.k; r.cap = a.cap; r.splits = a.splits; r.queue = a.queue; r.counts = a.counts;
+    r.metric = a.metric; r.k = a.k; r.cap = a.cap; r.splits = a.splits * flat_tc_parts_per_split(a); r.queue = a.queue; r.counts = a.counts;
     r.nq_pad = flat_tc_nq_pad(a.nq); r.out = a.out;
-    const int P = next_pow2(std::max(2, a.splits * a.kprime));
+    // a one-term pass B leaves up to cap entries per (split, query): everything within the band of the k'-th
+    const int P = next_pow2(std::max(2, r.splits * (one_term_b(a) ? a.cap : a.kprime)));
+    if (sizeof(uint64_t) * (size_t)P > 48 * 1024) {
+        e = cudaFuncSetAttribute(flat_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * (size_t)P));
+        if (e != cudaSuccess) return e;
+    }
     flat_rescore_kernel<<<(unsigned)a.nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(r, P);
     return cudaGetLastError();
 }

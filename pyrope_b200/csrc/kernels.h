@@ -58,6 +58,8 @@ bool flat_tc_twopass(int dim, int64_t n_scan, int kprime);
 size_t flat_tc_gmax_floats(int64_t nq, int64_t n_scan);
 int flat_tc_pick_splits_seeded(int64_t nq, int64_t n_scan, int kprime, int num_sms);
 bool flat_tc_supported(int dim, int k);
+// queue / counts parts per (split, query): 2 on the two-pass path (column halves), else 1
+int flat_tc_parts_per_split(const FlatTcParams& p);
 int flat_tc_margin(int k);
 int flat_tc_cap(int kprime);
 int flat_tc_pick_splits(int64_t nq, int64_t n_scan, int kprime, int num_sms);

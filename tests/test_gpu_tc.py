@@ -161,3 +161,22 @@ def test_two_pass_threshold_matches_oracle_and_one_pass(gpu, force_tc, monkeypat
         one.add(base)
         assert_batch_equivalent(_s(one, q, 20), got, ctx=f"one-pass vs two-pass metric={metric}")
         monkeypatch.delenv("PYROPE_TC_ONEPASS")
+
+
+@pytest.mark.parametrize("nq,metric", [(60, orc.L2), (300, orc.IP)])
+def test_flat_tc_two_pass_one_term_many_splits(gpu, force_tc, nq, metric):
+    """The two-pass threshold path (d <= 256, >= 16,384 rows, k' >= 32) with few query tiles, i.e. many row
+    splits x two column halves: pass A group maxima, one-TF32 pass B with band pruning, exact re-score of every
+    survivor.  Also run with near-duplicate rows, where a whole cluster sits inside the rounding band."""
+    rng = np.random.default_rng(77 + nq)
+    base = rng.random((70_000, 32), dtype=np.float32)
+    base[5000:5400] = base[4999] + rng.random((400, 32), dtype=np.float32) * 1e-4   # 400 rows within the band of each other
+    q = rng.random((nq, 32), dtype=np.float32)
+    q[:8] = base[4999] + 1e-3
+    ref = orc.FlatIndex(32, metric)
+    ref.add_batch(base)
+    ix = gpu.GpuIndex(gpu.FLAT, 32, gpu.L2 if metric == orc.L2 else gpu.INNER_PRODUCT)
+    ix.add(base)
+    for k in (40, 100):
+        assert_batch_equivalent(ref.search_batch(q, k), _s(ix, q, k), ctx=f"two-pass one-term nq={nq} k={k}")
+    assert ix.last_search_kernel()[0] == "flat_tc_kernel"
