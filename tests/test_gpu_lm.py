@@ -187,3 +187,48 @@ def test_lm_repeated_searches_reuse_scratch(gpu, mid):
     for nq, k, nprobe in ((300, 10, 8), (64, 100, 2), (200, 1, 16), (300, 10, 8)):
         assert_batch_equivalent(ref.search_batch(q[:nq], k, nprobe=nprobe), _s(ix, q[:nq], k, nprobe=nprobe),
                                 ctx=f"lm repeat nq={nq} k={k} nprobe={nprobe}")
+
+
+def test_lm_fixed_point_tables_adversarial(gpu):
+    """The scan works on 16-bit fixed-point tables (8 queries per lookup) and re-scores everything within the
+    rounding band of the k-th best.  Stress the band: thousands of duplicated vectors (identical codes, i.e. exact
+    ties that overflow the per-pair pool regions and go through the redo path), near-duplicates separated by less
+    than one quantisation step, rows of very different magnitude (a coarse scale for some queries) and queries
+    far outside the data."""
+    rng = np.random.default_rng(2024)
+    dim = 128
+    base = rng.random((12_000, dim), dtype=np.float32)
+    base[1000:3000] = base[999]                                            # 2,000 exact duplicates
+    base[3000:3600] = base[2999] + rng.random((600, dim), dtype=np.float32) * 2e-4   # inside one quantisation step
+    base[6000:6500] *= 40.0                                                # large rows: large residuals, coarse scale
+    ref, ix = _pair(gpu, base, dim, 12)
+    q = rng.random((96, dim), dtype=np.float32)
+    q[:10] = base[999] + 1e-3      # next to the duplicates
+    q[10:20] = base[2999] + 1e-4   # next to the near-duplicates
+    q[20:26] *= 40.0               # next to the large rows
+    q[26:30] = 500.0               # far from everything
+    for k, nprobe in ((10, 12), (3, 4), (64, 12), (300, 6)):
+        assert_batch_equivalent(ref.search_batch(q, k, nprobe=nprobe), _s(ix, q, k, nprobe=nprobe),
+                                ctx=f"lm adversarial k={k} nprobe={nprobe}")
+    # scores are the reference's values wherever the ids agree (ties may permute ids)
+    rid, rsc, _ = ref.search_batch(q, 10, nprobe=12)
+    gid, gsc, _ = _s(ix, q, 10, nprobe=12)
+    same = rid == gid
+    np.testing.assert_array_equal(rsc[same], gsc[same])
+
+
+def test_lm_random_shape_sweep(gpu):
+    """Random (n, nlist, nq, k, nprobe, deletes-before-build) draws against the oracle."""
+    rng = np.random.default_rng(99)
+    for trial in range(6):
+        dim = int(rng.choice([64, 128]))
+        n = int(rng.integers(3_000, 9_000))
+        nlist = int(rng.integers(3, 40))
+        nq = int(rng.integers(1, 200))
+        k = int(rng.choice([1, 5, 10, 50, 128]))
+        nprobe = int(rng.integers(1, nlist + 3))
+        base = rng.standard_normal((n, dim)).astype(np.float32) * rng.choice([0.1, 1.0, 7.0])
+        q = rng.standard_normal((nq, dim)).astype(np.float32)
+        ref, ix = _pair(gpu, base, dim, nlist)
+        assert_batch_equivalent(ref.search_batch(q, k, nprobe=nprobe), _s(ix, q, k, nprobe=nprobe),
+                                ctx=f"lm sweep trial={trial} dim={dim} n={n} nlist={nlist} nq={nq} k={k} nprobe={nprobe}")
