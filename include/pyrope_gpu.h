@@ -94,6 +94,13 @@ int pyrope_index_shadow_row(pyrope_index *h, int64_t row, int shadowed);
  * pyrope_index_load by a shim whose labels are process-local id ordinals. */
 int pyrope_index_set_labels(pyrope_index *h, int64_t n_rows, const int64_t *labels_by_row);
 
+/* BruteForceVectorIndex.EnableQuantization (BruteForceVectorIndex.cs:23-40), FLAT only: while on, added / upserted
+ * rows also get an 8-bit copy (ScalarQuantizer.Quantize, ScalarQuantizer.cs:22-62: per-vector min / max) and Search
+ * ranks by the integer distance between the quantised query and the quantised rows (:297-336: -L2Squared8Bit for
+ * L2, DotProduct8Bit for inner product and cosine).  Rows written while it was off have no quantised form: MaxScans
+ * counts them, results never contain them (:312-322). */
+int pyrope_index_set_quantization(pyrope_index *h, int enable);
+
 /* ---- build: replaces IVectorIndex.Build (IvfFlatVectorIndex.cs:85-145, IvfPqVectorIndex.cs:55-116;
  *      FLAT is a no-op, BruteForceVectorIndex.cs:56).  Training follows KMeansUtils.Train
  *      (KMeansUtils.cs:10-68: System.Random init seed 42 / 123 / 42+m, <=10 Lloyd iterations,
@@ -246,6 +253,7 @@ int pyrope_vindex_create(int kind, int dim, int metric, int nlist, int pq_m, int
 int pyrope_vindex_create_delta(pyrope_vindex *head, pyrope_vindex *tail, pyrope_vindex **out);
 int pyrope_vindex_destroy(pyrope_vindex *v);
 int pyrope_vindex_native(pyrope_vindex *v, pyrope_index **out); /* row-ordinal handle (NULL for a delta) */
+int pyrope_vindex_set_quantization(pyrope_vindex *v, int enable); /* BruteForceVectorIndex.EnableQuantization */
 int pyrope_vindex_add(pyrope_vindex *v, const char *id, const float *vec, int len);
 int pyrope_vindex_upsert(pyrope_vindex *v, const char *id, const float *vec, int len);
 int pyrope_vindex_delete(pyrope_vindex *v, const char *id, int *removed_out);

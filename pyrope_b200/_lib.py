@@ -49,6 +49,7 @@ SIGNATURES = {
     "pyrope_index_delete_row": (C.c_int, [vp, C.c_int64]),
     "pyrope_index_shadow_row": (C.c_int, [vp, C.c_int64, C.c_int]),
     "pyrope_index_set_labels": (C.c_int, [vp, C.c_int64, vp]),
+    "pyrope_index_set_quantization": (C.c_int, [vp, C.c_int]),
     "pyrope_index_build": (C.c_int, [vp]),
     "pyrope_index_set_train_params": (C.c_int, [vp, C.c_int64, C.c_int]),
     "pyrope_index_set_codebooks": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "pyrope_vindex_create_delta": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "pyrope_vindex_destroy": (C.c_int, [vp]),
     "pyrope_vindex_native": (C.c_int, [vp, C.POINTER(vp)]),
+    "pyrope_vindex_set_quantization": (C.c_int, [vp, C.c_int]),
     "pyrope_vindex_add": (C.c_int, [vp, C.c_char_p, vp, C.c_int]),
     "pyrope_vindex_upsert": (C.c_int, [vp, C.c_char_p, vp, C.c_int]),
     "pyrope_vindex_delete": (C.c_int, [vp, C.c_char_p, i32p]),
@@ -200,6 +202,9 @@ class GpuIndex:
 
     def shadow_row(self, row, shadowed=True):
         check(load().pyrope_index_shadow_row(self._h, row, 1 if shadowed else 0))
+
+    def set_quantization(self, enable: bool):
+        check(load().pyrope_index_set_quantization(self._h, 1 if enable else 0))
 
     # ---- build
     def build(self):

@@ -151,6 +151,7 @@ struct Workspace {
     DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probes_raw, probe_scores, probe_cnt, allow, qnorm,
         qhi, qlo, tcq, tcc,  // tensor-core path: split queries, candidate queues, counts
         tcg, tct,            // two-pass threshold: group maxima, per-query tau
+        q8,                  // SQ8: quantised queries
         hq, hs, hl, hc,      // h*: staging for the host-pointer entry point
         lm;                  // list-major IVF_PQ scan scratch
 };
@@ -193,6 +194,13 @@ struct pyrope_index {
     int64_t max_train_rows = 0;
     int max_iter = 0;
     int shard_rank = 0, shard_world = 1;
+
+    // FLAT with EnableQuantization (BruteForceVectorIndex.cs:36-40): byte copy of the rows, X8[cap][dpad], and which rows
+    // have one (rows written while the flag was off do not, :176-181, :209-214)
+    bool sq8 = false;
+    int dpad = 0;
+    int64_t x8_cap = 0;
+    DevBuf x8, qvalid8;
 
     // row ordinal -> location: >=0 buffer slot, <=-2 list position (-2-pos), -1 gone
     std::vector<int64_t> row_loc;
@@ -267,6 +275,28 @@ int seg_append(Index* h, int64_t n, const float* X, bool x_on_device, const int6
     return PYROPE_OK;
 }
 
+// SQ8 copies of segment rows [slot0, slot0 + n): quantised if the flag is on, else marked as having none
+int sq8_rows(Index* h, int64_t slot0, int64_t n) {
+    if (h->kind != PYROPE_FLAT || (!h->sq8 && !h->x8.p) || n <= 0) return PYROPE_OK;
+    Segment& s = h->seg;
+    cudaStream_t st = h->stream;
+    if (s.cap > h->x8_cap) {
+        const size_t old_rows = (size_t)std::min<int64_t>(h->x8_cap, s.nslots);
+        TRY(h->x8.ensure((size_t)s.cap * h->dpad, old_rows * h->dpad, st, true));
+        const size_t old_q = h->qvalid8.bytes;
+        TRY(h->qvalid8.ensure((size_t)s.cap, old_rows, st, true));
+        if (h->qvalid8.bytes > old_q) CK(cudaMemsetAsync(h->qvalid8.as<uint8_t>() + old_rows, 0, h->qvalid8.bytes - old_rows, st));
+        h->x8_cap = s.cap;
+    }
+    if (h->sq8)
+        CK(launch_sq8_quantize(s.X.as<float>() + slot0 * s.dim, n, s.dim, s.dim, h->x8.as<uint8_t>() + slot0 * h->dpad, h->dpad,
+                               h->qvalid8.as<uint8_t>() + slot0, st));
+    else
+        CK(cudaMemsetAsync(h->qvalid8.as<uint8_t>() + slot0, 0, (size_t)n, st));
+    CK(cudaStreamSynchronize(st));
+    return PYROPE_OK;
+}
+
 int add_common(Index* h, int64_t n, const float* X, bool dev, const int64_t* labels, int64_t* first_row_out) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     if (n < 0 || (n > 0 && !X)) return fail(PYROPE_ERR_INVALID_ARG, "vector is null");
@@ -276,8 +306,10 @@ int add_common(Index* h, int64_t n, const float* X, bool dev, const int64_t* lab
     if (n == 0) return PYROPE_OK;
     if (h->kind != PYROPE_FLAT) h->row_loc.resize((size_t)(first + n), -1);
     h->next_row += n;
+    const int64_t slot0 = h->seg.nslots;
     int r = seg_append(h, n, X, dev, labels, dev, first);
     if (r != PYROPE_OK) h->next_row = first;  // nothing was published
+    else if (h->kind == PYROPE_FLAT) r = sq8_rows(h, slot0, n);
     return r;
 }
 
@@ -917,14 +949,16 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     int max_parts = kMergeMaxCandidates / k;
     if (max_parts < 1) max_parts = 1;
     if (groups > max_parts - (scan_seg ? 1 : 0)) groups = std::max(1, max_parts - (scan_seg ? 1 : 0));
-    const bool use_tc_seg = scan_seg && h->tc_mode != 0 && flat_tc_supported(dim, k) &&
+    const bool use_sq8 = scan_seg && h->kind == PYROPE_FLAT && h->sq8;
+    const bool use_tc_seg = scan_seg && !use_sq8 && h->tc_mode != 0 && flat_tc_supported(dim, k) &&
                             (h->tc_mode == 1 || seg_scan >= 8192);
     // the fast coarse stage ranks Pc >= P candidate lists; they are re-ranked in the reference's arithmetic
     const int Pc = std::min(h->nc, std::min(P + 8, kMaxTopK));
     const bool use_tc_coarse = scan_lists && !ext_probes && h->tc_mode != 0 && flat_tc_supported(dim, Pc) &&
                                (h->tc_mode == 1 || h->nc >= 2048);
     int seg_splits = 0;
-    if (scan_seg) seg_splits = use_tc_seg ? 1 : flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
+    if (scan_seg) seg_splits = use_tc_seg ? 1 : use_sq8 ? sq8_pick_splits(nq, seg_scan, k, g_num_sms)
+                                                        : flat_scan_pick_splits(nq, seg_scan, k, g_num_sms, std::max(1, max_parts - groups));
     const int parts = seg_splits + groups;
     if ((int64_t)parts * k > kMergeMaxCandidates)
         return fail(PYROPE_ERR_UNSUPPORTED, "topK %d too large for %d partial lists", k, parts);
@@ -1033,6 +1067,18 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         if (seg.tc_dirty) { h->tc_seg.invalidate(); seg.tc_dirty = false; }
         TRY(run_tc(h->tc_seg, seg.X.as<float>(), seg.nslots, seg_scan, seg.ndead > 0 ? seg.dead.as<uint8_t>() : nullptr,
                    seg.norms.as<float>(), seg.labels.as<int64_t>(), k, po));
+    } else if (use_sq8) {
+        // quantised branch of BruteForceVectorIndex.Search (:297-336): the query gets its own min / max, rows are
+        // ranked by the integer distance between the byte vectors
+        TRY(ws.q8.ensure((size_t)nq * h->dpad, 0, st));
+        CK(launch_sq8_quantize(dQ, nq, dim, dim, ws.q8.as<uint8_t>(), h->dpad, nullptr, st));
+        PairOut po = out;
+        po.part_base = 0;
+        CK(launch_sq8_scan(ws.q8.as<uint8_t>(), nq, h->dpad, h->x8.as<uint8_t>(), seg_scan,
+                           seg.ndead > 0 ? seg.dead.as<uint8_t>() : nullptr, h->qvalid8.as<uint8_t>(), seg.labels.as<int64_t>(),
+                           h->metric, k, seg_splits, po, st));
+        launches += 2;
+        h->dom_kernel = "sq8_scan_kernel";
     } else if (scan_seg) {
         int cap = flat_scan_cap(k);
         TRY(ws.queue.ensure(sizeof(uint64_t) * (size_t)seg_splits * nq * cap, 0, st));
@@ -1235,6 +1281,7 @@ int pyrope_index_update_row(pyrope_index* h, int64_t row, const float* x) {
     CK(cudaMemcpyAsync(s.X.as<float>() + slot * s.dim, x, sizeof(float) * s.dim, cudaMemcpyHostToDevice, st));
     if (s.cosine) CK(launch_row_norms_exact(s.X.as<float>() + slot * s.dim, 1, s.dim, s.dim, s.norms.as<float>() + slot, st));
     s.tc_dirty = true;
+    if (h->kind == PYROPE_FLAT) TRY(sq8_rows(h, slot, 1));  // :209-214: quantised form refreshed, or reset to empty
     if (s.dead_h[(size_t)slot]) {  // FLAT Upsert un-deletes (BruteForceVectorIndex.cs:200-203)
         CK(cudaMemsetAsync(s.dead.as<uint8_t>() + slot, 0, 1, st));
         s.dead_h[(size_t)slot] = 0;
@@ -1331,6 +1378,23 @@ int pyrope_index_set_labels(pyrope_index* h, int64_t n_rows, const int64_t* labe
         CK(cudaMemcpyAsync(dl.p, labels_by_row, sizeof(int64_t) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
         CK(launch_gather_rows(dl.p, 8, h->list_rows.as<int64_t>(), h->list_total, h->list_labels.p, st));
         CK(cudaStreamSynchronize(st));
+    }
+    return PYROPE_OK;
+}
+
+int pyrope_index_set_quantization(pyrope_index* h, int enable) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (h->kind != PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "only the FLAT index has a quantised scan");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->sq8 = enable != 0;
+    if (h->sq8 && !h->x8.p) {  // first use: rows that exist already have no quantised form (added while the flag was off)
+        h->dpad = (h->dim + 15) / 16 * 16;
+        const int64_t cap = std::max<int64_t>(h->seg.cap, 1);
+        TRY(h->x8.ensure((size_t)cap * h->dpad, 0, h->stream, true));
+        TRY(h->qvalid8.ensure((size_t)cap, 0, h->stream, true));
+        CK(cudaMemsetAsync(h->qvalid8.p, 0, h->qvalid8.bytes, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->x8_cap = cap;
     }
     return PYROPE_OK;
 }

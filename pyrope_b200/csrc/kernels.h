@@ -85,6 +85,15 @@ cudaError_t launch_assign_from_shortlist(int metric, int dim, int64_t n, const f
 // scatter: dst[idx[i]] = src[i]
 cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
 
+// ---- FLAT, 8-bit scalar quantised (sq8.cu): ScalarQuantizer.Quantize:22-62 and the quantised branch of
+// BruteForceVectorIndex.Search:297-336 (integer distances between byte vectors, VectorMath.cs:441-680)
+cudaError_t launch_sq8_quantize(const float* X, int64_t n, int dim, int64_t ldx, uint8_t* out, int dpad, uint8_t* qvalid,
+                                cudaStream_t st);
+int sq8_pick_splits(int64_t nq, int64_t n_scan, int k, int num_sms);
+cudaError_t launch_sq8_scan(const uint8_t* Q8, int64_t nq, int dpad, const uint8_t* X8, int64_t n_scan, const uint8_t* dead,
+                            const uint8_t* qvalid, const int64_t* labels, int metric, int k, int splits, PairOut out,
+                            cudaStream_t st);
+
 // ---- K6: merge ------------------------------------------------------------------------------
 // in: candidate (score,label) at address part*part_stride + q*q_stride + j, j < k_in.
 // dedupe: a candidate whose label already occurs in a LOWER part is dropped (DeltaVectorIndex.cs:98-110: the

@@ -352,6 +352,13 @@ int pyrope_vindex_native(pyrope_vindex* v, pyrope_index** out) {
     return PYROPE_OK;
 }
 
+int pyrope_vindex_set_quantization(pyrope_vindex* v, int enable) {
+    if (!v) return vfail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (v->d || v->kind != PYROPE_FLAT) return vfail(PYROPE_ERR_INVALID_STATE, "EnableQuantization exists on BruteForceVectorIndex only");
+    std::unique_lock<std::shared_mutex> g(v->lock);
+    return vpass(pyrope_index_set_quantization(v->h, enable));
+}
+
 int pyrope_vindex_add(pyrope_vindex* v, const char* id, const float* vec, int len) {
     if (!v) return vfail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     std::unique_lock<std::shared_mutex> g(v->lock);

@@ -218,6 +218,16 @@ class BruteForceVectorIndex(_Leaf):
     def __init__(self, dimension: int, metric: VectorMetric = VectorMetric.L2):
         self._kind, self._nlist, self._m, self._k = _lib.FLAT, 0, 0, 0
         self._create(_lib.FLAT, dimension, metric)
+        self._quant = False
+
+    @property
+    def EnableQuantization(self) -> bool:  # BruteForceVectorIndex.cs:36-40
+        return self._quant
+
+    @EnableQuantization.setter
+    def EnableQuantization(self, value: bool):
+        _ck(_lib.load().pyrope_vindex_set_quantization(self._v, 1 if value else 0))
+        self._quant = bool(value)
 
 
 class IvfFlatVectorIndex(_Leaf):

@@ -428,3 +428,21 @@ def test_fvecs_streams_into_an_index(vi, tmp_path):  # FvecsReader.cs -> pyrope_
     bad = pg.GpuIndex(pg.FLAT, 16, pg.L2)
     with pytest.raises(ValueError, match="dimension"):
         fm.AddFvecs(bad, str(p))
+
+
+def test_bruteforce_quantization_flag(vi):  # BruteForceVectorIndexTests.cs:68-108
+    index = vi.BruteForceVectorIndex(12, vi.VectorMetric.L2)
+    index.EnableQuantization = True
+    vec1 = np.zeros(12, np.float32)
+    vec1[0] = 1.0
+    index.Add("a", vec1)
+    res = index.Search(vec1, 1)
+    assert len(res) == 1 and res[0].Id == "a"
+    # an upsert while the flag is off resets the quantised form: invisible to quantised search afterwards (:84-108)
+    index.EnableQuantization = False
+    index.Upsert("a", vec1)
+    index.EnableQuantization = True
+    assert index.Search(vec1, 1) == []
+    ivf = vi.IvfFlatVectorIndex(4)  # the flag exists on BruteForceVectorIndex only
+    import pyrope_b200 as pg
+    assert pg.load().pyrope_vindex_set_quantization(ivf._v, 1) == pg._lib.ERR_INVALID_STATE
