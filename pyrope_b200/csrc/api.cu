@@ -1060,6 +1060,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         return PYROPE_OK;
     }
 
+    bool direct_out = false;
     // ---- buffer / base scan
     if (scan_seg && use_tc_seg) {
         PairOut po = out;
@@ -1135,6 +1136,11 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             pp.codes = h->list_codes.as<uint8_t>(); pp.dead = ldead; pp.labels = h->list_labels.as<int64_t>();
             pp.k = k; pp.groups = groups; pp.force_generic = h->pq_force_generic;
             pp.out = out; pp.out.part_base = seg_splits;
+            if (use_lm && parts == 1) {  // the only part: the final kernel writes the search's output itself, no merge pass
+                pp.out = PairOut{d_scores, d_rows, 1, 0};
+                pp.out_counts = d_counts;
+                direct_out = true;
+            }
             if (use_lm) {
                 TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc, dim, h->max_list_len), 0, st));
                 pp.max_list_len = h->max_list_len;
@@ -1152,8 +1158,10 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         ++launches;
     }
     CK(cudaEventRecord(h->ev[2], st));
-    CK(launch_merge_pairs(nq, parts, k, k, out.scores, out.labels, k, (int64_t)parts * k, d_scores, d_rows, d_counts, st));
-    ++launches;
+    if (!direct_out) {
+        CK(launch_merge_pairs(nq, parts, k, k, out.scores, out.labels, k, (int64_t)parts * k, d_scores, d_rows, d_counts, st));
+        ++launches;
+    }
     CK(cudaEventRecord(h->ev[3], st));
     h->ev_valid = true;
     h->last_launches = launches;

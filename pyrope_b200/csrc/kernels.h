@@ -143,6 +143,7 @@ struct IvfPqScanParams {
     int k; int groups;
     int force_generic;                       // tests: run the simple kernel
     PairOut out;
+    int32_t* out_counts = nullptr;           // list-major path only: results per query, when `out` is the final output
 };
 cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
 // List-major variant (pq_lm.cu): (query, probe) pairs grouped by list, four queries per work item share

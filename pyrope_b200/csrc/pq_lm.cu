@@ -902,6 +902,7 @@ struct LmFinalParams {
     const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k; int kc;
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits): bounds every pool entry's error
     PairOut out;
+    int32_t* counts;           // nullable: results per query (when this kernel writes the search's final output)
 };
 
 template <int SUB>
@@ -972,6 +973,7 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     __syncthreads();
     bitonic_sort_desc<false>(keys, P3, tid, blockDim.x);
     const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
+    if (tid == 0 && p.counts) p.counts[q] = kk;
     for (int i = tid; i < p.k; i += blockDim.x) {
         if (i < kk) {
             const uint64_t key = keys[i];
@@ -1149,7 +1151,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub;
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
     fp.probes = p.probes; fp.P = P;
-    fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out;
+    fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out; fp.counts = p.out_counts;
     const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, L.pool_cap));
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
