@@ -504,11 +504,15 @@ struct RescoreParams {
     PairOut out;
 };
 
+// The survivors of a query are spread over `splits` queues; they pass through a window of P keys in shared memory:
+// load up to P - (kept so far), score the new ones exactly, sort, keep the best k, repeat.  P >= 2k and P covers the
+// usual total, so almost every query takes one round; only a query whose queues hold far more than expected (a band
+// full of near-ties) takes several.
 __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [P]
     __shared__ int s_total;
-    __shared__ int s_off[64];
+    __shared__ int s_off[65];
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -517,68 +521,79 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int 
             s_off[s] = t;
             t += p.counts[(int64_t)s * p.nq_pad + q];
         }
+        s_off[p.splits] = t;
         s_total = t;
     }
     __syncthreads();
     const int total = s_total;
-    P = min(P, next_pow2(max(total, 2)));  // sort only as much as there is (block-uniform)
-    for (int i = total + tid; i < P; i += blockDim.x) keys[i] = 0ull;
     const float* qv = p.Q + q * p.dim;
     const bool vec_ok = (p.dim % 4 == 0);
     const float qn = p.metric == kCosine ? p.qnorm[q] : 0.f;
-    // gather every split's survivors first (independent loads), then score them in one flat loop
-    for (int s = 0; s < p.splits; ++s) {
-        const int c = (s + 1 < p.splits ? s_off[s + 1] : total) - s_off[s];
-        const uint64_t* src = p.queue + ((int64_t)s * p.nq_pad + q) * p.cap;
-        for (int i = tid; i < c; i += blockDim.x) keys[s_off[s] + i] = __ldcg(src + i);
-    }
-    __syncthreads();
     const int hl = lane & 15, half = lane >> 4;  // two candidates per warp, 16 lanes each
-    for (int i0 = warp * 2; i0 < total; i0 += 16) {
-        const int i = i0 + half;
-        const bool on = i < total;
-        const uint32_t pos = on ? key_pos(keys[i]) : 0u;
-        const float* x = p.X + (int64_t)pos * p.dim;
-        float a = 0.f;
-        if (on) {
-            if (vec_ok) {
-                for (int d = hl * 4; d < p.dim; d += 64) {
-                    float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
-                    float4 qq = __ldg(reinterpret_cast<const float4*>(qv + d));
-                    if (p.metric == kL2) {
-                        float d0 = qq.x - xv.x, d1 = qq.y - xv.y, d2 = qq.z - xv.z, d3 = qq.w - xv.w;
-                        a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
-                    } else {
-                        a = fmaf(qq.x, xv.x, a); a = fmaf(qq.y, xv.y, a); a = fmaf(qq.z, xv.z, a); a = fmaf(qq.w, xv.w, a);
+    int kept = 0, off = 0, sorted_n = 0;
+    do {
+        const int n_new = min(total - off, P - kept);
+        // gather: flat candidate index g -> (split, position) through the prefix sums
+        for (int i = tid; i < n_new; i += blockDim.x) {
+            const int g = off + i;
+            int sidx = 0;
+            while (sidx + 1 < p.splits && s_off[sidx + 1] <= g) ++sidx;
+            keys[kept + i] = __ldcg(p.queue + ((int64_t)sidx * p.nq_pad + q) * p.cap + (g - s_off[sidx]));
+        }
+        __syncthreads();
+        for (int i0 = kept + warp * 2; i0 < kept + n_new; i0 += 16) {
+            const int i = i0 + half;
+            const bool on = i < kept + n_new;
+            const uint32_t pos = on ? key_pos(keys[i]) : 0u;
+            const float* x = p.X + (int64_t)pos * p.dim;
+            float a = 0.f;
+            if (on) {
+                if (vec_ok) {
+                    for (int d = hl * 4; d < p.dim; d += 64) {
+                        float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
+                        float4 qq = __ldg(reinterpret_cast<const float4*>(qv + d));
+                        if (p.metric == kL2) {
+                            float d0 = qq.x - xv.x, d1 = qq.y - xv.y, d2 = qq.z - xv.z, d3 = qq.w - xv.w;
+                            a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
+                        } else {
+                            a = fmaf(qq.x, xv.x, a); a = fmaf(qq.y, xv.y, a); a = fmaf(qq.z, xv.z, a); a = fmaf(qq.w, xv.w, a);
+                        }
+                    }
+                } else {
+                    for (int d = hl; d < p.dim; d += 16) {
+                        float xv = __ldg(x + d), qq = __ldg(qv + d);
+                        if (p.metric == kL2) { float df = qq - xv; a = fmaf(df, df, a); }
+                        else a = fmaf(qq, xv, a);
                     }
                 }
-            } else {
-                for (int d = hl; d < p.dim; d += 16) {
-                    float xv = __ldg(x + d), qq = __ldg(qv + d);
-                    if (p.metric == kL2) { float df = qq - xv; a = fmaf(df, df, a); }
-                    else a = fmaf(qq, xv, a);
-                }
             }
-        }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);  // within each half warp
-        if (on && hl == 0) {
-            float score;
-            if (p.metric == kL2) score = -a;
-            else if (p.metric == kIP) score = a;
-            else {
-                float xn = p.xnorm[pos];
-                score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : a / (qn * xn);
+            for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);  // within each half warp
+            if (on && hl == 0) {
+                float score;
+                if (p.metric == kL2) score = -a;
+                else if (p.metric == kIP) score = a;
+                else {
+                    float xn = p.xnorm[pos];
+                    score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : a / (qn * xn);
+                }
+                keys[i] = make_key(score, pos);
             }
-            keys[i] = make_key(score, pos);
         }
-    }
-    __syncthreads();
-    bitonic_sort_desc<false>(keys, P, tid, blockDim.x);
+        const int n = kept + n_new;
+        const int P2 = next_pow2(max(n, 2));  // sort only as much as there is (block-uniform)
+        for (int i = n + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
+        off += n_new;
+        kept = min(n, p.k);
+        sorted_n = n;
+    } while (off < total);
+    const int have = min(sorted_n, total);
     const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
     for (int i = tid; i < p.k; i += blockDim.x) {
-        uint64_t key = (i < P) ? keys[i] : 0ull;
-        if (i < total && key) {
+        uint64_t key = (i < have) ? keys[i] : 0ull;
+        if (key) {
             uint32_t pos = key_pos(key);
             p.out.scores[ob + i] = key_score(key);
             p.out.labels[ob + i] = p.labels ? p.labels[pos] : (int64_t)pos;
@@ -841,12 +856,10 @@ cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
     r.Q = a.Q; r.nq = a.nq; r.dim = a.dim; r.X = a.X; r.xnorm = a.xnorm; r.qnorm = a.qnorm; r.labels = a.labels;
     r.metric = a.metric; r.k = a.k; r.cap = a.cap; r.splits = a.splits * flat_tc_parts_per_split(a); r.queue = a.queue; r.counts = a.counts;
     r.nq_pad = flat_tc_nq_pad(a.nq); r.out = a.out;
-    // a one-term pass B leaves up to cap entries per (split, query): everything within the band of the k'-th
-    const int P = next_pow2(std::max(2, r.splits * (one_term_b(a) ? a.cap : a.kprime)));
-    if (sizeof(uint64_t) * (size_t)P > 48 * 1024) {
-        e = cudaFuncSetAttribute(flat_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * (size_t)P));
-        if (e != cudaSuccess) return e;
-    }
+    // window of the re-score: room for the usual k' + band per query and at least 2k, never more than 4,096 keys
+    // (32 KiB, so that many queries' CTAs stay resident); bigger totals take several rounds inside the kernel
+    const int usual = a.kprime * 2 + 64;
+    const int P = std::min(4096, next_pow2(std::max(std::max(2 * a.k, usual), 64)));
     flat_rescore_kernel<<<(unsigned)a.nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(r, P);
     return cudaGetLastError();
 }
