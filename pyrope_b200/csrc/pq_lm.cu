@@ -179,6 +179,7 @@ struct LmParams {
     const float* thr0;         // [nq] seed bound the buckets are laid over (0: query was not seeded)
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits)
     int2* redo; int32_t* redo_cnt;
+    int32_t* item_ctr;   // next unclaimed work item (zero-initialised): CTAs claim items as they go
 };
 
 // ---- grouping (query, probe) pairs by list ---------------------------------------------------------
@@ -494,8 +495,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     const int K = p.ksub;
     const int blk = LM_HDR + p.dim * 32;
     const int n_items = *p.n_items;
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int my_n = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+    // Items are claimed dynamically (one atomicAdd per item, two items ahead of the scan): lists differ a lot in
+    // length, and with few items per CTA a static assignment leaves SMs idle at the end.  s_item[i % stages] holds
+    // the global index of this CTA's i-th item, -1 once the counter ran past the end.
+    __shared__ int s_item[LM_BLK_STAGES];
 
     const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: item block stage s arrived (TMA)
     const uint32_t bar_full = smem_u32(&s_mbar[LM_BLK_STAGES]);         // +8*b: table half b built
@@ -521,11 +524,20 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    auto hdr_ptr = [&](int i) { return p.iblk + (size_t)(first + (size_t)i * stride) * blk; };
-    auto issue_block = [&](int i) {  // one thread: TMA of item i's block (header + residual queries)
+    // one thread: claim this CTA's i-th item and start the TMA of its block (header + residual queries); past the
+    // end, publish -1 and complete the barrier phase by hand so that every waiter wakes up and leaves
+    auto claim_block = [&](int i) -> bool {
         const uint32_t br = bar_blk + 8 * (i % LM_BLK_STAGES);
-        mbar_expect_tx(br, (uint32_t)blk);
-        bulk_g2s(smem_u32(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), hdr_ptr(i), (uint32_t)blk, br);
+        const int g = atomicAdd(p.item_ctr, 1);
+        if (g < n_items) {
+            s_item[i % LM_BLK_STAGES] = g;
+            mbar_expect_tx(br, (uint32_t)blk);  // release: the index above is visible to whoever sees the phase complete
+            bulk_g2s(smem_u32(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), p.iblk + (size_t)g * blk, (uint32_t)blk, br);
+            return true;
+        }
+        s_item[i % LM_BLK_STAGES] = -1;
+        mbar_arrive(br);
+        return false;
     };
 
     if (builder) {
@@ -552,7 +564,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             pn[j] = s;
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (tid == LM_SCAN_WARPS * 32 && my_n > 0) issue_block(0);
+        bool more = false;  // the claiming thread: items may be left
+        if (tid == LM_SCAN_WARPS * 32) more = claim_block(0);
         // Hand-over runs on the BUILDER warps (they have the slack), one warp per slot, two items behind the build:
         // hand the slot's candidates to the pair's private region of the query's pool (plain
         // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
@@ -642,16 +655,18 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         auto hand_over = [&](int i) {  // item i: wait until every scan warp has left it, then empty its queues
             const int b = i & 1;
             mbar_wait(bar_done + 8 * b, (uint32_t)(i >> 1) & 1u);
-            finalize(reinterpret_cast<const LmHeader*>(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), first + i * stride,
+            finalize(reinterpret_cast<const LmHeader*>(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), s_item[i % LM_BLK_STAGES],
                      qkeys + b * (LM_QS * LM_QC), s_qcnt + b * LM_QS);
         };
         const unsigned long long magic2 = pack2(8388608.f, 8388608.f);  // 2^23: the sum's low mantissa bits are the integer
         const unsigned long long quarter = pack2(0.25f, 0.25f);          // t = -2 r  =>  |r|^2 = sum t^2 / 4
-        for (int i = 0; i < my_n; ++i) {
+        int i = 0;
+        for (;; ++i) {
             const int b = i & 1;
             if (i >= 2) hand_over(i - 2);  // frees table half b and queue set b (the scanners wait for bar_full before reusing them)
-            if (tid == LM_SCAN_WARPS * 32 && i + 1 < my_n) issue_block(i + 1);
+            if (more) more = claim_block(i + 1);
             mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
+            if (s_item[i % LM_BLK_STAGES] < 0) break;  // no item i: items 0 .. i-1 were this CTA's share
             const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
             const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
             // the builders run one item ahead of the scanners: pull this item's codes from HBM into L2 now, so the
@@ -704,7 +719,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * b);  // release: this warp's table stores are visible to the waiters
         }
-        for (int i = max(my_n - 2, 0); i < my_n; ++i) hand_over(i);
+        if (i >= 1) hand_over(i - 1);  // item i-2 was handed over at the top of the last round
     } else {
         // =================================== scanners ===================================
         // lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
@@ -719,8 +734,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         // codes stream straight from L2/HBM, one coalesced 16-byte row per lane, LM_PF chunks of 256 rows ahead; the
         // first chunks of item i+1 are requested before item i is handed over, so they arrive behind the barrier
         uint4 cq[LM_PF];
-        auto prefetch_item = [&](int i) {
+        auto prefetch_item = [&](int i) -> bool {  // false: this CTA has no i-th item
             mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
+            if (s_item[i % LM_BLK_STAGES] < 0) return false;
             const LmHeader* h = reinterpret_cast<const LmHeader*>(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX);
             const int nv = h->nvec;
             const uint4* cp = reinterpret_cast<const uint4*>(p.codes) + h->vbeg;
@@ -730,9 +746,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 cq[u] = make_uint4(0u, 0u, 0u, 0u);
                 if (v < nv) cq[u] = __ldg(cp + v);
             }
+            return true;
         };
-        if (my_n > 0) prefetch_item(0);
-        for (int i = 0; i < my_n; ++i) {
+        bool have = prefetch_item(0);
+        for (int i = 0; have; ++i) {
             const int b = i & 1;
             const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;  // arrived: prefetch_item(i) waited for it
             const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
@@ -831,7 +848,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     }
                 }
             }
-            if (i + 1 < my_n) prefetch_item(i + 1);
+            have = prefetch_item(i + 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_done + 8 * b);  // release: this warp's pushes; it no longer reads table half b
         }
@@ -991,7 +1008,7 @@ inline int lm_maxseg(int64_t) { return 1; }  // one item covers a whole list (co
 
 struct LmLayout {
     size_t zero_bytes;  // leading region cleared per search
-    size_t lcnt, lcur, pool_cnt, pool_thr, sinv_max, hist, thr0, redo_cnt, scanned, cmax, loff, nit, ioff, pairq, pairp, item_list, redo, iblk, pool, temp, total;
+    size_t lcnt, lcur, pool_cnt, pool_thr, sinv_max, hist, thr0, redo_cnt, item_ctr, scanned, cmax, loff, nit, ioff, pairq, pairp, item_list, redo, iblk, pool, temp, total;
     size_t temp_bytes;
     int64_t max_items;
     int pool_cap, pslots, blk, kc;
@@ -1012,6 +1029,7 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.hist = o; o += align_up(sizeof(uint32_t) * (size_t)nq * LM_HB, 256);
     L.thr0 = o; o += align_up(sizeof(float) * (size_t)nq, 256);
     L.redo_cnt = o; o += 256;
+    L.item_ctr = o; o += 256;
     L.scanned = o; o += 256;
     L.zero_bytes = o;
     L.cmax = o; o += 256;
@@ -1130,7 +1148,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     sp.iblk = iblk; sp.n_items = ioff + p.nlist;
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
-    sp.redo = redo; sp.redo_cnt = redo_cnt;
+    sp.redo = redo; sp.redo_cnt = redo_cnt; sp.item_ctr = reinterpret_cast<int32_t*>(base + L.item_ctr);
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;
     const int64_t grid = std::min<int64_t>(num_sms, L.max_items);
