@@ -14,7 +14,7 @@ SOURCES = ["api.cu", "flat.cu", "ivf.cu", "pq.cu", "pq_lm.cu", "ivf_lm.cu", "bui
 HEADERS = ["common.cuh", "kernels.h", "exact_arith.cuh", "dotnet_random.h", "../../include/pyrope_gpu.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-EXTRA = os.environ.get("PYROPE_NVCC_EXTRA", "").split()  # e.g. -DPYROPE_LM_TIMING for the per-phase cycle counters
+EXTRA = os.environ.get("PYROPE_NVCC_EXTRA", "").split()  # extra nvcc flags for experiments (e.g. a -D switch)
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",

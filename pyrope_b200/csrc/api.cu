@@ -404,11 +404,6 @@ struct AssignScratch {
     DevBuf qhi, qlo, tcq, tcc, flag, idx, nsel, temp, sub_assign, xg;
 };
 
-__global__ void flag_fill_kernel(uint8_t* f, int64_t n, uint8_t v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) f[i] = v;
-}
-
 // KMeansUtils.FindNearestCentroid for n rows, bit-exact.  Small tables: exhaustive exact kernel.
 // Large tables (>= 2048 centroids): tensor-core proxy scores shortlist k' = 17 centroids per row, the
 // shortlist is re-evaluated in the reference's fp32 order (first index wins ties), and any row whose

@@ -124,22 +124,13 @@ __device__ __forceinline__ unsigned long long pack2(float a, float b) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
     return d;
 }
-__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
     unsigned long long d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 
 
-#define LM_T(i) do { } while (0)
 
 // ---- TMEM as a constant table: the PQ codebook lives in tensor memory for the CTA's lifetime -------------
 template <int N>
