@@ -372,6 +372,41 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    exchange = "none"
+    if split_coarse and w["kind"] == "IVF_PQ" and not args.no_threshold_exchange:
+        # share per-query thresholds between the ranks while their scan kernels run (NVLink peer memory, CUDA IPC):
+        # one unshared step is kept to check that the merged result is the same with the exchange on
+        # (every rank runs the same collectives whether or not its own set-up succeeds)
+        ref_sc, ref_rw = m_sc.clone(), m_rw.clone()
+        ok = True
+        try:
+            handle = ix.threshold_exchange_handle(nq)
+        except Exception as ex:
+            log(f"rank {rank}: threshold exchange unavailable ({ex})")
+            handle, ok = bytes(64), False
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).cuda()
+        allh = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh.view(-1), mine)
+        if ok:
+            try:
+                ix.threshold_exchange_open(world, rank, bytes(allh.cpu().numpy().tobytes()))
+            except Exception as ex:
+                log(f"rank {rank}: threshold exchange unavailable ({ex})")
+                ok = False
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = bool(flag.item())
+        barrier()
+        for _ in range(2):
+            step()
+        barrier()
+        same = bool(torch.equal(ref_rw, m_rw)) and bool(torch.equal(ref_sc, m_sc))
+        log(f"rank {rank}: threshold exchange {'on' if all_ok else 'partly on'}, merged result identical to the unshared search: {same}")
+        if ok and (not same or not all_ok):  # all or nothing
+            ix.threshold_exchange_close()
+        barrier()
+        if same and all_ok:
+            exchange = "in-kernel atomicMax of per-query thresholds into the peers' arrays (NVLink peer memory)"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -516,7 +551,8 @@ def run_ours(args):
                        f"{w['n'] * w.get('m', w['dim'] * 4) / 1e6:.0f} MB scanned region vs 126 MB L2)",
                        "parallelism": f"lists sharded list_id % {world}" if w["kind"] != "FLAT" else f"rows sharded in {world} blocks",
                        **recall, "exchange": ("nccl all_gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
-                                   ("nccl all_gather of per-rank top-k + on-device merge" if world > 1 else "none"), **build_info},
+                                   ("nccl all_gather of per-rank top-k + on-device merge" if world > 1 else "none") +
+                                   ("" if exchange == "none" else " + " + exchange), **build_info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * args.steps),
             "roofline": roofline, "cpu_baseline": cpu,
         }
@@ -604,6 +640,8 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("PYROPE_BENCH_SCALE", "1.0")))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-threshold-exchange", action="store_true",
+                    help="multi-GPU IVF_PQ: do not share thresholds between the ranks' scan kernels")
     ap.add_argument("--recall-queries", type=int, default=200, help="queries used for the recall@10 read-out (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -119,6 +119,16 @@ int pyrope_index_set_codebooks(pyrope_index *h, int n_centroids, const float *ce
  * are dropped at the next pyrope_index_build.  Every rank sees all rows and all queries; per-rank
  * top-k lists are exchanged with NCCL allgather and reduced by pyrope_topk_merge_device. */
 int pyrope_index_set_shard(pyrope_index *h, int rank, int world);
+/* Multi-GPU IVF_PQ (list-major scan): share per-query thresholds between the ranks while their scan kernels run.  A
+ * bound one rank proves for a query (k candidates at or below it) holds on every rank, so every tightening is also
+ * written with atomicMax into the peers' published arrays over NVLink peer memory — the one exchange on this path
+ * that lives inside a kernel.  Each rank: _handle (allocates its array for batches of up to max_queries queries,
+ * returns a 64-byte CUDA IPC handle), all-gather the handles, _open (handles = world x 64 bytes, own slot ignored).
+ * Requires that every rank searches the SAME batch between two collectives (pyrope_index_search_batch_probed_device
+ * after the probe all-gather does); a shard may then return fewer than k rows (the rest cannot be in the global top k). */
+int pyrope_index_threshold_exchange_handle(pyrope_index *h, int64_t max_queries, void *handle_out);
+int pyrope_index_threshold_exchange_open(pyrope_index *h, int world, int rank, const void *handles);
+int pyrope_index_threshold_exchange_close(pyrope_index *h); /* stop publishing / reading; the own array stays mapped */
 int pyrope_index_is_built(pyrope_index *h, int *out);
 /* ICentroidsProvider.GetCentroids (IvfFlatVectorIndex.cs:314-325): n_out = 0 until built.
  * centroids_out may be NULL to query the count. */

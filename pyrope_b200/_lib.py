@@ -54,6 +54,9 @@ SIGNATURES = {
     "pyrope_index_set_train_params": (C.c_int, [vp, C.c_int64, C.c_int]),
     "pyrope_index_set_codebooks": (C.c_int, [vp, C.c_int, vp, vp]),
     "pyrope_index_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
+    "pyrope_index_threshold_exchange_handle": (C.c_int, [vp, C.c_int64, vp]),
+    "pyrope_index_threshold_exchange_open": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "pyrope_index_threshold_exchange_close": (C.c_int, [vp]),
     "pyrope_index_is_built": (C.c_int, [vp, i32p]),
     "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
@@ -220,6 +223,18 @@ class GpuIndex:
 
     def set_shard(self, rank, world):
         check(load().pyrope_index_set_shard(self._h, rank, world))
+
+    def threshold_exchange_handle(self, max_queries: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(load().pyrope_index_threshold_exchange_handle(self._h, max_queries, buf))
+        return buf.raw
+
+    def threshold_exchange_open(self, world: int, rank: int, handles: bytes):
+        assert len(handles) == 64 * world
+        check(load().pyrope_index_threshold_exchange_open(self._h, world, rank, handles))
+
+    def threshold_exchange_close(self):
+        check(load().pyrope_index_threshold_exchange_close(self._h))
 
     def is_built(self) -> bool:
         out = C.c_int32(0)

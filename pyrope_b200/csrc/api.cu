@@ -202,6 +202,12 @@ struct pyrope_index {
     int64_t x8_cap = 0;
     DevBuf x8, qvalid8;
 
+    // multi-GPU threshold exchange (list-major IVF_PQ): this rank's published array (peers write into it over NVLink)
+    // and the peers' arrays opened through CUDA IPC
+    DevBuf thr_pub;
+    int64_t thr_cap = 0;
+    std::vector<uint32_t*> peer_thr;
+
     // row ordinal -> location: >=0 buffer slot, <=-2 list position (-2-pos), -1 gone
     std::vector<int64_t> row_loc;
     bool lists_loc_valid = true;
@@ -1136,6 +1142,14 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                 pp.out_counts = d_counts;
                 direct_out = true;
             }
+            if (use_lm && !h->peer_thr.empty() && nq <= h->thr_cap) {
+                // bounds the peers prove for this batch land here while the scan runs; the all-gather of the probe lists
+                // that precedes this call orders this clear after every peer's previous batch
+                CK(cudaMemsetAsync(h->thr_pub.p, 0, sizeof(uint32_t) * (size_t)nq, st));
+                pp.thr_pub = h->thr_pub.as<uint32_t>();
+                pp.n_peers = (int)h->peer_thr.size();
+                for (int r = 0; r < pp.n_peers; ++r) pp.peer_thr[r] = h->peer_thr[(size_t)r];
+            }
             if (use_lm) {
                 TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc, dim, h->max_list_len), 0, st));
                 pp.max_list_len = h->max_list_len;
@@ -1236,6 +1250,8 @@ int pyrope_index_create(int kind, int dim, int metric, int nlist, int pq_m, int 
 int pyrope_index_destroy(pyrope_index* h) {
     if (!h) return PYROPE_OK;
     cudaStreamSynchronize(h->stream);
+    for (uint32_t* pp : h->peer_thr) cudaIpcCloseMemHandle(pp);
+    h->peer_thr.clear();
     if (h->last_stream) cudaStreamSynchronize(h->last_stream);
     for (int i = 0; i < 5; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1446,6 +1462,54 @@ int pyrope_index_set_shard(pyrope_index* h, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return fail(PYROPE_ERR_INVALID_ARG, "bad shard %d/%d", rank, world);
     h->shard_rank = rank;
     h->shard_world = world;
+    return PYROPE_OK;
+}
+
+int pyrope_index_threshold_exchange_handle(pyrope_index* h, int64_t max_queries, void* handle_out) {
+    if (!h || !handle_out || max_queries <= 0) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    if (h->kind != PYROPE_IVF_PQ) return fail(PYROPE_ERR_INVALID_STATE, "threshold exchange exists on the IVF_PQ list-major path only");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->peer_thr.empty()) return fail(PYROPE_ERR_INVALID_STATE, "peers are already attached");
+    TRY(h->thr_pub.ensure(sizeof(uint32_t) * (size_t)max_queries, 0, h->stream, true));
+    CK(cudaMemsetAsync(h->thr_pub.p, 0, h->thr_pub.bytes, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->thr_cap = max_queries;
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, h->thr_pub.p));
+    memcpy(handle_out, &hd, sizeof hd);
+    return PYROPE_OK;
+}
+
+int pyrope_index_threshold_exchange_open(pyrope_index* h, int world, int rank, const void* handles) {
+    if (!h || !handles) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(PYROPE_ERR_INVALID_ARG, "world must be 2..8");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->thr_pub.p) return fail(PYROPE_ERR_INVALID_STATE, "call pyrope_index_threshold_exchange_handle first");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles + (size_t)r * sizeof hd, sizeof hd);
+        void* pp = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&pp, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (uint32_t* q : h->peer_thr) cudaIpcCloseMemHandle(q);
+            h->peer_thr.clear();
+            return fail(PYROPE_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+        h->peer_thr.push_back(reinterpret_cast<uint32_t*>(pp));
+    }
+    return PYROPE_OK;
+}
+
+int pyrope_index_threshold_exchange_close(pyrope_index* h) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    std::lock_guard<std::mutex> g(h->mu);
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->last_stream) CK(cudaStreamSynchronize(h->last_stream));
+    for (uint32_t* pp : h->peer_thr) cudaIpcCloseMemHandle(pp);
+    h->peer_thr.clear();  // this rank's own array stays allocated: peers may still write into it
     return PYROPE_OK;
 }
 

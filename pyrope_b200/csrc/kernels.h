@@ -144,6 +144,13 @@ struct IvfPqScanParams {
     int force_generic;                       // tests: run the simple kernel
     PairOut out;
     int32_t* out_counts = nullptr;           // list-major path only: results per query, when `out` is the final output
+    // list-major path, multi-GPU: thresholds shared between the ranks WHILE the scan kernels run.  A bound one rank
+    // proves for query q (k candidates at or below it) holds on every rank, so each tightening is also written,
+    // with atomicMax over NVLink peer memory, into the peers' published arrays; thr_pub is this rank's own array
+    // (what the peers write into), read next to the local threshold.  All nullptr / 0 on one GPU.
+    uint32_t* thr_pub = nullptr;
+    uint32_t* peer_thr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_peers = 0;
 };
 cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
 // List-major variant (pq_lm.cu): (query, probe) pairs grouped by list, four queries per work item share

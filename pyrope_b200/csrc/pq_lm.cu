@@ -171,6 +171,9 @@ struct LmParams {
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits)
     int2* redo; int32_t* redo_cnt;
     int32_t* item_ctr;   // next unclaimed work item (zero-initialised): CTAs claim items as they go
+    const uint32_t* thr_pub;   // multi-GPU: bounds published by the peer ranks for this batch (nullable)
+    uint32_t* peer_thr[7];     // multi-GPU: the peers' published arrays (NVLink peer memory)
+    int n_peers;
 };
 
 // ---- grouping (query, probe) pairs by list ---------------------------------------------------------
@@ -562,6 +565,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
         // approximate (fixed point), so beyond the k best the region also keeps whatever lies within twice the
         // rounding bound of the k-th: one of those may be the better one once re-scored.
+        // a tighter bound for query q: locally, and (multi-GPU) into every peer's published array — k candidates at or
+        // below it exist in the whole base, whichever shard found them
+        auto tighten = [&](int q, uint32_t ord) {
+            if (atomicMax(p.pool_thr + q, ord) < ord)
+                for (int r = 0; r < p.n_peers; ++r) atomicMax(p.peer_thr[r] + q, ord);
+        };
         auto finalize = [&](const LmHeader* hd, int gitem, uint64_t* qk, int* qcnt) {
             const int j = bw;
             int* cntp = &qcnt[j];
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                         if (lane == 0) {
                             p.pool_cnt[ps] = kept;
                             // k candidates whose true distance is at most dk + err each: a bound of the k-th best
-                            if (n >= p.k) atomicMax(p.pool_thr + q, score_to_ord(-(dk + err)) - 1u);
+                            if (n >= p.k) tighten(q, score_to_ord(-(dk + err)) - 1u);
                         }
                         // Across pairs: count the candidates per distance bucket; once the running count reaches k
                         // the bucket's upper edge (+ the rounding bound) is a bound of the query's k-th best.
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                                     // than the seed bound)
                                     const float edge = bk == LM_HB - 1 ? t0 * 1.01f + 2.f * err : lo + wid * (float)(bk + 1);
                                     const float errq = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
-                                    atomicMax(p.pool_thr + q, score_to_ord(-(edge * 1.00001f + errq)) - 1u);
+                                    tighten(q, score_to_ord(-(edge * 1.00001f + errq)) - 1u);
                                 }
                             }
                         }
@@ -760,7 +769,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     const int myq = hd->qid[lane];
                     if (myq >= 0) {
                         const float mys = hd->s[lane];
-                        const uint32_t mytu = __ldcg(p.pool_thr + myq);
+                        uint32_t mytu = __ldcg(p.pool_thr + myq);
+                        if (p.thr_pub) mytu = max(mytu, __ldcg(p.thr_pub + myq));  // a bound a peer rank proved
                         const float tau = mytu ? -ord_to_score(mytu) : INFINITY;
                         ti = (int)fminf(fmaxf(tau, 0.f) * mys + (LM_QERR + 1.f), 32767.f);
                         inv = 1.f / mys;
@@ -1140,6 +1150,8 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
     sp.redo = redo; sp.redo_cnt = redo_cnt; sp.item_ctr = reinterpret_cast<int32_t*>(base + L.item_ctr);
+    sp.thr_pub = p.thr_pub; sp.n_peers = p.n_peers;
+    for (int r = 0; r < 7; ++r) sp.peer_thr[r] = r < p.n_peers ? p.peer_thr[r] : nullptr;
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;
     const int64_t grid = std::min<int64_t>(num_sms, L.max_items);
