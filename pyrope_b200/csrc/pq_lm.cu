@@ -568,8 +568,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         // a tighter bound for query q: locally, and (multi-GPU) into every peer's published array — k candidates at or
         // below it exist in the whole base, whichever shard found them
         auto tighten = [&](int q, uint32_t ord) {
-            if (atomicMax(p.pool_thr + q, ord) < ord)
+            if (p.n_peers == 0) {
+                atomicMax(p.pool_thr + q, ord);  // result unused: a reduction, nothing to wait for
+            } else if (atomicMax(p.pool_thr + q, ord) < ord) {
                 for (int r = 0; r < p.n_peers; ++r) atomicMax(p.peer_thr[r] + q, ord);
+            }
         };
         auto finalize = [&](const LmHeader* hd, int gitem, uint64_t* qk, int* qcnt) {
             const int j = bw;
