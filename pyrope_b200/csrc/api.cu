@@ -1686,6 +1686,10 @@ int pyrope_index_load(pyrope_index* h, const char* path) {
         if (s.cosine && nslots) CK(launch_row_norms_exact(s.X.as<float>(), nslots, dim, dim, s.norms.as<float>(), st));
         s.tc_dirty = true;
         h->tc_seg.invalidate();
+        if (h->kind == PYROPE_FLAT && h->x8.p) {  // the byte copies are not part of a snapshot: rebuild (flag on) or drop them
+            h->x8_cap = 0;
+            TRY(sq8_rows(h, 0, nslots));
+        }
         h->built = io.rv<int32_t>() != 0; h->frozen = io.rv<int32_t>() != 0; h->nc = io.rv<int32_t>();
         h->shard_rank = io.rv<int32_t>(); h->shard_world = io.rv<int32_t>();
         TRY(io.rdev(h->centroids, st));
@@ -2079,6 +2083,8 @@ int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows
                                               ts.norms.as<float>() + over_dst[(size_t)i], st));
             ts.tc_dirty = true;
             CK(cudaStreamSynchronize(st));
+            if (tl->kind == PYROPE_FLAT)
+                for (int64_t i = 0; i < no; ++i) TRY(sq8_rows(tl, over_dst[(size_t)i], 1));
             if (tail_rows_out)
                 for (int64_t i = 0; i < no; ++i)
                     tail_rows_out[over_src[(size_t)i]] =
@@ -2103,8 +2109,10 @@ int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows
             const int64_t first = tl->next_row;
             if (tl->kind != PYROPE_FLAT) tl->row_loc.resize((size_t)(first + na), -1);
             tl->next_row += na;
+            const int64_t slot0 = ts.nslots;
             int r = seg_append(tl, na, ax, true, al, true, first);
             if (r != PYROPE_OK) { tl->next_row = first; return r; }
+            if (tl->kind == PYROPE_FLAT) TRY(sq8_rows(tl, slot0, na));  // a FLAT tail with EnableQuantization
             if (tail_rows_out)
                 for (int64_t i = 0; i < na; ++i) tail_rows_out[app_src[(size_t)i]] = first + i;
         }
