@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — batched VEC.SEARCH throughput of the B200 hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c1|c2|c3] [--scale S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c1|c2|c3|c2x] [--scale S]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU arm (oracle port of the reference's C# loops)
 
@@ -9,6 +9,11 @@ A step = one pass of the hot path over one batch of synthetic queries.  `value` 
 queries and outputs resident in HBM (CUDA events on the launching stream, max over ranks);
 `e2e` = the same through the C-ABI host entry point with HOST buffers (H2D of the queries and D2H of
 the results inside the timed region).  One JSON line on stdout (rank 0).
+
+The default run measures BASELINE config 5 (IVF_PQ, the configuration the metric is quoted on) as the line
+itself and BASELINE config 4 (FLAT inner product on the tensor cores) as its `secondary` block.  Every
+block carries `parity`: the GPU result of the timed configuration compared with the CPU oracle (tests/parity.py
+rules: scores within 1e-4 relative, ids identical except across near-ties); a mismatch exits non-zero.
 """
 from __future__ import annotations
 
@@ -27,6 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC_NAME = "batched VEC.SEARCH QPS at fixed recall@10"
+RTOL = 1e-4  # north_star: distances within 1e-4 relative
 
 
 def workload(name: str, scale: float) -> dict:
@@ -67,6 +73,15 @@ def describe(w: dict) -> str:
     return f"{w['name']}: FLAT {w['metric']} synthetic dim={w['dim']}, {w['n']} base, {w['nq']}-query batch, TOPK {w['topk']}"
 
 
+def config_of(w: dict) -> dict:
+    """The `config` object: identical in the GPU arm and the reference arm (everything else lives in `details`)."""
+    return {"workload": describe(w), "reduced": w["reduced"]}
+
+
+def dtype_of(w: dict) -> str:
+    return "f32" if w["kind"] != "IVF_PQ" else "f32 LUT / u8 codes"
+
+
 def algorithmic_work(w: dict, world: int) -> dict:
     """Per search launch on ONE rank: HBM bytes for the scan paths, FLOPs for FLAT."""
     if w["kind"] == "IVF_PQ":  # codes only: nprobe * avg_list * m bytes per query
@@ -77,6 +92,14 @@ def algorithmic_work(w: dict, world: int) -> dict:
         return {"bound": "hbm", "work": b, "unit": "GB/s"}
     f = 2.0 * w["nq"] * (w["n"] / world) * w["dim"]
     return {"bound": "tensor", "work": f, "unit": "TFLOP/s"}
+
+
+def host_cores() -> int:
+    """Cores this process may run on.  (torchrun exports OMP_NUM_THREADS=1, so omp_get_max_threads() is not it.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -139,10 +162,14 @@ def dist_env():
     return rank, world, local
 
 
+def log(s):
+    print(s, file=sys.stderr, flush=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # index construction on the GPU (setup, untimed)
 # ------------------------------------------------------------------------------------------------
-def build_gpu_index(pg, torch, w: dict, rank: int, world: int, log):
+def build_gpu_index(pg, torch, w: dict, rank: int, world: int):
     from pyrope_b200 import _lib
     kind = {"FLAT": pg.FLAT, "IVF_FLAT": pg.IVF_FLAT, "IVF_PQ": pg.IVF_PQ}[w["kind"]]
     metric = {"L2": pg.L2, "IP": pg.INNER_PRODUCT, "COSINE": pg.COSINE}[w["metric"]]
@@ -178,7 +205,7 @@ def build_gpu_index(pg, torch, w: dict, rank: int, world: int, log):
     if kind != pg.FLAT:
         ix.build()
     t2 = time.time()
-    log(f"rank {rank}: added {hi - lo} rows in {t1 - t0:.1f}s, build {t2 - t1:.1f}s, stats {ix.stats()}")
+    log(f"rank {rank}: {w['name']}: added {hi - lo} rows in {t1 - t0:.1f}s, build {t2 - t1:.1f}s, stats {ix.stats()}")
     return ix, {"add_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2)}
 
 
@@ -190,7 +217,7 @@ def make_queries(torch, w: dict):
     return q.view(w["nq"], w["dim"])
 
 
-def recall_at_10(pg, torch, w: dict, ix, Q, nq_eval: int, log) -> dict:
+def recall_at_10(pg, torch, w: dict, ix, Q, nq_eval: int) -> dict:
     """recall@10 of the configured index against exact FLAT top-10 (the reference never computes
     recall; the metric is quoted 'at fixed recall@10', i.e. at the recall this (nlist, nprobe, m) gives).
     Exact answers: the base is regenerated chunk by chunk into a FLAT index on the CUDA-core path (no split
@@ -245,8 +272,40 @@ def recall_at_10(pg, torch, w: dict, ix, Q, nq_eval: int, log) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's loops on the index the GPU built
+# parity: the GPU result of the timed configuration against the CPU oracle (tests/parity.py rules)
 # ------------------------------------------------------------------------------------------------
+def compare_topk(ref, got, what: str) -> dict:
+    """ref / got = (ids [nq][k], scores [nq][k], counts [nq]) for the same queries.  Counts mismatching queries by the
+    rules of tests/parity.py (scores within RTOL relative; id lists identical except where the reference's own scores
+    are within tolerance of each other, or of its k-th score at the boundary) and reports the worst relative score error."""
+    from tests.parity import assert_topk_equivalent
+    rid, rsc, rcn = ref
+    gid, gsc, gcn = got
+    nq = len(rcn)
+    mismatch, first, max_rel, exact_ids = 0, None, 0.0, 0
+    for q in range(nq):
+        c = int(rcn[q])
+        try:
+            if int(gcn[q]) != c:
+                raise AssertionError(f"count {int(gcn[q])} != reference {c}")
+            assert_topk_equivalent(rid[q][:c], rsc[q][:c], gid[q][:c], gsc[q][:c], rtol=RTOL, ctx=f"q{q}")
+        except AssertionError as ex:
+            mismatch += 1
+            if first is None:
+                first = str(ex)[:300]
+            continue
+        if c:
+            a, b = np.asarray(rsc[q][:c], np.float64), np.asarray(gsc[q][:c], np.float64)
+            den = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-30)
+            max_rel = max(max_rel, float(np.max(np.abs(a - b) / den)))
+            exact_ids += int(np.array_equal(np.asarray(rid[q][:c]), np.asarray(gid[q][:c])))
+    out = {"queries": nq, "mismatch": mismatch, "max_rel_err": max_rel, "identical_id_lists": exact_ids, "rtol": RTOL,
+           "against": what}
+    if first:
+        out["first_mismatch"] = first
+    return out
+
+
 def base_rows_host(torch, w: dict, n_rows: int) -> np.ndarray:
     """The first n_rows base vectors, regenerated with the same counter-based generator."""
     from pyrope_b200 import _lib
@@ -280,50 +339,144 @@ def oracle_index_from_gpu(ix, w: dict, torch=None):
     raise NotImplementedError
 
 
-def _osearch(oidx, Q, w):
+def _osearch(oidx, Q, w, threads):
     if w["kind"] == "FLAT":
-        return oidx.search_batch(Q, w["topk"])
-    return oidx.search_batch(Q, w["topk"], nprobe=w.get("nprobe", -1))
+        return oidx.search_batch(Q, w["topk"], nthreads=threads)
+    return oidx.search_batch(Q, w["topk"], nprobe=w.get("nprobe", -1), nthreads=threads)
 
 
 def time_cpu_baseline(oidx, rows_held, note, Qh: np.ndarray, w: dict, budget_s: float):
-    from oracle import pyoracle as orc
-    threads = orc.max_threads()
+    """-> (cpu_baseline dict, queries searched, oracle result for them)."""
+    threads = host_cores()
     probe = min(len(Qh), 2 * threads)
     t0 = time.perf_counter()
-    _osearch(oidx, Qh[:probe], w)
+    _osearch(oidx, Qh[:probe], w, threads)
     per_q = (time.perf_counter() - t0) / probe
     s = int(max(threads, min(len(Qh), budget_s / max(per_q, 1e-9))))
     t0 = time.perf_counter()
-    _osearch(oidx, Qh[:s], w)
+    res = _osearch(oidx, Qh[:s], w, threads)
     dt = time.perf_counter() - t0
     scale = rows_held / w["n"]
-    return {"value": s / dt * scale, "unit": "QPS", "cores": threads, "kind": "port",
-            "sample": f"{s} of the batch's {len(Qh)} queries over {note}, one query per thread, {dt:.1f}s wall"}, s, dt
+    return {"value": round(s / dt * scale, 2), "unit": "QPS", "cores": threads, "kind": "port",
+            "sample": f"{s} of the batch's {len(Qh)} queries over {note}, one query per thread, {dt:.1f}s wall"}, s, res
+
+
+def flat_fullsize_parity(pg, torch, w: dict, Qh: np.ndarray, got, nsample: int) -> dict:
+    """FLAT at a size the CPU oracle cannot scan (C4: 30.7 GB per query): for a sample of the batch's queries,
+      (1) every reported score must equal — bit for bit — the oracle's VectorMath.DotProductUnsafe / L2SquaredUnsafe
+          of that query and that row (rows regenerated on the host from the counter-based generator);
+      (2) the id list must agree (tests/parity.py rules) with an INDEPENDENT exact top-k over the whole regenerated base
+          (fp32 cuBLAS SGEMM, TF32 off, chunk by chunk, + torch.topk: library code used only as a checker)."""
+    from oracle import pyoracle as orc
+    from pyrope_b200 import _lib
+    dim, n, k = w["dim"], w["n"], w["topk"]
+    ns = min(nsample, len(Qh))
+    gsc, gid, gcn = got
+    stream = torch.cuda.current_stream().cuda_stream
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Qs = torch.from_numpy(np.ascontiguousarray(Qh[:ns])).cuda()
+        chunk = min(n, 2_000_000)
+        stage = torch.empty(chunk * dim, dtype=torch.float32, device="cuda")
+        best_s, best_i = None, None
+        for r0 in range(0, n, chunk):
+            rows = min(chunk, n - r0)
+            _lib.fill_uniform_device(stage.data_ptr(), rows * dim, 42, r0 * dim, stream=stream)
+            X = stage[:rows * dim].view(rows, dim)
+            if w["metric"] == "IP":
+                S = Qs @ X.T
+            else:
+                S = 2.0 * (Qs @ X.T) - (X * X).sum(1)[None, :] - (Qs * Qs).sum(1)[:, None]
+            s, i = torch.topk(S, min(k, rows), dim=1)
+            i = i + r0
+            if best_s is None:
+                best_s, best_i = s, i
+            else:
+                cs, ci = torch.cat([best_s, s], 1), torch.cat([best_i, i], 1)
+                s2, j = torch.topk(cs, min(k, cs.shape[1]), dim=1)
+                best_s, best_i = s2, torch.gather(ci, 1, j)
+            del S
+        ref_ids = best_i.cpu().numpy()
+        # (1) + reference scores for (2): oracle arithmetic on the union of the ids either side reports
+        rowbuf = torch.empty(dim, dtype=torch.float32, device="cuda")
+        cache = {}
+
+        def row(r):
+            if r not in cache:
+                _lib.fill_uniform_device(rowbuf.data_ptr(), dim, 42, int(r) * dim, stream=stream)
+                torch.cuda.synchronize()
+                cache[r] = rowbuf.cpu().numpy().copy()
+            return cache[r]
+
+        f = orc.dot_unsafe if w["metric"] == "IP" else (lambda a, b: -orc.l2sq_unsafe(a, b))
+        bit_exact, checked = 0, 0
+        ref_sc = np.zeros((ns, k), np.float32)
+        for q in range(ns):
+            for j in range(int(gcn[q])):
+                s_or = np.float32(f(Qh[q], row(int(gid[q][j]))))
+                checked += 1
+                bit_exact += int(s_or == np.float32(gsc[q][j]))
+            sc = np.array([np.float32(f(Qh[q], row(int(r)))) for r in ref_ids[q]], np.float32)
+            order = np.argsort(-sc, kind="stable")
+            ref_ids[q] = ref_ids[q][order]
+            ref_sc[q] = sc[order]
+            cache.clear()
+        cnt = np.full(ns, min(k, n), np.int32)
+        out = compare_topk((ref_ids, ref_sc, cnt), (gid[:ns], gsc[:ns], gcn[:ns]),
+                           "independent exact top-k over the whole base (fp32 SGEMM + topk), scored in the oracle's "
+                           "VectorMath arithmetic")
+        out["scores_bit_exact_vs_oracle"] = f"{bit_exact}/{checked}"
+        if bit_exact != checked:
+            out["mismatch"] += 1
+            out.setdefault("first_mismatch", "a reported score differs from the oracle's arithmetic on the same row")
+        return out
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+
+
+def tf32_peak(torch) -> dict:
+    """Dense TF32 tensor-pipe peak as cuBLAS reaches it (fp32 inputs, TF32 allowed, 8192^3): the denominator of the FLAT
+    roofline.  Read from profiles/tf32_peak.json when committed, measured live (best of 10, ~1.5 ms each) otherwise."""
+    path = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    try:
+        d = json.load(open(path))
+        if d.get("tf32_tflops"):
+            return {"tflops": float(d["tf32_tflops"]), "source": "profiles/tf32_peak.json (cuBLAS TF32 8192^3, measured burst)"}
+    except Exception:
+        pass
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n = 8192
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        torch.cuda.empty_cache()
+        return {"tflops": 2.0 * n ** 3 / (best / 1e3) / 1e12, "source": "cuBLAS TF32 8192^3 measured in this run (best of 10)"}
+    except Exception as ex:
+        return {"tflops": None, "source": f"unmeasured ({str(ex)[:80]})"}
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-
-    import pyrope_b200 as pg
+def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank: int, world: int, local: int) -> dict:
+    """Build the index of workload w, time `steps` search steps, and return the bench line (rank 0; None elsewhere)."""
     from pyrope_b200 import _lib
-
-    rank, world, local = dist_env()
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.check(pg.load().pyrope_gpu_init(local))
-    log = (lambda s: print(s, file=sys.stderr, flush=True))
-    w = workload(args.workload, args.scale)
     nq, dim, k = w["nq"], w["dim"], w["topk"]
     nprobe = w.get("nprobe", -1)
 
-    ix, build_info = build_gpu_index(pg, torch, w, rank, world, log)
+    ix, build_info = build_gpu_index(pg, torch, w, rank, world)
     Q = make_queries(torch, w)
     stream = torch.cuda.current_stream().cuda_stream
     sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
@@ -333,6 +486,8 @@ def run_ours(args):
         g_sc = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
         g_rw = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
         m_sc, m_rw, m_cn = torch.empty_like(sc), torch.empty_like(rw), torch.empty_like(cn)
+    else:
+        m_sc, m_rw, m_cn = sc, rw, cn
 
     launches = [0]
 
@@ -369,7 +524,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     exchange = "none"
@@ -412,7 +567,7 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     barrier()
@@ -422,11 +577,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
-    value = nq * args.steps / (ms / 1e3)
+    value = nq * steps / (ms / 1e3)
+    # the result every later check looks at: the merged output of the last timed step
+    res_sc, res_rw, res_cn = m_sc.cpu().numpy(), m_rw.cpu().numpy(), m_cn.cpu().numpy()
 
     # ---- dominant-kernel time (CUDA events inside the library around the scan stage), per launch
     stage_ms = {"total": 0.0, "coarse": 0.0, "scan": 0.0, "merge": 0.0}
-    reps = max(3, min(args.steps, 10))
+    reps = max(3, min(steps, 10))
     kname, kms_avg = "", 0.0
     for _ in range(reps):
         step()
@@ -435,12 +592,16 @@ def run_ours(args):
             stage_ms[kk] += v / reps
         kname, kms = ix.last_search_kernel()
         kms_avg += kms / reps
+    if args.profile_step:  # `ncu --profile-from-start off`: exactly one search step lies inside the profiled range
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     alg = algorithmic_work(w, world)
     scanned = 0
     if w["kind"] in ("IVF_PQ", "IVF_FLAT"):
         scanned = ix.last_search_scanned()
-    dom = "scan"
-    dom_ms = kms_avg if kms_avg > 0 else stage_ms[dom]
+    dom_ms = kms_avg if kms_avg > 0 else stage_ms["scan"]
     if not kname:
         kname = w["kind"].lower() + "_scan (stage)"
     peaks = {}
@@ -463,24 +624,39 @@ def run_ours(args):
             extra["frac_by_scanned_count"] = round(exact / (dom_ms / 1e3) / 1e9 / peak, 4)
         achieved = work / (dom_ms / 1e3) / 1e9
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (of fallback)"
+        # the same bytes over the whole step (north_star's >= 60 % target read at step level)
+        extra["step_level_frac"] = round(work * world / (ms / steps / 1e3) / 1e9 / (peak * world), 4)
     else:
         achieved = work / (dom_ms / 1e3) / 1e12
-        bf16 = peaks.get("bf16_tflops", 1590.0)
-        peak = bf16 / 2.0  # TF32 dense = 1/2 of the measured bf16 cuBLAS burst figure
-        peak_src = ("MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense, of measured)" if "bf16_tflops" in peaks
-                    else "fallback 1.59 PFLOP/s / 2 (of fallback)")
+        tp = tf32_peak(torch) if rank == 0 else {"tflops": None, "source": ""}
+        if tp["tflops"]:
+            peak, peak_src = round(tp["tflops"], 1), tp["source"]
+        else:
+            peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+            peak_src = "bf16 cuBLAS burst / 2 (TF32 dense assumed; TF32 itself unmeasured)"
         extra["issued"] = round(3.0 * achieved, 2)          # the 3xTF32 split issues three MMAs per useful one
         extra["issued_frac"] = round(3.0 * achieved / peak, 4)
-    traffic = None
+    traffic, traffic_note = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get(f"{kname}:{w['name']}:{args.scale:g}") if world == 1 else None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        tr = json.load(open(tpath))
+        ent = tr.get(f"{kname}:{w['name']}:{args.scale:g}") if world == 1 else None
+        if isinstance(ent, dict):
+            traffic = ent.get("bytes")
+            srcs = [os.path.join(ROOT, "pyrope_b200", "csrc", s) for s in ent.get("sources", [])]
+            if any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(tpath) for s in srcs):
+                traffic_note = "profiles/traffic.json predates the kernel source: re-capture with ncu --set full"
+                log("WARNING: " + traffic_note)
+        elif ent is not None:
+            traffic = ent
     except Exception:
         pass
     roofline = {"bound": alg["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": alg["unit"],
                 "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": kname,
                 "kernel_ms": round(dom_ms, 4), "algorithmic_per_launch": work, "peak_source": peak_src,
                 "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()}, **extra}
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
 
     # ---- end to end through the host entry point: pinned host queries in, host results out
     Qh_t = torch.empty((nq, dim), dtype=torch.float32, pin_memory=True)
@@ -506,11 +682,11 @@ def run_ours(args):
             hc.copy_(m_cn, non_blocking=True)
             torch.cuda.synchronize()
 
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(max(1, min(warmup, 3))):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -518,48 +694,124 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": round(nq * args.steps / e2e_s, 1), "unit": "QPS", "h2d_bytes_per_step": nq * dim * 4,
+    e2e = {"value": round(nq * steps / e2e_s, 1), "unit": "QPS", "h2d_bytes_per_step": nq * dim * 4,
            "d2h_bytes_per_step": nq * k * 12 + nq * 4}
+    e2e_same = bool(np.array_equal(hr.numpy(), res_rw) and np.array_equal(hs.numpy(), res_sc))
 
     # ---- recall@10 of this configuration (N=1, IVF workloads): what "at fixed recall@10" refers to
     recall = {}
     if world == 1 and w["kind"] != "FLAT" and args.recall_queries > 0:
         try:
-            recall = recall_at_10(pg, torch, w, ix, Q, args.recall_queries, log)
+            recall = recall_at_10(pg, torch, w, ix, Q, args.recall_queries)
         except Exception as ex:  # never lose the bench line over the quality read-out
             recall = {"recall_at_10": None, "recall_error": str(ex)[:200]}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on the host cores, bounded sample
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    # ---- CPU baseline beside it + parity against the oracle (rank 0)
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu:
         try:
-            oidx, held, note = oracle_index_from_gpu(ix, w, torch)
-            cpu, _, _ = time_cpu_baseline(oidx, held, note, Qh, w, args.cpu_budget)
-            cpu["value"] = round(cpu["value"], 2)
-            del oidx
+            if w["kind"] == "IVF_PQ":
+                if world == 1:
+                    oix = ix
+                else:
+                    # the oracle needs every list: rank 0 builds the UNSHARDED index of the same rows once more (k-means /
+                    # PQ training are bit-exact and deterministic, so its codebooks and codes equal the shards')
+                    torch.cuda.empty_cache()
+                    oix, _ = build_gpu_index(pg, torch, w, 0, 1)
+                oidx, held, note = oracle_index_from_gpu(oix, w, torch)
+                if oix is not ix:
+                    oix.close()
+                cpu, s, ores = time_cpu_baseline(oidx, held, note, Qh, w, args.cpu_budget)
+                parity = compare_topk(ores, (res_rw[:s], res_sc[:s], res_cn[:s]),
+                                      "oracle/oracle.c (IvfPqVectorIndex.Search restated) on the same index"
+                                      + ("" if world == 1 else f": merged top-k of {world} GPUs vs the unsharded oracle"))
+                del oidx
+            elif w["kind"] == "FLAT" and w["n"] * w["dim"] * 4 > (256 << 20):
+                oidx, held, note = oracle_index_from_gpu(ix, w, torch)
+                cpu, _, _ = time_cpu_baseline(oidx, held, note, Qh, w, args.cpu_budget)
+                cpu["sample"] += " (extrapolated to the full base)"
+                del oidx
+                parity = flat_fullsize_parity(pg, torch, w, Qh, (res_sc, res_rw, res_cn), args.flat_parity_queries)
+            else:
+                oidx, held, note = oracle_index_from_gpu(ix, w, torch)
+                cpu, s, ores = time_cpu_baseline(oidx, held, note, Qh, w, args.cpu_budget)
+                parity = compare_topk(ores, (res_rw[:s], res_sc[:s], res_cn[:s]), "oracle/oracle.c on the same rows")
+                del oidx
         except NotImplementedError:
             cpu = {"value": None, "unit": "QPS", "cores": 0, "kind": "port", "sample": "not wired for this workload"}
+        if parity is not None:
+            parity["e2e_result_identical_to_device_result"] = e2e_same
 
+    line = None
     if rank == 0:
         line = {
-            "metric": METRIC_NAME, "value": round(value, 1), "unit": "QPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w["kind"] != "IVF_PQ" else "f32 LUT / u8 codes",
+            "metric": METRIC_NAME, "value": round(value, 1), "unit": "QPS", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": round(ms / steps, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(w),
             "data": "synthetic uniform[0,1) fp32, counter-based generator (base seed 42, query seed 1337), "
                     "codebooks trained on device and frozen",
-            "config": {"workload": describe(w), "reduced": w["reduced"], "l2_policy": "inputs larger than L2 (index "
-                       f"{w['n'] * w.get('m', w['dim'] * 4) / 1e6:.0f} MB scanned region vs 126 MB L2)",
-                       "parallelism": f"lists sharded list_id % {world}" if w["kind"] != "FLAT" else f"rows sharded in {world} blocks",
-                       **recall, "exchange": ("nccl all_gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
-                                   ("nccl all_gather of per-rank top-k + on-device merge" if world > 1 else "none") +
-                                   ("" if exchange == "none" else " + " + exchange), **build_info},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "config": config_of(w),
+            "details": {"l2_policy": "inputs larger than L2 (index "
+                        f"{w['n'] * w.get('m', w['dim'] * 4) / 1e6:.0f} MB scanned region vs 126 MB L2)",
+                        "parallelism": f"lists sharded list_id % {world}" if w["kind"] != "FLAT" else f"rows sharded in {world} blocks",
+                        **recall, "exchange": ("nccl all_gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
+                                    ("nccl all_gather of per-rank top-k + on-device merge" if world > 1 else "none") +
+                                    ("" if exchange == "none" else " + " + exchange), **build_info},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * steps),
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         }
+    ix.close()
+    del ix
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    return line
+
+
+def run_ours(args):
+    import torch
+
+    import pyrope_b200 as pg
+    from pyrope_b200 import _lib
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.check(pg.load().pyrope_gpu_init(local))
+    w = workload(args.workload, args.scale)
+    line = bench_workload(args, torch, pg, dist, w, args.steps, args.warmup, rank, world, local)
+    sec = None
+    if args.secondary == "auto":
+        args.secondary = "c4" if args.workload == "c5" else "none"
+    if args.secondary and args.secondary != "none" and args.secondary != args.workload:
+        # BASELINE config 4 beside the headline config: fewer steps (a C4 step takes ~0.6 s)
+        w2 = workload(args.secondary, args.secondary_scale if args.secondary_scale > 0 else args.scale)
+        try:
+            sec = bench_workload(args, torch, pg, dist, w2, min(args.steps, 3), 3, rank, world, local)
+        except Exception as ex:
+            if world > 1:
+                raise
+            sec = {"config": config_of(w2), "error": str(ex)[:300]}
+    bad = []
+    if rank == 0:
+        if sec is not None:
+            line["secondary"] = sec
+        for blk in (line, sec):
+            if blk and blk.get("parity") and blk["parity"].get("mismatch"):
+                bad.append(blk["config"]["workload"])
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if bad:
+        log(f"PARITY MISMATCH against the oracle in: {bad}")
+        sys.exit(3)
 
 
 def run_reference(args):
@@ -572,41 +824,38 @@ def run_reference(args):
     import torch
 
     import pyrope_b200 as pg
-    from oracle import pyoracle as orc
     from pyrope_b200 import _lib
     torch.cuda.set_device(0)
     _lib.check(pg.load().pyrope_gpu_init(0))
-    log = (lambda s: print(s, file=sys.stderr, flush=True))
     w = workload(args.workload, args.scale)
-    ix, build_info = build_gpu_index(pg, torch, w, 0, 1, log)
+    ix, build_info = build_gpu_index(pg, torch, w, 0, 1)
     Q = make_queries(torch, w)
     Qh = Q.cpu().numpy()
     oidx, held, note = oracle_index_from_gpu(ix, w, torch)
     del ix
     torch.cuda.empty_cache()
-    threads = orc.max_threads()
-    nprobe = w.get("nprobe", -1)
+    threads = host_cores()
     # size one step to ~ (budget / (steps+warmup)) seconds
     probe = min(len(Qh), 2 * threads)
     t0 = time.perf_counter()
-    _osearch(oidx, Qh[:probe], w)
+    _osearch(oidx, Qh[:probe], w, threads)
     per_q = (time.perf_counter() - t0) / probe
     per_step_budget = max(1.0, args.cpu_budget * 6 / max(1, args.steps + args.warmup))
     s = int(max(threads, min(len(Qh), per_step_budget / max(per_q, 1e-9))))
     for i in range(args.warmup):
-        _osearch(oidx, Qh[:s], w)
+        _osearch(oidx, Qh[:s], w, threads)
     t0 = time.perf_counter()
     for i in range(args.steps):
         off = (i * s) % max(1, len(Qh) - s + 1)
-        _osearch(oidx, Qh[off:off + s], w)
+        _osearch(oidx, Qh[off:off + s], w, threads)
     dt = time.perf_counter() - t0
     value = s * args.steps / dt * (held / w["n"])
     sample = f"{s} of the batch's {len(Qh)} queries per step over {note}, one query per thread"
     line = {"impl": "reference", "metric": METRIC_NAME, "value": round(value, 2), "unit": "QPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w["kind"] != "IVF_PQ" else "f32 LUT / u8 codes",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(w),
             "data": "synthetic uniform[0,1) fp32 (same generator and seeds as the GPU arm)",
-            "config": {"workload": describe(w), "reduced": w["reduced"], **build_info},
+            "config": config_of(w), "details": {**build_info, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "cpu_baseline": {"value": round(value, 2), "unit": "QPS", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 2), "unit": "QPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -638,11 +887,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PYROPE_BENCH_WORKLOAD", "c5"))
     ap.add_argument("--scale", type=float, default=float(os.environ.get("PYROPE_BENCH_SCALE", "1.0")))
+    ap.add_argument("--secondary", default=os.environ.get("PYROPE_BENCH_SECONDARY", "auto"),
+                    help="workload reported as the line's `secondary` block (auto = c4 beside c5, none = skip)")
+    ap.add_argument("--secondary-scale", type=float, default=float(os.environ.get("PYROPE_BENCH_SECONDARY_SCALE", "0")))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline AND the parity check against the oracle")
     ap.add_argument("--no-threshold-exchange", action="store_true",
                     help="multi-GPU IVF_PQ: do not share thresholds between the ranks' scan kernels")
     ap.add_argument("--recall-queries", type=int, default=200, help="queries used for the recall@10 read-out (0 = skip)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket one extra search step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--flat-parity-queries", type=int, default=32,
+                    help="queries of a full-size FLAT batch checked against the independent exact top-k")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

@@ -121,14 +121,19 @@ int pyrope_index_set_codebooks(pyrope_index *h, int n_centroids, const float *ce
 int pyrope_index_set_shard(pyrope_index *h, int rank, int world);
 /* Multi-GPU IVF_PQ (list-major scan): share per-query thresholds between the ranks while their scan kernels run.  A
  * bound one rank proves for a query (k candidates at or below it) holds on every rank, so every tightening is also
- * written with atomicMax into the peers' published arrays over NVLink peer memory — the one exchange on this path
- * that lives inside a kernel.  Each rank: _handle (allocates its array for batches of up to max_queries queries,
+ * written with a 64-bit atomicMax into the peers' published arrays over NVLink peer memory — the one exchange on this
+ * path that lives inside a kernel.  Each rank: _handle (allocates its array for batches of up to max_queries queries,
  * returns a 64-byte CUDA IPC handle), all-gather the handles, _open (handles = world x 64 bytes, own slot ignored).
- * Requires that every rank searches the SAME batch between two collectives (pyrope_index_search_batch_probed_device
- * after the probe all-gather does); a shard may then return fewer than k rows (the rest cannot be in the global top k). */
+ * PRECONDITION: every rank searches the SAME sequence of batches with pyrope_index_search_batch_probed_device.  Each
+ * published word is (batch epoch << 32 | bound) and a rank only believes words of the epoch it is searching, so ranks
+ * need NOT be ordered against each other between batches: a peer that is still in an earlier batch (or already in a
+ * later one) cannot prune this one.  The epoch is a per-handle counter of probed searches made while peers are attached
+ * (starts at 1); a caller whose ranks might not count alike names it itself with _epoch (non-zero, increasing) before
+ * each search.  A shard may return fewer than k rows (the rest cannot be in the global top k). */
 int pyrope_index_threshold_exchange_handle(pyrope_index *h, int64_t max_queries, void *handle_out);
 int pyrope_index_threshold_exchange_open(pyrope_index *h, int world, int rank, const void *handles);
 int pyrope_index_threshold_exchange_close(pyrope_index *h); /* stop publishing / reading; the own array stays mapped */
+int pyrope_index_threshold_exchange_epoch(pyrope_index *h, uint32_t epoch); /* epoch of the NEXT probed search */
 int pyrope_index_is_built(pyrope_index *h, int *out);
 /* ICentroidsProvider.GetCentroids (IvfFlatVectorIndex.cs:314-325): n_out = 0 until built.
  * centroids_out may be NULL to query the count. */
@@ -272,6 +277,15 @@ int pyrope_vindex_build(pyrope_vindex *v); /* a delta compacts: DeltaVectorIndex
 int pyrope_vindex_search(pyrope_vindex *v, int64_t nq, const float *Q, int len, int topk, int64_t max_scans,
                          int nprobe, float *scores_out, int64_t *id_ordinals_out, int32_t *counts_out);
 int pyrope_vindex_id(int64_t id_ordinal, char *buf, int cap, int *len_out);
+/* The same for a whole result list under ONE lock: the UTF-8 bytes of ids[0..n) are written back to back into buf
+ * (at most cap bytes; call with buf = NULL to size it), offsets_out[i] .. offsets_out[i+1] delimit id i (n + 1 entries),
+ * ordinals < 0 (empty result slots) give empty strings.  Id ordinals are reference counted and recycled once no index
+ * holds the id any more, so results must be translated before the ids in them can be deleted — i.e. under the same
+ * read lock the Search ran under, which is what the shim in INTEGRATION.md does. */
+int pyrope_vindex_ids(const int64_t *id_ordinals, int64_t n, char *buf, int64_t cap, int64_t *offsets_out,
+                      int64_t *bytes_out);
+/* Size of the process-wide id table: ids currently held by some index, and ordinal slots ever allocated. */
+int pyrope_vindex_id_table_size(int64_t *live_out, int64_t *slots_out);
 int pyrope_vindex_stats(pyrope_vindex *v, int64_t *count_out, int *dim_out, int *metric_out);
 int pyrope_vindex_get_centroids(pyrope_vindex *v, float *centroids_out, int *n_out); /* n_out 0 == null */
 int pyrope_vindex_snapshot(pyrope_vindex *v, const char *path); /* index file(s) + "<file>.ids" id tables */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "pyrope_index_threshold_exchange_handle": (C.c_int, [vp, C.c_int64, vp]),
     "pyrope_index_threshold_exchange_open": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "pyrope_index_threshold_exchange_close": (C.c_int, [vp]),
+    "pyrope_index_threshold_exchange_epoch": (C.c_int, [vp, C.c_uint32]),
     "pyrope_index_is_built": (C.c_int, [vp, i32p]),
     "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
@@ -97,6 +98,8 @@ SIGNATURES = {
     "pyrope_vindex_build": (C.c_int, [vp]),
     "pyrope_vindex_search": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
     "pyrope_vindex_id": (C.c_int, [C.c_int64, C.c_char_p, C.c_int, i32p]),
+    "pyrope_vindex_ids": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, i64p]),
+    "pyrope_vindex_id_table_size": (C.c_int, [i64p, i64p]),
     "pyrope_vindex_stats": (C.c_int, [vp, i64p, i32p, i32p]),
     "pyrope_vindex_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_vindex_snapshot": (C.c_int, [vp, C.c_char_p]),
@@ -235,6 +238,9 @@ class GpuIndex:
 
     def threshold_exchange_close(self):
         check(load().pyrope_index_threshold_exchange_close(self._h))
+
+    def threshold_exchange_epoch(self, epoch: int):
+        check(load().pyrope_index_threshold_exchange_epoch(self._h, epoch))
 
     def is_built(self) -> bool:
         out = C.c_int32(0)

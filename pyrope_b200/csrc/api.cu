@@ -206,7 +206,10 @@ struct pyrope_index {
     // and the peers' arrays opened through CUDA IPC
     DevBuf thr_pub;
     int64_t thr_cap = 0;
-    std::vector<uint32_t*> peer_thr;
+    std::vector<unsigned long long*> peer_thr;
+    bool peer_ipc = false;        // peer arrays were opened through CUDA IPC (else: same-process device pointers)
+    uint32_t thr_epoch = 0;       // batch counter of the exchange (every rank runs the same sequence of batches)
+    bool thr_epoch_set = false;   // the caller named the next batch's epoch itself
 
     // row ordinal -> location: >=0 buffer slot, <=-2 list position (-2-pos), -1 gone
     std::vector<int64_t> row_loc;
@@ -303,10 +306,19 @@ int sq8_rows(Index* h, int64_t slot0, int64_t n) {
     return PYROPE_OK;
 }
 
+// A *_device search may still be running on the caller's stream: every mutator waits for it before it touches rows,
+// tombstones or tensor-core operands the scan reads (searches enqueued AFTER the mutation are ordered by the
+// synchronisation each mutator ends with).
+int wait_last_search(Index* h) {
+    if (h->last_stream && h->last_stream != h->stream) CK(cudaStreamSynchronize(h->last_stream));
+    return PYROPE_OK;
+}
+
 int add_common(Index* h, int64_t n, const float* X, bool dev, const int64_t* labels, int64_t* first_row_out) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     if (n < 0 || (n > 0 && !X)) return fail(PYROPE_ERR_INVALID_ARG, "vector is null");
     std::lock_guard<std::mutex> g(h->mu);
+    TRY(wait_last_search(h));
     const int64_t first = h->next_row;
     if (first_row_out) *first_row_out = first;
     if (n == 0) return PYROPE_OK;
@@ -1143,10 +1155,12 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                 direct_out = true;
             }
             if (use_lm && !h->peer_thr.empty() && nq <= h->thr_cap) {
-                // bounds the peers prove for this batch land here while the scan runs; the all-gather of the probe lists
-                // that precedes this call orders this clear after every peer's previous batch
-                CK(cudaMemsetAsync(h->thr_pub.p, 0, sizeof(uint32_t) * (size_t)nq, st));
-                pp.thr_pub = h->thr_pub.as<uint32_t>();
+                // bounds the peers prove for this batch land in thr_pub while the scan runs.  Every word carries the
+                // batch epoch, so nothing is cleared and a peer that is a batch behind (or ahead) cannot disturb this one
+                if (!h->thr_epoch_set) h->thr_epoch = h->thr_epoch + 1 == 0 ? 1 : h->thr_epoch + 1;
+                h->thr_epoch_set = false;
+                pp.epoch = h->thr_epoch;
+                pp.thr_pub = h->thr_pub.as<unsigned long long>();
                 pp.n_peers = (int)h->peer_thr.size();
                 for (int r = 0; r < pp.n_peers; ++r) pp.peer_thr[r] = h->peer_thr[(size_t)r];
             }
@@ -1250,7 +1264,7 @@ int pyrope_index_create(int kind, int dim, int metric, int nlist, int pq_m, int 
 int pyrope_index_destroy(pyrope_index* h) {
     if (!h) return PYROPE_OK;
     cudaStreamSynchronize(h->stream);
-    for (uint32_t* pp : h->peer_thr) cudaIpcCloseMemHandle(pp);
+    for (unsigned long long* pp : h->peer_thr) if (h->peer_ipc) cudaIpcCloseMemHandle(pp);
     h->peer_thr.clear();
     if (h->last_stream) cudaStreamSynchronize(h->last_stream);
     for (int i = 0; i < 5; ++i)
@@ -1285,6 +1299,7 @@ int pyrope_index_update_row(pyrope_index* h, int64_t row, const float* x) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     if (!x) return fail(PYROPE_ERR_INVALID_ARG, "vector is null");
     std::lock_guard<std::mutex> g(h->mu);
+    TRY(wait_last_search(h));
     Segment& s = h->seg;
     int64_t slot;
     if (h->kind == PYROPE_FLAT) {
@@ -1314,6 +1329,7 @@ int pyrope_index_update_row(pyrope_index* h, int64_t row, const float* x) {
 int pyrope_index_delete_row(pyrope_index* h, int64_t row) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     std::lock_guard<std::mutex> g(h->mu);
+    TRY(wait_last_search(h));
     Segment& s = h->seg;
     cudaStream_t st = h->stream;
     if (h->kind == PYROPE_FLAT) {
@@ -1357,6 +1373,7 @@ int pyrope_index_delete_row(pyrope_index* h, int64_t row) {
 int pyrope_index_shadow_row(pyrope_index* h, int64_t row, int shadowed) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     std::lock_guard<std::mutex> g(h->mu);
+    TRY(wait_last_search(h));
     if (h->kind == PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "FLAT rows cannot be shadowed");
     if (row < 0 || row >= h->next_row) return fail(PYROPE_ERR_NOT_FOUND, "row %lld not found", (long long)row);
     TRY(rebuild_row_loc(h));
@@ -1380,6 +1397,7 @@ int pyrope_index_set_labels(pyrope_index* h, int64_t n_rows, const int64_t* labe
     if (n_rows < h->next_row || (n_rows > 0 && !labels_by_row))
         return fail(PYROPE_ERR_INVALID_ARG, "labels for %lld rows needed, %lld given", (long long)h->next_row, (long long)n_rows);
     std::lock_guard<std::mutex> g(h->mu);
+    TRY(wait_last_search(h));
     cudaStream_t st = h->stream;
     Segment& s = h->seg;
     if (s.nslots > 0) {
@@ -1405,6 +1423,7 @@ int pyrope_index_set_quantization(pyrope_index* h, int enable) {
     if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
     if (h->kind != PYROPE_FLAT) return fail(PYROPE_ERR_INVALID_STATE, "only the FLAT index has a quantised scan");
     std::lock_guard<std::mutex> g(h->mu);
+    TRY(wait_last_search(h));
     h->sq8 = enable != 0;
     if (h->sq8 && !h->x8.p) {  // first use: rows that exist already have no quantised form (added while the flag was off)
         h->dpad = (h->dim + 15) / 16 * 16;
@@ -1471,7 +1490,7 @@ int pyrope_index_threshold_exchange_handle(pyrope_index* h, int64_t max_queries,
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     std::lock_guard<std::mutex> g(h->mu);
     if (!h->peer_thr.empty()) return fail(PYROPE_ERR_INVALID_STATE, "peers are already attached");
-    TRY(h->thr_pub.ensure(sizeof(uint32_t) * (size_t)max_queries, 0, h->stream, true));
+    TRY(h->thr_pub.ensure(sizeof(unsigned long long) * (size_t)max_queries, 0, h->stream, true));
     CK(cudaMemsetAsync(h->thr_pub.p, 0, h->thr_pub.bytes, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->thr_cap = max_queries;
@@ -1494,12 +1513,13 @@ int pyrope_index_threshold_exchange_open(pyrope_index* h, int world, int rank, c
         cudaError_t e = cudaIpcOpenMemHandle(&pp, hd, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            for (uint32_t* q : h->peer_thr) cudaIpcCloseMemHandle(q);
+            for (unsigned long long* q : h->peer_thr) cudaIpcCloseMemHandle(q);
             h->peer_thr.clear();
             return fail(PYROPE_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
         }
-        h->peer_thr.push_back(reinterpret_cast<uint32_t*>(pp));
+        h->peer_thr.push_back(reinterpret_cast<unsigned long long*>(pp));
     }
+    h->peer_ipc = true;
     return PYROPE_OK;
 }
 
@@ -1508,8 +1528,17 @@ int pyrope_index_threshold_exchange_close(pyrope_index* h) {
     std::lock_guard<std::mutex> g(h->mu);
     CK(cudaStreamSynchronize(h->stream));
     if (h->last_stream) CK(cudaStreamSynchronize(h->last_stream));
-    for (uint32_t* pp : h->peer_thr) cudaIpcCloseMemHandle(pp);
+    for (unsigned long long* pp : h->peer_thr) if (h->peer_ipc) cudaIpcCloseMemHandle(pp);
     h->peer_thr.clear();  // this rank's own array stays allocated: peers may still write into it
+    return PYROPE_OK;
+}
+
+int pyrope_index_threshold_exchange_epoch(pyrope_index* h, uint32_t epoch) {
+    if (!h) return fail(PYROPE_ERR_INVALID_ARG, "index handle is null");
+    if (epoch == 0) return fail(PYROPE_ERR_INVALID_ARG, "epoch 0 is reserved (an empty word)");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->thr_epoch = epoch;
+    h->thr_epoch_set = true;
     return PYROPE_OK;
 }
 
@@ -1565,15 +1594,21 @@ namespace {
 struct SnapIO {
     FILE* f = nullptr;
     bool ok = true;
+    bool bounded = false;      // reading: `remaining` = bytes left in the file, no length field may exceed it
+    uint64_t remaining = 0;
+    uint64_t last_bytes = 0;   // byte count of the most recent rdev()
     std::vector<unsigned char> stage;
     void w(const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
-    void r(void* p, size_t n) { if (ok && n && fread(p, 1, n, f) != n) ok = false; }
+    void r(void* p, size_t n) {
+        if (bounded) { if (n > remaining) { ok = false; return; } remaining -= n; }
+        if (ok && n && fread(p, 1, n, f) != n) ok = false;
+    }
     template <typename T> void wv(T v) { w(&v, sizeof v); }
     template <typename T> T rv() { T v{}; r(&v, sizeof v); return v; }
     template <typename T> void wvec(const std::vector<T>& v) { wv<uint64_t>(v.size()); w(v.data(), sizeof(T) * v.size()); }
     template <typename T> void rvec(std::vector<T>& v) {
         uint64_t n = rv<uint64_t>();
-        if (!ok || n > ((uint64_t)1 << 40)) { ok = false; return; }
+        if (!ok || n > ((uint64_t)1 << 40) || (bounded && n * sizeof(T) > remaining)) { ok = false; return; }
         v.resize((size_t)n);
         r(v.data(), sizeof(T) * v.size());
     }
@@ -1590,7 +1625,9 @@ struct SnapIO {
     }
     int rdev(DevBuf& b, cudaStream_t st) {
         uint64_t bytes = rv<uint64_t>();
-        if (!ok || bytes > ((uint64_t)1 << 42)) { ok = false; return PYROPE_OK; }
+        last_bytes = 0;
+        if (!ok || bytes > ((uint64_t)1 << 42) || (bounded && bytes > remaining)) { ok = false; return PYROPE_OK; }
+        last_bytes = bytes;
         if (bytes == 0) return PYROPE_OK;
         TRY(b.ensure((size_t)bytes, 0, st, true));
         stage.resize(std::min<size_t>((size_t)bytes, (size_t)64 << 20));
@@ -1652,6 +1689,129 @@ int pyrope_index_snapshot(pyrope_index* h, const char* path) {
     return PYROPE_OK;
 }
 
+// Everything a snapshot holds, parsed into temporaries: pyrope_index_load validates the WHOLE file against the
+// index's shape (byte counts against nslots / dim / list_total / nc, offsets monotone and ending at list_total, row
+// ordinals inside [0, next_row), counters consistent with the flags) and only then swaps it into the live index, so
+// a truncated or corrupt file leaves the index exactly as it was.
+}  // extern "C"
+namespace {
+struct LoadedSnapshot {
+    int32_t nlist = 0;
+    int64_t next_row = 0, nslots = 0, live = 0, ndead = 0;
+    DevBuf X, labels, centroids, codebook, list_rows, list_labels, list_payload;
+    std::vector<uint8_t> dead_h, list_dead_h;
+    std::vector<int64_t> slot_row, free_stack, list_off_h;
+    std::vector<int32_t> ksub;
+    bool built = false, frozen = false;
+    int32_t nc = 0, shard_rank = 0, shard_world = 1;
+    int64_t list_total = 0;
+};
+
+// host copy of a device int64 array, checked to lie in [lo, hi) (allow_neg1: -1 is also fine)
+int check_i64_range(const DevBuf& b, int64_t n, int64_t lo, int64_t hi, bool allow_neg1, const char* what) {
+    std::vector<int64_t> v((size_t)std::min<int64_t>(n, (int64_t)1 << 22));
+    for (int64_t o = 0; o < n; o += (int64_t)v.size()) {
+        const int64_t c = std::min<int64_t>((int64_t)v.size(), n - o);
+        CK(cudaMemcpy(v.data(), b.as<int64_t>() + o, sizeof(int64_t) * (size_t)c, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < c; ++i) {
+            const int64_t x = v[(size_t)i];
+            if (!((x >= lo && x < hi) || (allow_neg1 && x == -1)))
+                return fail(PYROPE_ERR_INVALID_ARG, "corrupt snapshot: %s[%lld] = %lld out of range", what, (long long)(o + i), (long long)x);
+        }
+    }
+    return PYROPE_OK;
+}
+
+int parse_snapshot(Index* h, SnapIO& io, const char* path, LoadedSnapshot& L, cudaStream_t st) {
+    auto bad = [&](const char* what) { return fail(PYROPE_ERR_INVALID_ARG, "corrupt or truncated snapshot %s: %s", path, what); };
+    char magic[8];
+    io.r(magic, 8);
+    if (!io.ok || memcmp(magic, kSnapMagic, 8) != 0) return fail(PYROPE_ERR_INVALID_ARG, "%s is not a pyrope_gpu snapshot", path);
+    const int kind = io.rv<int32_t>(), dim = io.rv<int32_t>(), metric = io.rv<int32_t>();
+    L.nlist = io.rv<int32_t>();
+    const int m = io.rv<int32_t>(), k = io.rv<int32_t>();
+    if (!io.ok) return bad("header");
+    if (kind != h->kind || metric != h->metric || m != h->m || k != h->k) return fail(PYROPE_ERR_INVALID_ARG, "snapshot is of a different index type");
+    if (dim != h->dim) return fail(PYROPE_ERR_DIMENSION, "Vector dimension mismatch");
+    L.next_row = io.rv<int64_t>();
+    L.nslots = io.rv<int64_t>(); L.live = io.rv<int64_t>(); L.ndead = io.rv<int64_t>();
+    if (!io.ok || L.next_row < 0 || L.nslots < 0 || L.live < 0 || L.ndead < 0 || L.live + L.ndead != L.nslots ||
+        L.nslots > ((int64_t)1 << 40) / std::max(dim, 1))
+        return bad("row counters");
+    const bool ivf = kind != PYROPE_FLAT;
+    if (ivf ? L.nslots > L.next_row : L.nslots != L.next_row) return bad("more slots than rows ever added");
+    TRY(io.rdev(L.X, st));
+    if (!io.ok || io.last_bytes != sizeof(float) * (uint64_t)L.nslots * dim) return bad("row vectors");
+    TRY(io.rdev(L.labels, st));
+    if (!io.ok || io.last_bytes != sizeof(int64_t) * (uint64_t)L.nslots) return bad("row labels");
+    io.rvec(L.dead_h); io.rvec(L.slot_row); io.rvec(L.free_stack);
+    if (!io.ok || (int64_t)L.dead_h.size() != L.nslots) return bad("tombstone flags");
+    int64_t nd = 0;
+    for (uint8_t b : L.dead_h) nd += b ? 1 : 0;
+    if (nd != L.ndead) return bad("tombstone count");
+    if (ivf) {
+        if ((int64_t)L.slot_row.size() != L.nslots || (int64_t)L.free_stack.size() != L.ndead) return bad("buffer slot tables");
+        for (int64_t i = 0; i < L.nslots; ++i) {
+            const int64_t r = L.slot_row[(size_t)i];
+            if (L.dead_h[(size_t)i] ? r != -1 : (r < 0 || r >= L.next_row)) return bad("slot -> row table");
+        }
+        std::vector<uint8_t> seen((size_t)L.nslots, 0);
+        for (int64_t sl : L.free_stack) {
+            if (sl < 0 || sl >= L.nslots || !L.dead_h[(size_t)sl] || seen[(size_t)sl]) return bad("free-slot stack");
+            seen[(size_t)sl] = 1;
+        }
+    } else if (!L.slot_row.empty() || !L.free_stack.empty()) {
+        return bad("slot tables on a FLAT index");
+    }
+    L.built = io.rv<int32_t>() != 0; L.frozen = io.rv<int32_t>() != 0; L.nc = io.rv<int32_t>();
+    L.shard_rank = io.rv<int32_t>(); L.shard_world = io.rv<int32_t>();
+    if (!io.ok || L.nc < 0 || L.shard_world < 1 || L.shard_rank < 0 || L.shard_rank >= L.shard_world) return bad("build header");
+    if (!ivf && (L.built || L.nc != 0)) return bad("inverted lists on a FLAT index");
+    if (L.built && L.nc <= 0) return bad("built without centroids");
+    TRY(io.rdev(L.centroids, st));
+    if (!io.ok || (io.last_bytes != 0 && io.last_bytes != sizeof(float) * (uint64_t)L.nc * dim) || (L.built && io.last_bytes == 0))
+        return bad("centroids");
+    if (io.last_bytes == 0 && L.nc != 0 && !L.built) L.nc = 0;
+    TRY(io.rdev(L.codebook, st));
+    const uint64_t cb_bytes = kind == PYROPE_IVF_PQ ? sizeof(float) * (uint64_t)h->m * h->k * h->sub : 0;
+    if (!io.ok || (io.last_bytes != 0 && io.last_bytes != cb_bytes)) return bad("PQ codebooks");
+    const bool have_cb = io.last_bytes != 0;
+    io.rvec(L.ksub);
+    if (!io.ok || !(L.ksub.empty() || (kind == PYROPE_IVF_PQ && (int)L.ksub.size() == h->m))) return bad("codewords per subspace");
+    for (int32_t ks : L.ksub)
+        if (ks < 1 || ks > h->k) return bad("codewords per subspace");
+    if (kind == PYROPE_IVF_PQ && (L.built || !L.ksub.empty()) && (!have_cb || L.ksub.empty())) return bad("PQ codebooks missing");
+    L.list_total = io.rv<int64_t>();
+    if (!io.ok || L.list_total < 0 || L.list_total > L.next_row || (!L.built && L.list_total != 0)) return bad("list total");
+    if (L.built) {
+        io.rvec(L.list_off_h);
+        if (!io.ok || (int64_t)L.list_off_h.size() != (int64_t)L.nc + 1 || L.list_off_h[0] != 0 ||
+            L.list_off_h[(size_t)L.nc] != L.list_total)
+            return bad("list offsets");
+        for (int c = 0; c < L.nc; ++c)
+            if (L.list_off_h[(size_t)c + 1] < L.list_off_h[(size_t)c]) return bad("list offsets not monotone");
+        TRY(io.rdev(L.list_rows, st));
+        if (!io.ok || io.last_bytes != sizeof(int64_t) * (uint64_t)L.list_total) return bad("list rows");
+        TRY(io.rdev(L.list_labels, st));
+        if (!io.ok || io.last_bytes != sizeof(int64_t) * (uint64_t)L.list_total) return bad("list labels");
+        TRY(io.rdev(L.list_payload, st));
+        const uint64_t per = kind == PYROPE_IVF_FLAT ? sizeof(float) * (uint64_t)dim : (uint64_t)h->m;
+        if (!io.ok || io.last_bytes != per * (uint64_t)L.list_total) return bad("list vectors / codes");
+        io.rvec(L.list_dead_h);
+        if (!io.ok || !(L.list_dead_h.empty() || (int64_t)L.list_dead_h.size() == L.list_total)) return bad("list tombstones");
+        for (uint8_t b : L.list_dead_h)
+            if (b > 3) return bad("list tombstones");
+        if (L.list_total) TRY(check_i64_range(L.list_rows, L.list_total, 0, L.next_row, false, "list_rows"));
+        if (kind == PYROPE_IVF_PQ && L.list_total) {  // a code byte indexes its sub-codebook: ksub <= k <= 256 entries, zero padded to k
+            // (every byte value < k is addressable; k = 256 needs no check)
+        }
+    }
+    if (!io.ok) return bad("short read");
+    return PYROPE_OK;
+}
+}  // namespace
+extern "C" {
+
 int pyrope_index_load(pyrope_index* h, const char* path) {
     if (!h || !path || !*path) return fail(PYROPE_ERR_INVALID_ARG, "Path cannot be empty");
     std::lock_guard<std::mutex> g(h->mu);
@@ -1660,85 +1820,108 @@ int pyrope_index_load(pyrope_index* h, const char* path) {
     SnapIO io;
     io.f = fopen(path, "rb");
     if (!io.f) return fail(PYROPE_ERR_NOT_FOUND, "Snapshot file not found: %s", path);  // FileNotFoundException
+    if (fseek(io.f, 0, SEEK_END) == 0) { io.remaining = (uint64_t)std::max<long>(ftell(io.f), 0); io.bounded = true; }
+    rewind(io.f);
     cudaStream_t st = h->stream;
-    auto body = [&]() -> int {
-        char magic[8];
-        io.r(magic, 8);
-        if (!io.ok || memcmp(magic, kSnapMagic, 8) != 0) return fail(PYROPE_ERR_INVALID_ARG, "%s is not a pyrope_gpu snapshot", path);
-        const int kind = io.rv<int32_t>(), dim = io.rv<int32_t>(), metric = io.rv<int32_t>(), nlist = io.rv<int32_t>();
-        const int m = io.rv<int32_t>(), k = io.rv<int32_t>();
-        if (kind != h->kind || metric != h->metric || m != h->m || k != h->k) return fail(PYROPE_ERR_INVALID_ARG, "snapshot is of a different index type");
-        if (dim != h->dim) return fail(PYROPE_ERR_DIMENSION, "Vector dimension mismatch");
-        h->nlist = nlist;
-        h->next_row = io.rv<int64_t>();
-        Segment& s = h->seg;
-        s.clear();
-        const int64_t nslots = io.rv<int64_t>();
-        s.live = io.rv<int64_t>(); s.ndead = io.rv<int64_t>();
-        if (!io.ok || nslots < 0) return fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
-        TRY(s.reserve(std::max<int64_t>(nslots, 1), st, true));
-        s.nslots = nslots;
-        { DevBuf t; TRY(io.rdev(t, st)); if (t.p) CK(cudaMemcpy(s.X.p, t.p, sizeof(float) * (size_t)nslots * dim, cudaMemcpyDeviceToDevice)); }
-        { DevBuf t; TRY(io.rdev(t, st)); if (t.p) CK(cudaMemcpy(s.labels.p, t.p, sizeof(int64_t) * (size_t)nslots, cudaMemcpyDeviceToDevice)); }
-        io.rvec(s.dead_h); io.rvec(s.slot_row); io.rvec(s.free_stack);
-        if (!io.ok || (int64_t)s.dead_h.size() != nslots) return fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
-        if (nslots) CK(cudaMemcpy(s.dead.p, s.dead_h.data(), (size_t)nslots, cudaMemcpyHostToDevice));
-        if (s.cosine && nslots) CK(launch_row_norms_exact(s.X.as<float>(), nslots, dim, dim, s.norms.as<float>(), st));
-        s.tc_dirty = true;
-        h->tc_seg.invalidate();
-        if (h->kind == PYROPE_FLAT && h->x8.p) {  // the byte copies are not part of a snapshot: rebuild (flag on) or drop them
-            h->x8_cap = 0;
-            TRY(sq8_rows(h, 0, nslots));
-        }
-        h->built = io.rv<int32_t>() != 0; h->frozen = io.rv<int32_t>() != 0; h->nc = io.rv<int32_t>();
-        h->shard_rank = io.rv<int32_t>(); h->shard_world = io.rv<int32_t>();
-        TRY(io.rdev(h->centroids, st));
-        TRY(io.rdev(h->codebook, st));
-        io.rvec(h->ksub);
-        if (h->kind == PYROPE_IVF_PQ && !h->ksub.empty()) {
-            TRY(h->ksub_d.ensure(sizeof(int32_t) * h->ksub.size(), 0, st, true));
-            CK(cudaMemcpy(h->ksub_d.p, h->ksub.data(), sizeof(int32_t) * h->ksub.size(), cudaMemcpyHostToDevice));
-        }
-        h->list_total = io.rv<int64_t>();
-        h->lists_version++;
-        h->list_ndead = 0;
-        h->list_dead_h.clear();
-        h->list_dead.release();
-        h->max_list_len = 0;
-        if (h->built) {
-            io.rvec(h->list_off_h);
-            if (!io.ok || (int)h->list_off_h.size() != h->nc + 1) return fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
-            TRY(h->list_off.ensure(sizeof(int64_t) * h->list_off_h.size(), 0, st, true));
-            CK(cudaMemcpy(h->list_off.p, h->list_off_h.data(), sizeof(int64_t) * h->list_off_h.size(), cudaMemcpyHostToDevice));
-            for (int c = 0; c < h->nc; ++c) h->max_list_len = std::max(h->max_list_len, h->list_off_h[(size_t)c + 1] - h->list_off_h[(size_t)c]);
-            TRY(io.rdev(h->list_rows, st));
-            TRY(io.rdev(h->list_labels, st));
-            if (h->kind == PYROPE_IVF_FLAT) TRY(io.rdev(h->list_vecs, st)); else TRY(io.rdev(h->list_codes, st));
-            std::vector<uint8_t> ld;
-            io.rvec(ld);
-            if (!ld.empty()) {
-                TRY(ensure_list_dead(h));
-                h->list_dead_h = ld;
-                for (uint8_t b : ld) h->list_ndead += b ? 1 : 0;
-                CK(cudaMemcpy(h->list_dead.p, ld.data(), ld.size(), cudaMemcpyHostToDevice));
-            }
-            TRY(h->cnorms.ensure(sizeof(float) * (size_t)std::max(h->nc, 1), 0, st, true));
-            if (h->metric == kCosine) {
-                CK(launch_row_norms_exact(h->centroids.as<float>(), h->nc, dim, dim, h->cnorms.as<float>(), st));
-                if (h->kind == PYROPE_IVF_FLAT && h->list_total) {
-                    TRY(h->list_norms.ensure(sizeof(float) * (size_t)h->list_total, 0, st, true));
-                    CK(launch_row_norms_exact(h->list_vecs.as<float>(), h->list_total, dim, dim, h->list_norms.as<float>(), st));
-                }
-            }
-        }
-        h->tc_cent.invalidate();
-        if (h->kind != PYROPE_FLAT) { h->row_loc.assign((size_t)h->next_row, -1); h->lists_loc_valid = false; }
-        CK(cudaStreamSynchronize(st));
-        return io.ok ? PYROPE_OK : fail(PYROPE_ERR_INVALID_ARG, "truncated snapshot");
-    };
-    const int rc = body();
+    LoadedSnapshot L;
+    int rc = parse_snapshot(h, io, path, L, st);
     fclose(io.f);
-    return rc;
+    if (rc != PYROPE_OK) return rc;  // nothing of the live index was touched
+
+    // ---- commit: device allocations below can still fail (OOM), so the fallible part comes first
+    const int dim = h->dim;
+    Segment ns;
+    ns.dim = dim; ns.cosine = h->seg.cosine; ns.reuse_slots = h->seg.reuse_slots;
+    TRY(ns.reserve(std::max<int64_t>(L.nslots, 1), st, true));
+    DevBuf cnorms, list_norms, list_dead, list_off, ksub_d;
+    if (L.nslots) {
+        CK(cudaMemcpyAsync(ns.X.p, L.X.p, sizeof(float) * (size_t)L.nslots * dim, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ns.labels.p, L.labels.p, sizeof(int64_t) * (size_t)L.nslots, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ns.dead.p, L.dead_h.data(), (size_t)L.nslots, cudaMemcpyHostToDevice, st));
+        if (ns.cosine) CK(launch_row_norms_exact(ns.X.as<float>(), L.nslots, dim, dim, ns.norms.as<float>(), st));
+    }
+    if (h->kind == PYROPE_IVF_PQ && !L.ksub.empty()) {
+        TRY(ksub_d.ensure(sizeof(int32_t) * L.ksub.size(), 0, st, true));
+        CK(cudaMemcpyAsync(ksub_d.p, L.ksub.data(), sizeof(int32_t) * L.ksub.size(), cudaMemcpyHostToDevice, st));
+    }
+    int64_t list_ndead = 0, max_list_len = 0;
+    if (L.built) {
+        TRY(list_off.ensure(sizeof(int64_t) * L.list_off_h.size(), 0, st, true));
+        CK(cudaMemcpyAsync(list_off.p, L.list_off_h.data(), sizeof(int64_t) * L.list_off_h.size(), cudaMemcpyHostToDevice, st));
+        for (int c = 0; c < L.nc; ++c) max_list_len = std::max(max_list_len, L.list_off_h[(size_t)c + 1] - L.list_off_h[(size_t)c]);
+        if (!L.list_dead_h.empty()) {
+            TRY(list_dead.ensure((size_t)std::max<int64_t>(L.list_total, 1), 0, st, true));
+            CK(cudaMemcpyAsync(list_dead.p, L.list_dead_h.data(), L.list_dead_h.size(), cudaMemcpyHostToDevice, st));
+            for (uint8_t b : L.list_dead_h) list_ndead += b ? 1 : 0;
+        }
+        TRY(cnorms.ensure(sizeof(float) * (size_t)std::max(L.nc, 1), 0, st, true));
+        if (h->metric == kCosine) {
+            CK(launch_row_norms_exact(L.centroids.as<float>(), L.nc, dim, dim, cnorms.as<float>(), st));
+            if (h->kind == PYROPE_IVF_FLAT && L.list_total) {
+                TRY(list_norms.ensure(sizeof(float) * (size_t)L.list_total, 0, st, true));
+                CK(launch_row_norms_exact(L.list_payload.as<float>(), L.list_total, dim, dim, list_norms.as<float>(), st));
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+
+    // ---- nothing below can fail: swap the parsed state in
+    auto take = [](DevBuf& dst, DevBuf& src) { std::swap(dst.p, src.p); std::swap(dst.bytes, src.bytes); src.release(); };
+    Segment& s = h->seg;
+    take(s.X, ns.X); take(s.dead, ns.dead); take(s.labels, ns.labels); take(s.norms, ns.norms);
+    s.cap = ns.cap; s.nslots = L.nslots; s.live = L.live; s.ndead = L.ndead;
+    s.dead_h.swap(L.dead_h); s.slot_row.swap(L.slot_row); s.free_stack.swap(L.free_stack);
+    s.tc_dirty = true;
+    h->tc_seg.invalidate();
+    h->nlist = L.nlist;
+    h->next_row = L.next_row;
+    h->built = L.built; h->frozen = L.frozen; h->nc = L.nc;
+    h->shard_rank = L.shard_rank; h->shard_world = L.shard_world;
+    take(h->centroids, L.centroids); take(h->codebook, L.codebook);
+    h->ksub.swap(L.ksub);
+    if (ksub_d.p) take(h->ksub_d, ksub_d);
+    h->list_total = L.list_total;
+    h->lists_version++;
+    h->list_ndead = list_ndead;
+    h->list_dead_h.swap(L.list_dead_h);
+    take(h->list_dead, list_dead);
+    h->max_list_len = max_list_len;
+    if (L.built) {
+        h->list_off_h.swap(L.list_off_h);
+        take(h->list_off, list_off); take(h->list_rows, L.list_rows); take(h->list_labels, L.list_labels);
+        if (h->kind == PYROPE_IVF_FLAT) take(h->list_vecs, L.list_payload); else take(h->list_codes, L.list_payload);
+        take(h->cnorms, cnorms);
+        if (list_norms.p) take(h->list_norms, list_norms);
+    } else {
+        h->list_off_h.clear();
+    }
+    // SQ8 (FLAT): the reference's Load re-adds every row through InternalAdd (BruteForceVectorIndex.cs:93-97 ->
+    // :162-184), which quantises it iff the LOADING index has EnableQuantization on at that moment — the flag is a
+    // property of the object, not of the file.  Same here: with the flag on every loaded row gets its byte copy
+    // (ScalarQuantizer is deterministic, so re-quantising reproduces the bytes the snapshotting index held), with it
+    // off no loaded row has a quantised form (:312-322 keeps such rows invisible to a later quantised search).
+    if (h->kind == PYROPE_FLAT && (h->sq8 || h->x8.p)) {
+        h->x8_cap = 0;
+        sq8_rows(h, 0, L.nslots);  // best effort: the rows themselves are already in place
+    }
+    h->tc_cent.invalidate();
+    if (h->kind != PYROPE_FLAT) { h->row_loc.assign((size_t)h->next_row, -1); h->lists_loc_valid = false; }
+    return PYROPE_OK;
+}
+
+// header peek for the string-id layer: rows ever added according to the snapshot (validates the magic only)
+int pyrope_internal_snapshot_next_row(const char* path, int64_t* next_row_out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(PYROPE_ERR_NOT_FOUND, "Snapshot file not found: %s", path);
+    char magic[8];
+    int32_t hdr[6];
+    int64_t nr = -1;
+    const bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kSnapMagic, 8) == 0 &&
+                    fread(hdr, 4, 6, f) == 6 && fread(&nr, 8, 1, f) == 1 && nr >= 0;
+    fclose(f);
+    if (!ok) return fail(PYROPE_ERR_INVALID_ARG, "%s is not a pyrope_gpu snapshot", path);
+    *next_row_out = nr;
+    return PYROPE_OK;
 }
 
 int pyrope_index_stats(pyrope_index* h, int64_t* live_rows, int64_t* buffer_rows, int* dim, int* metric) {

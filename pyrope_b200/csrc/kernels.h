@@ -148,9 +148,12 @@ struct IvfPqScanParams {
     // proves for query q (k candidates at or below it) holds on every rank, so each tightening is also written,
     // with atomicMax over NVLink peer memory, into the peers' published arrays; thr_pub is this rank's own array
     // (what the peers write into), read next to the local threshold.  All nullptr / 0 on one GPU.
-    uint32_t* thr_pub = nullptr;
-    uint32_t* peer_thr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Words are (batch epoch << 32 | ordered bound), written with a 64-bit atomicMax: only words of the reader's own
+    // batch count, so no clearing and no ordering between batches is needed for correctness.
+    unsigned long long* thr_pub = nullptr;
+    unsigned long long* peer_thr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_peers = 0;
+    uint32_t epoch = 0;
 };
 cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
 // List-major variant (pq_lm.cu): (query, probe) pairs grouped by list, four queries per work item share

@@ -171,9 +171,13 @@ struct LmParams {
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits)
     int2* redo; int32_t* redo_cnt;
     int32_t* item_ctr;   // next unclaimed work item (zero-initialised): CTAs claim items as they go
-    const uint32_t* thr_pub;   // multi-GPU: bounds published by the peer ranks for this batch (nullable)
-    uint32_t* peer_thr[7];     // multi-GPU: the peers' published arrays (NVLink peer memory)
+    // multi-GPU: bounds published by the peer ranks (nullable) and the peers' arrays (NVLink peer memory).  A word is
+    // (batch epoch << 32 | ordered bound): a reader only believes a word of ITS batch, so a slow peer's late write for
+    // an earlier batch is inert whenever it lands, and atomicMax lets a newer batch's word replace an older one
+    const unsigned long long* thr_pub;
+    unsigned long long* peer_thr[7];
     int n_peers;
+    uint32_t epoch;
 };
 
 // ---- grouping (query, probe) pairs by list ---------------------------------------------------------
@@ -571,7 +575,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             if (p.n_peers == 0) {
                 atomicMax(p.pool_thr + q, ord);  // result unused: a reduction, nothing to wait for
             } else if (atomicMax(p.pool_thr + q, ord) < ord) {
-                for (int r = 0; r < p.n_peers; ++r) atomicMax(p.peer_thr[r] + q, ord);
+                const unsigned long long w = ((unsigned long long)p.epoch << 32) | ord;
+                for (int r = 0; r < p.n_peers; ++r) atomicMax(p.peer_thr[r] + q, w);
             }
         };
         auto finalize = [&](const LmHeader* hd, int gitem, uint64_t* qk, int* qcnt) {
@@ -773,7 +778,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     if (myq >= 0) {
                         const float mys = hd->s[lane];
                         uint32_t mytu = __ldcg(p.pool_thr + myq);
-                        if (p.thr_pub) mytu = max(mytu, __ldcg(p.thr_pub + myq));  // a bound a peer rank proved
+                        if (p.thr_pub) {  // a bound a peer rank proved for THIS batch
+                            const unsigned long long w = __ldcg(p.thr_pub + myq);
+                            if ((uint32_t)(w >> 32) == p.epoch) mytu = max(mytu, (uint32_t)w);
+                        }
                         const float tau = mytu ? -ord_to_score(mytu) : INFINITY;
                         ti = (int)fminf(fmaxf(tau, 0.f) * mys + (LM_QERR + 1.f), 32767.f);
                         inv = 1.f / mys;
@@ -1153,7 +1161,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
     sp.redo = redo; sp.redo_cnt = redo_cnt; sp.item_ctr = reinterpret_cast<int32_t*>(base + L.item_ctr);
-    sp.thr_pub = p.thr_pub; sp.n_peers = p.n_peers;
+    sp.thr_pub = p.thr_pub; sp.n_peers = p.n_peers; sp.epoch = p.epoch;
     for (int r = 0; r < 7; ++r) sp.peer_thr[r] = r < p.n_peers ? p.peer_thr[r] : nullptr;
     e = cudaFuncSetAttribute(ivfpq_lm_scan_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
     if (e != cudaSuccess) return e;

@@ -23,6 +23,9 @@
 
 #include "../../include/pyrope_gpu.h"
 
+// api.cu (internal, not part of the public header): rows ever added according to a snapshot's header
+extern "C" int pyrope_internal_snapshot_next_row(const char* path, int64_t* next_row_out);
+
 namespace {
 
 thread_local std::string g_verr;
@@ -47,17 +50,27 @@ int vpass(int rc) {
         if (_r != PYROPE_OK) return vpass(_r); \
     } while (0)
 
-// process-wide id table: string -> ordinal (the row label), ordinal -> string
+// process-wide id table: string -> ordinal (the row label), ordinal -> string.  Entries are reference counted — one
+// reference per leaf index whose row_of holds the id — and an ordinal whose count drops to zero is recycled, so a
+// long-lived server with id churn does not grow the table without bound.  (A caller turns search results into strings
+// before it lets go of the index's read lock, as the reference's Search does by returning the strings themselves.)
+struct IdEntry { std::string s; int64_t refs = 0; bool used = false; };
 std::mutex g_id_mu;
-std::vector<std::string> g_ids;
+std::vector<IdEntry> g_ids;
+std::vector<int64_t> g_free_gids;
 std::unordered_map<std::string, int64_t> g_gid_of;
 
+// find or create; a fresh entry has no references yet (id_ref / id_drop_if_unreferenced follow)
 int64_t intern_id(const std::string& id) {
     std::lock_guard<std::mutex> g(g_id_mu);
     auto it = g_gid_of.find(id);
     if (it != g_gid_of.end()) return it->second;
-    const int64_t gid = (int64_t)g_ids.size();
-    g_ids.push_back(id);
+    int64_t gid;
+    if (!g_free_gids.empty()) { gid = g_free_gids.back(); g_free_gids.pop_back(); }
+    else { gid = (int64_t)g_ids.size(); g_ids.emplace_back(); }
+    g_ids[(size_t)gid].s = id;
+    g_ids[(size_t)gid].refs = 0;
+    g_ids[(size_t)gid].used = true;
     g_gid_of.emplace(id, gid);
     return gid;
 }
@@ -65,6 +78,28 @@ int64_t lookup_id(const std::string& id) {
     std::lock_guard<std::mutex> g(g_id_mu);
     auto it = g_gid_of.find(id);
     return it == g_gid_of.end() ? -1 : it->second;
+}
+void id_ref(int64_t gid) {
+    std::lock_guard<std::mutex> g(g_id_mu);
+    if (gid >= 0 && gid < (int64_t)g_ids.size() && g_ids[(size_t)gid].used) g_ids[(size_t)gid].refs++;
+}
+void id_release_locked(int64_t gid) {
+    IdEntry& e = g_ids[(size_t)gid];
+    g_gid_of.erase(e.s);
+    e.s.clear();
+    e.s.shrink_to_fit();
+    e.used = false;
+    e.refs = 0;
+    g_free_gids.push_back(gid);
+}
+void id_unref(int64_t gid) {
+    std::lock_guard<std::mutex> g(g_id_mu);
+    if (gid < 0 || gid >= (int64_t)g_ids.size() || !g_ids[(size_t)gid].used) return;
+    if (--g_ids[(size_t)gid].refs <= 0) id_release_locked(gid);
+}
+void id_drop_if_unreferenced(int64_t gid) {  // an Add that failed after interning a brand-new id
+    std::lock_guard<std::mutex> g(g_id_mu);
+    if (gid >= 0 && gid < (int64_t)g_ids.size() && g_ids[(size_t)gid].used && g_ids[(size_t)gid].refs <= 0) id_release_locked(gid);
 }
 
 bool blank(const char* id) {  // string.IsNullOrWhiteSpace
@@ -95,6 +130,22 @@ struct pyrope_vindex {
         if ((int64_t)gid_of_row.size() <= row) gid_of_row.resize((size_t)row + 1, -1);
         gid_of_row[(size_t)row] = gid;
     }
+    // row_of owns one reference per id it holds
+    void set_row(int64_t gid, int64_t row) {
+        auto it = row_of.find(gid);
+        if (it == row_of.end()) { row_of.emplace(gid, row); id_ref(gid); }
+        else it->second = row;
+    }
+    std::unordered_map<int64_t, int64_t>::iterator drop(std::unordered_map<int64_t, int64_t>::iterator it) {
+        const int64_t gid = it->first;
+        auto nx = row_of.erase(it);
+        id_unref(gid);
+        return nx;
+    }
+    void drop_all() {
+        for (auto& kv : row_of) id_unref(kv.first);
+        row_of.clear();
+    }
 };
 
 namespace {
@@ -111,7 +162,7 @@ int check_vec(const V* v, const float* vec, int len) {
 int leaf_add_new(V* v, int64_t gid, const float* vec) {
     int64_t row = -1;
     VTRY(pyrope_index_add_batch(v->h, 1, vec, &gid, &row));
-    v->row_of[gid] = row;
+    v->set_row(gid, row);
     v->note_row(row, gid);
     if (v->kind != PYROPE_FLAT) v->buffered.insert(gid);
     return PYROPE_OK;
@@ -137,12 +188,17 @@ int leaf_add(V* v, const char* id, const float* vec, int len, bool upsert) {
     int r = check_vec(v, vec, len);  // IVF_PQ stores any array and fails at Build; the device copy cannot
     if (r != PYROPE_OK) return r;
     const int64_t gid = intern_id(id);
-    if (v->kind != PYROPE_FLAT) return leaf_buffer_set(v, gid, vec);
-    auto it = v->row_of.find(gid);
-    if (it == v->row_of.end()) return leaf_add_new(v, gid, vec);
-    if (!upsert)  // BruteForceVectorIndex.cs:141-144
-        return vfail(PYROPE_ERR_INVALID_STATE, "Vector with id '%s' already exists.", id);
-    return vpass(pyrope_index_update_row(v->h, it->second, vec));  // :203-206 in place, scan position kept
+    int rc;
+    if (v->kind != PYROPE_FLAT) rc = leaf_buffer_set(v, gid, vec);
+    else {
+        auto it = v->row_of.find(gid);
+        if (it == v->row_of.end()) rc = leaf_add_new(v, gid, vec);
+        else if (!upsert)  // BruteForceVectorIndex.cs:141-144
+            rc = vfail(PYROPE_ERR_INVALID_STATE, "Vector with id '%s' already exists.", id);
+        else rc = vpass(pyrope_index_update_row(v->h, it->second, vec));  // :203-206 in place, scan position kept
+    }
+    if (rc != PYROPE_OK) id_drop_if_unreferenced(gid);
+    return rc;
 }
 
 int leaf_delete(V* v, const char* id, bool* removed) {
@@ -158,7 +214,7 @@ int leaf_delete(V* v, const char* id, bool* removed) {
     if (v->kind == PYROPE_FLAT) {  // BruteForceVectorIndex.cs:231-254: tombstone, id leaves the map
         VTRY(pyrope_index_delete_row(v->h, row));
         v->gid_of_row[(size_t)row] = -1;
-        v->row_of.erase(it);
+        v->drop(it);
         *removed = true;
         return PYROPE_OK;
     }
@@ -174,7 +230,7 @@ int leaf_delete(V* v, const char* id, bool* removed) {
             it->second = sh->second;
             v->shadowed.erase(sh);
         } else {
-            v->row_of.erase(it);
+            v->drop(it);
         }
         *removed = true;
         return PYROPE_OK;
@@ -189,7 +245,7 @@ int leaf_delete(V* v, const char* id, bool* removed) {
         v->shadowed.erase(sh);
     }
     v->buffered.erase(gid);
-    v->row_of.erase(it);
+    v->drop(it);
     *removed = true;
     return PYROPE_OK;
 }
@@ -203,7 +259,7 @@ void leaf_after_build(V* v, bool had_buffer) {
         for (auto it = v->row_of.begin(); it != v->row_of.end();) {
             if (!v->buffered.count(it->first)) {
                 v->gid_of_row[(size_t)it->second] = -1;
-                it = v->row_of.erase(it);
+                it = v->drop(it);
             } else {
                 ++it;
             }
@@ -247,7 +303,7 @@ int leaf_save_ids(const V* v, const std::string& path) {
         for (size_t r = 0; ok && r < v->gid_of_row.size(); ++r) {
             const int64_t gid = v->gid_of_row[r];
             if (gid < 0) continue;
-            const std::string& s = g_ids[(size_t)gid];
+            const std::string& s = g_ids[(size_t)gid].s;
             int64_t state = 0;  // 0 current row (list or FLAT), 1 current row in the buffer, 2 shadowed list row
             auto ro = v->row_of.find(gid);
             if (ro != v->row_of.end() && ro->second == (int64_t)r) state = v->buffered.count(gid) ? 1 : 0;
@@ -261,43 +317,80 @@ int leaf_save_ids(const V* v, const std::string& path) {
     return PYROPE_OK;
 }
 
-int leaf_load_ids(V* v, const std::string& path) {
+// The id table of a snapshot, parsed and validated on its own: pyrope_vindex_load reads it BEFORE the index file is
+// loaded and applies it after, so a missing or corrupt table never leaves freshly loaded rows under foreign labels.
+struct LoadedIds {
+    int64_t nrows = 0, built = 0;
+    std::vector<std::pair<int64_t, std::string>> rows;  // (row ordinal, id)
+    std::vector<int64_t> state;                         // 0 current, 1 current + buffered, 2 shadowed list row
+};
+int leaf_parse_ids(const std::string& path, LoadedIds& L) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return vfail(PYROPE_ERR_NOT_FOUND, "Snapshot file not found. (%s)", path.c_str());
-    int64_t magic = 0, nrows = 0, built = 0, live = 0;
-    bool ok = get64(f, &magic) && magic == 0x5044495650ll && get64(f, &nrows) && get64(f, &built) && get64(f, &live) &&
-              nrows >= 0 && live >= 0 && live <= nrows;
-    std::vector<int64_t> gid_of_row((size_t)(ok ? nrows : 0), -1);
-    std::unordered_map<int64_t, int64_t> row_of, shadowed;
-    std::unordered_set<int64_t> buffered;
+    int64_t magic = 0, live = 0;
+    bool ok = get64(f, &magic) && magic == 0x5044495650ll && get64(f, &L.nrows) && get64(f, &L.built) && get64(f, &live) &&
+              L.nrows >= 0 && live >= 0 && live <= L.nrows;
+    std::vector<uint8_t> seen((size_t)(ok ? L.nrows : 0), 0);
     std::string s;
     for (int64_t i = 0; ok && i < live; ++i) {
         int64_t r = 0, state = 0, len = 0;
-        ok = get64(f, &r) && get64(f, &state) && get64(f, &len) && r >= 0 && r < nrows && len >= 0 && len < (1 << 20);
+        ok = get64(f, &r) && get64(f, &state) && get64(f, &len) && r >= 0 && r < L.nrows && !seen[(size_t)r] && state >= 0 &&
+             state <= 2 && len >= 0 && len < (1 << 20);
         if (!ok) break;
+        seen[(size_t)r] = 1;
         s.resize((size_t)len);
         ok = len == 0 || fread(&s[0], 1, (size_t)len, f) == (size_t)len;
         if (!ok) break;
-        const int64_t gid = intern_id(s);
-        gid_of_row[(size_t)r] = gid;
-        if (state == 2) shadowed[gid] = r;
-        else {
-            row_of[gid] = r;
-            if (state == 1) buffered.insert(gid);
-        }
+        L.rows.emplace_back(r, s);
+        L.state.push_back(state);
     }
     fclose(f);
     if (!ok) return vfail(PYROPE_ERR_INVALID_ARG, "%s is not a pyrope id table", path.c_str());
-    // the rows in the library's snapshot carry the labels of the process that wrote it: re-label them
-    std::vector<int64_t> labels((size_t)nrows);
-    for (int64_t r = 0; r < nrows; ++r) labels[(size_t)r] = gid_of_row[(size_t)r] >= 0 ? gid_of_row[(size_t)r] : r;
-    VTRY(pyrope_index_set_labels(v->h, nrows, labels.data()));
+    return PYROPE_OK;
+}
+int leaf_apply_ids(V* v, const LoadedIds& L) {
+    std::vector<int64_t> gid_of_row((size_t)L.nrows, -1);
+    std::unordered_map<int64_t, int64_t> row_of, shadowed;
+    std::unordered_set<int64_t> buffered;
+    for (size_t i = 0; i < L.rows.size(); ++i) {
+        const int64_t r = L.rows[i].first, gid = intern_id(L.rows[i].second);
+        gid_of_row[(size_t)r] = gid;
+        if (L.state[i] == 2) shadowed[gid] = r;
+        else {
+            if (row_of.emplace(gid, r).second) id_ref(gid);
+            else row_of[gid] = r;
+            if (L.state[i] == 1) buffered.insert(gid);
+        }
+    }
+    for (auto& kv : shadowed)  // a shadowed row without its buffered copy cannot be written by leaf_save_ids; keep the id alive anyway
+        if (!row_of.count(kv.first)) { row_of.emplace(kv.first, kv.second); id_ref(kv.first); }
+    // the rows in the library's snapshot carry the labels of the process that wrote it: re-label them.  Rows that are
+    // gone get -1, which no search returns and no live id ordinal equals.
+    int rc = pyrope_index_set_labels(v->h, L.nrows, gid_of_row.data());
+    if (rc != PYROPE_OK) {
+        for (auto& kv : row_of) id_unref(kv.first);
+        return vpass(rc);
+    }
+    v->drop_all();
     v->gid_of_row.swap(gid_of_row);
     v->row_of.swap(row_of);
     v->shadowed.swap(shadowed);
     v->buffered.swap(buffered);
-    v->built = built != 0;
+    v->built = L.built != 0;
     return PYROPE_OK;
+}
+// index file + id table of one leaf, all or nothing as far as validation goes
+int leaf_load(V* v, const std::string& path) {
+    LoadedIds L;
+    int r = leaf_parse_ids(path + ".ids", L);
+    if (r != PYROPE_OK) return r;
+    int64_t next_row = -1;
+    VTRY(pyrope_internal_snapshot_next_row(path.c_str(), &next_row));
+    if (L.nrows < next_row)
+        return vfail(PYROPE_ERR_INVALID_ARG, "%s.ids covers %lld rows, the snapshot holds %lld", path.c_str(), (long long)L.nrows,
+                     (long long)next_row);
+    VTRY(pyrope_index_load(v->h, path.c_str()));
+    return leaf_apply_ids(v, L);
 }
 
 }  // namespace
@@ -342,6 +435,7 @@ int pyrope_vindex_destroy(pyrope_vindex* v) {
     if (!v) return PYROPE_OK;
     if (v->d) pyrope_delta_destroy(v->d);  // the two sides stay alive: they were only borrowed
     if (v->h) pyrope_index_destroy(v->h);
+    v->drop_all();
     delete v;
     return PYROPE_OK;
 }
@@ -418,12 +512,12 @@ int pyrope_vindex_build(pyrope_vindex* v) {
         const int64_t gid = moved_gids[i], row = tail_rows[i];
         auto it = tl->row_of.find(gid);
         if (it != tl->row_of.end() && !tl->buffered.count(gid) && it->second != row) tl->shadowed[gid] = it->second;
-        tl->row_of[gid] = row;
+        tl->set_row(gid, row);
         tl->note_row(row, gid);
         if (tl->kind != PYROPE_FLAT) tl->buffered.insert(gid);
     }
     std::fill(hd->gid_of_row.begin(), hd->gid_of_row.end(), (int64_t)-1);  // _head.Delete(id) for every moved id
-    hd->row_of.clear();
+    hd->drop_all();
     leaf_after_build(tl, had_buffer);
     return PYROPE_OK;
 }
@@ -445,14 +539,41 @@ int pyrope_vindex_search(pyrope_vindex* v, int64_t nq, const float* Q, int len, 
 
 int pyrope_vindex_id(int64_t gid, char* buf, int cap, int* len_out) {
     std::lock_guard<std::mutex> g(g_id_mu);
-    if (gid < 0 || gid >= (int64_t)g_ids.size()) return vfail(PYROPE_ERR_NOT_FOUND, "unknown id ordinal %lld", (long long)gid);
-    const std::string& s = g_ids[(size_t)gid];
+    if (gid < 0 || gid >= (int64_t)g_ids.size() || !g_ids[(size_t)gid].used)
+        return vfail(PYROPE_ERR_NOT_FOUND, "unknown id ordinal %lld", (long long)gid);
+    const std::string& s = g_ids[(size_t)gid].s;
     if (len_out) *len_out = (int)s.size();
     if (buf && cap > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
         memcpy(buf, s.data(), n);
         buf[n] = 0;
     }
+    return PYROPE_OK;
+}
+
+int pyrope_vindex_ids(const int64_t* gids, int64_t n, char* buf, int64_t cap, int64_t* offsets_out, int64_t* bytes_out) {
+    if (n < 0 || (n > 0 && (!gids || !offsets_out))) return vfail(PYROPE_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(g_id_mu);  // one lock for the whole result list
+    int64_t o = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        offsets_out[i] = o;
+        const int64_t gid = gids[i];
+        if (gid < 0) continue;  // an empty result slot: zero-length string
+        if (gid >= (int64_t)g_ids.size() || !g_ids[(size_t)gid].used)
+            return vfail(PYROPE_ERR_NOT_FOUND, "unknown id ordinal %lld", (long long)gid);
+        const std::string& s = g_ids[(size_t)gid].s;
+        if (buf && o + (int64_t)s.size() <= cap) memcpy(buf + o, s.data(), s.size());
+        o += (int64_t)s.size();
+    }
+    offsets_out[n] = o;
+    if (bytes_out) *bytes_out = o;
+    return PYROPE_OK;
+}
+
+int pyrope_vindex_id_table_size(int64_t* live_out, int64_t* slots_out) {
+    std::lock_guard<std::mutex> g(g_id_mu);
+    if (live_out) *live_out = (int64_t)g_gid_of.size();
+    if (slots_out) *slots_out = (int64_t)g_ids.size();
     return PYROPE_OK;
 }
 
@@ -494,18 +615,14 @@ int pyrope_vindex_load(pyrope_vindex* v, const char* path) {
     if (blank(path)) return vfail(PYROPE_ERR_INVALID_ARG, "Path cannot be empty. (Parameter 'path')");
     std::unique_lock<std::shared_mutex> g(v->lock);
     const std::string base(path);
-    if (!v->d) {
-        VTRY(pyrope_index_load(v->h, path));
-        return leaf_load_ids(v, base + ".ids");
-    }
+    if (!v->d) return leaf_load(v, base);
     for (int side = 0; side < 2; ++side) {  // DeltaVectorIndex.cs:200-216: each side only if its file exists
         V* leaf = side == 0 ? v->head : v->tail;
         const std::string p = base + (side == 0 ? ".head" : ".tail");
         FILE* f = fopen(p.c_str(), "rb");
         if (!f) continue;
         fclose(f);
-        VTRY(pyrope_index_load(leaf->h, p.c_str()));
-        int r = leaf_load_ids(leaf, p + ".ids");
+        int r = leaf_load(leaf, p);
         if (r != PYROPE_OK) return r;
     }
     return PYROPE_OK;

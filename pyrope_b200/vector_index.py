@@ -88,6 +88,20 @@ def _id_string(ordinal: int) -> str:
     return buf.raw[:n.value].decode("utf-8")
 
 
+def _id_strings(ordinals: np.ndarray) -> list[str]:
+    """pyrope_vindex_ids: every id of a result list under one lock (empty slots, ordinal -1, give '')."""
+    L = _lib.load()
+    o = _np(ordinals, np.int64)
+    n = o.size
+    off = np.zeros(n + 1, np.int64)
+    nbytes = C.c_int64(0)
+    _ck(L.pyrope_vindex_ids(_p(o), n, None, 0, _p(off), C.byref(nbytes)))
+    buf = C.create_string_buffer(max(1, nbytes.value))
+    _ck(L.pyrope_vindex_ids(_p(o), n, buf, nbytes.value, _p(off), C.byref(nbytes)))
+    raw = buf.raw
+    return [raw[off[i]:off[i + 1]].decode("utf-8") for i in range(n)]
+
+
 def _idb(id_):
     return None if id_ is None else str(id_).encode("utf-8")
 
@@ -148,9 +162,10 @@ class _VectorIndex:
         ms = -1 if options is None or options.MaxScans is None else int(options.MaxScans)
         npb = -1 if options is None or options.NProbe is None else int(options.NProbe)
         _ck(_lib.load().pyrope_vindex_search(self._v, nq, _p(Q), ln, int(topK), ms, npb, _p(scores), _p(ids), _p(counts)))
+        names = _id_strings(ids.reshape(-1))  # one call, one lock for the whole result list
         out = []
         for i in range(nq):
-            out.append([SearchResult(_id_string(int(ids[i, j])), float(scores[i, j])) for j in range(int(counts[i]))])
+            out.append([SearchResult(names[i * kk + j], float(scores[i, j])) for j in range(int(counts[i]))])
         return out
 
     def Snapshot(self, path: str):
