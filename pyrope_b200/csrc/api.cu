@@ -153,6 +153,7 @@ struct Workspace {
         tcg, tct,            // two-pass threshold: group maxima, per-query tau
         q8,                  // SQ8: quantised queries
         hq, hs, hl, hc,      // h*: staging for the host-pointer entry point
+        ctc,                 // query-stationary coarse probe scratch
         lm;                  // list-major IVF_PQ scan scratch
 };
 
@@ -967,7 +968,9 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                             (h->tc_mode == 1 || seg_scan >= 8192);
     // the fast coarse stage ranks Pc >= P candidate lists; they are re-ranked in the reference's arithmetic
     const int Pc = std::min(h->nc, std::min(P + 8, kMaxTopK));
-    const bool use_tc_coarse = scan_lists && !ext_probes && h->tc_mode != 0 && flat_tc_supported(dim, Pc) &&
+    // large centroid tables (and dim <= 128): the query-stationary one-TF32 probe with exact ranking of the survivors
+    const bool use_ctc = scan_lists && !ext_probes && h->tc_mode != 0 && h->nc >= 2048 && coarse_tc_supported(dim, h->nc, P);
+    const bool use_tc_coarse = !use_ctc && scan_lists && !ext_probes && h->tc_mode != 0 && flat_tc_supported(dim, Pc) &&
                                (h->tc_mode == 1 || h->nc >= 2048);
     int seg_splits = 0;
     if (scan_seg) seg_splits = use_tc_seg ? 1 : use_sq8 ? sq8_pick_splits(nq, seg_scan, k, g_num_sms)
@@ -988,7 +991,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         qnorm = ws.qnorm.as<float>();
     }
 
-    if (use_tc_seg || use_tc_coarse) {
+    if (use_tc_seg || use_tc_coarse || use_ctc) {
         TRY(ws.qhi.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
         TRY(ws.qlo.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
         CK(launch_tc_prepare(dQ, nq, dim, h->metric, nullptr, ws.qhi.as<float>(), ws.qlo.as<float>(), nullptr, nullptr, 0, st));
@@ -1003,6 +1006,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         tp.X = X; tp.Xhi = op.hi.as<float>(); tp.Xlo = op.lo.as<float>(); tp.n_rows = n_rows; tp.n_scan = n_scan_rows;
         tp.scale = op.scale.as<float>(); tp.bias = op.bias.as<float>(); tp.xnorm = xnorm; tp.qnorm = qnorm; tp.labels = labels;
         tp.metric = h->metric; tp.k = kk; tp.kprime = kk + flat_tc_margin(kk); tp.cap = flat_tc_cap(tp.kprime);
+        tp.arith = (h->kind == PYROPE_FLAT) ? 1 : 2;  // BruteForceVectorIndex scores with the *Unsafe variants, IVF with L2Squared / DotProduct
         const bool twopass = flat_tc_twopass(dim, n_scan_rows, tp.kprime);
         tp.splits = twopass ? flat_tc_pick_splits_seeded(nq, n_scan_rows, tp.kprime, g_num_sms)
                             : flat_tc_pick_splits(nq, n_scan_rows, tp.kprime, g_num_sms);
@@ -1036,6 +1040,18 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     }
     if (ext_probes) {
         // supplied by the caller
+    } else if (use_ctc) {
+        TcOperand& op = h->tc_cent;
+        if (op.dirty || op.rows_valid < h->nc) ++launches;
+        TRY(ensure_tc_operand(op, h->centroids.as<float>(), h->nc, dim, h->metric, nullptr, st));
+        TRY(ws.ctc.ensure(coarse_tc_scratch_bytes(nq, h->nc), 0, st));
+        CoarseTcParams cp{};
+        cp.Q = dQ; cp.Qhi = ws.qhi.as<float>(); cp.nq = nq; cp.dim = dim; cp.metric = h->metric;
+        cp.C = h->centroids.as<float>(); cp.Chi = op.hi.as<float>(); cp.cnorms = h->cnorms.as<float>(); cp.nc = h->nc;
+        cp.scale = op.scale.as<float>(); cp.bias = op.bias.as<float>(); cp.amax = op.amax.as<float>();
+        cp.nprobe = P; cp.probes_out = ws.probes.as<int64_t>(); cp.scratch = ws.ctc.p; cp.num_sms = g_num_sms;
+        CK(launch_coarse_tc(cp, st));
+        launches += coarse_tc_launches();
     } else if (scan_lists) {
         TRY(ws.probes_raw.ensure(sizeof(int64_t) * (size_t)nq * Pc, 0, st));
         TRY(ws.probe_scores.ensure(sizeof(float) * (size_t)nq * Pc, 0, st));

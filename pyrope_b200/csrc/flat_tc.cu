@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact_arith.cuh"
 #include "kernels.h"
 
 namespace pyrope {
@@ -501,8 +502,59 @@ struct RescoreParams {
     const float* X; const float* xnorm; const float* qnorm; const int64_t* labels;
     int metric, k, cap, splits;
     const uint64_t* queue; const int32_t* counts; int64_t nq_pad;
+    int arith;  // 1: VectorMath.*Unsafe order (BruteForceVectorIndex.cs:350-356), 2: VectorMath.L2Squared / DotProduct order (IVF)
     PairOut out;
 };
+
+// The reference's evaluation orders, warp-cooperative, separate multiply and add (exact_arith.cuh conventions).
+// a1 = L2SquaredUnsafe / DotProductUnsafe (VectorMath.cs:128-253): four 8-lane accumulators over 32-element blocks =
+// 32 independent running sums, one per lane (coalesced 128-byte loads); final = ((a1 + a2) + a3) + a4 per lane j, then
+// the pairwise horizontal sum; a separate accumulator for 1-3 leftover 8-blocks; scalar tail.  One candidate per warp.
+template <int OP>
+__device__ __forceinline__ float a1_eval_warp(const float* q, const float* __restrict__ x, int n, int lane) {
+    int i = 0;
+    float sum = 0.f;
+    if (n >= 32) {
+        float acc = 0.f;
+        for (; i <= n - 32; i += 32) acc = __fadd_rn(acc, exact::term<OP>(q[i + lane], __ldg(x + i + lane)));
+        const int j = lane & 7;
+        const float v1 = __shfl_sync(0xffffffffu, acc, j), v2 = __shfl_sync(0xffffffffu, acc, 8 + j);
+        const float v3 = __shfl_sync(0xffffffffu, acc, 16 + j), v4 = __shfl_sync(0xffffffffu, acc, 24 + j);
+        float fin = __fadd_rn(__fadd_rn(__fadd_rn(v1, v2), v3), v4);
+        fin = __fadd_rn(fin, __shfl_xor_sync(0xffffffffu, fin, 1));
+        fin = __fadd_rn(fin, __shfl_xor_sync(0xffffffffu, fin, 2));
+        fin = __fadd_rn(fin, __shfl_xor_sync(0xffffffffu, fin, 4));
+        sum = __fadd_rn(sum, fin);
+    }
+    if (i <= n - 8) {
+        float acc = 0.f;
+        for (; i <= n - 8; i += 8)
+            if (lane < 8) acc = __fadd_rn(acc, exact::term<OP>(q[i + lane], __ldg(x + i + lane)));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+        sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, acc, 0));
+    }
+    for (; i < n; ++i) sum = __fadd_rn(sum, exact::term<OP>(q[i], __ldg(x + i)));
+    return sum;
+}
+// a2 = L2Squared / DotProduct (VectorMath.cs:8-70): one 8-lane accumulator stepping 8 elements.  Eight consecutive
+// lanes (j = lane & 7) share a candidate: four candidates per warp.
+template <int OP>
+__device__ __forceinline__ float a2_eval_oct(const float* q, const float* __restrict__ x, int n, int j) {
+    int i = 0;
+    float sum = 0.f;
+    if (n >= 8) {
+        float acc = 0.f;
+        for (; i <= n - 8; i += 8) acc = __fadd_rn(acc, exact::term<OP>(q[i + j], __ldg(x + i + j)));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+        sum = __fadd_rn(sum, acc);
+    }
+    for (; i < n; ++i) sum = __fadd_rn(sum, exact::term<OP>(q[i], __ldg(x + i)));
+    return sum;
+}
 
 // The survivors of a query are spread over `splits` queues; they pass through a window of P keys in shared memory:
 // load up to P - (kept so far), score the new ones exactly, sort, keep the best k, repeat.  P >= 2k and P covers the
@@ -526,10 +578,12 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int 
     }
     __syncthreads();
     const int total = s_total;
-    const float* qv = p.Q + q * p.dim;
-    const bool vec_ok = (p.dim % 4 == 0);
+    float* qv = reinterpret_cast<float*>(keys + P);  // the query, staged once
+    for (int d = tid; d < p.dim; d += blockDim.x) qv[d] = p.Q[q * p.dim + d];
     const float qn = p.metric == kCosine ? p.qnorm[q] : 0.f;
-    const int hl = lane & 15, half = lane >> 4;  // two candidates per warp, 16 lanes each
+    // survivors are scored in the REFERENCE's arithmetic: what is reported (and ranked) is the oracle's value bit for bit
+    const int cpw = p.arith == 1 ? 1 : 4;       // candidates per warp and pass
+    const int sub = p.arith == 1 ? 0 : lane >> 3;
     int kept = 0, off = 0, sorted_n = 0;
     do {
         const int n_new = min(total - off, P - kept);
@@ -541,41 +595,21 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(RescoreParams p, int 
             keys[kept + i] = __ldcg(p.queue + ((int64_t)sidx * p.nq_pad + q) * p.cap + (g - s_off[sidx]));
         }
         __syncthreads();
-        for (int i0 = kept + warp * 2; i0 < kept + n_new; i0 += 16) {
-            const int i = i0 + half;
+        for (int i0 = kept + warp * cpw; i0 < kept + n_new; i0 += (blockDim.x >> 5) * cpw) {
+            const int i = i0 + sub;
             const bool on = i < kept + n_new;
-            const uint32_t pos = on ? key_pos(keys[i]) : 0u;
+            const uint32_t pos = on ? key_pos(keys[i]) : key_pos(keys[i0]);  // idle lanes shadow a live candidate (shuffles stay uniform)
             const float* x = p.X + (int64_t)pos * p.dim;
-            float a = 0.f;
-            if (on) {
-                if (vec_ok) {
-                    for (int d = hl * 4; d < p.dim; d += 64) {
-                        float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
-                        float4 qq = __ldg(reinterpret_cast<const float4*>(qv + d));
-                        if (p.metric == kL2) {
-                            float d0 = qq.x - xv.x, d1 = qq.y - xv.y, d2 = qq.z - xv.z, d3 = qq.w - xv.w;
-                            a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
-                        } else {
-                            a = fmaf(qq.x, xv.x, a); a = fmaf(qq.y, xv.y, a); a = fmaf(qq.z, xv.z, a); a = fmaf(qq.w, xv.w, a);
-                        }
-                    }
-                } else {
-                    for (int d = hl; d < p.dim; d += 16) {
-                        float xv = __ldg(x + d), qq = __ldg(qv + d);
-                        if (p.metric == kL2) { float df = qq - xv; a = fmaf(df, df, a); }
-                        else a = fmaf(qq, xv, a);
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);  // within each half warp
-            if (on && hl == 0) {
+            float a;
+            if (p.arith == 1) a = p.metric == kL2 ? a1_eval_warp<0>(qv, x, p.dim, lane) : a1_eval_warp<1>(qv, x, p.dim, lane);
+            else a = p.metric == kL2 ? a2_eval_oct<0>(qv, x, p.dim, lane & 7) : a2_eval_oct<1>(qv, x, p.dim, lane & 7);
+            if (on && (p.arith == 1 ? lane == 0 : (lane & 7) == 0)) {
                 float score;
                 if (p.metric == kL2) score = -a;
                 else if (p.metric == kIP) score = a;
                 else {
-                    float xn = p.xnorm[pos];
-                    score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : a / (qn * xn);
+                    const float xn = p.xnorm[pos];
+                    score = (qn < 1e-6f || xn < 1e-6f) ? 0.f : __fdiv_rn(a, __fmul_rn(qn, xn));
                 }
                 keys[i] = make_key(score, pos);
             }
@@ -860,7 +894,8 @@ cudaError_t launch_flat_tc(const FlatTcParams& a, cudaStream_t st) {
     // (32 KiB, so that many queries' CTAs stay resident); bigger totals take several rounds inside the kernel
     const int usual = a.kprime * 2 + 64;
     const int P = std::min(4096, next_pow2(std::max(std::max(2 * a.k, usual), 64)));
-    flat_rescore_kernel<<<(unsigned)a.nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(r, P);
+    r.arith = a.arith == 1 ? 1 : 2;
+    flat_rescore_kernel<<<(unsigned)a.nq, 256, sizeof(uint64_t) * (size_t)P + sizeof(float) * (size_t)a.dim, st>>>(r, P);
     return cudaGetLastError();
 }
 

@@ -45,6 +45,7 @@ struct FlatTcParams {
     const float* xnorm; const float* qnorm;  // cosine re-score
     const int64_t* labels;
     int metric, k, kprime, cap, splits;
+    int arith = 2;                           // re-score order: 1 = VectorMath.*Unsafe (FLAT index), 2 = L2Squared / DotProduct (IVF)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the tcgen05 kernel alone
     uint64_t* queue; int32_t* counts;        // scratch [splits][nq_pad][cap], [splits][nq_pad]
     const float* amax = nullptr;             // optional: max_r |scale_r||x_r| of the operand => pass A runs 1xTF32
@@ -84,6 +85,24 @@ cudaError_t launch_assign_from_shortlist(int metric, int dim, int64_t n, const f
                                          uint8_t* flag, cudaStream_t st);
 // scatter: dst[idx[i]] = src[i]
 cudaError_t launch_scatter_i32(const int32_t* src, const int64_t* idx, int64_t n, int32_t* dst, cudaStream_t st);
+
+// ---- coarse probe of a batched IVF search, query tile resident in shared memory (coarse_tc.cu) -----------------
+// Replaces the centroid ranking of IvfFlatVectorIndex.cs:186-198 / IvfPqVectorIndex.cs:141-150 for a batch: one-TF32
+// tensor-core scores pick the few centroids per query that can be among the nprobe best, those are ranked in the
+// reference's own arithmetic.  probes_out [nq][nprobe] list ids, best first, -1 = none.
+constexpr int kCoarseTcCap = 512;     // candidate positions kept per query before the exhaustive fallback
+constexpr int kCoarseTcMargin = 8;    // k' = nprobe + margin unit maxima bound the threshold
+struct CoarseTcParams {
+    const float* Q; const float* Qhi; int64_t nq; int dim; int metric;
+    const float* C; const float* Chi; const float* cnorms; int64_t nc;
+    const float* scale; const float* bias; const float* amax;   // proxy terms of the centroid operand (TcOperand)
+    int nprobe; int64_t* probes_out;
+    void* scratch; int num_sms;
+};
+bool coarse_tc_supported(int dim, int64_t nc, int nprobe);
+size_t coarse_tc_scratch_bytes(int64_t nq, int64_t nc);
+int coarse_tc_launches();
+cudaError_t launch_coarse_tc(const CoarseTcParams& p, cudaStream_t st);
 
 // ---- FLAT, 8-bit scalar quantised (sq8.cu): ScalarQuantizer.Quantize:22-62 and the quantised branch of
 // BruteForceVectorIndex.Search:297-336 (integer distances between byte vectors, VectorMath.cs:441-680)
