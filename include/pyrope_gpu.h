@@ -134,6 +134,11 @@ int pyrope_index_threshold_exchange_handle(pyrope_index *h, int64_t max_queries,
 int pyrope_index_threshold_exchange_open(pyrope_index *h, int world, int rank, const void *handles);
 int pyrope_index_threshold_exchange_close(pyrope_index *h); /* stop publishing / reading; the own array stays mapped */
 int pyrope_index_threshold_exchange_epoch(pyrope_index *h, uint32_t epoch); /* epoch of the NEXT probed search */
+/* The same exchange between indexes of ONE process (pyrope_sharded_*): _array (re)allocates this index's array and returns
+ * its device pointer, _attach takes every shard's pointer (world entries, own slot ignored; peer access between the
+ * devices must be enabled).  _close detaches. */
+int pyrope_index_threshold_exchange_array(pyrope_index *h, int64_t max_queries, void **d_array_out);
+int pyrope_index_threshold_exchange_attach(pyrope_index *h, int world, int rank, void *const *arrays);
 int pyrope_index_is_built(pyrope_index *h, int *out);
 /* ICentroidsProvider.GetCentroids (IvfFlatVectorIndex.cs:314-325): n_out = 0 until built.
  * centroids_out may be NULL to query the count. */
@@ -220,6 +225,54 @@ const char *pyrope_batcher_last_error(void);
 int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float *d_scores,
                              const int64_t *d_rows, float *d_scores_out, int64_t *d_rows_out,
                              int32_t *d_counts_out, void *stream);
+
+/* The same with label de-duplication (dedupe != 0): a candidate whose row label already occurs in a LOWER part is
+ * dropped — DeltaVectorIndex.cs:98-110's "one entry per id, the first list wins". */
+int pyrope_topk_merge_dedupe_device(int64_t nq, int parts, int k_in, int k_out, const float *d_scores,
+                                    const int64_t *d_rows, float *d_scores_out, int64_t *d_rows_out,
+                                    int32_t *d_counts_out, int dedupe, void *stream);
+
+/* ---- ONE index over the N GPUs of a box, one process (csrc/sharded.cu; SURVEY §8e "single process, 8 devices, one
+ *      stream per device"): what a GpuVectorIndex constructed at Services/VectorIndexRegistry.cs:81-113 holds when
+ *      the registry is configured with several devices.  One pyrope_index per device, one host thread per device.
+ *      FLAT: rows dealt to the shards in consecutive blocks per add call (global row ordinals are the labels).
+ *      IVF_*: every shard sees every row, Build keeps the inverted lists with list_id % N == shard; centroids and PQ
+ *      codebooks are replicated (training is deterministic, the replicas agree bit for bit).
+ *      Search: each shard ranks centroids for its slice of the batch and writes the probe lists into every peer's
+ *      buffer over NVLink (peer stores + CUDA events, no host hop); every shard scans its lists for all queries, the
+ *      IVF_PQ scan kernels exchange thresholds through peer memory while they run; local top-k lists land in device
+ *      0's gather buffer and are merged there (one entry per row label).  Results equal the single-GPU index's.
+ *      MaxScans (an insertion-/probe-order budget) cannot be split: max_scans >= 0 with N > 1 -> UNSUPPORTED.
+ *      Errors: pyrope_sharded_last_error().  Calls on one handle are serialised internally. */
+typedef struct pyrope_sharded pyrope_sharded;
+/* devices: n_devices CUDA ordinals, or NULL for 0..n_devices-1 (1 <= n_devices <= 8; peers must be NVLink/P2P reachable) */
+int pyrope_sharded_create(int n_devices, const int *devices, int kind, int dim, int metric, int nlist, int pq_m,
+                          int pq_k, pyrope_sharded **out);
+int pyrope_sharded_destroy(pyrope_sharded *s);
+int pyrope_sharded_device_count(pyrope_sharded *s, int *out);
+/* the per-device index (and its CUDA ordinal) — for device-resident feeds: make that device current, then use the
+ * pyrope_index_* calls; afterwards tell the sharded object the global row count with _note_rows */
+int pyrope_sharded_shard(pyrope_sharded *s, int i, pyrope_index **index_out, int *device_out);
+int pyrope_sharded_note_rows(pyrope_sharded *s, int64_t total_rows);
+int pyrope_sharded_set_train_params(pyrope_sharded *s, int64_t max_train_rows, int max_iter);
+int pyrope_sharded_set_codebooks(pyrope_sharded *s, int n_centroids, const float *centroids, const float *pq_codebooks);
+/* IVectorIndex.Add for n rows (host pointers); labels NULL = global row ordinals; first_row_out = first ordinal */
+int pyrope_sharded_add_batch(pyrope_sharded *s, int64_t n, const float *X, const int64_t *labels,
+                             int64_t *first_row_out);
+int pyrope_sharded_delete_row(pyrope_sharded *s, int64_t row);
+int pyrope_sharded_build(pyrope_sharded *s);
+int pyrope_sharded_stats(pyrope_sharded *s, int64_t *live_rows_out);
+/* IVectorIndex.Search for nq queries over all shards: host buffers in / out (H2D of the queries to every device and
+ * the D2H of the merged result inside the call). */
+int pyrope_sharded_search_batch(pyrope_sharded *s, int64_t nq, const float *Q, int topk, int64_t max_scans,
+                                int nprobe, float *scores_out, int64_t *rows_out, int32_t *counts_out);
+/* the same with queries and outputs resident on the FIRST shard's device (the queries still travel to the peers) */
+int pyrope_sharded_search_batch_device(pyrope_sharded *s, int64_t nq, const float *dQ_dev0, int topk,
+                                       int64_t max_scans, int nprobe, float *d_scores_dev0, int64_t *d_rows_dev0,
+                                       int32_t *d_counts_dev0);
+/* device time (ms, CUDA events on the first shard's stream) of the most recent search: queries available -> merged result */
+int pyrope_sharded_last_search_ms(pyrope_sharded *s, float *ms_out);
+const char *pyrope_sharded_last_error(void);
 
 /* ---- Head+Tail on device: replaces DeltaVectorIndex (Vector/DeltaVectorIndex.cs) when BOTH sides are GPU
  *      indexes — a small mutable FLAT head and an IVF_FLAT / IVF_PQ / FLAT tail (VectorIndexRegistry.cs:110-111).

@@ -58,6 +58,24 @@ SIGNATURES = {
     "pyrope_index_threshold_exchange_open": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "pyrope_index_threshold_exchange_close": (C.c_int, [vp]),
     "pyrope_index_threshold_exchange_epoch": (C.c_int, [vp, C.c_uint32]),
+    "pyrope_index_threshold_exchange_array": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
+    "pyrope_index_threshold_exchange_attach": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "pyrope_topk_merge_dedupe_device": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]),
+    "pyrope_sharded_create": (C.c_int, [C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "pyrope_sharded_destroy": (C.c_int, [vp]),
+    "pyrope_sharded_device_count": (C.c_int, [vp, i32p]),
+    "pyrope_sharded_shard": (C.c_int, [vp, C.c_int, C.POINTER(vp), i32p]),
+    "pyrope_sharded_note_rows": (C.c_int, [vp, C.c_int64]),
+    "pyrope_sharded_set_train_params": (C.c_int, [vp, C.c_int64, C.c_int]),
+    "pyrope_sharded_set_codebooks": (C.c_int, [vp, C.c_int, vp, vp]),
+    "pyrope_sharded_add_batch": (C.c_int, [vp, C.c_int64, vp, vp, i64p]),
+    "pyrope_sharded_delete_row": (C.c_int, [vp, C.c_int64]),
+    "pyrope_sharded_build": (C.c_int, [vp]),
+    "pyrope_sharded_stats": (C.c_int, [vp, i64p]),
+    "pyrope_sharded_search_batch": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
+    "pyrope_sharded_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
+    "pyrope_sharded_last_search_ms": (C.c_int, [vp, f32p]),
+    "pyrope_sharded_last_error": (C.c_char_p, []),
     "pyrope_index_is_built": (C.c_int, [vp, i32p]),
     "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
@@ -338,6 +356,96 @@ class GpuIndex:
         """PQ codes scored by the last batched IVF_PQ search (sum of probed list lengths)."""
         out = C.c_int64(0)
         check(load().pyrope_index_last_search_scanned(self._h, C.byref(out)))
+        return out.value
+
+
+class ShardedIndex:
+    """One index over several GPUs of the box, driven by this one process (pyrope_sharded_*, csrc/sharded.cu)."""
+
+    def __init__(self, n_devices: int, kind: int, dim: int, metric: int = L2, nlist: int = 100, m: int = 4, k: int = 256,
+                 devices=None):
+        s = vp()
+        dv = _np(devices, np.int32) if devices is not None else None
+        self._ck(load().pyrope_sharded_create(n_devices, dv.ctypes.data_as(i32p) if dv is not None else None, kind, dim,
+                                              metric, nlist, m, k, C.byref(s)))
+        self._s, self.n, self.kind, self.dim, self.metric, self.nlist, self.m, self.k = s, n_devices, kind, dim, metric, nlist, m, k
+
+    @staticmethod
+    def _ck(rc):
+        if rc != OK:
+            msg = load().pyrope_sharded_last_error()
+            raise PyropeGpuError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+    def close(self):
+        if getattr(self, "_s", None):
+            load().pyrope_sharded_destroy(self._s)
+            self._s = None
+
+    __del__ = close
+
+    def shard(self, i: int):
+        """(borrowed GpuIndex view of shard i, its CUDA device ordinal)"""
+        h, dev = vp(), C.c_int32(0)
+        self._ck(load().pyrope_sharded_shard(self._s, i, C.byref(h), C.byref(dev)))
+        g = GpuIndex.__new__(GpuIndex)
+        g._h, g.kind, g.dim, g.metric, g.nlist, g.m, g.k = h, self.kind, self.dim, self.metric, self.nlist, self.m, self.k
+        g.close = lambda: None
+        g._owner = self
+        return g, dev.value
+
+    def note_rows(self, total: int):
+        self._ck(load().pyrope_sharded_note_rows(self._s, total))
+
+    def set_train_params(self, max_train_rows=0, max_iter=0):
+        self._ck(load().pyrope_sharded_set_train_params(self._s, max_train_rows, max_iter))
+
+    def set_codebooks(self, centroids, pq_codebooks=None):
+        c = _np(centroids, np.float32)
+        cb = _np(pq_codebooks, np.float32) if pq_codebooks is not None else None
+        self._ck(load().pyrope_sharded_set_codebooks(self._s, c.shape[0], _p(c), _p(cb)))
+
+    def add(self, X, labels=None) -> int:
+        X = _np(X, np.float32)
+        if X.ndim == 1:
+            X = X[None, :]
+        if X.shape[1] != self.dim:
+            raise PyropeGpuError(ERR_DIMENSION, "Vector dimension mismatch")
+        lab = _np(labels, np.int64) if labels is not None else None
+        first = C.c_int64(-1)
+        self._ck(load().pyrope_sharded_add_batch(self._s, X.shape[0], _p(X), _p(lab), C.byref(first)))
+        return first.value
+
+    def delete_row(self, row: int) -> bool:
+        rc = load().pyrope_sharded_delete_row(self._s, row)
+        if rc == ERR_NOT_FOUND:
+            return False
+        self._ck(rc)
+        return True
+
+    def build(self):
+        self._ck(load().pyrope_sharded_build(self._s))
+
+    def stats(self) -> int:
+        out = C.c_int64(0)
+        self._ck(load().pyrope_sharded_stats(self._s, C.byref(out)))
+        return out.value
+
+    def search(self, Q, topk: int, max_scans: int = -1, nprobe: int = -1):
+        Q = _np(Q, np.float32)
+        if Q.ndim == 1:
+            Q = Q[None, :]
+        nq, kk = Q.shape[0], max(topk, 1)
+        scores, rows, counts = np.zeros((nq, kk), np.float32), np.full((nq, kk), -1, np.int64), np.zeros(nq, np.int32)
+        self._ck(load().pyrope_sharded_search_batch(self._s, nq, _p(Q), topk, max_scans, nprobe, _p(scores), _p(rows), _p(counts)))
+        return scores, rows, counts
+
+    def search_device(self, q_ptr: int, nq: int, topk: int, scores_ptr: int, rows_ptr: int, counts_ptr: int, nprobe: int = -1):
+        self._ck(load().pyrope_sharded_search_batch_device(self._s, nq, vp(q_ptr), topk, -1, nprobe, vp(scores_ptr), vp(rows_ptr),
+                                                           vp(counts_ptr)))
+
+    def last_search_ms(self) -> float:
+        out = C.c_float(0)
+        self._ck(load().pyrope_sharded_last_search_ms(self._s, C.byref(out)))
         return out.value
 
 

@@ -1500,19 +1500,57 @@ int pyrope_index_set_shard(pyrope_index* h, int rank, int world) {
     return PYROPE_OK;
 }
 
-int pyrope_index_threshold_exchange_handle(pyrope_index* h, int64_t max_queries, void* handle_out) {
-    if (!h || !handle_out || max_queries <= 0) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+}  // extern "C"
+namespace {
+// this rank's published-threshold array: (re)allocated zeroed for batches of up to max_queries queries
+int thr_array_ensure(Index* h, int64_t max_queries) {
     if (h->kind != PYROPE_IVF_PQ) return fail(PYROPE_ERR_INVALID_STATE, "threshold exchange exists on the IVF_PQ list-major path only");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
-    std::lock_guard<std::mutex> g(h->mu);
+    if (max_queries <= h->thr_cap && h->thr_pub.p) return PYROPE_OK;
     if (!h->peer_thr.empty()) return fail(PYROPE_ERR_INVALID_STATE, "peers are already attached");
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->last_stream) CK(cudaStreamSynchronize(h->last_stream));
+    h->thr_pub.release();
     TRY(h->thr_pub.ensure(sizeof(unsigned long long) * (size_t)max_queries, 0, h->stream, true));
     CK(cudaMemsetAsync(h->thr_pub.p, 0, h->thr_pub.bytes, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->thr_cap = max_queries;
+    return PYROPE_OK;
+}
+}  // namespace
+extern "C" {
+
+int pyrope_index_threshold_exchange_handle(pyrope_index* h, int64_t max_queries, void* handle_out) {
+    if (!h || !handle_out || max_queries <= 0) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->peer_thr.empty()) return fail(PYROPE_ERR_INVALID_STATE, "peers are already attached");
+    TRY(thr_array_ensure(h, max_queries));
     cudaIpcMemHandle_t hd;
     CK(cudaIpcGetMemHandle(&hd, h->thr_pub.p));
     memcpy(handle_out, &hd, sizeof hd);
+    return PYROPE_OK;
+}
+
+int pyrope_index_threshold_exchange_array(pyrope_index* h, int64_t max_queries, void** d_array_out) {
+    if (!h || !d_array_out || max_queries <= 0) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    TRY(thr_array_ensure(h, max_queries));
+    *d_array_out = h->thr_pub.p;
+    return PYROPE_OK;
+}
+
+int pyrope_index_threshold_exchange_attach(pyrope_index* h, int world, int rank, void* const* arrays) {
+    if (!h || !arrays) return fail(PYROPE_ERR_INVALID_ARG, "null argument");
+    if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(PYROPE_ERR_INVALID_ARG, "world must be 2..8");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->thr_pub.p) return fail(PYROPE_ERR_INVALID_STATE, "call pyrope_index_threshold_exchange_array first");
+    if (!h->peer_thr.empty()) return fail(PYROPE_ERR_INVALID_STATE, "peers are already attached");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        if (!arrays[r]) { h->peer_thr.clear(); return fail(PYROPE_ERR_INVALID_ARG, "array of shard %d is null", r); }
+        h->peer_thr.push_back(reinterpret_cast<unsigned long long*>(arrays[r]));
+    }
+    h->peer_ipc = false;  // same-process device pointers (peer access enabled by the caller): nothing to close
     return PYROPE_OK;
 }
 
@@ -2060,15 +2098,20 @@ int pyrope_index_last_search_scanned(pyrope_index* h, int64_t* codes_out) {
     return PYROPE_OK;
 }
 
-int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float* d_scores, const int64_t* d_rows,
-                             float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream) {
+int pyrope_topk_merge_dedupe_device(int64_t nq, int parts, int k_in, int k_out, const float* d_scores, const int64_t* d_rows,
+                                    float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, int dedupe, void* stream) {
     if (nq < 0 || parts <= 0 || k_in <= 0 || k_out <= 0) return fail(PYROPE_ERR_INVALID_ARG, "bad merge shape");
     if ((int64_t)parts * k_in > kMergeMaxCandidates)
         return fail(PYROPE_ERR_UNSUPPORTED, "parts*k_in = %lld exceeds %d", (long long)parts * k_in, kMergeMaxCandidates);
     CK(launch_merge_pairs(nq, parts, k_in, k_out, d_scores, d_rows, nq * (int64_t)k_in, k_in, d_scores_out, d_rows_out,
-                          d_counts_out, (cudaStream_t)stream));
+                          d_counts_out, (cudaStream_t)stream, dedupe != 0));
     if (!stream) CK(cudaStreamSynchronize(nullptr));
     return PYROPE_OK;
+}
+
+int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float* d_scores, const int64_t* d_rows,
+                             float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream) {
+    return pyrope_topk_merge_dedupe_device(nq, parts, k_in, k_out, d_scores, d_rows, d_scores_out, d_rows_out, d_counts_out, 0, stream);
 }
 
 // ---- Head+Tail on device (DeltaVectorIndex.cs) ------------------------------------------------------

@@ -27,6 +27,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <vector>
 
 #include "common.cuh"
 #include "exact_arith.cuh"
@@ -48,6 +50,15 @@ constexpr int TERM_FLOATS = 8 * 2 * 2 * CN;  // per epilogue warp: [2 buffers][b
 constexpr size_t C_SMEM = (size_t)CKC * QCHUNK_BYTES + (size_t)XSTAGES * XSTAGE_BYTES + TERM_FLOATS * sizeof(float) + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One lane of a CONVERGED warp.  The single-thread roles (TMA producer, MMA issuer) must be entered through this and not
+// through `lane == 0`: ptxas knows elect.sync yields exactly one lane and keeps descriptors in uniform registers, whereas
+// under a plain divergent branch it wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop over the
+// "possibly several" active threads — measured 166 cycles of issue per tcgen05.mma against a 64-cycle tensor-pipe floor.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -172,7 +183,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0, qloads = 0;
             int64_t cur_qt = -1;
             for (int ui = 0; ui < nunit; ++ui) {
@@ -195,7 +206,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0, qloads = 0;
             int64_t cur_qt = -1;
             for (int ui = 0; ui < nunit; ++ui) {
@@ -348,13 +359,14 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
         float tau = -INFINITY;
         if (ntiles > kprime) {
             constexpr int R = TAU_MAXU / 32;
+            const int nr = (ntiles + 31) >> 5;  // occupied registers per lane (warp-uniform)
             uint32_t o[R];
             uint32_t lo = 0xffffffffu, hi = 0u;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = r * 32 + lane;
-                o[r] = i < ntiles ? score_to_ord(s_u[ql * ld + i]) : 0u;
-                if (i < ntiles) { lo = min(lo, o[r]); hi = max(hi, o[r]); }
+                o[r] = (r < nr && i < ntiles) ? score_to_ord(s_u[ql * ld + i]) : 0u;
+                if (r < nr && i < ntiles) { lo = min(lo, o[r]); hi = max(hi, o[r]); }
             }
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
@@ -362,9 +374,18 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
                 const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
                 int n = 0;
 #pragma unroll
-                for (int r = 0; r < R; ++r) n += o[r] >= mid;
+                for (int r = 0; r < R; ++r)
+                    if (r < nr) n += o[r] >= mid;
                 n = __reduce_add_sync(0xffffffffu, n);
-                if (n >= kprime) lo = mid; else hi = mid - 1u;
+                if (n == kprime) {  // exactly k' values at or above mid: the k'-th largest is the smallest of them
+                    uint32_t mn = 0xffffffffu;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r < nr && o[r] >= mid) mn = min(mn, o[r]);
+                    lo = hi = __reduce_min_sync(0xffffffffu, mn);
+                    break;
+                }
+                if (n > kprime) lo = mid; else hi = mid - 1u;
             }
             const float G = ord_to_score(lo);
             float qq = 0.f;
@@ -383,22 +404,22 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
 
 // ---- exact ranking of the survivors, in the reference's arithmetic ---------------------------------------------
 // VectorMath.L2Squared / DotProduct (VectorMath.cs:8-70): one 8-lane accumulator stepping 8 elements, pairwise
-// horizontal sum, scalar tail; separate multiply and add.  `a` in shared memory, `b` read with 128-bit loads.
+// horizontal sum, scalar tail; separate multiply and add.  Eight consecutive lanes (j = lane & 7) share a candidate:
+// lane j IS accumulator lane j, its 16 loads (d = 128) are independent of the add chain and all in flight at once.
 template <int OP>
-__device__ __forceinline__ float a2_eval_v4(const float* a, const float* __restrict__ b, int n) {
+__device__ __forceinline__ float a2_eval_oct(const float* q, const float* __restrict__ x, int n, int j) {
     int i = 0;
     float sum = 0.f;
     if (n >= 8) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (; i <= n - 8; i += 8) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + i)), b1 = __ldg(reinterpret_cast<const float4*>(b + i + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], exact::term<OP>(a[i + j], bb[j]));
-        }
-        sum = __fadd_rn(sum, exact::hsum8(acc));
+        float acc = 0.f;
+#pragma unroll 16
+        for (; i <= n - 8; i += 8) acc = __fadd_rn(acc, exact::term<OP>(q[i + j], __ldg(x + i + j)));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+        sum = __fadd_rn(sum, acc);
     }
-    for (; i < n; ++i) sum = __fadd_rn(sum, exact::term<OP>(a[i], __ldg(b + i)));
+    for (; i < n; ++i) sum = __fadd_rn(sum, exact::term<OP>(q[i], __ldg(x + i)));
     return sum;
 }
 
@@ -413,28 +434,28 @@ __global__ void __launch_bounds__(128) coarse_rank_kernel(const float* __restric
     float* qv = reinterpret_cast<float*>(keys + RANK_KEYS);     // [dim]
     __shared__ float s_qn;
     const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, j = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
     for (int d = tid; d < dim; d += blockDim.x) qv[d] = Q[q * dim + d];
     __syncthreads();
     if (METRIC == 2 && tid == 0) s_qn = exact::norm_eval(qv, dim);
     __syncthreads();
-    auto score = [&](int64_t l) -> float {
+    auto score = [&](int64_t l) -> float {  // all eight lanes of a group call this with the same l
         const float* cv = C + l * dim;
-        if (METRIC == 0) return -a2_eval_v4<0>(qv, cv, dim);
-        if (METRIC == 1) return a2_eval_v4<1>(qv, cv, dim);
+        if (METRIC == 0) return -a2_eval_oct<0>(qv, cv, dim, j);
+        if (METRIC == 1) return a2_eval_oct<1>(qv, cv, dim, j);
+        const float d = a2_eval_oct<1>(qv, cv, dim, j);
         const float cn = cnorms[l];
-        return (s_qn < 1e-6f || cn < 1e-6f) ? 0.f : __fdiv_rn(a2_eval_v4<1>(qv, cv, dim), __fmul_rn(s_qn, cn));
+        return (s_qn < 1e-6f || cn < 1e-6f) ? 0.f : __fdiv_rn(d, __fmul_rn(s_qn, cn));
     };
     const int have = qcnt[q];
     if (have <= cap) {
         const int P2 = next_pow2(max(max(have, P), 2));  // the output loop reads P keys: pad with empties
-        for (int i = tid; i < P2; i += blockDim.x) {
-            uint64_t key = 0ull;
-            if (i < have) {
-                const uint32_t l = qpos[q * cap + i];
-                key = make_key(score(l), l);
-            }
-            keys[i] = key;
+        for (int i0 = 0; i0 < P2; i0 += ngrp) {  // uniform trip count: the shuffles inside score() need whole warps
+            const int i = i0 + grp;
+            const bool on = i < have;
+            const uint32_t l = on ? qpos[q * cap + i] : 0u;
+            const float sc = score(l);
+            if (j == 0 && i < P2) keys[i] = on ? make_key(sc, l) : 0ull;
         }
         __syncthreads();
         bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
@@ -443,9 +464,11 @@ __global__ void __launch_bounds__(128) coarse_rank_kernel(const float* __restric
         for (int i = tid; i < RANK_KEYS; i += blockDim.x) keys[i] = 0ull;
         __syncthreads();
         for (int64_t c0 = 0; c0 < nc; c0 += RANK_KEYS / 2) {
-            for (int i = tid; i < RANK_KEYS / 2; i += blockDim.x) {
-                const int64_t l = c0 + i;
-                keys[RANK_KEYS / 2 + i] = l < nc ? make_key(score(l), (uint32_t)l) : 0ull;
+            for (int i0 = 0; i0 < RANK_KEYS / 2; i0 += ngrp) {
+                const int64_t l = c0 + i0 + grp;
+                const bool on = l < nc;
+                const float sc = score(on ? l : 0);
+                if (j == 0) keys[RANK_KEYS / 2 + i0 + grp] = on ? make_key(sc, (uint32_t)l) : 0ull;
             }
             __syncthreads();
             bitonic_sort_desc<false>(keys, RANK_KEYS, tid, blockDim.x);  // best 1024 so far end up in the front half
@@ -558,6 +581,16 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
         coarse_rank_kernel<1><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, a.probes_out, a.nprobe);
     else
         coarse_rank_kernel<2><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, a.probes_out, a.nprobe);
+    static const bool dbg = getenv("PYROPE_COARSE_DEBUG") != nullptr;
+    if (dbg) {  // survivors per query (debug aid, synchronises)
+        std::vector<int32_t> hc((size_t)a.nq);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hc.data(), p.qcnt, sizeof(int32_t) * hc.size(), cudaMemcpyDeviceToHost);
+        long long sum = 0, mx = 0, over = 0;
+        for (int32_t c : hc) { sum += c; mx = std::max<long long>(mx, c); over += c > p.cap; }
+        fprintf(stderr, "[coarse] survivors per query: mean %.1f max %lld, %lld of %lld queries ranked exhaustively (cap %d), groups %d%s\n",
+                (double)sum / (double)a.nq, mx, over, (long long)a.nq, p.cap, ngroups, p.fine ? " (32-column)" : "");
+    }
     return cudaGetLastError();
 }
 

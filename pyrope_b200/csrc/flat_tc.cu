@@ -37,6 +37,15 @@ constexpr int TMEM_COLS = 512;
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  The single-thread roles (TMA producer, MMA issuer) must be entered through this and not
+// through `lane == 0`: ptxas knows elect.sync yields exactly one lane and keeps descriptors in uniform registers, whereas
+// under a plain divergent branch it wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop over the
+// "possibly several" active threads — measured 166 cycles of issue per tcgen05.mma against a 64-cycle tensor-pipe floor.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -176,7 +185,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int ti = 0; ti < ntile; ++ti) {
                 const int n0 = (int)((t_begin + ti) * BN);
@@ -196,7 +205,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int ti = 0; ti < ntile; ++ti) {
                 const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;

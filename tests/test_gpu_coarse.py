@@ -24,8 +24,8 @@ def _frozen_pair(gpu, metric, dim, nlist, n, seed, dup=0):
     assigns and encodes, the oracle adopts the result, so a search compares the coarse ranking + scan alone."""
     rng = np.random.default_rng(seed)
     cent = rng.random((nlist, dim), dtype=np.float32)
-    if dup:
-        cent[100:100 + dup] = cent[7]            # a crowd of identical centroids
+    if dup:                                      # a crowd of near-identical centroids (distinct in fp32, one TF32 band)
+        cent[100:100 + dup] = cent[7] + (rng.random((dup, dim), dtype=np.float32) - 0.5) * 2e-3
     cb = (rng.random((16, 256, dim // 16), dtype=np.float32) - 0.5) * 0.5
     base = rng.random((n, dim), dtype=np.float32)
     gm = {"L2": gpu.L2, "IP": gpu.INNER_PRODUCT, "COSINE": gpu.COSINE}[metric]
@@ -61,7 +61,7 @@ def test_coarse_probe_matches_oracle(gpu, metric, dim, nlist, nprobe):
 
 
 def test_coarse_probe_with_a_crowd_of_duplicate_centroids(gpu):
-    """3,000 identical centroids sit inside one rounding band: queries near them overflow the candidate list and
+    """3,000 near-identical centroids sit inside one rounding band: queries near them overflow the candidate list and
     are ranked exhaustively; the result must still be the oracle's."""
     ix, ref, rng = _frozen_pair(gpu, "L2", 128, 20000, 60_000, seed=5, dup=3000)
     cent7 = ix.centroids()[7]
