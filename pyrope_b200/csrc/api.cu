@@ -1017,6 +1017,12 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             if (!getenv("PYROPE_TC_PASSA_3X")) tp.amax = op.amax.as<float>();
             launches += 3;
         }
+        if (!twopass && flat_tc_oneterm(dim, n_scan_rows, tp.kprime)) {
+            TRY(ws.tct.ensure(sizeof(float) * (2 * (size_t)flat_tc_nq_pad(nq) + 16), 0, st));  // (unused tau) | band | overflow flag
+            tp.tau_ws = ws.tct.as<float>();
+            tp.amax = op.amax.as<float>();
+            launches += 2;
+        }
         const int64_t nq_pad = flat_tc_nq_pad(nq);
         const size_t tparts = (size_t)tp.splits * flat_tc_parts_per_split(tp);
         TRY(ws.tcq.ensure(sizeof(uint64_t) * tparts * nq_pad * tp.cap, 0, st));
@@ -1044,7 +1050,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         TcOperand& op = h->tc_cent;
         if (op.dirty || op.rows_valid < h->nc) ++launches;
         TRY(ensure_tc_operand(op, h->centroids.as<float>(), h->nc, dim, h->metric, nullptr, st));
-        TRY(ws.ctc.ensure(coarse_tc_scratch_bytes(nq, h->nc), 0, st));
+        TRY(ws.ctc.ensure(coarse_tc_scratch_bytes(nq, h->nc, g_num_sms), 0, st));
         CoarseTcParams cp{};
         cp.Q = dQ; cp.Qhi = ws.qhi.as<float>(); cp.nq = nq; cp.dim = dim; cp.metric = h->metric;
         cp.C = h->centroids.as<float>(); cp.Chi = op.hi.as<float>(); cp.cnorms = h->cnorms.as<float>(); cp.nc = h->nc;

@@ -139,9 +139,11 @@ struct CoarseParams {
     float* umax;          // pass A out: [groups][nq_pad] maximum proxy score of a group: a whole unit (128 centroids) or,
     int fine;             //   fine = 1 (small tables: too few units to bound the k'-th best), each 32-column chunk of it
     const float* tau;     // pass B in: [nq_pad] accept s > tau
-    uint32_t* qpos;       // pass B out: [nq][cap] centroid positions
-    int32_t* qcnt;        //             [nq] (zero-initialised; may run past cap: overflow)
-    int cap;
+    // pass B out: survivors' centroid positions.  A query's units are spread over a few CTAs ("parts": the CTAs whose unit
+    // ranges touch its query tile); each (query, part) list is private to ONE thread — plain stores, no atomics.
+    uint32_t* qpos;       // [nq_pad][parts][cap]
+    int32_t* qcnt;        // [nq_pad][parts] (zero-initialised; a count above cap marks an overflow)
+    int cap, parts;
 };
 
 template <bool PASS_B>
@@ -270,13 +272,31 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         int64_t cur_qt = -1, gq = 0;
         bool qvalid = false;
         float tau = INFINITY;
+        int cnt = 0;
+        uint32_t* myq = nullptr;
+        int32_t* mycnt = nullptr;
         for (int ui = 0; ui < nunit; ++ui) {
             const int64_t u = u0 + ui, qt = u / p.ntiles, nt = u - qt * p.ntiles;
             if (qt != cur_qt) {
+                if (PASS_B && mycnt && qvalid) *mycnt = cnt;  // close the list of the query tile this CTA leaves
                 cur_qt = qt;
                 gq = qt * CQ + hf * 128 + ew * 32 + lane;
                 qvalid = gq < p.nq;
-                if (PASS_B) tau = qvalid ? __ldg(p.tau + gq) : INFINITY;
+                if (PASS_B) {
+                    tau = qvalid ? __ldg(p.tau + gq) : INFINITY;
+                    // part = this CTA's rank among the CTAs whose ranges touch query tile qt (the first one holds unit qt * ntiles)
+                    const int64_t first_cta = ((qt * p.ntiles + 1) * (int64_t)gridDim.x + total - 1) / total - 1;
+                    const int part = (int)((int64_t)blockIdx.x - first_cta);
+                    if (part >= 0 && part < p.parts) {
+                        myq = p.qpos + ((size_t)gq * p.parts + part) * p.cap;
+                        mycnt = p.qcnt + (size_t)gq * p.parts + part;
+                        cnt = 0;
+                    } else {  // cannot happen with the launcher's bound on parts; if it did, the query is ranked exhaustively
+                        myq = p.qpos + (size_t)gq * p.parts * p.cap;
+                        mycnt = p.qcnt + (size_t)gq * p.parts;
+                        cnt = p.cap + 1;
+                    }
+                }
             }
             const uint32_t buf = ui & 1, aph = (ui >> 1) & 1;
             if (ui + 1 < nunit) load_terms(ui + 1);  // consumed after this unit
@@ -313,8 +333,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     while (mask) {  // rare: ~1 survivor per 600 scores
                         const int j = __ffs(mask) - 1;
                         mask &= mask - 1u;
-                        const int slot = atomicAdd(p.qcnt + gq, 1);
-                        if (slot < p.cap) p.qpos[gq * p.cap + slot] = (uint32_t)(nt * CN + c * 32 + j);
+                        if (cnt < p.cap) myq[cnt] = (uint32_t)(nt * CN + c * 32 + j);
+                        ++cnt;
                     }
                 }
             }
@@ -324,6 +344,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             if (ui + 1 < nunit) store_terms(buf ^ 1);
         }
+        if (PASS_B && mycnt && qvalid) *mycnt = cnt;
     }
 
     tc_fence_before();
@@ -341,6 +362,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // 32 queries per block: the unit maxima arrive [unit][query] (coalesced), are transposed through shared memory and
 // each warp runs a register-resident bisection for 8 queries.
 constexpr int TAU_MAXU = 1024;  // units per query handled in registers (32 per lane): 131,072 centroids
+template <int R>  // registers per lane: groups <= 32 R
 __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict__ umax, int64_t nq_pad, int ntiles, int64_t nq,
                                                         int kprime, const float* __restrict__ Q, int dim,
                                                         const float* __restrict__ amax, float* tau_out) {
@@ -358,7 +380,6 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
         if (q >= nq) break;
         float tau = -INFINITY;
         if (ntiles > kprime) {
-            constexpr int R = TAU_MAXU / 32;
             const int nr = (ntiles + 31) >> 5;  // occupied registers per lane (warp-uniform)
             uint32_t o[R];
             uint32_t lo = 0xffffffffu, hi = 0u;
@@ -404,63 +425,89 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
 
 // ---- exact ranking of the survivors, in the reference's arithmetic ---------------------------------------------
 // VectorMath.L2Squared / DotProduct (VectorMath.cs:8-70): one 8-lane accumulator stepping 8 elements, pairwise
-// horizontal sum, scalar tail; separate multiply and add.  Eight consecutive lanes (j = lane & 7) share a candidate:
-// lane j IS accumulator lane j, its 16 loads (d = 128) are independent of the add chain and all in flight at once.
+// horizontal sum ((v0+v1)+(v2+v3))+((v4+v5)+(v6+v7)), scalar tail; separate multiply and add.  FOUR consecutive lanes share
+// a candidate: lane t owns accumulator lanes 2t and 2t+1 (one 64-bit load per step, all 16 loads of a d = 128 row in
+// flight at once), so the first level of the horizontal tree is a local add and two shuffles finish it.
 template <int OP>
-__device__ __forceinline__ float a2_eval_oct(const float* q, const float* __restrict__ x, int n, int j) {
+__device__ __forceinline__ float a2_eval_quad(const float* q, const float* __restrict__ x, int n, int t) {
     int i = 0;
     float sum = 0.f;
     if (n >= 8) {
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll 16
-        for (; i <= n - 8; i += 8) acc = __fadd_rn(acc, exact::term<OP>(q[i + j], __ldg(x + i + j)));
+        for (; i <= n - 8; i += 8) {
+            const float2 xv = __ldg(reinterpret_cast<const float2*>(x + i + 2 * t));
+            const float2 qv = *reinterpret_cast<const float2*>(q + i + 2 * t);
+            a0 = __fadd_rn(a0, exact::term<OP>(qv.x, xv.x));
+            a1 = __fadd_rn(a1, exact::term<OP>(qv.y, xv.y));
+        }
+        float acc = __fadd_rn(a0, a1);
         acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
         acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
-        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
         sum = __fadd_rn(sum, acc);
     }
     for (; i < n; ++i) sum = __fadd_rn(sum, exact::term<OP>(q[i], __ldg(x + i)));
     return sum;
 }
 
-constexpr int RANK_KEYS = 2048;  // sort window: survivors (<= cap <= 1024) or, exhaustively, 1024 kept + 1024 new
+constexpr int RANK_KEYS = 2048;  // sort window: survivors (<= 1024) or, exhaustively, 1024 kept + 1024 new
+constexpr int RANK_MAXPARTS = 160;
 template <int METRIC>
 __global__ void __launch_bounds__(128) coarse_rank_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ C,
                                                          const float* __restrict__ cnorms, int64_t nc,
                                                          const uint32_t* __restrict__ qpos, const int32_t* __restrict__ qcnt, int cap,
-                                                         int64_t* pout, int P) {
+                                                         int parts, int64_t* pout, int P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [RANK_KEYS]
-    float* qv = reinterpret_cast<float*>(keys + RANK_KEYS);     // [dim]
+    uint32_t* spos = reinterpret_cast<uint32_t*>(keys + RANK_KEYS);  // [1024]
+    float* qv = reinterpret_cast<float*>(spos + 1024);          // [dim]
     __shared__ float s_qn;
+    __shared__ int s_off[RANK_MAXPARTS + 1];
+    __shared__ int s_over;
     const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x, j = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
+    const int tid = threadIdx.x, t = tid & 3, grp = tid >> 2, ngrp = blockDim.x >> 2;
     for (int d = tid; d < dim; d += blockDim.x) qv[d] = Q[q * dim + d];
+    if (tid == 0) {  // offsets of the (few) per-CTA lists of this query
+        int o = 0, over = 0;
+        for (int pt = 0; pt < parts; ++pt) {
+            const int c = qcnt[q * parts + pt];
+            s_off[pt] = o;
+            over |= c > cap;
+            o += min(c, cap);
+        }
+        s_off[parts] = o;
+        s_over = over || o > 1024;
+    }
     __syncthreads();
     if (METRIC == 2 && tid == 0) s_qn = exact::norm_eval(qv, dim);
+    const int have = s_off[parts];
+    const bool exhaustive = s_over != 0;
+    if (!exhaustive)
+        for (int pt = 0; pt < parts; ++pt)
+            for (int i = s_off[pt] + tid; i < s_off[pt + 1]; i += blockDim.x) spos[i] = qpos[((size_t)q * parts + pt) * cap + (i - s_off[pt])];
     __syncthreads();
-    auto score = [&](int64_t l) -> float {  // all eight lanes of a group call this with the same l
+    auto score = [&](int64_t l) -> float {  // the four lanes of a group call this with the same l
         const float* cv = C + l * dim;
-        if (METRIC == 0) return -a2_eval_oct<0>(qv, cv, dim, j);
-        if (METRIC == 1) return a2_eval_oct<1>(qv, cv, dim, j);
-        const float d = a2_eval_oct<1>(qv, cv, dim, j);
+        if (METRIC == 0) return -a2_eval_quad<0>(qv, cv, dim, t);
+        if (METRIC == 1) return a2_eval_quad<1>(qv, cv, dim, t);
+        const float d = a2_eval_quad<1>(qv, cv, dim, t);
         const float cn = cnorms[l];
         return (s_qn < 1e-6f || cn < 1e-6f) ? 0.f : __fdiv_rn(d, __fmul_rn(s_qn, cn));
     };
-    const int have = qcnt[q];
-    if (have <= cap) {
+    if (!exhaustive) {
         const int P2 = next_pow2(max(max(have, P), 2));  // the output loop reads P keys: pad with empties
-        for (int i0 = 0; i0 < P2; i0 += ngrp) {  // uniform trip count: the shuffles inside score() need whole warps
+        for (int i = have + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
+        for (int i0 = 0; i0 < have; i0 += ngrp) {  // uniform trip count: the shuffles inside score() need whole warps
             const int i = i0 + grp;
             const bool on = i < have;
-            const uint32_t l = on ? qpos[q * cap + i] : 0u;
+            const uint32_t l = spos[on ? i : i0];
             const float sc = score(l);
-            if (j == 0 && i < P2) keys[i] = on ? make_key(sc, l) : 0ull;
+            if (t == 0 && on) keys[i] = make_key(sc, l);
         }
         __syncthreads();
         bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
     } else {
-        // the candidate list overflowed (a crowd of centroids inside one rounding band): rank every centroid
+        // a candidate list overflowed (a crowd of centroids inside one rounding band): rank every centroid
         for (int i = tid; i < RANK_KEYS; i += blockDim.x) keys[i] = 0ull;
         __syncthreads();
         for (int64_t c0 = 0; c0 < nc; c0 += RANK_KEYS / 2) {
@@ -468,7 +515,7 @@ __global__ void __launch_bounds__(128) coarse_rank_kernel(const float* __restric
                 const int64_t l = c0 + i0 + grp;
                 const bool on = l < nc;
                 const float sc = score(on ? l : 0);
-                if (j == 0) keys[RANK_KEYS / 2 + i0 + grp] = on ? make_key(sc, (uint32_t)l) : 0ull;
+                if (t == 0) keys[RANK_KEYS / 2 + i0 + grp] = on ? make_key(sc, (uint32_t)l) : 0ull;
             }
             __syncthreads();
             bitonic_sort_desc<false>(keys, RANK_KEYS, tid, blockDim.x);  // best 1024 so far end up in the front half
@@ -514,18 +561,23 @@ int coarse_groups(int64_t nc, int kprime, int* fine) {
     return 0;
 }
 
-struct CoarseLayout { size_t umax, tau, qcnt, qpos, total; int64_t nq_pad, qtiles, ntiles; };
-CoarseLayout coarse_layout(int64_t nq, int64_t nc) {
+struct CoarseLayout { size_t umax, tau, qcnt, qpos, total; int64_t nq_pad, qtiles, ntiles; int grid, parts, cap; };
+CoarseLayout coarse_layout(int64_t nq, int64_t nc, int num_sms) {
     CoarseLayout L{};
     L.qtiles = (nq + CQ - 1) / CQ;
     L.nq_pad = L.qtiles * CQ;
     L.ntiles = (nc + CN - 1) / CN;
+    L.grid = (int)std::min<int64_t>(num_sms, L.qtiles * L.ntiles);
+    // CTAs whose contiguous unit ranges can touch one query tile
+    L.parts = (int)std::min<int64_t>(L.grid, (L.grid + L.qtiles - 1) / L.qtiles + 2);
+    // survivors per (query, part): ~110 per query in all at C5; room for skew, the whole budget when one CTA holds the tile
+    L.cap = L.parts <= 2 ? kCoarseTcCap : kCoarseTcCap / 2;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t o = 0;
-    L.qcnt = o; o += al(sizeof(int32_t) * (size_t)nq);
+    L.qcnt = o; o += al(sizeof(int32_t) * (size_t)L.nq_pad * L.parts);
     L.tau = o; o += al(sizeof(float) * (size_t)L.nq_pad);
     L.umax = o; o += al(sizeof(float) * (size_t)std::min<int64_t>(L.ntiles * (CN / 32), std::max<int64_t>(L.ntiles, TAU_MAXU)) * (size_t)L.nq_pad);
-    L.qpos = o; o += al(sizeof(uint32_t) * (size_t)nq * kCoarseTcCap);
+    L.qpos = o; o += al(sizeof(uint32_t) * (size_t)L.nq_pad * L.parts * L.cap);
     L.total = o;
     return L;
 }
@@ -539,12 +591,13 @@ bool coarse_tc_supported(int dim, int64_t nc, int nprobe) {
     return dim % 4 == 0 && dim >= 8 && dim <= CKC * CBK && nprobe >= 1 && nprobe <= kCoarseTcCap / 2 &&
            coarse_groups(nc, nprobe + kCoarseTcMargin, &fine) > 0 && nc < ((int64_t)1 << 31) && !getenv("PYROPE_COARSE_STREAMING");
 }
-size_t coarse_tc_scratch_bytes(int64_t nq, int64_t nc) { return coarse_layout(nq, nc).total; }
+size_t coarse_tc_scratch_bytes(int64_t nq, int64_t nc, int num_sms) { return coarse_layout(nq, nc, num_sms).total; }
 int coarse_tc_launches() { return 5; }  // clear, pass A, threshold, pass B, exact ranking
 
 cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
-    const CoarseLayout L = coarse_layout(a.nq, a.nc);
+    const CoarseLayout L = coarse_layout(a.nq, a.nc, a.num_sms);
+    if (L.parts > RANK_MAXPARTS) return cudaErrorInvalidValue;
     unsigned char* base = reinterpret_cast<unsigned char*>(a.scratch);
     CUtensorMap mq, mx;
     if (!make_map(&mq, a.Qhi, a.nq, a.dim, CQ) || !make_map(&mx, a.Chi, a.nc, a.dim, CN)) return cudaErrorInvalidValue;
@@ -555,41 +608,52 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     p.tau = reinterpret_cast<float*>(base + L.tau);
     p.qpos = reinterpret_cast<uint32_t*>(base + L.qpos);
     p.qcnt = reinterpret_cast<int32_t*>(base + L.qcnt);
-    p.cap = kCoarseTcCap;
-    cudaError_t e = cudaMemsetAsync(p.qcnt, 0, sizeof(int32_t) * (size_t)a.nq, st);
+    p.cap = L.cap; p.parts = L.parts;
+    cudaError_t e = cudaMemsetAsync(p.qcnt, 0, sizeof(int32_t) * (size_t)L.nq_pad * L.parts, st);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(coarse_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(coarse_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
     if (e != cudaSuccess) return e;
-    const int64_t total = L.qtiles * L.ntiles;
-    const unsigned grid = (unsigned)std::min<int64_t>(a.num_sms, total);
+    const unsigned grid = (unsigned)L.grid;
     const int kprime = a.nprobe + kCoarseTcMargin;
     const int ngroups = coarse_groups(a.nc, kprime, &p.fine);
     if (ngroups <= 0) return cudaErrorInvalidValue;
     const size_t tsm = sizeof(float) * 32 * ((size_t)ngroups + 1);
-    e = cudaFuncSetAttribute(coarse_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-    if (e != cudaSuccess) return e;
     coarse_tc_kernel<false><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
-    coarse_tau_kernel<<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
-        p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau));
+    if (ngroups <= 512) {
+        e = cudaFuncSetAttribute(coarse_tau_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        if (e != cudaSuccess) return e;
+        coarse_tau_kernel<16><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
+            p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau));
+    } else {
+        e = cudaFuncSetAttribute(coarse_tau_kernel<TAU_MAXU / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        if (e != cudaSuccess) return e;
+        coarse_tau_kernel<TAU_MAXU / 32><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
+            p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau));
+    }
     coarse_tc_kernel<true><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
-    const size_t rsm = sizeof(uint64_t) * RANK_KEYS + sizeof(float) * (size_t)a.dim;
+    const size_t rsm = sizeof(uint64_t) * RANK_KEYS + sizeof(uint32_t) * 1024 + sizeof(float) * (size_t)a.dim;
     if (a.metric == kL2)
-        coarse_rank_kernel<0><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, a.probes_out, a.nprobe);
+        coarse_rank_kernel<0><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
     else if (a.metric == kIP)
-        coarse_rank_kernel<1><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, a.probes_out, a.nprobe);
+        coarse_rank_kernel<1><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
     else
-        coarse_rank_kernel<2><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, a.probes_out, a.nprobe);
+        coarse_rank_kernel<2><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
     static const bool dbg = getenv("PYROPE_COARSE_DEBUG") != nullptr;
     if (dbg) {  // survivors per query (debug aid, synchronises)
-        std::vector<int32_t> hc((size_t)a.nq);
+        std::vector<int32_t> hc((size_t)a.nq * p.parts);
         cudaStreamSynchronize(st);
         cudaMemcpy(hc.data(), p.qcnt, sizeof(int32_t) * hc.size(), cudaMemcpyDeviceToHost);
         long long sum = 0, mx = 0, over = 0;
-        for (int32_t c : hc) { sum += c; mx = std::max<long long>(mx, c); over += c > p.cap; }
-        fprintf(stderr, "[coarse] survivors per query: mean %.1f max %lld, %lld of %lld queries ranked exhaustively (cap %d), groups %d%s\n",
-                (double)sum / (double)a.nq, mx, over, (long long)a.nq, p.cap, ngroups, p.fine ? " (32-column)" : "");
+        for (int64_t q = 0; q < a.nq; ++q) {
+            long long tq = 0;
+            bool ov = false;
+            for (int pt = 0; pt < p.parts; ++pt) { const int c = hc[(size_t)q * p.parts + pt]; tq += c; ov |= c > p.cap; }
+            sum += tq; mx = std::max(mx, tq); over += ov || tq > 1024;
+        }
+        fprintf(stderr, "[coarse] survivors per query: mean %.1f max %lld, %lld of %lld queries ranked exhaustively (parts %d x cap %d), groups %d%s\n",
+                (double)sum / (double)a.nq, mx, over, (long long)a.nq, p.parts, p.cap, ngroups, p.fine ? " (32-column)" : "");
     }
     return cudaGetLastError();
 }

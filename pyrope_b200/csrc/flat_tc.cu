@@ -505,6 +505,20 @@ __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __rest
     }
 }
 
+// ---- single one-TF32 pass (long K: the FLAT scan of BASELINE config 4): no pass A, every query starts cold and prunes
+// with the rounding band of the one-term product, eps_q = 2 x 2^-10 (1 + 2^-7) |q| max_r(|scale_r| |x_r|) (see above).
+__global__ void __launch_bounds__(128) tc_band_kernel(const float* __restrict__ Q, int dim, int64_t nq, const float* __restrict__ amax,
+                                                     float* band_out, int* overflow) {
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 0;
+    if (q >= nq) return;
+    float qq = 0.f;
+    for (int d = lane; d < dim; d += 32) { const float v = __ldg(Q + q * dim + d); qq = fmaf(v, v, qq); }
+    qq = warp_sum(qq);
+    if (lane == 0) band_out[q] = 2.f * 9.85e-4f * sqrtf(qq) * __ldg(amax) * 1.0001f + 1e-30f;
+}
+
 // ---- exact fp32 re-score of the survivors + final ordering -------------------------------------
 struct RescoreParams {
     const float* Q; int64_t nq; int dim;
@@ -747,6 +761,11 @@ int flat_tc_parts_per_split(const FlatTcParams& a) { return (a.gmax_ws && a.tau_
 int flat_tc_cap(int kprime) { return std::min(512, std::max(128, next_pow2(4 * kprime + 32))); }
 int64_t flat_tc_nq_pad(int64_t nq) { return (nq + BM - 1) / BM * BM; }
 
+// long K (many MMAs per tile): the scan is bound by operand traffic and MMAs, not by the epilogue — one TF32 term with
+// band pruning instead of the three-term split
+bool flat_tc_oneterm(int dim, int64_t n_scan, int kprime) {
+    return dim > 256 && n_scan >= 65536 && kprime <= 224 && !getenv("PYROPE_TC_3X");
+}
 bool flat_tc_twopass(int dim, int64_t n_scan, int kprime) {
     // epilogue-bound regime only: short K (few MMAs per tile), a long stream and a wide k'
     return dim <= 256 && n_scan >= 16384 && kprime >= 32 && !getenv("PYROPE_TC_ONEPASS");
@@ -840,6 +859,16 @@ static bool one_term_b(const FlatTcParams& a) { return a.gmax_ws && a.tau_ws && 
 
 cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
+    if (!a.gmax_ws && a.tau_ws && a.amax) {
+        // ONE one-TF32 pass with band pruning (a third of the MMAs and half the operand traffic of the 3xTF32 split);
+        // a queue that cannot be pruned below its capacity raises the flag and the three-term pass behind redoes the batch
+        const int64_t nq_pad = flat_tc_nq_pad(a.nq);
+        tc_band_kernel<<<(unsigned)((a.nq + 3) / 4), 128, 0, st>>>(a.Q, a.dim, a.nq, a.amax, a.tau_ws + nq_pad,
+                                                                   reinterpret_cast<int*>(a.tau_ws + 2 * nq_pad));
+        cudaError_t e = launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st, 1);
+        if (e != cudaSuccess) return e;
+        return launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st, 2);
+    }
     if (a.gmax_ws && a.tau_ws) {  // two-pass threshold
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);

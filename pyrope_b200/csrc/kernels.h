@@ -56,6 +56,8 @@ struct FlatTcParams {
 // two-pass threshold (group maxima -> per-query tau -> filtered pass): worth it only when the tile is
 // epilogue-bound (small dim) and the stream is long
 bool flat_tc_twopass(int dim, int64_t n_scan, int kprime);
+// single one-TF32 pass with band pruning + exact re-score (tau_ws and amax set, gmax_ws null): long-K FLAT scans
+bool flat_tc_oneterm(int dim, int64_t n_scan, int kprime);
 size_t flat_tc_gmax_floats(int64_t nq, int64_t n_scan);
 int flat_tc_pick_splits_seeded(int64_t nq, int64_t n_scan, int kprime, int num_sms);
 bool flat_tc_supported(int dim, int k);
@@ -100,7 +102,7 @@ struct CoarseTcParams {
     void* scratch; int num_sms;
 };
 bool coarse_tc_supported(int dim, int64_t nc, int nprobe);
-size_t coarse_tc_scratch_bytes(int64_t nq, int64_t nc);
+size_t coarse_tc_scratch_bytes(int64_t nq, int64_t nc, int num_sms);
 int coarse_tc_launches();
 cudaError_t launch_coarse_tc(const CoarseTcParams& p, cudaStream_t st);
 

@@ -57,7 +57,8 @@ constexpr int LM_PF = 4;            // code chunks (256 rows each) a scan warp k
 constexpr int LM_HDR = 96;          // item-block header bytes
 constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;  // [256 codes][16 tables][8 queries] u16
-constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 32;
+constexpr int LM_ROWS_OFF = 128;     // stage layout: header | pad | eight query rows | the list's centroid row (raw fp32)
+constexpr int LM_BLK_MAX = LM_ROWS_OFF + (LM_QS + 1) * LM_MAX_DIM * 4;
 constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + 2 * LM_QS * LM_QC * 8;
 // Fixed-point lookup tables: entry = round(T * s) with s = LM_QMAX / B, B >= every table value of that (query,
 // item); 16 entries sum to < 2^15, so two queries share one 32-bit add and bit 15 is free for the threshold test.
@@ -163,12 +164,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct LmParams {
     int dim, ksub, k;
     const float* codebook; const uint8_t* codes; const uint8_t* dead;
-    const unsigned char* iblk; const int32_t* n_items;
+    const unsigned char* iblk; const int32_t* n_items;  // item headers (LM_HDR bytes each)
+    const float* Q; const float* centroids;              // rows the builders fetch by TMA
+    const float* cmax;                                   // [16] max codeword norm per sub-quantiser
     unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots;  // pool [nq][pslots][kc], counts [nq][pslots]
     int kc;              // pool entries per (query, probe) pair: k plus room for candidates tied within the rounding band
     uint32_t* hist;            // [nq][LM_HB] candidates per distance bucket (zero-initialised)
     const float* thr0;         // [nq] seed bound the buckets are laid over (0: query was not seeded)
-    const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits)
+    uint32_t* sinv_max;        // [nq] max 1/scale over the query's items (float bits; raised by the builders)
     int2* redo; int32_t* redo_cnt;
     int32_t* item_ctr;   // next unclaimed work item (zero-initialised): CTAs claim items as they go
     // multi-GPU: bounds published by the peer ranks (nullable) and the peers' arrays (NVLink peer memory).  A word is
@@ -227,17 +230,15 @@ __global__ void lm_fill_items_kernel(const int32_t* __restrict__ nit, const int3
     for (int g = 0; g < n; ++g) item_list[o + g] = l;
 }
 
-// one warp per item: header + the four residual queries t = -2 (q - c), interleaved per dimension
+// one thread per item: the header (list, code range, eight query ids and their pool slots).  The residual queries and
+// the fixed-point scales are formed by the scan kernel's builder warps from the raw rows (fetched by TMA), so an item
+// costs 96 bytes of HBM traffic instead of a 4 KiB block.
 struct LmPrep {
     const int32_t* ioff; const int32_t* item_list; const int32_t* loff; const int32_t* pairq; const int32_t* pairp;
     const int64_t* list_off; int nlist;
-    int maxseg;
-    const float* Q; const float* centroids; int dim;
-    unsigned char* iblk; int blk;
-    const float* cmax;     // [16] max codeword norm per sub-quantiser
-    uint32_t* sinv_max;    // [nq] max over the query's items of 1 / scale, as float bits (zero-initialised)
+    unsigned char* iblk;
 };
-// max_e |codeword(m, e)| per sub-quantiser (slightly rounded up): the table bound of lm_prepare_kernel
+// max_e |codeword(m, e)| per sub-quantiser (slightly rounded up): the table bound used by the builders
 __global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ codebook, int K, int sub, float* cmax) {
     __shared__ uint32_t s_mx[16];
     const int e = threadIdx.x;
@@ -253,70 +254,24 @@ __global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ 
     __syncthreads();
     if (e < 16) cmax[e] = __uint_as_float(s_mx[e]);
 }
-__global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
-    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) lm_header_kernel(LmPrep a) {
+    const int w = (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (w >= a.ioff[a.nlist]) return;
-    const int l = a.item_list[w], rel = w - a.ioff[l];
+    const int l = a.item_list[w], g = w - a.ioff[l];
     const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
-    const int g = rel;
     const int pbeg = a.loff[l], pend = a.loff[l + 1];
-    int qid[LM_QS], psl[LM_QS];
+    LmHeader h{};
+    h.list = l;
+    h.vbeg = beg;
+    h.nvec = (int)len;
 #pragma unroll
     for (int j = 0; j < LM_QS; ++j) {
         const int idx = pbeg + LM_QS * g + j;
-        qid[j] = idx < pend ? a.pairq[idx] : -1;
-        psl[j] = idx < pend ? a.pairp[idx] : 0;
+        h.qid[j] = idx < pend ? a.pairq[idx] : -1;
+        h.pslot[j] = (short)(idx < pend ? a.pairp[idx] : 0);
+        h.s[j] = 0.f;  // filled in shared memory by the builders
     }
-    unsigned char* blkp = a.iblk + (size_t)w * a.blk;
-    const int sub = a.dim >> 4, D0 = lane * 4;
-    const bool on = lane * 4 < a.dim;
-    const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;  // the lane's four dimensions lie in one sub-vector
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
-    float scale[LM_QS];
-#pragma unroll
-    for (int h = 0; h < LM_QS / 4; ++h) {  // queries 4h .. 4h+3 form one float4-interleaved half
-        float4 t[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 q = c;
-            if (on && qid[4 * h + j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[4 * h + j] * a.dim) + lane);
-            t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
-            // fixed-point scale: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
-            float r2 = 0.25f * (t[j].x * t[j].x + t[j].y * t[j].y + t[j].z * t[j].z + t[j].w * t[j].w);
-            if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
-            float b = on ? sqrtf(r2) * 1.000001f + cm : 0.f;
-            b *= b;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-            scale[4 * h + j] = qid[4 * h + j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
-        }
-        if (on) {
-            // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
-            // table build read 256 contiguous bytes per d (no bank conflicts)
-            float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR + (size_t)h * a.dim * 16);
-            dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
-            dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
-            dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
-            dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
-        }
-    }
-    if (lane == 0) {
-        LmHeader h{};
-        h.list = l;
-        h.vbeg = beg;
-        h.nvec = (int)len;
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = (short)psl[j]; h.s[j] = scale[j]; }
-        *reinterpret_cast<LmHeader*>(blkp) = h;
-    }
-    if (lane < LM_QS) {
-        float mys = 0.f;
-        int myq = -1;
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j) { mys = lane == j ? scale[j] : mys; myq = lane == j ? qid[j] : myq; }
-        if (myq >= 0) atomicMax(a.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
-    }
+    *reinterpret_cast<LmHeader*>(a.iblk + (size_t)w * LM_HDR) = h;
 }
 
 // ---- plain ADC pieces shared by the seed and redo kernels ------------------------------------------------
@@ -482,7 +437,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     unsigned char* lut0 = smem;                                                    // [2][256][16] x 8 u16
     unsigned char* rbuf = lut0 + 2 * LM_LUT_BYTES;                                  // [3] item blocks
     uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_BLK_STAGES * LM_BLK_MAX);  // [2][QS][QC]
-    __shared__ __align__(8) uint64_t s_mbar[LM_BLK_STAGES + 4];
+    __shared__ __align__(8) uint64_t s_mbar[2 * LM_BLK_STAGES + 4];
     __shared__ int s_qcnt[2 * LM_QS];
     __shared__ int s_ti[LM_SCAN_WARPS * LM_QS];     // per scan warp: integer thresholds of its current item (-1: slot unused)
     __shared__ float s_inv[LM_SCAN_WARPS * LM_QS];  // per scan warp: 1 / s_j
@@ -491,18 +446,19 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool builder = warp >= LM_SCAN_WARPS;
     const int K = p.ksub;
-    const int blk = LM_HDR + p.dim * 32;
+    const int rowb = p.dim * 4;  // bytes of one raw query / centroid row
     const int n_items = *p.n_items;
     // Items are claimed dynamically (one atomicAdd per item, two items ahead of the scan): lists differ a lot in
     // length, and with few items per CTA a static assignment leaves SMs idle at the end.  s_item[i % stages] holds
     // the global index of this CTA's i-th item, -1 once the counter ran past the end.
     __shared__ int s_item[LM_BLK_STAGES];
 
-    const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: item block stage s arrived (TMA)
+    const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: the rows of stage s arrived (TMA): the item is usable
     const uint32_t bar_full = smem_u32(&s_mbar[LM_BLK_STAGES]);         // +8*b: table half b built
     const uint32_t bar_done = smem_u32(&s_mbar[LM_BLK_STAGES + 2]);     // +8*b: every scan warp has left the item in half b
+    const uint32_t bar_hdr = smem_u32(&s_mbar[LM_BLK_STAGES + 4]);      // +8*s: the header of stage s arrived (TMA)
     if (tid == 0) {
-        for (int i = 0; i < LM_BLK_STAGES; ++i) mbar_init(bar_blk + 8 * i, 1);
+        for (int i = 0; i < LM_BLK_STAGES; ++i) { mbar_init(bar_blk + 8 * i, 1); mbar_init(bar_hdr + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, LM_BUILD_WARPS); mbar_init(bar_done + 8 * i, LM_SCAN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -522,20 +478,40 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // one thread: claim this CTA's i-th item and start the TMA of its block (header + residual queries); past the
-    // end, publish -1 and complete the barrier phase by hand so that every waiter wakes up and leaves
-    auto claim_block = [&](int i) -> bool {
-        const uint32_t br = bar_blk + 8 * (i % LM_BLK_STAGES);
+    // one thread, two steps, two and one items ahead of the build:
+    //   claim_hdr(i)  take the next unclaimed work item as this CTA's i-th and start the TMA of its 96-byte header; past
+    //                 the end, publish -1 and complete the phase by hand so that every waiter wakes up and leaves;
+    //   fetch_rows(i) the header names the list and up to eight queries: one bulk copy per raw row (the centroid and the
+    //                 queries, dim fp32 each) into the stage, all completing on bar_blk — the barrier everybody else waits on.
+    auto claim_hdr = [&](int i) -> bool {
+        const int stg = i % LM_BLK_STAGES;
+        const uint32_t br = bar_hdr + 8 * stg;
         const int g = atomicAdd(p.item_ctr, 1);
         if (g < n_items) {
-            s_item[i % LM_BLK_STAGES] = g;
-            mbar_expect_tx(br, (uint32_t)blk);  // release: the index above is visible to whoever sees the phase complete
-            bulk_g2s(smem_u32(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), p.iblk + (size_t)g * blk, (uint32_t)blk, br);
+            s_item[stg] = g;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written by the generic proxy (scales)
+            mbar_expect_tx(br, (uint32_t)LM_HDR);
+            bulk_g2s(smem_u32(rbuf + stg * LM_BLK_MAX), p.iblk + (size_t)g * LM_HDR, (uint32_t)LM_HDR, br);
             return true;
         }
-        s_item[i % LM_BLK_STAGES] = -1;
+        s_item[stg] = -1;
         mbar_arrive(br);
         return false;
+    };
+    auto fetch_rows = [&](int i) {
+        const int stg = i % LM_BLK_STAGES;
+        mbar_wait(bar_hdr + 8 * stg, (uint32_t)(i / LM_BLK_STAGES) & 1u);
+        const uint32_t br = bar_blk + 8 * stg;
+        if (s_item[stg] < 0) { mbar_arrive(br); return; }
+        unsigned char* stp = rbuf + stg * LM_BLK_MAX;
+        const LmHeader* h = reinterpret_cast<const LmHeader*>(stp);
+        int nqv = 0;
+#pragma unroll
+        for (int j = 0; j < LM_QS; ++j) nqv += h->qid[j] >= 0;  // slots fill in order
+        mbar_expect_tx(br, (uint32_t)((nqv + 1) * rowb));  // release: the item index above is visible to whoever sees the phase complete
+        bulk_g2s(smem_u32(stp + LM_ROWS_OFF + LM_QS * rowb), p.centroids + (size_t)h->list * p.dim, (uint32_t)rowb, br);
+        for (int j = 0; j < nqv; ++j)
+            bulk_g2s(smem_u32(stp + LM_ROWS_OFF + j * rowb), p.Q + (size_t)h->qid[j] * p.dim, (uint32_t)rowb, br);
     };
 
     if (builder) {
@@ -563,7 +539,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         bool more = false;  // the claiming thread: items may be left
-        if (tid == LM_SCAN_WARPS * 32) more = claim_block(0);
+        if (tid == LM_SCAN_WARPS * 32) {
+            more = claim_hdr(0);
+            if (more) more = claim_hdr(1);
+            fetch_rows(0);
+        }
+        const float cmx = __ldg(p.cmax + m);  // max codeword norm of this thread's sub-quantiser
         // Hand-over runs on the BUILDER warps (they have the slack), one warp per slot, two items behind the build:
         // hand the slot's candidates to the pair's private region of the query's pool (plain
         // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
@@ -672,11 +653,14 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         for (;; ++i) {
             const int b = i & 1;
             if (i >= 2) hand_over(i - 2);  // frees table half b and queue set b (the scanners wait for bar_full before reusing them)
-            if (more) more = claim_block(i + 1);
+            if (tid == LM_SCAN_WARPS * 32 && s_item[i % LM_BLK_STAGES] >= 0) {  // item i exists, so header i+1 was claimed
+                if (more) more = claim_hdr(i + 2);
+                fetch_rows(i + 1);  // (or publishes "no such item" for everybody waiting on bar_blk)
+            }
             mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
             if (s_item[i % LM_BLK_STAGES] < 0) break;  // no item i: items 0 .. i-1 were this CTA's share
-            const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
-            const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
+            unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
+            LmHeader* hd = reinterpret_cast<LmHeader*>(blkp);
             // the builders run one item ahead of the scanners: pull this item's codes from HBM into L2 now, so the
             // scanners' loads (a few hundred rows ahead at most) find them there
             if (tid == LM_SCAN_WARPS * 32 && hd->nvec > 0)
@@ -689,17 +673,57 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 // whatever an earlier item left there (or the initial zeros): at most LM_QMAX each, so the sums of the
                 // unused lanes stay below 2^15 and never disturb their neighbours
                 if (hd->qid[4 * h] < 0) continue;
-                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + h * p.dim + m;  // slot d*16 + m
+                // residual queries t = -2 (q - c) of this thread's sub-vector, straight from the raw rows; an unused slot
+                // of a used half gets t = 0 and scale 0 (its table entries are 0)
+                const float* rows = reinterpret_cast<const float*>(blkp + LM_ROWS_OFF);
+                float cc[SUB];
+#pragma unroll
+                for (int d4 = 0; d4 < SUB / 4; ++d4) {
+                    const float4 v = *reinterpret_cast<const float4*>(rows + LM_QS * p.dim + m * SUB + 4 * d4);
+                    cc[4 * d4 + 0] = v.x; cc[4 * d4 + 1] = v.y; cc[4 * d4 + 2] = v.z; cc[4 * d4 + 3] = v.w;
+                }
+                float tq[4][SUB];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool used = hd->qid[4 * h + j] >= 0;
+#pragma unroll
+                    for (int d4 = 0; d4 < SUB / 4; ++d4) {
+                        float4 v = make_float4(cc[4 * d4], cc[4 * d4 + 1], cc[4 * d4 + 2], cc[4 * d4 + 3]);
+                        if (used) v = *reinterpret_cast<const float4*>(rows + (4 * h + j) * p.dim + m * SUB + 4 * d4);
+                        tq[j][4 * d4 + 0] = -2.f * (v.x - cc[4 * d4 + 0]); tq[j][4 * d4 + 1] = -2.f * (v.y - cc[4 * d4 + 1]);
+                        tq[j][4 * d4 + 2] = -2.f * (v.z - cc[4 * d4 + 2]); tq[j][4 * d4 + 3] = -2.f * (v.w - cc[4 * d4 + 3]);
+                    }
+                }
                 unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
 #pragma unroll
                 for (int d = 0; d < SUB; ++d) {
-                    const ulonglong2 v = rt[d * 16];
-                    t01[d] = v.x; t23[d] = v.y;
-                    rr01 = ffma2(v.x, v.x, rr01);
-                    rr23 = ffma2(v.y, v.y, rr23);
+                    t01[d] = pack2(tq[0][d], tq[1][d]); t23[d] = pack2(tq[2][d], tq[3][d]);
+                    rr01 = ffma2(t01[d], t01[d], rr01);
+                    rr23 = ffma2(t23[d], t23[d], rr23);
                 }
-                const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
-                const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
+                // fixed-point scale of each query: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
+                // (triangle inequality), s = LM_QMAX / B.  |r_m|^2 = sum t^2 / 4 sits in this thread; the maximum over the 16
+                // sub-quantisers is a butterfly over the half warp.  Every builder warp computes the same four numbers.
+                float sc4[4];
+                {
+                    const float r2[4] = {0.25f * __uint_as_float((uint32_t)rr01), 0.25f * __uint_as_float((uint32_t)(rr01 >> 32)),
+                                         0.25f * __uint_as_float((uint32_t)rr23), 0.25f * __uint_as_float((uint32_t)(rr23 >> 32))};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float bnd = sqrtf(r2[j]) * 1.000001f + cmx;
+                        bnd *= bnd;
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
+                        sc4[j] = hd->qid[4 * h + j] >= 0 ? LM_QMAX / (bnd * 1.00001f + 1e-30f) : 0.f;
+                    }
+                }
+                if (bw == 0 && lane < 4) {  // publish: the scanners and the hand-over read the scales from the header
+                    const float mys = lane == 0 ? sc4[0] : lane == 1 ? sc4[1] : lane == 2 ? sc4[2] : sc4[3];
+                    hd->s[4 * h + lane] = mys;
+                    const int myq = hd->qid[4 * h + lane];
+                    if (myq >= 0) atomicMax(p.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
+                }
+                const unsigned long long s01 = pack2(sc4[0], sc4[1]), s23 = pack2(sc4[2], sc4[3]);
                 unsigned char* lw = lut + eb * 256 + m * 16 + h * 8;
                 uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
                 tmem_ld<SUB>(tcb, cw[0]);
@@ -770,6 +794,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             // threshold becomes an integer bound, accept sum <= floor(s * tau) + QERR (rounded up)
             int* ti_w = s_ti + warp * LM_QS;
             float* inv_w = s_inv + warp * LM_QS;
+            // acquire: the builders' table stores AND the scales they put into the header (hd->s)
+            mbar_wait(bar_full + 8 * b, (uint32_t)(i >> 1) & 1u);
             {
                 int ti = -1;
                 float inv = 0.f;
@@ -797,7 +823,6 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 const int t0 = ti_w[2 * u], t1 = ti_w[2 * u + 1];
                 th[u] = (t0 >= 0 ? (0x8000u | (uint32_t)t0) : 0x7fffu) | ((t1 >= 0 ? (0x8000u | (uint32_t)t1) : 0x7fffu) << 16);
             }
-            mbar_wait(bar_full + 8 * b, (uint32_t)(i >> 1) & 1u);  // acquire: the builders' table stores
             const unsigned char* lut = lut0 + b * LM_LUT_BYTES;
             // two chunks (rows v0 and v1 = v0 + 256) per iteration: 32 independent table reads in flight per lane
             for (int c = warp; c * 32 < nvec; c += 2 * LM_SCAN_WARPS) {
@@ -1053,7 +1078,7 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.max_items = (npairs / LM_QS + std::min<int64_t>(npairs, nlist) + 1) * maxseg;
     L.item_list = o; o += align_up(sizeof(int32_t) * (size_t)L.max_items, 256);
     L.redo = o; o += align_up(sizeof(int2) * (size_t)L.max_items * LM_QS, 256);
-    L.blk = LM_HDR + dim * 32;
+    L.blk = LM_HDR;
     L.iblk = o; o += align_up((size_t)L.blk * (size_t)L.max_items, 256);
     L.pslots = P * maxseg;
     L.kc = lm_kc(k);
@@ -1131,14 +1156,13 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     lm_fill_pairs_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, P, p.list_off, loff, lcur, pairq, pairp);
 
     LmPrep pa{};
-    pa.maxseg = lm_maxseg(p.max_list_len); pa.pairp = pairp;
+    pa.pairp = pairp;
     lm_fill_items_kernel<<<lb, 256, 0, st>>>(nit, ioff, p.nlist, item_list);
     pa.item_list = item_list;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
-    pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
-    pa.cmax = cmax; pa.sinv_max = sinv_max;
+    pa.iblk = iblk;
     mark();
-    lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
+    lm_header_kernel<<<(unsigned)((L.max_items + 255) / 256), 256, 0, st>>>(pa);
     mark();
 
     if (!fork) {
@@ -1158,6 +1182,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmParams sp{};
     sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = p.codebook; sp.codes = p.codes; sp.dead = p.dead;
     sp.iblk = iblk; sp.n_items = ioff + p.nlist;
+    sp.Q = p.Q; sp.centroids = p.centroids; sp.cmax = cmax;
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
     sp.redo = redo; sp.redo_cnt = redo_cnt; sp.item_ctr = reinterpret_cast<int32_t*>(base + L.item_ctr);
