@@ -59,7 +59,8 @@ constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;  // [256 codes][16 tables][8 queries] u16
 constexpr int LM_ROWS_OFF = 128;     // stage layout: header | pad | eight query rows | the list's centroid row (raw fp32)
 constexpr int LM_BLK_MAX = LM_ROWS_OFF + (LM_QS + 1) * LM_MAX_DIM * 4;
-constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + 2 * LM_QS * LM_QC * 8;
+constexpr int LM_QSETS = 3;         // candidate-queue sets: item i pushes into set i % 3 while item i-2's set is still being handed over
+constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + LM_QSETS * LM_QS * LM_QC * 8;
 // Fixed-point lookup tables: entry = round(T * s) with s = LM_QMAX / B, B >= every table value of that (query,
 // item); 16 entries sum to < 2^15, so two queries share one 32-bit add and bit 15 is free for the threshold test.
 constexpr float LM_QMAX = 2046.f;
@@ -84,6 +85,12 @@ static_assert(sizeof(LmHeader) == LM_HDR, "header size");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a converged warp (see flat_tc.cu: under `lane == 0` ptxas serialises every uniform-datapath instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -166,12 +173,11 @@ struct LmParams {
     const float* codebook; const uint8_t* codes; const uint8_t* dead;
     const unsigned char* iblk; const int32_t* n_items;  // item headers (LM_HDR bytes each)
     const float* Q; const float* centroids;              // rows the builders fetch by TMA
-    const float* cmax;                                   // [16] max codeword norm per sub-quantiser
     unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots;  // pool [nq][pslots][kc], counts [nq][pslots]
     int kc;              // pool entries per (query, probe) pair: k plus room for candidates tied within the rounding band
     uint32_t* hist;            // [nq][LM_HB] candidates per distance bucket (zero-initialised)
     const float* thr0;         // [nq] seed bound the buckets are laid over (0: query was not seeded)
-    uint32_t* sinv_max;        // [nq] max 1/scale over the query's items (float bits; raised by the builders)
+    const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits)
     int2* redo; int32_t* redo_cnt;
     int32_t* item_ctr;   // next unclaimed work item (zero-initialised): CTAs claim items as they go
     // multi-GPU: bounds published by the peer ranks (nullable) and the peers' arrays (NVLink peer memory).  A word is
@@ -230,12 +236,15 @@ __global__ void lm_fill_items_kernel(const int32_t* __restrict__ nit, const int3
     for (int g = 0; g < n; ++g) item_list[o + g] = l;
 }
 
-// one thread per item: the header (list, code range, eight query ids and their pool slots).  The residual queries and
-// the fixed-point scales are formed by the scan kernel's builder warps from the raw rows (fetched by TMA), so an item
-// costs 96 bytes of HBM traffic instead of a 4 KiB block.
+// one warp per item: the header (list, code range, eight query ids, their pool slots, their fixed-point scales).  The
+// residual queries themselves are formed by the scan kernel's builder warps from the raw rows (fetched by TMA), so an
+// item costs 96 bytes of HBM traffic instead of a 4 KiB block written here and read back there.
 struct LmPrep {
     const int32_t* ioff; const int32_t* item_list; const int32_t* loff; const int32_t* pairq; const int32_t* pairp;
     const int64_t* list_off; int nlist;
+    const float* Q; const float* centroids; int dim;
+    const float* cmax;     // [16] max codeword norm per sub-quantiser
+    uint32_t* sinv_max;    // [nq] max over the query's items of 1 / scale, as float bits (zero-initialised)
     unsigned char* iblk;
 };
 // max_e |codeword(m, e)| per sub-quantiser (slightly rounded up): the table bound used by the builders
@@ -255,23 +264,55 @@ __global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ 
     if (e < 16) cmax[e] = __uint_as_float(s_mx[e]);
 }
 __global__ void __launch_bounds__(256) lm_header_kernel(LmPrep a) {
-    const int w = (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= a.ioff[a.nlist]) return;
     const int l = a.item_list[w], g = w - a.ioff[l];
     const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
     const int pbeg = a.loff[l], pend = a.loff[l + 1];
-    LmHeader h{};
-    h.list = l;
-    h.vbeg = beg;
-    h.nvec = (int)len;
+    int qid[LM_QS], psl[LM_QS];
 #pragma unroll
     for (int j = 0; j < LM_QS; ++j) {
         const int idx = pbeg + LM_QS * g + j;
-        h.qid[j] = idx < pend ? a.pairq[idx] : -1;
-        h.pslot[j] = (short)(idx < pend ? a.pairp[idx] : 0);
-        h.s[j] = 0.f;  // filled in shared memory by the builders
+        qid[j] = idx < pend ? a.pairq[idx] : -1;
+        psl[j] = idx < pend ? a.pairp[idx] : 0;
     }
-    *reinterpret_cast<LmHeader*>(a.iblk + (size_t)w * LM_HDR) = h;
+    // fixed-point scale of every (query, item): each table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
+    // (triangle inequality), s = LM_QMAX / B.  Lane l holds dimensions 4l .. 4l+3 (one sub-vector, or half of one).
+    const int sub = a.dim >> 4, D0 = lane * 4;
+    const bool on = lane * 4 < a.dim;
+    const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
+    float scale[LM_QS];
+#pragma unroll
+    for (int j = 0; j < LM_QS; ++j) {
+        float4 q = c;
+        if (on && qid[j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[j] * a.dim) + lane);
+        const float dx = q.x - c.x, dy = q.y - c.y, dz = q.z - c.z, dw = q.w - c.w;
+        float r2 = dx * dx + dy * dy + dz * dz + dw * dw;
+        if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
+        float b = on ? sqrtf(r2) * 1.000002f + cm : 0.f;
+        b *= b;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        scale[j] = qid[j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
+    }
+    if (lane == 0) {
+        LmHeader h{};
+        h.list = l;
+        h.vbeg = beg;
+        h.nvec = (int)len;
+#pragma unroll
+        for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = (short)psl[j]; h.s[j] = scale[j]; }
+        *reinterpret_cast<LmHeader*>(a.iblk + (size_t)w * LM_HDR) = h;
+    }
+    if (lane < LM_QS) {
+        float mys = 0.f;
+        int myq = -1;
+#pragma unroll
+        for (int j = 0; j < LM_QS; ++j) { mys = lane == j ? scale[j] : mys; myq = lane == j ? qid[j] : myq; }
+        if (myq >= 0) atomicMax(a.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
+    }
 }
 
 // ---- plain ADC pieces shared by the seed and redo kernels ------------------------------------------------
@@ -438,7 +479,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     unsigned char* rbuf = lut0 + 2 * LM_LUT_BYTES;                                  // [3] item blocks
     uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_BLK_STAGES * LM_BLK_MAX);  // [2][QS][QC]
     __shared__ __align__(8) uint64_t s_mbar[2 * LM_BLK_STAGES + 4];
-    __shared__ int s_qcnt[2 * LM_QS];
+    __shared__ int s_qcnt[LM_QSETS * LM_QS];
     __shared__ int s_ti[LM_SCAN_WARPS * LM_QS];     // per scan warp: integer thresholds of its current item (-1: slot unused)
     __shared__ float s_inv[LM_SCAN_WARPS * LM_QS];  // per scan warp: 1 / s_j
     __shared__ uint32_t s_tmem;
@@ -462,7 +503,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, LM_BUILD_WARPS); mbar_init(bar_done + 8 * i, LM_SCAN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 2 * LM_QS) s_qcnt[tid] = 0;
+    if (tid < LM_QSETS * LM_QS) s_qcnt[tid] = 0;
     for (int i = tid; i < 2 * LM_LUT_BYTES / 16; i += LM_THREADS) reinterpret_cast<uint4*>(lut0)[i] = make_uint4(0u, 0u, 0u, 0u);
 
     // The PQ codebook (m*k*sub fp32 = 128 KiB at d=128) is parked in TENSOR MEMORY for the CTA's lifetime:
@@ -539,12 +580,13 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         bool more = false;  // the claiming thread: items may be left
-        if (tid == LM_SCAN_WARPS * 32) {
+        // the claiming lane: one elected lane of builder warp 0 (elect.sync keeps the bulk-copy operands in uniform registers)
+        const bool claimer = bw == 0 && elect_one();
+        if (claimer) {
             more = claim_hdr(0);
             if (more) more = claim_hdr(1);
             fetch_rows(0);
         }
-        const float cmx = __ldg(p.cmax + m);  // max codeword norm of this thread's sub-quantiser
         // Hand-over runs on the BUILDER warps (they have the slack), one warp per slot, two items behind the build:
         // hand the slot's candidates to the pair's private region of the query's pool (plain
         // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
@@ -641,29 +683,31 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             if (lane == 0) *cntp = 0;
         };
 
-        auto hand_over = [&](int i) {  // item i: wait until every scan warp has left it, then empty its queues
-            const int b = i & 1;
-            mbar_wait(bar_done + 8 * b, (uint32_t)(i >> 1) & 1u);
+        // item i: wait until every scan warp has left it (that frees its table half) ...
+        auto wait_done = [&](int i) { mbar_wait(bar_done + 8 * (i & 1), (uint32_t)(i >> 1) & 1u); };
+        // ... and empty its queues.  The hand-over runs AFTER the next table is built and published, so the scanners never
+        // wait for it: queue sets rotate over three items (item i pushes into set i % 3 while set (i-2) % 3 is emptied).
+        auto hand_over = [&](int i) {
             finalize(reinterpret_cast<const LmHeader*>(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), s_item[i % LM_BLK_STAGES],
-                     qkeys + b * (LM_QS * LM_QC), s_qcnt + b * LM_QS);
+                     qkeys + (i % LM_QSETS) * (LM_QS * LM_QC), s_qcnt + (i % LM_QSETS) * LM_QS);
         };
         const unsigned long long magic2 = pack2(8388608.f, 8388608.f);  // 2^23: the sum's low mantissa bits are the integer
         const unsigned long long quarter = pack2(0.25f, 0.25f);          // t = -2 r  =>  |r|^2 = sum t^2 / 4
         int i = 0;
         for (;; ++i) {
             const int b = i & 1;
-            if (i >= 2) hand_over(i - 2);  // frees table half b and queue set b (the scanners wait for bar_full before reusing them)
-            if (tid == LM_SCAN_WARPS * 32 && s_item[i % LM_BLK_STAGES] >= 0) {  // item i exists, so header i+1 was claimed
+            if (i >= 2) wait_done(i - 2);  // table half b is free
+            if (claimer && s_item[i % LM_BLK_STAGES] >= 0) {  // item i exists, so header i+1 was claimed
                 if (more) more = claim_hdr(i + 2);
                 fetch_rows(i + 1);  // (or publishes "no such item" for everybody waiting on bar_blk)
             }
             mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
             if (s_item[i % LM_BLK_STAGES] < 0) break;  // no item i: items 0 .. i-1 were this CTA's share
-            unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
-            LmHeader* hd = reinterpret_cast<LmHeader*>(blkp);
+            const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
+            const LmHeader* hd = reinterpret_cast<const LmHeader*>(blkp);
             // the builders run one item ahead of the scanners: pull this item's codes from HBM into L2 now, so the
             // scanners' loads (a few hundred rows ahead at most) find them there
-            if (tid == LM_SCAN_WARPS * 32 && hd->nvec > 0)
+            if (claimer && hd->nvec > 0)
                 bulk_prefetch_l2(p.codes + (size_t)hd->vbeg * 16, (uint32_t)hd->nvec * 16u);
             unsigned char* lut = lut0 + b * LM_LUT_BYTES;
             // four queries at a time: |p|^2 + |r_m|^2 - 2 r_m.p, x s_j, rounded
@@ -701,29 +745,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     rr01 = ffma2(t01[d], t01[d], rr01);
                     rr23 = ffma2(t23[d], t23[d], rr23);
                 }
-                // fixed-point scale of each query: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
-                // (triangle inequality), s = LM_QMAX / B.  |r_m|^2 = sum t^2 / 4 sits in this thread; the maximum over the 16
-                // sub-quantisers is a butterfly over the half warp.  Every builder warp computes the same four numbers.
-                float sc4[4];
-                {
-                    const float r2[4] = {0.25f * __uint_as_float((uint32_t)rr01), 0.25f * __uint_as_float((uint32_t)(rr01 >> 32)),
-                                         0.25f * __uint_as_float((uint32_t)rr23), 0.25f * __uint_as_float((uint32_t)(rr23 >> 32))};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float bnd = sqrtf(r2[j]) * 1.000001f + cmx;
-                        bnd *= bnd;
-#pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
-                        sc4[j] = hd->qid[4 * h + j] >= 0 ? LM_QMAX / (bnd * 1.00001f + 1e-30f) : 0.f;
-                    }
-                }
-                if (bw == 0 && lane < 4) {  // publish: the scanners and the hand-over read the scales from the header
-                    const float mys = lane == 0 ? sc4[0] : lane == 1 ? sc4[1] : lane == 2 ? sc4[2] : sc4[3];
-                    hd->s[4 * h + lane] = mys;
-                    const int myq = hd->qid[4 * h + lane];
-                    if (myq >= 0) atomicMax(p.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
-                }
-                const unsigned long long s01 = pack2(sc4[0], sc4[1]), s23 = pack2(sc4[2], sc4[3]);
+                const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
+                const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
                 unsigned char* lw = lut + eb * 256 + m * 16 + h * 8;
                 uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
                 tmem_ld<SUB>(tcb, cw[0]);
@@ -750,8 +773,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * b);  // release: this warp's table stores are visible to the waiters
+            if (i >= 2) hand_over(i - 2);
         }
-        if (i >= 1) hand_over(i - 1);  // item i-2 was handed over at the top of the last round
+        // no item i: items i-2 (scan finished: waited for above) and i-1 are still to be handed over
+        if (i >= 2) hand_over(i - 2);
+        if (i >= 1) { wait_done(i - 1); hand_over(i - 1); }
     } else {
         // =================================== scanners ===================================
         // lane reads table (lane + t) & 15 at step t; op[i] packs the table byte offsets of steps 2i, 2i+1
@@ -788,14 +814,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             const int nvec = hd->nvec;
             const long long vbeg = hd->vbeg;
             const uint4* cp = reinterpret_cast<const uint4*>(p.codes) + vbeg;
-            uint64_t* qk = qkeys + b * (LM_QS * LM_QC);  // queues and counters alternate with the item parity, so this
-            int* qcnt = s_qcnt + b * LM_QS;              // item's pushes never meet the previous item's hand-over
+            uint64_t* qk = qkeys + (i % LM_QSETS) * (LM_QS * LM_QC);  // queue sets rotate over three items: this item's pushes
+            int* qcnt = s_qcnt + (i % LM_QSETS) * LM_QS;              // never meet the hand-over of item i-2 or i-1
             // every warp keeps its own copy of the slots' scalars (lanes 0-7 compute one slot each): the current
             // threshold becomes an integer bound, accept sum <= floor(s * tau) + QERR (rounded up)
             int* ti_w = s_ti + warp * LM_QS;
             float* inv_w = s_inv + warp * LM_QS;
-            // acquire: the builders' table stores AND the scales they put into the header (hd->s)
-            mbar_wait(bar_full + 8 * b, (uint32_t)(i >> 1) & 1u);
             {
                 int ti = -1;
                 float inv = 0.f;
@@ -823,6 +847,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 const int t0 = ti_w[2 * u], t1 = ti_w[2 * u + 1];
                 th[u] = (t0 >= 0 ? (0x8000u | (uint32_t)t0) : 0x7fffu) | ((t1 >= 0 ? (0x8000u | (uint32_t)t1) : 0x7fffu) << 16);
             }
+            mbar_wait(bar_full + 8 * b, (uint32_t)(i >> 1) & 1u);  // acquire: the builders' table stores
             const unsigned char* lut = lut0 + b * LM_LUT_BYTES;
             // two chunks (rows v0 and v1 = v0 + 256) per iteration: 32 independent table reads in flight per lane
             for (int c = warp; c * 32 < nvec; c += 2 * LM_SCAN_WARPS) {
@@ -1160,9 +1185,9 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     lm_fill_items_kernel<<<lb, 256, 0, st>>>(nit, ioff, p.nlist, item_list);
     pa.item_list = item_list;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
-    pa.iblk = iblk;
+    pa.iblk = iblk; pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.cmax = cmax; pa.sinv_max = sinv_max;
     mark();
-    lm_header_kernel<<<(unsigned)((L.max_items + 255) / 256), 256, 0, st>>>(pa);
+    lm_header_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
     mark();
 
     if (!fork) {
@@ -1182,7 +1207,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmParams sp{};
     sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = p.codebook; sp.codes = p.codes; sp.dead = p.dead;
     sp.iblk = iblk; sp.n_items = ioff + p.nlist;
-    sp.Q = p.Q; sp.centroids = p.centroids; sp.cmax = cmax;
+    sp.Q = p.Q; sp.centroids = p.centroids;
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
     sp.redo = redo; sp.redo_cnt = redo_cnt; sp.item_ctr = reinterpret_cast<int32_t*>(base + L.item_ctr);
