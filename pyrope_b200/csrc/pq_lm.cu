@@ -50,7 +50,9 @@ namespace {
 constexpr int LM_SCAN_WARPS = 8;    // warps 0-7 scan
 constexpr int LM_BUILD_WARPS = 8;   // the last 8 warps build the next item's tables and hand finished items over (one per query slot)
 constexpr int LM_THREADS = 32 * (LM_SCAN_WARPS + LM_BUILD_WARPS);  // one persistent CTA per SM
-constexpr int LM_BLK_STAGES = 5;    // item blocks in flight: arriving, being built from, being scanned, two awaiting hand-over
+constexpr int LM_BLK_STAGES = 7;    // item stages in flight: header claimed (i+2), rows arriving (i+1), built from (i), scanned (i-1),
+                                    // handed over (i-2) — and two more, because a stage may only be reused once EVERY builder warp has
+                                    // left its hand-over, which the pipeline proves two rounds later (wait_done(i+1) at round i+3)
 constexpr int LM_QS = 8;            // query slots per work item (two halves of four)
 constexpr int LM_QC = 256;          // candidate queue entries per slot (two sets: items alternate)
 constexpr int LM_PF = 4;            // code chunks (256 rows each) a scan warp keeps in flight (even: two per iteration)
@@ -60,7 +62,8 @@ constexpr int LM_LUT_BYTES = 256 * 256;  // [256 codes][16 tables][8 queries] u1
 constexpr int LM_ROWS_OFF = 128;     // stage layout: header | pad | eight query rows | the list's centroid row (raw fp32)
 constexpr int LM_BLK_MAX = LM_ROWS_OFF + (LM_QS + 1) * LM_MAX_DIM * 4;
 constexpr int LM_QSETS = 3;         // candidate-queue sets: item i pushes into set i % 3 while item i-2's set is still being handed over
-constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + LM_QSETS * LM_QS * LM_QC * 8;
+constexpr int LM_TBUF = LM_QS * LM_MAX_DIM * 4;  // residual queries of one item, interleaved for the table build (double buffered)
+constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + LM_QSETS * LM_QS * LM_QC * 8 + 2 * LM_TBUF;
 // Fixed-point lookup tables: entry = round(T * s) with s = LM_QMAX / B, B >= every table value of that (query,
 // item); 16 entries sum to < 2^15, so two queries share one 32-bit add and bit 15 is free for the threshold test.
 constexpr float LM_QMAX = 2046.f;
@@ -477,7 +480,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* lut0 = smem;                                                    // [2][256][16] x 8 u16
     unsigned char* rbuf = lut0 + 2 * LM_LUT_BYTES;                                  // [3] item blocks
-    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_BLK_STAGES * LM_BLK_MAX);  // [2][QS][QC]
+    uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_BLK_STAGES * LM_BLK_MAX);  // [QSETS][QS][QC]
+    unsigned char* tbuf = reinterpret_cast<unsigned char*>(qkeys + LM_QSETS * LM_QS * LM_QC);  // [2][2 halves][dim] float4
     __shared__ __align__(8) uint64_t s_mbar[2 * LM_BLK_STAGES + 4];
     __shared__ int s_qcnt[LM_QSETS * LM_QS];
     __shared__ int s_ti[LM_SCAN_WARPS * LM_QS];     // per scan warp: integer thresholds of its current item (-1: slot unused)
@@ -710,6 +714,27 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             if (claimer && hd->nvec > 0)
                 bulk_prefetch_l2(p.codes + (size_t)hd->vbeg * 16, (uint32_t)hd->nvec * 16u);
             unsigned char* lut = lut0 + b * LM_LUT_BYTES;
+            // The raw rows (eight queries + the list's centroid) become the residual queries t = -2 (q - c) ONCE, all 256
+            // builder threads together: thread (half h, dimension D) writes {t of queries 4h..4h+3} at slot (D % SUB) * 16 +
+            // D / SUB, so the 16 sub-quantiser lanes of the build below read 256 contiguous bytes per d.  An unused slot gets
+            // t = 0.  Double buffered by item parity; the named barrier (builder warps only) orders writers and readers.
+            {
+                const int bt = tid - LM_SCAN_WARPS * 32;
+                if (bt < 2 * p.dim) {
+                    const int hh = bt / p.dim, D = bt - hh * p.dim;
+                    const float* rows = reinterpret_cast<const float*>(blkp + LM_ROWS_OFF);
+                    const float c = rows[LM_QS * p.dim + D];
+                    float t[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float q = hd->qid[4 * hh + j] >= 0 ? rows[(4 * hh + j) * p.dim + D] : c;
+                        t[j] = -2.f * (q - c);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(tbuf + (i & 1) * LM_TBUF) + hh * p.dim;
+                    dst[(D % SUB) * 16 + D / SUB] = make_float4(t[0], t[1], t[2], t[3]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(LM_BUILD_WARPS * 32) : "memory");
+            }
             // four queries at a time: |p|^2 + |r_m|^2 - 2 r_m.p, x s_j, rounded
 #pragma unroll 1
             for (int h = 0; h < LM_QS / 4; ++h) {
@@ -717,33 +742,14 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 // whatever an earlier item left there (or the initial zeros): at most LM_QMAX each, so the sums of the
                 // unused lanes stay below 2^15 and never disturb their neighbours
                 if (hd->qid[4 * h] < 0) continue;
-                // residual queries t = -2 (q - c) of this thread's sub-vector, straight from the raw rows; an unused slot
-                // of a used half gets t = 0 and scale 0 (its table entries are 0)
-                const float* rows = reinterpret_cast<const float*>(blkp + LM_ROWS_OFF);
-                float cc[SUB];
-#pragma unroll
-                for (int d4 = 0; d4 < SUB / 4; ++d4) {
-                    const float4 v = *reinterpret_cast<const float4*>(rows + LM_QS * p.dim + m * SUB + 4 * d4);
-                    cc[4 * d4 + 0] = v.x; cc[4 * d4 + 1] = v.y; cc[4 * d4 + 2] = v.z; cc[4 * d4 + 3] = v.w;
-                }
-                float tq[4][SUB];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool used = hd->qid[4 * h + j] >= 0;
-#pragma unroll
-                    for (int d4 = 0; d4 < SUB / 4; ++d4) {
-                        float4 v = make_float4(cc[4 * d4], cc[4 * d4 + 1], cc[4 * d4 + 2], cc[4 * d4 + 3]);
-                        if (used) v = *reinterpret_cast<const float4*>(rows + (4 * h + j) * p.dim + m * SUB + 4 * d4);
-                        tq[j][4 * d4 + 0] = -2.f * (v.x - cc[4 * d4 + 0]); tq[j][4 * d4 + 1] = -2.f * (v.y - cc[4 * d4 + 1]);
-                        tq[j][4 * d4 + 2] = -2.f * (v.z - cc[4 * d4 + 2]); tq[j][4 * d4 + 3] = -2.f * (v.w - cc[4 * d4 + 3]);
-                    }
-                }
+                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(tbuf + (i & 1) * LM_TBUF) + h * p.dim + m;  // slot d*16 + m
                 unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
 #pragma unroll
                 for (int d = 0; d < SUB; ++d) {
-                    t01[d] = pack2(tq[0][d], tq[1][d]); t23[d] = pack2(tq[2][d], tq[3][d]);
-                    rr01 = ffma2(t01[d], t01[d], rr01);
-                    rr23 = ffma2(t23[d], t23[d], rr23);
+                    const ulonglong2 v = rt[d * 16];
+                    t01[d] = v.x; t23[d] = v.y;
+                    rr01 = ffma2(v.x, v.x, rr01);
+                    rr23 = ffma2(v.y, v.y, rr23);
                 }
                 const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
                 const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
