@@ -50,20 +50,18 @@ namespace {
 constexpr int LM_SCAN_WARPS = 8;    // warps 0-7 scan
 constexpr int LM_BUILD_WARPS = 8;   // the last 8 warps build the next item's tables and hand finished items over (one per query slot)
 constexpr int LM_THREADS = 32 * (LM_SCAN_WARPS + LM_BUILD_WARPS);  // one persistent CTA per SM
-constexpr int LM_BLK_STAGES = 7;    // item stages in flight: header claimed (i+2), rows arriving (i+1), built from (i), scanned (i-1),
-                                    // handed over (i-2) — and two more, because a stage may only be reused once EVERY builder warp has
-                                    // left its hand-over, which the pipeline proves two rounds later (wait_done(i+1) at round i+3)
+constexpr int LM_BLK_STAGES = 6;    // item blocks in flight: arriving (i+1), built from (i), scanned (i-1), handed over (i-2) — and two more,
+                                    // because a stage may only be reused once EVERY builder warp has left its hand-over, which the
+                                    // pipeline proves two rounds later (wait_done(i+1) at the top of round i+3, which claims block i+4)
 constexpr int LM_QS = 8;            // query slots per work item (two halves of four)
 constexpr int LM_QC = 256;          // candidate queue entries per slot (two sets: items alternate)
 constexpr int LM_PF = 4;            // code chunks (256 rows each) a scan warp keeps in flight (even: two per iteration)
 constexpr int LM_HDR = 96;          // item-block header bytes
 constexpr int LM_MAX_DIM = 128;     // m = 16, sub <= 8
 constexpr int LM_LUT_BYTES = 256 * 256;  // [256 codes][16 tables][8 queries] u16
-constexpr int LM_ROWS_OFF = 128;     // stage layout: header | pad | eight query rows | the list's centroid row (raw fp32)
-constexpr int LM_BLK_MAX = LM_ROWS_OFF + (LM_QS + 1) * LM_MAX_DIM * 4;
+constexpr int LM_BLK_MAX = LM_HDR + LM_MAX_DIM * 32;
 constexpr int LM_QSETS = 3;         // candidate-queue sets: item i pushes into set i % 3 while item i-2's set is still being handed over
-constexpr int LM_TBUF = LM_QS * LM_MAX_DIM * 4;  // residual queries of one item, interleaved for the table build (double buffered)
-constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + LM_QSETS * LM_QS * LM_QC * 8 + 2 * LM_TBUF;
+constexpr int LM_SMEM = 2 * LM_LUT_BYTES + LM_BLK_STAGES * LM_BLK_MAX + LM_QSETS * LM_QS * LM_QC * 8;
 // Fixed-point lookup tables: entry = round(T * s) with s = LM_QMAX / B, B >= every table value of that (query,
 // item); 16 entries sum to < 2^15, so two queries share one 32-bit add and bit 15 is free for the threshold test.
 constexpr float LM_QMAX = 2046.f;
@@ -174,8 +172,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct LmParams {
     int dim, ksub, k;
     const float* codebook; const uint8_t* codes; const uint8_t* dead;
-    const unsigned char* iblk; const int32_t* n_items;  // item headers (LM_HDR bytes each)
-    const float* Q; const float* centroids;              // rows the builders fetch by TMA
+    const unsigned char* iblk; const int32_t* n_items;
     unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots;  // pool [nq][pslots][kc], counts [nq][pslots]
     int kc;              // pool entries per (query, probe) pair: k plus room for candidates tied within the rounding band
     uint32_t* hist;            // [nq][LM_HB] candidates per distance bucket (zero-initialised)
@@ -239,18 +236,17 @@ __global__ void lm_fill_items_kernel(const int32_t* __restrict__ nit, const int3
     for (int g = 0; g < n; ++g) item_list[o + g] = l;
 }
 
-// one warp per item: the header (list, code range, eight query ids, their pool slots, their fixed-point scales).  The
-// residual queries themselves are formed by the scan kernel's builder warps from the raw rows (fetched by TMA), so an
-// item costs 96 bytes of HBM traffic instead of a 4 KiB block written here and read back there.
+// one warp per item: header + the four residual queries t = -2 (q - c), interleaved per dimension
 struct LmPrep {
     const int32_t* ioff; const int32_t* item_list; const int32_t* loff; const int32_t* pairq; const int32_t* pairp;
     const int64_t* list_off; int nlist;
+    int maxseg;
     const float* Q; const float* centroids; int dim;
+    unsigned char* iblk; int blk;
     const float* cmax;     // [16] max codeword norm per sub-quantiser
     uint32_t* sinv_max;    // [nq] max over the query's items of 1 / scale, as float bits (zero-initialised)
-    unsigned char* iblk;
 };
-// max_e |codeword(m, e)| per sub-quantiser (slightly rounded up): the table bound used by the builders
+// max_e |codeword(m, e)| per sub-quantiser (slightly rounded up): the table bound of lm_prepare_kernel
 __global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ codebook, int K, int sub, float* cmax) {
     __shared__ uint32_t s_mx[16];
     const int e = threadIdx.x;
@@ -266,11 +262,12 @@ __global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ 
     __syncthreads();
     if (e < 16) cmax[e] = __uint_as_float(s_mx[e]);
 }
-__global__ void __launch_bounds__(256) lm_header_kernel(LmPrep a) {
+__global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
     const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= a.ioff[a.nlist]) return;
-    const int l = a.item_list[w], g = w - a.ioff[l];
+    const int l = a.item_list[w], rel = w - a.ioff[l];
     const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
+    const int g = rel;
     const int pbeg = a.loff[l], pend = a.loff[l + 1];
     int qid[LM_QS], psl[LM_QS];
 #pragma unroll
@@ -279,26 +276,39 @@ __global__ void __launch_bounds__(256) lm_header_kernel(LmPrep a) {
         qid[j] = idx < pend ? a.pairq[idx] : -1;
         psl[j] = idx < pend ? a.pairp[idx] : 0;
     }
-    // fixed-point scale of every (query, item): each table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
-    // (triangle inequality), s = LM_QMAX / B.  Lane l holds dimensions 4l .. 4l+3 (one sub-vector, or half of one).
+    unsigned char* blkp = a.iblk + (size_t)w * a.blk;
     const int sub = a.dim >> 4, D0 = lane * 4;
     const bool on = lane * 4 < a.dim;
-    const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;
+    const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;  // the lane's four dimensions lie in one sub-vector
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
     if (on) c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
     float scale[LM_QS];
 #pragma unroll
-    for (int j = 0; j < LM_QS; ++j) {
-        float4 q = c;
-        if (on && qid[j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[j] * a.dim) + lane);
-        const float dx = q.x - c.x, dy = q.y - c.y, dz = q.z - c.z, dw = q.w - c.w;
-        float r2 = dx * dx + dy * dy + dz * dz + dw * dw;
-        if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
-        float b = on ? sqrtf(r2) * 1.000002f + cm : 0.f;
-        b *= b;
+    for (int h = 0; h < LM_QS / 4; ++h) {  // queries 4h .. 4h+3 form one float4-interleaved half
+        float4 t[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-        scale[j] = qid[j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
+        for (int j = 0; j < 4; ++j) {
+            float4 q = c;
+            if (on && qid[4 * h + j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[4 * h + j] * a.dim) + lane);
+            t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
+            // fixed-point scale: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
+            float r2 = 0.25f * (t[j].x * t[j].x + t[j].y * t[j].y + t[j].z * t[j].z + t[j].w * t[j].w);
+            if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
+            float b = on ? sqrtf(r2) * 1.000001f + cm : 0.f;
+            b *= b;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+            scale[4 * h + j] = qid[4 * h + j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
+        }
+        if (on) {
+            // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
+            // table build read 256 contiguous bytes per d (no bank conflicts)
+            float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR + (size_t)h * a.dim * 16);
+            dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+            dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+            dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+            dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+        }
     }
     if (lane == 0) {
         LmHeader h{};
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(256) lm_header_kernel(LmPrep a) {
         h.nvec = (int)len;
 #pragma unroll
         for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = (short)psl[j]; h.s[j] = scale[j]; }
-        *reinterpret_cast<LmHeader*>(a.iblk + (size_t)w * LM_HDR) = h;
+        *reinterpret_cast<LmHeader*>(blkp) = h;
     }
     if (lane < LM_QS) {
         float mys = 0.f;
@@ -481,8 +491,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     unsigned char* lut0 = smem;                                                    // [2][256][16] x 8 u16
     unsigned char* rbuf = lut0 + 2 * LM_LUT_BYTES;                                  // [3] item blocks
     uint64_t* qkeys = reinterpret_cast<uint64_t*>(rbuf + LM_BLK_STAGES * LM_BLK_MAX);  // [QSETS][QS][QC]
-    unsigned char* tbuf = reinterpret_cast<unsigned char*>(qkeys + LM_QSETS * LM_QS * LM_QC);  // [2][2 halves][dim] float4
-    __shared__ __align__(8) uint64_t s_mbar[2 * LM_BLK_STAGES + 4];
+    __shared__ __align__(8) uint64_t s_mbar[LM_BLK_STAGES + 4];
     __shared__ int s_qcnt[LM_QSETS * LM_QS];
     __shared__ int s_ti[LM_SCAN_WARPS * LM_QS];     // per scan warp: integer thresholds of its current item (-1: slot unused)
     __shared__ float s_inv[LM_SCAN_WARPS * LM_QS];  // per scan warp: 1 / s_j
@@ -491,19 +500,18 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool builder = warp >= LM_SCAN_WARPS;
     const int K = p.ksub;
-    const int rowb = p.dim * 4;  // bytes of one raw query / centroid row
+    const int blk = LM_HDR + p.dim * 32;
     const int n_items = *p.n_items;
     // Items are claimed dynamically (one atomicAdd per item, two items ahead of the scan): lists differ a lot in
     // length, and with few items per CTA a static assignment leaves SMs idle at the end.  s_item[i % stages] holds
     // the global index of this CTA's i-th item, -1 once the counter ran past the end.
     __shared__ int s_item[LM_BLK_STAGES];
 
-    const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: the rows of stage s arrived (TMA): the item is usable
+    const uint32_t bar_blk = smem_u32(&s_mbar[0]);                      // +8*s: item block stage s arrived (TMA)
     const uint32_t bar_full = smem_u32(&s_mbar[LM_BLK_STAGES]);         // +8*b: table half b built
     const uint32_t bar_done = smem_u32(&s_mbar[LM_BLK_STAGES + 2]);     // +8*b: every scan warp has left the item in half b
-    const uint32_t bar_hdr = smem_u32(&s_mbar[LM_BLK_STAGES + 4]);      // +8*s: the header of stage s arrived (TMA)
     if (tid == 0) {
-        for (int i = 0; i < LM_BLK_STAGES; ++i) { mbar_init(bar_blk + 8 * i, 1); mbar_init(bar_hdr + 8 * i, 1); }
+        for (int i = 0; i < LM_BLK_STAGES; ++i) mbar_init(bar_blk + 8 * i, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, LM_BUILD_WARPS); mbar_init(bar_done + 8 * i, LM_SCAN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -523,40 +531,20 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // one thread, two steps, two and one items ahead of the build:
-    //   claim_hdr(i)  take the next unclaimed work item as this CTA's i-th and start the TMA of its 96-byte header; past
-    //                 the end, publish -1 and complete the phase by hand so that every waiter wakes up and leaves;
-    //   fetch_rows(i) the header names the list and up to eight queries: one bulk copy per raw row (the centroid and the
-    //                 queries, dim fp32 each) into the stage, all completing on bar_blk — the barrier everybody else waits on.
-    auto claim_hdr = [&](int i) -> bool {
-        const int stg = i % LM_BLK_STAGES;
-        const uint32_t br = bar_hdr + 8 * stg;
+    // one thread: claim this CTA's i-th item and start the TMA of its block (header + residual queries); past the
+    // end, publish -1 and complete the barrier phase by hand so that every waiter wakes up and leaves
+    auto claim_block = [&](int i) -> bool {
+        const uint32_t br = bar_blk + 8 * (i % LM_BLK_STAGES);
         const int g = atomicAdd(p.item_ctr, 1);
         if (g < n_items) {
-            s_item[stg] = g;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written by the generic proxy (scales)
-            mbar_expect_tx(br, (uint32_t)LM_HDR);
-            bulk_g2s(smem_u32(rbuf + stg * LM_BLK_MAX), p.iblk + (size_t)g * LM_HDR, (uint32_t)LM_HDR, br);
+            s_item[i % LM_BLK_STAGES] = g;
+            mbar_expect_tx(br, (uint32_t)blk);  // release: the index above is visible to whoever sees the phase complete
+            bulk_g2s(smem_u32(rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX), p.iblk + (size_t)g * blk, (uint32_t)blk, br);
             return true;
         }
-        s_item[stg] = -1;
+        s_item[i % LM_BLK_STAGES] = -1;
         mbar_arrive(br);
         return false;
-    };
-    auto fetch_rows = [&](int i) {
-        const int stg = i % LM_BLK_STAGES;
-        mbar_wait(bar_hdr + 8 * stg, (uint32_t)(i / LM_BLK_STAGES) & 1u);
-        const uint32_t br = bar_blk + 8 * stg;
-        if (s_item[stg] < 0) { mbar_arrive(br); return; }
-        unsigned char* stp = rbuf + stg * LM_BLK_MAX;
-        const LmHeader* h = reinterpret_cast<const LmHeader*>(stp);
-        int nqv = 0;
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j) nqv += h->qid[j] >= 0;  // slots fill in order
-        mbar_expect_tx(br, (uint32_t)((nqv + 1) * rowb));  // release: the item index above is visible to whoever sees the phase complete
-        bulk_g2s(smem_u32(stp + LM_ROWS_OFF + LM_QS * rowb), p.centroids + (size_t)h->list * p.dim, (uint32_t)rowb, br);
-        for (int j = 0; j < nqv; ++j)
-            bulk_g2s(smem_u32(stp + LM_ROWS_OFF + j * rowb), p.Q + (size_t)h->qid[j] * p.dim, (uint32_t)rowb, br);
     };
 
     if (builder) {
@@ -583,14 +571,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             pn[j] = s;
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        bool more = false;  // the claiming thread: items may be left
-        // the claiming lane: one elected lane of builder warp 0 (elect.sync keeps the bulk-copy operands in uniform registers)
+        bool more = false;  // the claiming lane: items may be left
+        // one elected lane of builder warp 0 (elect.sync keeps the bulk-copy operands in uniform registers)
         const bool claimer = bw == 0 && elect_one();
-        if (claimer) {
-            more = claim_hdr(0);
-            if (more) more = claim_hdr(1);
-            fetch_rows(0);
-        }
+        if (claimer) more = claim_block(0);
         // Hand-over runs on the BUILDER warps (they have the slack), one warp per slot, two items behind the build:
         // hand the slot's candidates to the pair's private region of the query's pool (plain
         // stores: no returning atomics on this path) and tighten the query's threshold.  Candidate distances are
@@ -701,10 +685,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
         for (;; ++i) {
             const int b = i & 1;
             if (i >= 2) wait_done(i - 2);  // table half b is free
-            if (claimer && s_item[i % LM_BLK_STAGES] >= 0) {  // item i exists, so header i+1 was claimed
-                if (more) more = claim_hdr(i + 2);
-                fetch_rows(i + 1);  // (or publishes "no such item" for everybody waiting on bar_blk)
-            }
+            if (more) more = claim_block(i + 1);
             mbar_wait(bar_blk + 8 * (i % LM_BLK_STAGES), (uint32_t)(i / LM_BLK_STAGES) & 1u);
             if (s_item[i % LM_BLK_STAGES] < 0) break;  // no item i: items 0 .. i-1 were this CTA's share
             const unsigned char* blkp = rbuf + (i % LM_BLK_STAGES) * LM_BLK_MAX;
@@ -714,27 +695,6 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             if (claimer && hd->nvec > 0)
                 bulk_prefetch_l2(p.codes + (size_t)hd->vbeg * 16, (uint32_t)hd->nvec * 16u);
             unsigned char* lut = lut0 + b * LM_LUT_BYTES;
-            // The raw rows (eight queries + the list's centroid) become the residual queries t = -2 (q - c) ONCE, all 256
-            // builder threads together: thread (half h, dimension D) writes {t of queries 4h..4h+3} at slot (D % SUB) * 16 +
-            // D / SUB, so the 16 sub-quantiser lanes of the build below read 256 contiguous bytes per d.  An unused slot gets
-            // t = 0.  Double buffered by item parity; the named barrier (builder warps only) orders writers and readers.
-            {
-                const int bt = tid - LM_SCAN_WARPS * 32;
-                if (bt < 2 * p.dim) {
-                    const int hh = bt / p.dim, D = bt - hh * p.dim;
-                    const float* rows = reinterpret_cast<const float*>(blkp + LM_ROWS_OFF);
-                    const float c = rows[LM_QS * p.dim + D];
-                    float t[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float q = hd->qid[4 * hh + j] >= 0 ? rows[(4 * hh + j) * p.dim + D] : c;
-                        t[j] = -2.f * (q - c);
-                    }
-                    float4* dst = reinterpret_cast<float4*>(tbuf + (i & 1) * LM_TBUF) + hh * p.dim;
-                    dst[(D % SUB) * 16 + D / SUB] = make_float4(t[0], t[1], t[2], t[3]);
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(LM_BUILD_WARPS * 32) : "memory");
-            }
             // four queries at a time: |p|^2 + |r_m|^2 - 2 r_m.p, x s_j, rounded
 #pragma unroll 1
             for (int h = 0; h < LM_QS / 4; ++h) {
@@ -742,7 +702,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 // whatever an earlier item left there (or the initial zeros): at most LM_QMAX each, so the sums of the
                 // unused lanes stay below 2^15 and never disturb their neighbours
                 if (hd->qid[4 * h] < 0) continue;
-                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(tbuf + (i & 1) * LM_TBUF) + h * p.dim + m;  // slot d*16 + m
+                const ulonglong2* rt = reinterpret_cast<const ulonglong2*>(blkp + LM_HDR) + h * p.dim + m;  // slot d*16 + m
                 unsigned long long t01[SUB], t23[SUB], rr01 = 0ull, rr23 = 0ull;
 #pragma unroll
                 for (int d = 0; d < SUB; ++d) {
@@ -1109,7 +1069,7 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.max_items = (npairs / LM_QS + std::min<int64_t>(npairs, nlist) + 1) * maxseg;
     L.item_list = o; o += align_up(sizeof(int32_t) * (size_t)L.max_items, 256);
     L.redo = o; o += align_up(sizeof(int2) * (size_t)L.max_items * LM_QS, 256);
-    L.blk = LM_HDR;
+    L.blk = LM_HDR + dim * 32;
     L.iblk = o; o += align_up((size_t)L.blk * (size_t)L.max_items, 256);
     L.pslots = P * maxseg;
     L.kc = lm_kc(k);
@@ -1187,13 +1147,14 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     lm_fill_pairs_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, P, p.list_off, loff, lcur, pairq, pairp);
 
     LmPrep pa{};
-    pa.pairp = pairp;
+    pa.maxseg = lm_maxseg(p.max_list_len); pa.pairp = pairp;
     lm_fill_items_kernel<<<lb, 256, 0, st>>>(nit, ioff, p.nlist, item_list);
     pa.item_list = item_list;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
-    pa.iblk = iblk; pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.cmax = cmax; pa.sinv_max = sinv_max;
+    pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
+    pa.cmax = cmax; pa.sinv_max = sinv_max;
     mark();
-    lm_header_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
+    lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
     mark();
 
     if (!fork) {
@@ -1213,7 +1174,6 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmParams sp{};
     sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = p.codebook; sp.codes = p.codes; sp.dead = p.dead;
     sp.iblk = iblk; sp.n_items = ioff + p.nlist;
-    sp.Q = p.Q; sp.centroids = p.centroids;
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
     sp.redo = redo; sp.redo_cnt = redo_cnt; sp.item_ctr = reinterpret_cast<int32_t*>(base + L.item_ctr);
