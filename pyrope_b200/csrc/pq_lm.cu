@@ -39,6 +39,7 @@
 #include <cub/cub.cuh>
 
 #include <cstdio>
+#include <type_traits>
 
 #include "common.cuh"
 #include "exact_arith.cuh"
@@ -713,7 +714,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                 }
                 const float4 sh4 = *reinterpret_cast<const float4*>(hd->s + 4 * h);  // 0 for an unused slot: its entries are 0
                 const unsigned long long s01 = pack2(sh4.x, sh4.y), s23 = pack2(sh4.z, sh4.w);
-                unsigned char* lw = lut + eb * 256 + m * 16 + h * 8;
+                // slots fill in order: no fifth query = a compact table (8-byte entries, the scanners read it with LDS.64)
+                const bool compact = hd->qid[LM_QS / 2] < 0;
+                unsigned char* lw = compact ? lut + eb * 128 + m * 8 : lut + eb * 256 + m * 16 + h * 8;
+                const int jstride = compact ? (BT / 16) * 128 : (BT / 16) * 256;
                 uint32_t cw[2][SUB];  // codeword j+1 streams in from TMEM while codeword j is multiplied
                 tmem_ld<SUB>(tcb, cw[0]);
                 tmem_ld_wait();
@@ -733,7 +737,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     a23 = ffma2(a23, s23, magic2);
                     const uint32_t w0 = __byte_perm((uint32_t)a01, (uint32_t)(a01 >> 32), 0x5410);
                     const uint32_t w1 = __byte_perm((uint32_t)a23, (uint32_t)(a23 >> 32), 0x5410);
-                    *reinterpret_cast<uint2*>(lw + j * ((BT / 16) * 256)) = make_uint2(w0, w1);
+                    *reinterpret_cast<uint2*>(lw + j * jstride) = make_uint2(w0, w1);
                     if (j + 1 < EPT) tmem_ld_wait();
                 }
             }
@@ -815,7 +819,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
             }
             mbar_wait(bar_full + 8 * b, (uint32_t)(i >> 1) & 1u);  // acquire: the builders' table stores
             const unsigned char* lut = lut0 + b * LM_LUT_BYTES;
-            // two chunks (rows v0 and v1 = v0 + 256) per iteration: 32 independent table reads in flight per lane
+            // two chunks (rows v0 and v1 = v0 + 256) per iteration: 32 independent table reads in flight per lane.
+            // HALF: an item with at most four queries uses the compact table (LUT[e][m] = {q0..q3}, 8 bytes at e*128 + m*8):
+            // one LDS.64 — two crossbar wavefronts instead of four — per 32 (code, table) lookups.
+            auto scan_rows = [&](auto half_tag) {
+            constexpr bool HALF = decltype(half_tag)::value;
             for (int c = warp; c * 32 < nvec; c += 2 * LM_SCAN_WARPS) {
                 const int v0 = c * 32 + lane, v1 = v0 + LM_SCAN_WARPS * 32;
                 const uint4 cw0 = cq[0], cw1 = cq[1];
@@ -848,14 +856,23 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     const uint32_t sel = 0x7600u | (uint32_t)((t & 3) << 4) | (uint32_t)(4 + (t & 1));
                     const uint32_t aa = __byte_perm(wa[t >> 2], op[t >> 1], sel);
                     const uint32_t ab = __byte_perm(wb[t >> 2], op[t >> 1], sel);
-                    const uint4 ea = *reinterpret_cast<const uint4*>(lut + aa);
-                    const uint4 eb = *reinterpret_cast<const uint4*>(lut + ab);
-                    A0 += ea.x; A1 += ea.y; A2 += ea.z; A3 += ea.w;
-                    B0 += eb.x; B1 += eb.y; B2 += eb.z; B3 += eb.w;
+                    if (HALF) {
+                        const uint2 ea = *reinterpret_cast<const uint2*>(lut + (aa >> 1));
+                        const uint2 eb = *reinterpret_cast<const uint2*>(lut + (ab >> 1));
+                        A0 += ea.x; A1 += ea.y;
+                        B0 += eb.x; B1 += eb.y;
+                    } else {
+                        const uint4 ea = *reinterpret_cast<const uint4*>(lut + aa);
+                        const uint4 eb = *reinterpret_cast<const uint4*>(lut + ab);
+                        A0 += ea.x; A1 += ea.y; A2 += ea.z; A3 += ea.w;
+                        B0 += eb.x; B1 += eb.y; B2 += eb.z; B3 += eb.w;
+                    }
                 }
                 // bit 15 / 31 of (guarded threshold - sum) survives exactly where sum <= threshold
-                const uint32_t hita = v0 < nvec ? ((th[0] - A0) | (th[1] - A1) | (th[2] - A2) | (th[3] - A3)) & 0x80008000u : 0u;
-                const uint32_t hitb = v1 < nvec ? ((th[0] - B0) | (th[1] - B1) | (th[2] - B2) | (th[3] - B3)) & 0x80008000u : 0u;
+                const uint32_t ha = HALF ? ((th[0] - A0) | (th[1] - A1)) : ((th[0] - A0) | (th[1] - A1) | (th[2] - A2) | (th[3] - A3));
+                const uint32_t hb = HALF ? ((th[0] - B0) | (th[1] - B1)) : ((th[0] - B0) | (th[1] - B1) | (th[2] - B2) | (th[3] - B3));
+                const uint32_t hita = v0 < nvec ? ha & 0x80008000u : 0u;
+                const uint32_t hitb = v1 < nvec ? hb & 0x80008000u : 0u;
                 if (hita | hitb) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
@@ -864,7 +881,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                             if (!(p.dead && p.dead[gpos])) {
                                 const uint32_t acc[4] = {r ? B0 : A0, r ? B1 : A1, r ? B2 : A2, r ? B3 : A3};
 #pragma unroll
-                                for (int j = 0; j < LM_QS; ++j) {
+                                for (int j = 0; j < (HALF ? LM_QS / 2 : LM_QS); ++j) {
                                     const int sum = (int)((acc[j >> 1] >> (16 * (j & 1))) & 0xffffu);
                                     if (sum <= ti_w[j]) {
                                         const int pos = atomicAdd(&qcnt[j], 1);
@@ -876,6 +893,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) ivfpq_lm_scan_kernel(LmParams p
                     }
                 }
             }
+            };
+            if (hd->qid[LM_QS / 2] < 0) scan_rows(std::true_type{}); else scan_rows(std::false_type{});
             have = prefetch_item(i + 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_done + 8 * b);  // release: this warp's pushes; it no longer reads table half b
