@@ -814,6 +814,99 @@ def run_ours(args):
         sys.exit(3)
 
 
+
+def run_sharded_entry(args):
+    """bench.py --sharded-entry --gpus N: ONE process drives N GPUs through the library's multi-device entry point
+    (pyrope_sharded_*, csrc/sharded.cu) — what a C# GpuVectorIndex P/Invokes.  Same workload, same parity check; `value` is
+    batches through pyrope_sharded_search_batch_device (queries and results resident on the first device), `e2e` through
+    pyrope_sharded_search_batch (host buffers).  The call is synchronous, so both are wall-clock rates over K calls."""
+    import torch
+
+    import pyrope_b200 as pg
+    from pyrope_b200 import _lib
+    N = args.gpus
+    w = workload(args.workload, args.scale)
+    assert w["kind"] == "IVF_PQ", "the sharded-entry bench covers the IVF_PQ headline workload"
+    nq, dim, k, nprobe = w["nq"], w["dim"], w["topk"], w["nprobe"]
+    _lib.check(pg.load().pyrope_gpu_init(0))
+    sx = pg.ShardedIndex(N, pg.IVF_PQ, dim, pg.L2, nlist=w["nlist"], m=w["m"], k=w["k"])
+    ntrain = min(w["n"], max(40 * w["nlist"], 65536))
+    sx.set_train_params(ntrain, 4 if w["nlist"] > 1024 else 10)
+    tb0 = time.time()
+    chunk = min(w["n"], (1 << 31) // (dim * 4) // 2)
+    for r in range(N):  # device-resident feed: every shard sees every row (the lists it does not own are dropped at build)
+        shard, dev = sx.shard(r)
+        torch.cuda.set_device(dev)
+        _lib.check(pg.load().pyrope_gpu_init(dev))
+        shard.reserve(w["n"])
+        stage = torch.empty(chunk * dim, dtype=torch.float32, device=f"cuda:{dev}")
+        row = 0
+        while row < w["n"]:
+            c = min(chunk, w["n"] - row)
+            _lib.fill_uniform_device(stage.data_ptr(), c * dim, 42, row * dim, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            shard.add_device(stage.data_ptr(), c)
+            row += c
+        del stage
+        torch.cuda.empty_cache()
+    sx.note_rows(w["n"])
+    tb1 = time.time()
+    sx.build()
+    tb2 = time.time()
+    log(f"sharded entry: {N} shards fed in {tb1 - tb0:.1f}s, built in {tb2 - tb1:.1f}s, {sx.stats()} rows")
+    torch.cuda.set_device(0)
+    _lib.check(pg.load().pyrope_gpu_init(0))
+    Q = make_queries(torch, w)
+    sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    rw = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    cn = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        sx.search_device(Q.data_ptr(), nq, k, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), nprobe=nprobe)
+    sampler = ClockSampler(0)
+    sampler.start()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sx.search_device(Q.data_ptr(), nq, k, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), nprobe=nprobe)
+        dev_ms += sx.last_search_ms()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    Qh = Q.cpu().numpy()
+    for _ in range(2):
+        hs, hr, hc = sx.search(Qh, k, nprobe=nprobe)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hs, hr, hc = sx.search(Qh, k, nprobe=nprobe)
+    dte = time.perf_counter() - t0
+    same = bool(np.array_equal(hr, rw.cpu().numpy()) and np.array_equal(hs, sc.cpu().numpy()))
+    cpu, parity = None, None
+    if not args.no_cpu:
+        oix, _ = build_gpu_index(pg, torch, w, 0, 1)
+        oidx, held, note = oracle_index_from_gpu(oix, w, torch)
+        oix.close()
+        cpu, s, ores = time_cpu_baseline(oidx, held, note, Qh, w, args.cpu_budget)
+        parity = compare_topk(ores, (hr[:s], hs[:s], hc[:s]),
+                              f"oracle/oracle.c on the unsharded index: merged top-k of {N} GPUs behind pyrope_sharded_search_batch")
+        parity["e2e_result_identical_to_device_result"] = same
+    line = {"metric": METRIC_NAME, "value": round(nq * args.steps / dt, 1), "unit": "QPS", "n_gpus": N, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": dtype_of(w), "data": "synthetic uniform[0,1) fp32, counter-based generator",
+            "config": config_of(w),
+            "details": {"entry": "pyrope_sharded_search_batch_device: one process, one host thread and one stream per device, probe "
+                        "lists exchanged by peer stores over NVLink, in-kernel threshold exchange, merge on the first device",
+                        "device_ms_per_step_first_device": round(dev_ms / args.steps, 4), "add_s": round(tb1 - tb0, 2),
+                        "build_s": round(tb2 - tb1, 2)},
+            "clocks": clocks,
+            "e2e": {"value": round(nq * args.steps / dte, 1), "unit": "QPS", "h2d_bytes_per_step": nq * dim * 4 * N,
+                    "d2h_bytes_per_step": nq * k * 12 + nq * 4},
+            "cpu_baseline": cpu, "parity": parity}
+    emit(line)
+    sx.close()
+    if parity and parity.get("mismatch"):
+        sys.exit(3)
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path.  The C# engine cannot be built in this image
     (no dotnet), so this arm times the oracle port of its loops (oracle/oracle.c) with all host threads,
@@ -895,6 +988,8 @@ def main():
     ap.add_argument("--no-threshold-exchange", action="store_true",
                     help="multi-GPU IVF_PQ: do not share thresholds between the ranks' scan kernels")
     ap.add_argument("--recall-queries", type=int, default=200, help="queries used for the recall@10 read-out (0 = skip)")
+    ap.add_argument("--sharded-entry", action="store_true",
+                    help="one process drives --gpus N devices through pyrope_sharded_* (no torchrun)")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket one extra search step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--flat-parity-queries", type=int, default=32,
@@ -904,6 +999,8 @@ def main():
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.sharded_entry:
+        run_sharded_entry(args)
     else:
         run_ours(args)
 
