@@ -359,6 +359,15 @@ class GpuIndex:
         return out.value
 
 
+class _BorrowedIndex(GpuIndex):
+    """Row-ordinal view of a handle somebody else owns (a shard of a ShardedIndex): never destroys it."""
+
+    def close(self):
+        self._h = None
+
+    __del__ = close
+
+
 class ShardedIndex:
     """One index over several GPUs of the box, driven by this one process (pyrope_sharded_*, csrc/sharded.cu)."""
 
@@ -387,10 +396,9 @@ class ShardedIndex:
         """(borrowed GpuIndex view of shard i, its CUDA device ordinal)"""
         h, dev = vp(), C.c_int32(0)
         self._ck(load().pyrope_sharded_shard(self._s, i, C.byref(h), C.byref(dev)))
-        g = GpuIndex.__new__(GpuIndex)
+        g = _BorrowedIndex.__new__(_BorrowedIndex)
         g._h, g.kind, g.dim, g.metric, g.nlist, g.m, g.k = h, self.kind, self.dim, self.metric, self.nlist, self.m, self.k
-        g.close = lambda: None
-        g._owner = self
+        g._owner = self  # keep the sharded object alive while the view is in use
         return g, dev.value
 
     def note_rows(self, total: int):

@@ -111,3 +111,18 @@ def test_sharded_device_resident_search(gpu):
     np.testing.assert_array_equal(want[1], rw.cpu().numpy())
     assert sx.last_search_ms() > 0
     sx.close()
+
+
+def test_shard_views_are_borrowed(gpu):
+    """ShardedIndex.shard(i) hands out a view for device-resident feeds; dropping the view must not destroy the shard."""
+    import gc
+    base = orc.random_vectors(5_000, 32, 1)
+    sx = gpu.ShardedIndex(1, gpu.FLAT, 32, gpu.L2)
+    sx.add(base)
+    view, dev = sx.shard(0)
+    assert dev == 0 and view.stats()["live"] == 5_000
+    del view
+    gc.collect()
+    sc, rows, cnt = sx.search(base[:3], 1)
+    assert list(rows[:, 0]) == [0, 1, 2]
+    sx.close()
