@@ -191,6 +191,8 @@ struct pyrope_index {
     int64_t lm_nq = 0; int lm_P = 0, lm_k = 0;
     std::vector<int32_t> ksub;
     DevBuf ksub_d;
+    DevBuf pq_cmax;                    // list-major IVF_PQ: max codeword norm per sub-quantiser, valid for codebook_ptr
+    const void* cmax_for = nullptr;    // codebook buffer the cached bound was computed from (reset whenever it is rewritten)
     bool frozen = false;  // codebooks supplied by the caller
     int64_t max_train_rows = 0;
     int max_iter = 0;
@@ -779,6 +781,7 @@ int build_ivfpq(Index* h) {
         CK(launch_residuals(bd.X, ntrain, dim, h->centroids.as<float>(), assign.as<int32_t>(), res.as<float>(), st));
         TRY(h->codebook.ensure(sizeof(float) * (size_t)m * K * sub, 0, st, true));
         CK(cudaMemsetAsync(h->codebook.p, 0, sizeof(float) * (size_t)m * K * sub, st));
+        h->cmax_for = nullptr;
         h->ksub.assign((size_t)m, 0);
         DevBuf cb1;
         TRY(cb1.ensure(sizeof(float) * (size_t)K * sub, 0, st, true));
@@ -1187,6 +1190,13 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                 for (int r = 0; r < pp.n_peers; ++r) pp.peer_thr[r] = h->peer_thr[(size_t)r];
             }
             if (use_lm) {
+                if (h->cmax_for != h->codebook.p || !h->pq_cmax.p) {  // once per codebook
+                    TRY(h->pq_cmax.ensure(sizeof(float) * 16, 0, st, true));
+                    CK(launch_pq_cmax(h->codebook.as<float>(), h->k, dim / 16, h->pq_cmax.as<float>(), st));
+                    h->cmax_for = h->codebook.p;
+                    ++launches;
+                }
+                pp.cmax = h->pq_cmax.as<float>();
                 TRY(ws.lm.ensure(ivfpq_lm_scratch_bytes(nq, P, k, h->nc, dim, h->max_list_len), 0, st));
                 pp.max_list_len = h->max_list_len;
                 pp.ev_k0 = h->evk[0]; pp.ev_k1 = h->evk[1];
@@ -1488,6 +1498,7 @@ int pyrope_index_set_codebooks(pyrope_index* h, int n_centroids, const float* ce
         size_t cb = sizeof(float) * (size_t)h->m * h->k * h->sub;
         TRY(h->codebook.ensure(cb, 0, st, true));
         CK(cudaMemcpyAsync(h->codebook.p, pq_codebooks, cb, cudaMemcpyDefault, st));
+        h->cmax_for = nullptr;
         h->ksub.assign((size_t)h->m, h->k);
     }
     CK(cudaStreamSynchronize(st));
@@ -1938,6 +1949,7 @@ int pyrope_index_load(pyrope_index* h, const char* path) {
     h->built = L.built; h->frozen = L.frozen; h->nc = L.nc;
     h->shard_rank = L.shard_rank; h->shard_world = L.shard_world;
     take(h->centroids, L.centroids); take(h->codebook, L.codebook);
+    h->cmax_for = nullptr;
     h->ksub.swap(L.ksub);
     if (ksub_d.p) take(h->ksub_d, ksub_d);
     h->list_total = L.list_total;

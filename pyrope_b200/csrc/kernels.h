@@ -160,6 +160,7 @@ struct IvfPqScanParams {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // kernel overlaps the grouping / item-block kernels
     const float* centroids;                  // [nlist][dim]
     const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
+    const float* cmax = nullptr;             // optional [16]: max codeword norm per sub-quantiser (launch_pq_cmax), cached per index
     const uint8_t* codes; const uint8_t* dead; const int64_t* labels;
     int k; int groups;
     int force_generic;                       // tests: run the simple kernel
@@ -185,6 +186,8 @@ int ivfpq_lm_launches();
 cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, int k, int nlist, int dim,
                                    int64_t max_list_len, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st);
+// max_e |codeword(m, e)| for the 16 sub-quantisers of the list-major path (depends on the codebook only)
+cudaError_t launch_pq_cmax(const float* codebook, int ksub, int sub, float* cmax16, cudaStream_t st);
 // ProductQuantizer.ComputeDistanceTable for nq queries (parity tests): table [nq][m][k]
 cudaError_t launch_pq_distance_table(const float* Q, int64_t nq, int dim, const float* codebook,
                                      int m, int k, float* table, cudaStream_t st);

@@ -206,35 +206,37 @@ __global__ void lm_count_kernel(const int64_t* __restrict__ probes, int64_t npai
     for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
     if ((threadIdx.x & 31) == 0 && len) atomicAdd(scanned, len);
 }
-__global__ void lm_items_per_list_kernel(const int32_t* __restrict__ lcnt, const int64_t* __restrict__ list_off, int nlist,
-                                         int32_t* nit) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nlist) return;
-    int v = 0;
-    if (i < nlist) {
-        v = (lcnt[i] + LM_QS - 1) / LM_QS;
+// (items, pairs) of a list packed into one 64-bit word, so ONE exclusive scan yields both offsets: pair offset in the
+// low half, item offset in the high half (sums stay far below 2^32: at most nq * nprobe pairs)
+struct LmPackOp {
+    const int32_t* lcnt; int nlist;
+    __host__ __device__ unsigned long long operator()(int i) const {
+        const unsigned c = i < nlist ? (unsigned)lcnt[i] : 0u;
+        return ((unsigned long long)((c + LM_QS - 1) / LM_QS) << 32) | c;
     }
-    nit[i] = v;
-}
-__global__ void lm_fill_pairs_kernel(const int64_t* __restrict__ probes, int64_t npairs, int P,
-                                     const int64_t* __restrict__ list_off, const int32_t* __restrict__ loff, int32_t* lcur,
-                                     int32_t* pairq, int32_t* pairp) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npairs) return;
-    const int64_t l = probes[i];
-    if (l >= 0 && list_off[l + 1] > list_off[l]) {
-        const int slot = loff[l] + atomicAdd(&lcur[l], 1);
-        pairq[slot] = (int32_t)(i / P);
-        pairp[slot] = (int32_t)(i % P);
+};
+// one launch after the scan: unpack the offsets (loff / ioff, [nlist + 1]), write the item -> list map, scatter the pairs
+__global__ void lm_fill_kernel(const int64_t* __restrict__ probes, int64_t npairs, int P, const int64_t* __restrict__ list_off,
+                               const unsigned long long* __restrict__ poff, int nlist, int32_t* loff, int32_t* ioff, int32_t* lcur,
+                               int32_t* pairq, int32_t* pairp, int32_t* item_list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nlist) {
+        const unsigned long long w = poff[i];
+        loff[i] = (int32_t)(uint32_t)w;
+        ioff[i] = (int32_t)(w >> 32);
+        if (i < nlist) {
+            const int n = (int)(poff[i + 1] >> 32) - (int)(w >> 32), o = (int)(w >> 32);
+            for (int g = 0; g < n; ++g) item_list[o + g] = (int)i;
+        }
     }
-}
-
-// item -> list map: thread per list writes its (few) items
-__global__ void lm_fill_items_kernel(const int32_t* __restrict__ nit, const int32_t* __restrict__ ioff, int nlist, int32_t* item_list) {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlist) return;
-    const int n = nit[l], o = ioff[l];
-    for (int g = 0; g < n; ++g) item_list[o + g] = l;
+    if (i < npairs) {
+        const int64_t l = probes[i];
+        if (l >= 0 && list_off[l + 1] > list_off[l]) {
+            const int slot = (int)(uint32_t)poff[l] + atomicAdd(&lcur[l], 1);
+            pairq[slot] = (int32_t)(i / P);
+            pairp[slot] = (int32_t)(i % P);
+        }
+    }
 }
 
 // one warp per item: header + the four residual queries t = -2 (q - c), interleaved per dimension
@@ -965,6 +967,7 @@ struct LmFinalParams {
     const int64_t* probes; int P;
     const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k; int kc;
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits): bounds every pool entry's error
+    int keys_cap;              // keys in the sort window (the list ranges sit behind it in shared memory)
     PairOut out;
     int32_t* counts;           // nullable: results per query (when this kernel writes the search's final output)
 };
@@ -978,6 +981,15 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     __shared__ int s_n, s_m;
     if (tid == 0) { s_n = 0; s_m = 0; }
     __syncthreads();
+    // the probed lists' code ranges, once per query: a survivor's list is found by a shared-memory search below instead of
+    // dependent global loads per survivor
+    long long* s_lo = reinterpret_cast<long long*>(keys + p.keys_cap);
+    long long* s_hi = s_lo + p.P;
+    for (int sl = tid; sl < p.P; sl += blockDim.x) {
+        const int64_t l = __ldg(p.probes + q * p.P + sl);
+        s_lo[sl] = l >= 0 ? __ldg(p.list_off + l) : 0;
+        s_hi[sl] = l >= 0 ? __ldg(p.list_off + l + 1) : 0;
+    }
     for (int sl = tid; sl < p.pslots; sl += blockDim.x) {  // gather the pairs' private regions
         const size_t ps = (size_t)q * p.pslots + sl;
         const int c = min(p.pool_cnt[ps], p.kc);
@@ -1011,10 +1023,9 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
         const uint32_t pos = key_pos(keys[i]);
         int lo = 0;  // the list holding pos is one of this query's probed lists: test them in parallel
         for (int p0 = 0; p0 < p.P; p0 += 32) {
-            const int64_t l = p0 + lane < p.P ? __ldg(p.probes + q * p.P + p0 + lane) : -1;
-            const bool hit = l >= 0 && __ldg(p.list_off + l) <= (int64_t)pos && (int64_t)pos < __ldg(p.list_off + l + 1);
+            const bool hit = p0 + lane < p.P && s_lo[p0 + lane] <= (long long)pos && (long long)pos < s_hi[p0 + lane];
             const unsigned mh = __ballot_sync(0xffffffffu, hit);
-            if (mh) { lo = (int)__shfl_sync(0xffffffffu, l, __ffs(mh) - 1); break; }
+            if (mh) { lo = (int)__ldg(p.probes + q * p.P + p0 + __ffs(mh) - 1); break; }
         }
         float dm = 0.f;
         if (lane < 16) {
@@ -1081,7 +1092,7 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.zero_bytes = o;
     L.cmax = o; o += 256;
     L.loff = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
-    L.nit = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
+    L.nit = o; o += align_up(sizeof(unsigned long long) * ((size_t)nlist + 2), 256);  // packed (item, pair) offsets
     L.ioff = o; o += align_up(sizeof(int32_t) * ((size_t)nlist + 1), 256);
     L.pairq = o; o += align_up(sizeof(int32_t) * (size_t)npairs, 256);
     L.pairp = o; o += align_up(sizeof(int32_t) * (size_t)npairs, 256);
@@ -1095,7 +1106,11 @@ LmLayout lm_layout(int64_t nq, int P, int k, int nlist, int dim, int64_t max_lis
     L.pool_cap = L.pslots * L.kc;
     L.pool = o; o += align_up(sizeof(unsigned long long) * (size_t)nq * L.pool_cap, 256);
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int32_t*)nullptr, (int32_t*)nullptr, nlist + 1);
+    {
+        cub::TransformInputIterator<unsigned long long, LmPackOp, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0),
+                                                                                                     LmPackOp{nullptr, nlist});
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, it, (unsigned long long*)nullptr, nlist + 1);
+    }
     L.temp_bytes = tb + 256;
     L.temp = o; o += align_up(L.temp_bytes, 256);
     L.total = o;
@@ -1119,7 +1134,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     int32_t* redo_cnt = reinterpret_cast<int32_t*>(base + L.redo_cnt);
     unsigned long long* scanned = reinterpret_cast<unsigned long long*>(base + L.scanned);
     int32_t* loff = reinterpret_cast<int32_t*>(base + L.loff);
-    int32_t* nit = reinterpret_cast<int32_t*>(base + L.nit);
+    unsigned long long* poff = reinterpret_cast<unsigned long long*>(base + L.nit);
     int32_t* ioff = reinterpret_cast<int32_t*>(base + L.ioff);
     int32_t* pairq = reinterpret_cast<int32_t*>(base + L.pairq);
     int32_t* pairp = reinterpret_cast<int32_t*>(base + L.pairp);
@@ -1155,19 +1170,21 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
         ivfpq_lm_seed_kernel<<<(unsigned)((p.nq + SEED_NQ - 1) / SEED_NQ), 256, seed_smem, sst>>>(sd);
         cudaEventRecord(p.ev_join, p.aux_stream);
     }
-    const unsigned gb = (unsigned)((npairs + 255) / 256), lb = (unsigned)((p.nlist + 1 + 255) / 256);
-    lm_cmax_kernel<<<1, 256, 0, st>>>(p.codebook, p.ksub, p.dim / 16, cmax);
+    const unsigned gb = (unsigned)((npairs + 255) / 256);
+    if (p.cmax) cmax = const_cast<float*>(p.cmax);  // cached per index: depends on the codebook only
+    else lm_cmax_kernel<<<1, 256, 0, st>>>(p.codebook, p.ksub, p.dim / 16, cmax);
     lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt, scanned);
-    lm_items_per_list_kernel<<<lb, 256, 0, st>>>(lcnt, p.list_off, p.nlist, nit);
-    e = cub::DeviceScan::ExclusiveSum(temp, tb, lcnt, loff, p.nlist + 1, st);
-    if (e != cudaSuccess) return e;
-    e = cub::DeviceScan::ExclusiveSum(temp, tb, nit, ioff, p.nlist + 1, st);
-    if (e != cudaSuccess) return e;
-    lm_fill_pairs_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, P, p.list_off, loff, lcur, pairq, pairp);
+    {
+        cub::TransformInputIterator<unsigned long long, LmPackOp, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0),
+                                                                                                     LmPackOp{lcnt, p.nlist});
+        e = cub::DeviceScan::ExclusiveSum(temp, tb, it, poff, p.nlist + 1, st);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned fb = (unsigned)((std::max<int64_t>(npairs, p.nlist + 1) + 255) / 256);
+    lm_fill_kernel<<<fb, 256, 0, st>>>(p.probes, npairs, P, p.list_off, poff, p.nlist, loff, ioff, lcur, pairq, pairp, item_list);
 
     LmPrep pa{};
     pa.maxseg = lm_maxseg(p.max_list_len); pa.pairp = pairp;
-    lm_fill_items_kernel<<<lb, 256, 0, st>>>(nit, ioff, p.nlist, item_list);
     pa.item_list = item_list;
     pa.ioff = ioff; pa.loff = loff; pa.pairq = pairq; pa.list_off = p.list_off; pa.nlist = p.nlist;
     pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
@@ -1219,7 +1236,8 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
     fp.probes = p.probes; fp.P = P;
     fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out; fp.counts = p.out_counts;
-    const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, L.pool_cap));
+    fp.keys_cap = next_pow2(std::max(2, L.pool_cap));
+    const size_t fsm = sizeof(uint64_t) * (size_t)fp.keys_cap + 2 * sizeof(long long) * (size_t)P;
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
     ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, (L.pool_cap <= 2048 ? 128 : 256), fsm, st>>>(fp);
@@ -1235,9 +1253,9 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
         }
         int nredo = 0;
         cudaMemcpy(&nredo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost);
-        int nit = 0;
-        cudaMemcpy(&nit, ioff + p.nlist, sizeof(int), cudaMemcpyDeviceToHost);
-        fprintf(stderr, " items=%d redo=%d\n", nit, nredo);
+        int nitems = 0;
+        cudaMemcpy(&nitems, ioff + p.nlist, sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, " items=%d redo=%d\n", nitems, nredo);
         for (int i = 0; i < nsev; ++i) cudaEventDestroy(sev[i]);
     }
     return cudaGetLastError();
@@ -1258,8 +1276,8 @@ size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist, int dim,
     return lm_layout(nq, nprobe, k, nlist, dim, max_list_len).total;
 }
 
-// codeword bound, count, items-per-list, 2 scans, pair fill, item fill, prepare, seed, scan, redo, final
-int ivfpq_lm_launches() { return 12; }
+// count, scan (2), fill, prepare, seed, scan, redo, final (+ the codeword bound when it is not cached)
+int ivfpq_lm_launches() { return 9; }
 
 // codes scored by the most recent list-major search that used `scratch` (sum of probed list lengths)
 cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, int k, int nlist, int dim,
@@ -1269,6 +1287,11 @@ cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, 
                                     cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(st);
+}
+
+cudaError_t launch_pq_cmax(const float* codebook, int ksub, int sub, float* cmax16, cudaStream_t st) {
+    lm_cmax_kernel<<<1, 256, 0, st>>>(codebook, ksub, sub, cmax16);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st) {
