@@ -450,7 +450,8 @@ __device__ __forceinline__ float a2_eval_quad(const float* q, const float* __res
     return sum;
 }
 
-constexpr int RANK_KEYS = 2048;  // sort window: survivors (<= 1024) or, exhaustively, 1024 kept + 1024 new
+constexpr int RANK_KEYS = 1024;  // sort window: survivors (<= 512) or, exhaustively, 512 kept + 512 new (nprobe <= 256)
+constexpr int RANK_SPOS = 512;   // survivor positions staged in shared memory
 constexpr int RANK_MAXPARTS = 160;
 template <int METRIC>
 __global__ void __launch_bounds__(128) coarse_rank_kernel(const float* __restrict__ Q, int dim, const float* __restrict__ C,
@@ -459,24 +460,28 @@ __global__ void __launch_bounds__(128) coarse_rank_kernel(const float* __restric
                                                          int parts, int64_t* pout, int P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);     // [RANK_KEYS]
-    uint32_t* spos = reinterpret_cast<uint32_t*>(keys + RANK_KEYS);  // [1024]
-    float* qv = reinterpret_cast<float*>(spos + 1024);          // [dim]
+    uint32_t* spos = reinterpret_cast<uint32_t*>(keys + RANK_KEYS);  // [RANK_SPOS]
+    float* qv = reinterpret_cast<float*>(spos + RANK_SPOS);     // [dim]
     __shared__ float s_qn;
     __shared__ int s_off[RANK_MAXPARTS + 1];
     __shared__ int s_over;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, t = tid & 3, grp = tid >> 2, ngrp = blockDim.x >> 2;
     for (int d = tid; d < dim; d += blockDim.x) qv[d] = Q[q * dim + d];
-    if (tid == 0) {  // offsets of the (few) per-CTA lists of this query
-        int o = 0, over = 0;
-        for (int pt = 0; pt < parts; ++pt) {
-            const int c = qcnt[q * parts + pt];
-            s_off[pt] = o;
-            over |= c > cap;
-            o += min(c, cap);
-        }
-        s_off[parts] = o;
-        s_over = over || o > 1024;
+    // offsets of the (few) per-CTA lists of this query: counts loaded in parallel, summed by one thread from shared memory
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+    for (int pt = tid; pt < parts; pt += blockDim.x) {
+        const int c = qcnt[q * parts + pt];
+        if (c > cap) s_over = 1;
+        s_off[pt + 1] = min(c, cap);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int o = 0;
+        s_off[0] = 0;
+        for (int pt = 0; pt < parts; ++pt) { o += s_off[pt + 1]; s_off[pt + 1] = o; }
+        if (o > RANK_SPOS) s_over = 1;
     }
     __syncthreads();
     if (METRIC == 2 && tid == 0) s_qn = exact::norm_eval(qv, dim);
@@ -633,7 +638,7 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
             p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau));
     }
     coarse_tc_kernel<true><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
-    const size_t rsm = sizeof(uint64_t) * RANK_KEYS + sizeof(uint32_t) * 1024 + sizeof(float) * (size_t)a.dim;
+    const size_t rsm = sizeof(uint64_t) * RANK_KEYS + sizeof(uint32_t) * RANK_SPOS + sizeof(float) * (size_t)a.dim;
     if (a.metric == kL2)
         coarse_rank_kernel<0><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
     else if (a.metric == kIP)

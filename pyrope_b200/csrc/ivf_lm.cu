@@ -20,7 +20,7 @@
 //   ivf_lm_final_kernel  best k of the pool, RE-SCORED in the reference's evaluation order
 //                        (VectorMath.L2Squared / DotProduct, VectorMath.cs:8-70) so reported scores are the
 //                        oracle's bit for bit, then ordered.
-// Shapes: L2 / inner product, dim % 4 == 0 and dim <= 128, no MaxScans budget; everything else takes ivf.cu.
+// Shapes: L2 / inner product / cosine, dim % 4 == 0 and dim <= 128, no MaxScans budget; everything else takes ivf.cu.
 #include <cub/cub.cuh>
 
 #include <cstdio>
@@ -103,10 +103,17 @@ __device__ __forceinline__ float warp_score(const float4 qv, const float4 xv) {
     if (METRIC == kL2) {
         const float d0 = qv.x - xv.x, d1 = qv.y - xv.y, d2 = qv.z - xv.z, d3 = qv.w - xv.w;
         a = -(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))));
-    } else {
+    } else {  // inner product; Cosine callers scale by 1 / |x| (inv_norm)
         a = fmaf(qv.x, xv.x, fmaf(qv.y, xv.y, fmaf(qv.z, xv.z, qv.w * xv.w)));
     }
     return warp_sum(a);
+}
+
+// Cosine ranks a query's rows by q.x / |x| (its own norm is a positive constant): the proxy every kernel below compares and
+// queues; the final kernel re-scores with VectorMath.Cosine's guards (0 below 1e-6, VectorMath.cs:102-109).
+__device__ __forceinline__ float inv_norm(const float* __restrict__ norms, int64_t pos) {
+    const float n = __ldg(norms + pos);
+    return n < 1e-6f ? 0.f : 1.f / n;
 }
 
 // ---- seed: a lower bound of every query's k-th best score -------------------------------------------------
@@ -114,6 +121,7 @@ struct FlSeed {
     const float* Q; int64_t nq; int dim; const int64_t* probes; int P;
     const float* vecs; const uint8_t* dead; const int64_t* list_off;
     uint32_t* pool_thr; int k;
+    const float* norms;  // Cosine: |x| per list entry
 };
 template <int METRIC>
 __global__ void __launch_bounds__(256) ivf_lm_seed_kernel(FlSeed a) {
@@ -144,7 +152,8 @@ __global__ void __launch_bounds__(256) ivf_lm_seed_kernel(FlSeed a) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 if (ok[u] && got < FSEED) {
-                    const float s = warp_score<METRIC>(qv, xv[u]);
+                    float s = warp_score<METRIC>(qv, xv[u]);
+                    if (METRIC == kCosine) s *= inv_norm(a.norms, beg + v0 + u);
 #pragma unroll
                     for (int w = 0; w < U; ++w)
                         if ((got >> 5) == w && (got & 31) == lane) sc[w] = s;
@@ -185,6 +194,7 @@ struct FlParams {
     const int2* items; const int32_t* n_items; const int32_t* pair_off; const int32_t* pairq; const int32_t* pairp;
     unsigned long long* pool; int32_t* pool_cnt; uint32_t* pool_thr; int pslots; int k;
     int2* redo; int32_t* redo_cnt;
+    const float* norms;  // Cosine: |x| per list entry
 };
 
 template <int METRIC>
@@ -271,8 +281,9 @@ __global__ void __launch_bounds__(FT, 2) ivf_lm_scan_kernel(FlParams p) {
                     vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
                 }
             }
-            const float score = METRIC == kL2 ? -vals[0] : vals[0];
+            float score = METRIC == kL2 ? -vals[0] : vals[0];
             const int64_t row = v + (lane >> 4);
+            if (METRIC == kCosine && row < len) score *= inv_norm(p.norms, beg + row);
             if (row < len && score > thr) {
                 const int64_t gpos = beg + row;
                 if (!(p.dead && p.dead[gpos])) {
@@ -349,6 +360,7 @@ struct FlRedo {
     const int2* redo; const int32_t* redo_cnt;
     unsigned long long* pool; int32_t* pool_cnt; int pslots; int k;
     const uint32_t* pool_thr;  // the query's current threshold: a valid bound, so the redo queue starts warm
+    const float* norms;
 };
 template <int METRIC>
 __global__ void __launch_bounds__(256) ivf_lm_redo_kernel(FlRedo a) {
@@ -377,7 +389,8 @@ __global__ void __launch_bounds__(256) ivf_lm_redo_kernel(FlRedo a) {
             for (int64_t v = c0 + warp; v < min(len, c0 + 256); v += 8) {
                 float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (lane * 4 < a.dim) xv = __ldg(reinterpret_cast<const float4*>(a.vecs + (beg + v) * a.dim) + lane);
-                const float s = warp_score<METRIC>(qv, xv);
+                float s = warp_score<METRIC>(qv, xv);
+                if (METRIC == kCosine) s *= inv_norm(a.norms, beg + v);
                 if (lane == 0 && !(a.dead && a.dead[beg + v])) Qu.push(make_key(s, (uint32_t)(beg + v)));
             }
             __syncthreads();
@@ -393,6 +406,7 @@ __global__ void __launch_bounds__(256) ivf_lm_redo_kernel(FlRedo a) {
 struct FlFinal {
     const float* Q; int dim; const float* vecs; const int64_t* labels;
     const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k; int metric;
+    const float* norms; const float* qnorm;  // Cosine
     PairOut out;
 };
 __global__ void __launch_bounds__(256) ivf_lm_final_kernel(FlFinal p) {
@@ -427,7 +441,11 @@ __global__ void __launch_bounds__(256) ivf_lm_final_kernel(FlFinal p) {
     for (int i = tid; i < kk; i += blockDim.x) {
         const uint32_t pos = key_pos(keys[i]);
         const float* x = p.vecs + (size_t)pos * p.dim;
-        const float s = p.metric == kL2 ? -exact::a2_eval<0>(qs, x, p.dim) : exact::a2_eval<1>(qs, x, p.dim);
+        float s = p.metric == kL2 ? -exact::a2_eval<0>(qs, x, p.dim) : exact::a2_eval<1>(qs, x, p.dim);
+        if (p.metric == kCosine) {  // VectorMath.Cosine (VectorMath.cs:102-109) on the stored norms
+            const float qn = p.qnorm[q], xn = p.norms[pos];
+            s = (qn < 1e-6f || xn < 1e-6f) ? 0.f : __fdiv_rn(s, __fmul_rn(qn, xn));
+        }
         keys[i] = make_key(s, pos);
     }
     __syncthreads();
@@ -521,14 +539,14 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
 
     FlSeed sd{};
     sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.vecs = p.vecs; sd.dead = p.dead;
-    sd.list_off = p.list_off; sd.pool_thr = pool_thr; sd.k = p.k;
+    sd.list_off = p.list_off; sd.pool_thr = pool_thr; sd.k = p.k; sd.norms = p.norms;
     if (p.k <= FSEED) ivf_lm_seed_kernel<METRIC><<<(unsigned)((p.nq + 7) / 8), 256, 0, st>>>(sd);
 
     FlParams sp{};
     sp.Q = p.Q; sp.dim = p.dim; sp.vecs = p.vecs; sp.dead = p.dead; sp.list_off = p.list_off;
     sp.items = items; sp.n_items = ioff + nlist; sp.pair_off = loff; sp.pairq = pairq; sp.pairp = pairp;
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = P; sp.k = p.k;
-    sp.redo = redo; sp.redo_cnt = redo_cnt;
+    sp.redo = redo; sp.redo_cnt = redo_cnt; sp.norms = p.norms;
     if (p.ev_k0) cudaEventRecord(p.ev_k0, st);
     ivf_lm_scan_kernel<METRIC><<<(unsigned)std::min<int64_t>(2 * num_sms, L.max_items), FT, 0, st>>>(sp);
     if (p.ev_k1) cudaEventRecord(p.ev_k1, st);
@@ -536,12 +554,12 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
     FlRedo rd{};
     rd.Q = p.Q; rd.dim = p.dim; rd.vecs = p.vecs; rd.dead = p.dead; rd.list_off = p.list_off; rd.items = items;
     rd.pair_off = loff; rd.pairp = pairp; rd.redo = redo; rd.redo_cnt = redo_cnt; rd.pool = pool; rd.pool_cnt = pool_cnt;
-    rd.pslots = P; rd.k = p.k; rd.pool_thr = pool_thr;
+    rd.pslots = P; rd.k = p.k; rd.pool_thr = pool_thr; rd.norms = p.norms;
     ivf_lm_redo_kernel<METRIC><<<(unsigned)(2 * num_sms), 256, sizeof(uint64_t) * FREDO_QCAP, st>>>(rd);
 
     FlFinal fp{};
     fp.Q = p.Q; fp.dim = p.dim; fp.vecs = p.vecs; fp.labels = p.labels; fp.pool = pool; fp.pool_cnt = pool_cnt;
-    fp.pslots = P; fp.k = p.k; fp.metric = METRIC; fp.out = p.out;
+    fp.pslots = P; fp.k = p.k; fp.metric = METRIC; fp.out = p.out; fp.norms = p.norms; fp.qnorm = p.qnorm;
     const size_t fsm = sizeof(uint64_t) * (size_t)next_pow2(std::max(2, P * p.k)) + sizeof(float) * (size_t)p.dim;
     e = cudaFuncSetAttribute(ivf_lm_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
@@ -552,7 +570,7 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
 }  // namespace
 
 bool ivfflat_lm_supported(int dim, int metric, int nprobe, int k, int64_t nq, int64_t list_total, bool has_budget) {
-    if (has_budget || (metric != kL2 && metric != kIP)) return false;
+    if (has_budget || (metric != kL2 && metric != kIP && metric != kCosine)) return false;
     if (dim % 4 != 0 || dim > 128 || dim < 4) return false;
     if (k < 1 || k > kMaxTopK || (int64_t)nprobe * k > 16384) return false;
     if (nq * nprobe >= ((int64_t)1 << 29) || list_total >= ((int64_t)1 << 32)) return false;
@@ -563,7 +581,9 @@ int ivfflat_lm_launches() { return 10; }  // count, items-per-list, 2 scans, pai
 
 cudaError_t launch_ivfflat_scan_lm(const IvfFlatScanParams& p, int nlist, void* scratch, int num_sms, cudaStream_t st) {
     if (p.nq <= 0) return cudaSuccess;
-    return p.metric == kL2 ? launch_fl<kL2>(p, nlist, scratch, num_sms, st) : launch_fl<kIP>(p, nlist, scratch, num_sms, st);
+    if (p.metric == kL2) return launch_fl<kL2>(p, nlist, scratch, num_sms, st);
+    if (p.metric == kIP) return launch_fl<kIP>(p, nlist, scratch, num_sms, st);
+    return launch_fl<kCosine>(p, nlist, scratch, num_sms, st);
 }
 
 cudaError_t ivfflat_lm_scanned_rows(const void* scratch, int64_t nq, int nprobe, int k, int nlist, unsigned long long* out,

@@ -100,3 +100,24 @@ def test_ivfflat_lm_edge_shapes(gpu):
     for nq, k, nprobe in ((80, 10, 3), (64, 50, 2), (80, 10, 3)):   # scratch re-initialised between searches
         assert_batch_equivalent(ref.search_batch(q[:nq], k, nprobe=nprobe), _s(ix, q[:nq], k, nprobe=nprobe),
                                 ctx=f"ivf lm repeat nq={nq} k={k}")
+
+
+def test_ivf_lm_cosine_matches_oracle(gpu):
+    """Cosine on the list-major IVF_FLAT scan: rows are ranked by q.x / |x| on the way, the survivors re-scored with
+    VectorMath.Cosine on the stored norms (IvfFlatVectorIndex.cs:351-360) — incl. a zero row and a zero query."""
+    rng = np.random.default_rng(17)
+    base = (rng.random((12_000, 64), dtype=np.float32) - 0.5)
+    base[123] = 0.0
+    Q = (rng.random((200, 64), dtype=np.float32) - 0.5)
+    Q[7] = 0.0
+    ref = orc.IvfFlatIndex(64, orc.COSINE, nlist=24)
+    ref.add_batch(base)
+    ref.build()
+    ix = gpu.GpuIndex(gpu.IVF_FLAT, 64, gpu.COSINE, nlist=24)
+    ix.add(base)
+    ix.build()
+    np.testing.assert_array_equal(ref.centroids(), ix.centroids())
+    for k, nprobe in ((10, 6), (100, 3)):
+        sc, rows, cnt = ix.search(Q, k, nprobe=nprobe)
+        assert ix.last_search_kernel()[0] == "ivf_lm_scan_kernel"
+        assert_batch_equivalent(ref.search_batch(Q, k, nprobe=nprobe), (rows, sc, cnt), ctx=f"ivf lm cosine k={k} nprobe={nprobe}")
