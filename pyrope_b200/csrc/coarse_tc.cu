@@ -183,66 +183,83 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
+    // Both single-thread roles walk the units with running counters (query tile, centroid tile, stage, phase): the MMA
+    // issuer is ONE thread whose every instruction costs a full dependent latency, so its loop must hold nothing but the
+    // barrier waits and the UTCHMMAs (a 64-bit division per unit and a modulo + three descriptor builds per K chunk made
+    // it as slow as the tensor pipe: 3,900 cycles per unit against 2,048 of MMAs).
+    const int64_t qt0 = u0 / p.ntiles;
+    const int nt0 = (int)(u0 - qt0 * p.ntiles), ntiles_i = (int)p.ntiles;
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            uint32_t it = 0, qloads = 0;
-            int64_t cur_qt = -1;
+            uint32_t s = 0, ph = 0, qloads = 0;
+            int64_t qt = qt0;
+            int nt = nt0;
+            bool newq = true;
             for (int ui = 0; ui < nunit; ++ui) {
-                const int64_t u = u0 + ui, qt = u / p.ntiles, nt = u - qt * p.ntiles;
-                if (qt != cur_qt) {  // swap the resident query tile: every MMA that read the old one has retired
+                if (newq) {  // swap the resident query tile: every MMA that read the old one has retired
                     if (qloads > 0) mbar_wait(qempty, (qloads - 1) & 1);
                     mbar_expect_tx(qfull, (uint32_t)(KC * QCHUNK_BYTES));
                     for (int kc = 0; kc < KC; ++kc)
                         tma_load_2d(smem_u32(qs + kc * QCHUNK_BYTES), &map_q, qfull, kc * CBK, (int)(qt * CQ));
-                    cur_qt = qt;
                     ++qloads;
+                    newq = false;
                 }
-                for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % XSTAGES, ph = (it / XSTAGES) & 1;
+                const int n0 = nt * CN;
+                for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(xempty0 + 8 * s, ph ^ 1);
                     mbar_expect_tx(xfull0 + 8 * s, XSTAGE_BYTES);
-                    tma_load_2d(smem_u32(xs + s * XSTAGE_BYTES), &map_x, xfull0 + 8 * s, kc * CBK, (int)(nt * CN));
+                    tma_load_2d(smem_u32(xs) + s * XSTAGE_BYTES, &map_x, xfull0 + 8 * s, kc * CBK, n0);
+                    if (++s == XSTAGES) { s = 0; ph ^= 1; }
                 }
+                if (++nt == ntiles_i) { nt = 0; ++qt; newq = true; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (elect_one()) {
-            uint32_t it = 0, qloads = 0;
-            int64_t cur_qt = -1;
+            uint32_t s = 0, ph = 0, qloads = 0;
+            int nt = nt0;
+            bool newq = true;
+            // descriptors are base + offset: the stage / chunk offsets are added to the start-address field (16-byte units)
+            const uint64_t xd_base = make_sw128_desc(smem_u32(xs));
+            const uint64_t qd_base = make_sw128_desc(smem_u32(qs));
+            constexpr uint64_t kXStep = XSTAGE_BYTES >> 4, kQStep = QCHUNK_BYTES >> 4, kHalf = (128 * 128) >> 4;
             for (int ui = 0; ui < nunit; ++ui) {
-                const int64_t u = u0 + ui, qt = u / p.ntiles;
-                if (qt != cur_qt) {
+                if (newq) {
                     mbar_wait(qfull, qloads & 1);
-                    tc_fence_after();
-                    cur_qt = qt;
                     ++qloads;
+                    newq = false;
                 }
                 const uint32_t buf = ui & 1, aph = (ui >> 1) & 1;
                 mbar_wait(tempty0 + 8 * buf, aph ^ 1);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + buf * (2 * CN);
-                for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % XSTAGES, ph = (it / XSTAGES) & 1;
-                    mbar_wait(xfull0 + 8 * s, ph);
-                    tc_fence_after();
-                    const uint64_t xd = make_sw128_desc(smem_u32(xs + s * XSTAGE_BYTES));
-                    const uint64_t qd0 = make_sw128_desc(smem_u32(qs + kc * QCHUNK_BYTES));
-                    const uint64_t qd1 = make_sw128_desc(smem_u32(qs + kc * QCHUNK_BYTES + 128 * 128));
 #pragma unroll
-                    for (int k4 = 0; k4 < CBK / 8; ++k4) {
-                        if (kc * CBK + k4 * 8 >= p.dim) break;
-                        const uint64_t adv = (uint64_t)(k4 * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                        tc_mma_tf32(d0, qd0 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
-                        tc_mma_tf32(d0 + CN, qd1 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
+                for (int kc = 0; kc < CKC; ++kc) {
+                    if (kc < KC) {
+                        mbar_wait(xfull0 + 8 * s, ph);
+                        tc_fence_after();
+                        const uint64_t xd = xd_base + (uint64_t)s * kXStep;
+                        const uint64_t qd0 = qd_base + (uint64_t)kc * kQStep, qd1 = qd0 + kHalf;
+#pragma unroll
+                        for (int k4 = 0; k4 < CBK / 8; ++k4) {
+                            if (kc * CBK + k4 * 8 < p.dim) {
+                                const uint64_t adv = (uint64_t)(k4 * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
+                                tc_mma_tf32(d0, qd0 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
+                                tc_mma_tf32(d0 + CN, qd1 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
+                            }
+                        }
+                        tc_commit(xempty0 + 8 * s);  // frees the centroid stage when these MMAs retire
+                        if (++s == XSTAGES) { s = 0; ph ^= 1; }
                     }
-                    tc_commit(xempty0 + 8 * s);  // frees the centroid stage when these MMAs retire
                 }
                 tc_commit(tfull0 + 8 * buf);     // both halves of the unit complete
-                // last unit of this query tile: its retirement frees the resident tile
-                const bool last_of_qt = (ui + 1 == nunit) || ((u + 1) / p.ntiles != qt);
-                if (last_of_qt) tc_commit(qempty);
+                if (++nt == ntiles_i) {          // last unit of this query tile: its retirement frees the resident tile
+                    nt = 0;
+                    newq = true;
+                    tc_commit(qempty);
+                }
             }
         }
     } else if (warp >= 4) {
@@ -251,8 +268,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         float* sbias = sterms + (warp - 4) * (4 * CN);  // [2][CN] bias then [2][CN] scale, private to the warp
         float* sscale = sbias + 2 * CN;
         float nb[CN / 32], ns[CN / 32];
-        auto load_terms = [&](int ui) {
-            const int64_t u = u0 + ui, nt = u % p.ntiles;
+        auto load_terms = [&](int nt) {
 #pragma unroll
             for (int j = 0; j < CN / 32; ++j) {
                 const int64_t pos = nt * CN + lane + j * 32;
@@ -268,7 +284,9 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             __syncwarp();
         };
-        if (nunit > 0) { load_terms(0); store_terms(0); }
+        if (nunit > 0) { load_terms(nt0); store_terms(0); }
+        int64_t qt = qt0;
+        int nt = nt0;
         int64_t cur_qt = -1, gq = 0;
         bool qvalid = false;
         float tau = INFINITY;
@@ -276,7 +294,6 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         uint32_t* myq = nullptr;
         int32_t* mycnt = nullptr;
         for (int ui = 0; ui < nunit; ++ui) {
-            const int64_t u = u0 + ui, qt = u / p.ntiles, nt = u - qt * p.ntiles;
             if (qt != cur_qt) {
                 if (PASS_B && mycnt && qvalid) *mycnt = cnt;  // close the list of the query tile this CTA leaves
                 cur_qt = qt;
@@ -299,7 +316,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
             }
             const uint32_t buf = ui & 1, aph = (ui >> 1) & 1;
-            if (ui + 1 < nunit) load_terms(ui + 1);  // consumed after this unit
+            const int nt_next = nt + 1 == ntiles_i ? 0 : nt + 1;
+            if (ui + 1 < nunit) load_terms(nt_next);  // consumed after this unit
             mbar_wait(tfull0 + 8 * buf, aph);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (2 * CN) + hf * CN;
@@ -343,6 +361,8 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             if (ui + 1 < nunit) store_terms(buf ^ 1);
+            nt = nt_next;
+            if (nt == 0) ++qt;
         }
         if (PASS_B && mycnt && qvalid) *mycnt = cnt;
     }
