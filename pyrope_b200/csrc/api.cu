@@ -191,6 +191,10 @@ struct pyrope_index {
     int64_t lm_nq = 0; int lm_P = 0, lm_k = 0;
     std::vector<int32_t> ksub;
     DevBuf ksub_d;
+    // list-major IVF_PQ with m < 16: the equivalent 16-table quantiser (kernels.h, IvfPqScanParams::lm_codebook) and the
+    // codes repeated to 16 bytes per row; rebuilt lazily after the codebook / the lists were replaced
+    DevBuf lm_cb16, lm_codes16;
+    bool lm_cb16_ok = false, lm_codes16_ok = false;
     DevBuf pq_cmax;                    // list-major IVF_PQ: max codeword norm per sub-quantiser, valid for codebook_ptr
     const void* cmax_for = nullptr;    // codebook buffer the cached bound was computed from (reset whenever it is rewritten)
     bool frozen = false;  // codebooks supplied by the caller
@@ -781,7 +785,7 @@ int build_ivfpq(Index* h) {
         CK(launch_residuals(bd.X, ntrain, dim, h->centroids.as<float>(), assign.as<int32_t>(), res.as<float>(), st));
         TRY(h->codebook.ensure(sizeof(float) * (size_t)m * K * sub, 0, st, true));
         CK(cudaMemsetAsync(h->codebook.p, 0, sizeof(float) * (size_t)m * K * sub, st));
-        h->cmax_for = nullptr;
+        h->cmax_for = nullptr; h->lm_cb16_ok = false;
         h->ksub.assign((size_t)m, 0);
         DevBuf cb1;
         TRY(cb1.ensure(sizeof(float) * (size_t)K * sub, 0, st, true));
@@ -812,6 +816,7 @@ int build_ivfpq(Index* h) {
     TRY(finish_lists(h, bd, assign.as<int32_t>(), nc, sc, codes.p, m, newcodes));
     std::swap(h->list_codes.p, newcodes.p);
     std::swap(h->list_codes.bytes, newcodes.bytes);
+    h->lm_codes16_ok = false;
     CK(cudaStreamSynchronize(st));
     return PYROPE_OK;
 }
@@ -1190,9 +1195,26 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                 for (int r = 0; r < pp.n_peers; ++r) pp.peer_thr[r] = h->peer_thr[(size_t)r];
             }
             if (use_lm) {
+                if (h->m != 16) {  // the scan's 16-table view of this quantiser
+                    if (!h->lm_cb16_ok) {
+                        TRY(h->lm_cb16.ensure(sizeof(float) * (size_t)h->k * dim, 0, st, true));
+                        CK(launch_pq_lm_expand_codebook(h->codebook.as<float>(), h->m, h->k, dim, h->lm_cb16.as<float>(), st));
+                        h->lm_cb16_ok = true;
+                        h->cmax_for = nullptr;
+                        ++launches;
+                    }
+                    if (!h->lm_codes16_ok) {
+                        TRY(h->lm_codes16.ensure((size_t)std::max<int64_t>(h->list_total, 1) * 16, 0, st, true));
+                        CK(launch_pq_lm_expand_codes(h->list_codes.as<uint8_t>(), h->list_total, h->m, h->lm_codes16.as<uint8_t>(), st));
+                        h->lm_codes16_ok = true;
+                        ++launches;
+                    }
+                    pp.lm_codebook = h->lm_cb16.as<float>();
+                    pp.lm_codes = h->lm_codes16.as<uint8_t>();
+                }
                 if (h->cmax_for != h->codebook.p || !h->pq_cmax.p) {  // once per codebook
                     TRY(h->pq_cmax.ensure(sizeof(float) * 16, 0, st, true));
-                    CK(launch_pq_cmax(h->codebook.as<float>(), h->k, dim / 16, h->pq_cmax.as<float>(), st));
+                    CK(launch_pq_cmax(pp.lm_codebook ? pp.lm_codebook : h->codebook.as<float>(), h->k, dim / 16, h->pq_cmax.as<float>(), st));
                     h->cmax_for = h->codebook.p;
                     ++launches;
                 }
@@ -1498,7 +1520,7 @@ int pyrope_index_set_codebooks(pyrope_index* h, int n_centroids, const float* ce
         size_t cb = sizeof(float) * (size_t)h->m * h->k * h->sub;
         TRY(h->codebook.ensure(cb, 0, st, true));
         CK(cudaMemcpyAsync(h->codebook.p, pq_codebooks, cb, cudaMemcpyDefault, st));
-        h->cmax_for = nullptr;
+        h->cmax_for = nullptr; h->lm_cb16_ok = false;
         h->ksub.assign((size_t)h->m, h->k);
     }
     CK(cudaStreamSynchronize(st));
@@ -1949,7 +1971,7 @@ int pyrope_index_load(pyrope_index* h, const char* path) {
     h->built = L.built; h->frozen = L.frozen; h->nc = L.nc;
     h->shard_rank = L.shard_rank; h->shard_world = L.shard_world;
     take(h->centroids, L.centroids); take(h->codebook, L.codebook);
-    h->cmax_for = nullptr;
+    h->cmax_for = nullptr; h->lm_cb16_ok = false;
     h->ksub.swap(L.ksub);
     if (ksub_d.p) take(h->ksub_d, ksub_d);
     h->list_total = L.list_total;
@@ -1962,6 +1984,7 @@ int pyrope_index_load(pyrope_index* h, const char* path) {
         h->list_off_h.swap(L.list_off_h);
         take(h->list_off, list_off); take(h->list_rows, L.list_rows); take(h->list_labels, L.list_labels);
         if (h->kind == PYROPE_IVF_FLAT) take(h->list_vecs, L.list_payload); else take(h->list_codes, L.list_payload);
+        h->lm_codes16_ok = false;
         take(h->cnorms, cnorms);
         if (list_norms.p) take(h->list_norms, list_norms);
     } else {

@@ -405,7 +405,7 @@ template <int R>  // registers per lane: groups <= 32 R
 __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict__ umax, int64_t nq_pad, int ntiles, int64_t nq,
                                                         int kprime, const float* __restrict__ Q, int dim,
                                                         const float* __restrict__ amax, float* tau_out,
-                                                        const float* __restrict__ C, int64_t c_bytes) {
+                                                        const float* __restrict__ C, int64_t c_bytes, float eband) {
     extern __shared__ float s_u[];  // [32][ntiles + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // The exact ranking (two kernels from now) reads ~100 scattered fp32 centroid rows per query: pull the table from
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
             float qq = 0.f;
             for (int d = lane; d < dim; d += 32) { const float v = __ldg(Q + q * dim + d); qq = fmaf(v, v, qq); }
             qq = warp_sum(qq);
-            const float E = 9.85e-4f * sqrtf(qq) * __ldg(amax);  // 2^-10 (1 + 2^-7) |q| A
+            const float E = eband * sqrtf(qq) * __ldg(amax);  // 2^-10 (1 + 2^-7) |q| A
             // accept s > tau: everything >= G - 2E, with room for the fp32 rounding of the proxy itself and for the
             // difference between exact arithmetic and the reference's evaluation order (both ~1e-6 relative)
             tau = G - 2.f * E - 4e-6f * fabsf(G) - 1e-30f;
@@ -655,6 +655,9 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     if (L.parts > RANK_MAXPARTS) return cudaErrorInvalidValue;
     unsigned char* base = reinterpret_cast<unsigned char*>(a.scratch);
     CUtensorMap mq, mx;
+    // (Feeding the fp32 table itself to kind::tf32 - truncation, band 1.5x - was measured: 45% more survivors on the
+    // C5 centroids, and the exact ranking gathers them from HBM either way: 0.35 ms instead of 0.28.)
+    const float eband = 9.85e-4f;  // 2^-10 (1 + 2^-7): both operands rounded to nearest tf32
     if (!make_map(&mq, a.Qhi, a.nq, a.dim, CQ) || !make_map(&mx, a.Chi, a.nc, a.dim, CN)) return cudaErrorInvalidValue;
     CoarseParams p{};
     p.nq = a.nq; p.n_scan = a.nc; p.dim = a.dim; p.qtiles = L.qtiles; p.ntiles = L.ntiles; p.nq_pad = L.nq_pad;
@@ -670,26 +673,33 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(coarse_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
     if (e != cudaSuccess) return e;
+    static const bool dbg = getenv("PYROPE_COARSE_DEBUG") != nullptr;
+    cudaEvent_t dev[5];
+    auto mark = [&](int i) { if (dbg) { cudaEventCreate(&dev[i]); cudaEventRecord(dev[i], st); } };
     const unsigned grid = (unsigned)L.grid;
     const int kprime = a.nprobe + kCoarseTcMargin;
     const int ngroups = coarse_groups(a.nc, kprime, &p.fine);
     if (ngroups <= 0) return cudaErrorInvalidValue;
     const size_t tsm = sizeof(float) * 32 * ((size_t)ngroups + 1);
+    mark(0);
     coarse_tc_kernel<false><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
+    mark(1);
     if (ngroups <= 512) {
         e = cudaFuncSetAttribute(coarse_tau_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return e;
         coarse_tau_kernel<16><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
             p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau), a.C,
-            (int64_t)sizeof(float) * a.nc * a.dim);
+            (int64_t)sizeof(float) * a.nc * a.dim, eband);
     } else {
         e = cudaFuncSetAttribute(coarse_tau_kernel<TAU_MAXU / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return e;
         coarse_tau_kernel<TAU_MAXU / 32><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
             p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau), a.C,
-            (int64_t)sizeof(float) * a.nc * a.dim);
+            (int64_t)sizeof(float) * a.nc * a.dim, eband);
     }
+    mark(2);
     coarse_tc_kernel<true><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
+    mark(3);
     const size_t rsm = sizeof(uint64_t) * RANK_KEYS + sizeof(uint32_t) * RANK_SPOS + sizeof(float) * (size_t)a.dim;
     if (a.metric == kL2)
         coarse_rank_kernel<0><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
@@ -697,8 +707,13 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
         coarse_rank_kernel<1><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
     else
         coarse_rank_kernel<2><<<(unsigned)a.nq, 128, rsm, st>>>(a.Q, a.dim, a.C, a.cnorms, a.nc, p.qpos, p.qcnt, p.cap, p.parts, a.probes_out, a.nprobe);
-    static const bool dbg = getenv("PYROPE_COARSE_DEBUG") != nullptr;
-    if (dbg) {  // survivors per query (debug aid, synchronises)
+    mark(4);
+    if (dbg) {  // per-kernel times and survivors per query (debug aid, synchronises)
+        cudaEventSynchronize(dev[4]);
+        float ms[4];
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], dev[i], dev[i + 1]);
+        fprintf(stderr, "[coarse] pass A %.3f ms, threshold %.3f, pass B %.3f, exact ranking %.3f\n", ms[0], ms[1], ms[2], ms[3]);
+        for (int i = 0; i < 5; ++i) cudaEventDestroy(dev[i]);
         std::vector<int32_t> hc((size_t)a.nq * p.parts);
         cudaStreamSynchronize(st);
         cudaMemcpy(hc.data(), p.qcnt, sizeof(int32_t) * hc.size(), cudaMemcpyDeviceToHost);

@@ -161,6 +161,12 @@ struct IvfPqScanParams {
     const float* centroids;                  // [nlist][dim]
     const float* codebook; int m; int ksub;  // [m][ksub][dim/m]
     const float* cmax = nullptr;             // optional [16]: max codeword norm per sub-quantiser (launch_pq_cmax), cached per index
+    // list-major path, m < 16 (m divides 16): the scan runs on the EQUIVALENT 16-table quantiser - every codeword cut
+    // into 16/m pieces of dim/16 dimensions, every code byte repeated 16/m times (launch_pq_lm_expand_*): the same
+    // squared distance, summed in 16 parts instead of m.  Only the approximate stages read these two; the final
+    // re-score uses `codebook` / `codes` in the reference's own order.  nullptr when m = 16.
+    const float* lm_codebook = nullptr;      // [16][ksub][dim/16]
+    const uint8_t* lm_codes = nullptr;       // [total][16]
     const uint8_t* codes; const uint8_t* dead; const int64_t* labels;
     int k; int groups;
     int force_generic;                       // tests: run the simple kernel
@@ -179,10 +185,12 @@ struct IvfPqScanParams {
 };
 cudaError_t launch_ivfpq_scan(const IvfPqScanParams& p, cudaStream_t st);
 // List-major variant (pq_lm.cu): (query, probe) pairs grouped by list, four queries per work item share
-// one pass over the list's codes; writes ONE part (p.groups is ignored).  m = 16, dim/m in {4, 8}.
+// one pass over the list's codes; writes ONE part (p.groups is ignored).  m in {1, 2, 4, 8, 16}, dim/16 in {4, 8}.
 bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total, int64_t max_list_len);
 size_t ivfpq_lm_scratch_bytes(int64_t nq, int nprobe, int k, int nlist, int dim, int64_t max_list_len);
 int ivfpq_lm_launches();
+cudaError_t launch_pq_lm_expand_codebook(const float* codebook, int m, int ksub, int dim, float* cb16, cudaStream_t st);
+cudaError_t launch_pq_lm_expand_codes(const uint8_t* codes, int64_t n, int m, uint8_t* codes16, cudaStream_t st);
 cudaError_t ivfpq_lm_scanned_codes(const void* scratch, int64_t nq, int nprobe, int k, int nlist, int dim,
                                    int64_t max_list_len, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st);

@@ -962,8 +962,8 @@ __global__ void __launch_bounds__(256) ivfpq_lm_redo_kernel(LmRedo a) {
 // ---- pool -> candidates within the rounding band of the k-th, exact re-score, final order -----------------
 struct LmFinalParams {
     const float* Q; int dim;
-    const float* centroids; const float* codebook; int ksub;
-    const uint8_t* codes; const int64_t* list_off; int nlist; const int64_t* labels;
+    const float* centroids; const float* codebook; int ksub; int m;  // the index's own quantiser: [m][ksub][dim/m]
+    const uint8_t* codes; const int64_t* list_off; int nlist; const int64_t* labels;  // codes [total][m]
     const int64_t* probes; int P;
     const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k; int kc;
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits): bounds every pool entry's error
@@ -985,6 +985,7 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     // dependent global loads per survivor
     long long* s_lo = reinterpret_cast<long long*>(keys + p.keys_cap);
     long long* s_hi = s_lo + p.P;
+    float* s_res = reinterpret_cast<float*>(s_hi + p.P) + warp * p.dim;  // m < 16: this warp's residual query
     for (int sl = tid; sl < p.P; sl += blockDim.x) {
         const int64_t l = __ldg(p.probes + q * p.P + sl);
         s_lo[sl] = l >= 0 ? __ldg(p.list_off + l) : 0;
@@ -1027,18 +1028,30 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
             const unsigned mh = __ballot_sync(0xffffffffu, hit);
             if (mh) { lo = (int)__ldg(p.probes + q * p.P + p0 + __ffs(mh) - 1); break; }
         }
-        float dm = 0.f;
-        if (lane < 16) {
-            float r[SUB];
+        float dm = 0.f, dist = 0.f;
+        if (p.m == 16) {
+            if (lane < 16) {
+                float r[SUB];
 #pragma unroll
-            for (int d = 0; d < SUB; ++d)
-                r[d] = __fsub_rn(__ldg(p.Q + q * p.dim + lane * SUB + d), __ldg(p.centroids + (size_t)lo * p.dim + lane * SUB + d));
-            const int code = p.codes[(size_t)pos * 16 + lane];
-            dm = exact::a1_l2_fixed<SUB>(r, p.codebook + ((size_t)lane * p.ksub + code) * SUB);
+                for (int d = 0; d < SUB; ++d)
+                    r[d] = __fsub_rn(__ldg(p.Q + q * p.dim + lane * SUB + d), __ldg(p.centroids + (size_t)lo * p.dim + lane * SUB + d));
+                const int code = p.codes[(size_t)pos * 16 + lane];
+                dm = exact::a1_l2_fixed<SUB>(r, p.codebook + ((size_t)lane * p.ksub + code) * SUB);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 16; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, mi));
+        } else {
+            // fewer, longer sub-vectors (dim/m = 16 .. 128): L2SquaredUnsafe's four-accumulator form applies from 32 on
+            const int subr = p.dim / p.m;
+            for (int d = lane; d < p.dim; d += 32)
+                s_res[d] = __fsub_rn(__ldg(p.Q + q * p.dim + d), __ldg(p.centroids + (size_t)lo * p.dim + d));
+            __syncwarp();
+            if (lane < p.m) {
+                const int code = p.codes[(size_t)pos * p.m + lane];
+                dm = exact::a1_l2_eval(s_res + lane * subr, p.codebook + ((size_t)lane * p.ksub + code) * subr, subr);
+            }
+            for (int mi = 0; mi < p.m; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, mi));
         }
-        float dist = 0.f;
-#pragma unroll
-        for (int mi = 0; mi < 16; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, mi));
         __syncwarp();
         if (lane == 0) keys[i] = make_key(-dist, pos);
     }
@@ -1121,6 +1134,10 @@ template <int SUB>
 cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st) {
     const int P = p.nprobe;
     const int64_t npairs = p.nq * P;
+    // the approximate stages (seed, scan, redo) run on 16 tables: the index's own when m = 16, else the equivalent split
+    const float* cb16 = p.lm_codebook ? p.lm_codebook : p.codebook;
+    const uint8_t* codes16 = p.lm_codes ? p.lm_codes : p.codes;
+    if (p.m != 16 && (!p.lm_codebook || !p.lm_codes)) return cudaErrorInvalidValue;
     const LmLayout L = lm_layout(p.nq, P, p.k, p.nlist, p.dim, p.max_list_len);
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
     int32_t* lcnt = reinterpret_cast<int32_t*>(base + L.lcnt);
@@ -1162,7 +1179,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
         cudaStreamWaitEvent(p.aux_stream, p.ev_fork, 0);
         LmSeed sd{};
         sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
-        sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
+        sd.codebook = cb16; sd.ksub = p.ksub; sd.codes = codes16; sd.dead = p.dead; sd.list_off = p.list_off;
         sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k); sd.thr0 = thr0;
         const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
         e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
@@ -1172,7 +1189,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     }
     const unsigned gb = (unsigned)((npairs + 255) / 256);
     if (p.cmax) cmax = const_cast<float*>(p.cmax);  // cached per index: depends on the codebook only
-    else lm_cmax_kernel<<<1, 256, 0, st>>>(p.codebook, p.ksub, p.dim / 16, cmax);
+    else lm_cmax_kernel<<<1, 256, 0, st>>>(cb16, p.ksub, p.dim / 16, cmax);
     lm_count_kernel<<<gb, 256, 0, st>>>(p.probes, npairs, p.list_off, lcnt, scanned);
     {
         cub::TransformInputIterator<unsigned long long, LmPackOp, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0),
@@ -1196,7 +1213,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     if (!fork) {
         LmSeed sd{};
         sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.centroids = p.centroids;
-        sd.codebook = p.codebook; sd.ksub = p.ksub; sd.codes = p.codes; sd.dead = p.dead; sd.list_off = p.list_off;
+        sd.codebook = cb16; sd.ksub = p.ksub; sd.codes = codes16; sd.dead = p.dead; sd.list_off = p.list_off;
         sd.pool_thr = pool_thr; sd.k = p.k; sd.sample = std::max(512, 16 * p.k); sd.thr0 = thr0;
         const size_t seed_smem = sizeof(float) * ((size_t)SEED_NQ * 4096 + (size_t)SEED_NQ * SEED_CAP + (size_t)SEED_NQ * p.dim);
         e = cudaFuncSetAttribute(ivfpq_lm_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem);
@@ -1208,7 +1225,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     mark();
 
     LmParams sp{};
-    sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = p.codebook; sp.codes = p.codes; sp.dead = p.dead;
+    sp.dim = p.dim; sp.ksub = p.ksub; sp.k = p.k; sp.codebook = cb16; sp.codes = codes16; sp.dead = p.dead;
     sp.iblk = iblk; sp.n_items = ioff + p.nlist;
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = L.pslots; sp.kc = L.kc;
     sp.hist = hist; sp.thr0 = thr0; sp.sinv_max = sinv_max;
@@ -1223,8 +1240,8 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     if (p.ev_k1) cudaEventRecord(p.ev_k1, st);
 
     LmRedo rd{};
-    rd.Q = p.Q; rd.dim = p.dim; rd.centroids = p.centroids; rd.codebook = p.codebook; rd.ksub = p.ksub;
-    rd.codes = p.codes; rd.dead = p.dead; rd.iblk = iblk; rd.blk = L.blk; rd.redo = redo; rd.redo_cnt = redo_cnt;
+    rd.Q = p.Q; rd.dim = p.dim; rd.centroids = p.centroids; rd.codebook = cb16; rd.ksub = p.ksub;
+    rd.codes = codes16; rd.dead = p.dead; rd.iblk = iblk; rd.blk = L.blk; rd.redo = redo; rd.redo_cnt = redo_cnt;
     rd.pool = pool; rd.pool_cnt = pool_cnt; rd.pslots = L.pslots; rd.k = p.k; rd.kc = L.kc; rd.pool_thr = pool_thr;
     const size_t redo_smem = sizeof(uint64_t) * REDO_QCAP + sizeof(float) * (4096 + (size_t)p.dim);
     mark();
@@ -1232,15 +1249,17 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     mark();
 
     LmFinalParams fp{};
-    fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub;
+    fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub; fp.m = p.m;
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
     fp.probes = p.probes; fp.P = P;
     fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out; fp.counts = p.out_counts;
     fp.keys_cap = next_pow2(std::max(2, L.pool_cap));
-    const size_t fsm = sizeof(uint64_t) * (size_t)fp.keys_cap + 2 * sizeof(long long) * (size_t)P;
+    const int fthreads = L.pool_cap <= 2048 ? 128 : 256;
+    const size_t fsm = sizeof(uint64_t) * (size_t)fp.keys_cap + 2 * sizeof(long long) * (size_t)P +
+                       (p.m == 16 ? 0 : sizeof(float) * (size_t)(fthreads / 32) * p.dim);
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
-    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, (L.pool_cap <= 2048 ? 128 : 256), fsm, st>>>(fp);
+    ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, fthreads, fsm, st>>>(fp);
     mark();
     if (stage_dbg && nsev == 7) {
         cudaEventSynchronize(sev[6]);
@@ -1261,11 +1280,43 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     return cudaGetLastError();
 }
 
+// ---- the equivalent 16-table quantiser of an m < 16 index ------------------------------------------------------
+// |r_m - p|^2 over a sub-vector of dim/m dimensions is the sum of the same expression over its 16/m pieces of dim/16
+// dimensions, all addressed by the one code byte: piece v = m * (16/m) + j of codeword e is p[j * dim/16 ...].
+__global__ void lm_expand_codebook_kernel(const float* __restrict__ cb, int m, int ksub, int dim, float* __restrict__ cb16) {
+    const int sub16 = dim / 16, subr = dim / m, per = 16 / m;
+    const int64_t n = (int64_t)16 * ksub * sub16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % sub16), e = (int)((i / sub16) % ksub), v = (int)(i / ((int64_t)sub16 * ksub));
+        cb16[i] = cb[((size_t)(v / per) * ksub + e) * subr + (v % per) * sub16 + d];
+    }
+}
+__global__ void lm_expand_codes_kernel(const uint8_t* __restrict__ codes, int64_t n, int m, uint4* __restrict__ codes16) {
+    const int per = 16 / m;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int v = 0; v < 16; ++v) w[v >> 2] |= (uint32_t)codes[r * m + v / per] << (8 * (v & 3));
+        codes16[r] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 }  // namespace
 
+cudaError_t launch_pq_lm_expand_codebook(const float* codebook, int m, int ksub, int dim, float* cb16, cudaStream_t st) {
+    lm_expand_codebook_kernel<<<64, 256, 0, st>>>(codebook, m, ksub, dim, cb16);
+    return cudaGetLastError();
+}
+cudaError_t launch_pq_lm_expand_codes(const uint8_t* codes, int64_t n, int m, uint8_t* codes16, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    lm_expand_codes_kernel<<<grid, 256, 0, st>>>(codes, n, m, reinterpret_cast<uint4*>(codes16));
+    return cudaGetLastError();
+}
+
 bool ivfpq_lm_supported(int dim, int m, int ksub, int nprobe, int k, int64_t nq, int64_t list_total, int64_t max_list_len) {
-    if (m != 16 || ksub > 256 || ksub < 1) return false;
-    const int sub = dim / m;
+    // m < 16 runs on the equivalent 16-table quantiser (IvfPqScanParams::lm_codebook)
+    if (m < 1 || m > 16 || 16 % m != 0 || dim % 16 != 0 || ksub > 256 || ksub < 1) return false;
+    const int sub = dim / 16;
     if (sub != 4 && sub != 8) return false;
     if (k < 1 || k > kMaxTopK || (int64_t)nprobe * lm_kc(k) * lm_maxseg(max_list_len) > 16384 || nprobe > 32767) return false;
     if (nq * nprobe >= ((int64_t)1 << 29) || list_total >= ((int64_t)1 << 32)) return false;
@@ -1296,7 +1347,7 @@ cudaError_t launch_pq_cmax(const float* codebook, int ksub, int sub, float* cmax
 
 cudaError_t launch_ivfpq_scan_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cudaStream_t st) {
     if (p.nq <= 0) return cudaSuccess;
-    return (p.dim / p.m == 8) ? launch_lm<8>(p, scratch, num_sms, st) : launch_lm<4>(p, scratch, num_sms, st);
+    return (p.dim / 16 == 8) ? launch_lm<8>(p, scratch, num_sms, st) : launch_lm<4>(p, scratch, num_sms, st);
 }
 
 }  // namespace pyrope

@@ -232,3 +232,58 @@ def test_lm_random_shape_sweep(gpu):
         ref, ix = _pair(gpu, base, dim, nlist)
         assert_batch_equivalent(ref.search_batch(q, k, nprobe=nprobe), _s(ix, q, k, nprobe=nprobe),
                                 ctx=f"lm sweep trial={trial} dim={dim} n={n} nlist={nlist} nq={nq} k={k} nprobe={nprobe}")
+
+
+# ------------------------------------------------------------------------------------------------
+# m < 16: the scan runs on the equivalent 16-table quantiser, the re-score on the index's own
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,m", [(128, 8), (128, 4), (64, 4), (64, 8), (64, 2), (128, 2), (64, 1)])
+def test_lm_fewer_sub_quantisers(gpu, dim, m):
+    """ProductQuantizer accepts any m that divides dim (ProductQuantizer.cs:18-19; m = 4 is the registry default,
+    VectorIndexRegistry.cs:96-106).  Codes and codebooks stay [m]; the list-major kernels see every codeword cut
+    into 16/m pieces.  Scores must still be the reference's (sub-vectors of 16..64 floats: L2SquaredUnsafe's
+    remainder accumulator, and its four-accumulator block from 32 on)."""
+    base = orc.random_vectors(8_000, dim, 31 + m)
+    q = orc.random_vectors(150, dim, 32 + m)
+    ref, ix = _pair(gpu, base, dim, 16, m=m)
+    for k, nprobe in ((10, 4), (100, 2), (1, 16)):
+        rid, rsc, rcn = ref.search_batch(q, k, nprobe=nprobe)
+        got = _s(ix, q, k, nprobe=nprobe)
+        assert ix.last_search_kernel()[0] == "ivfpq_lm_scan_kernel"
+        assert_batch_equivalent((rid, rsc, rcn), got, ctx=f"lm dim={dim} m={m} k={k} nprobe={nprobe}")
+        same = rid == got[0]
+        if m > 1:  # one sub-quantiser = at most 256 distinct distances per list: rows tie by the hundred
+            assert same.mean() > 0.99
+        np.testing.assert_array_equal(rsc[same], got[1][same])
+        np.testing.assert_array_equal(rsc, got[1])  # the score LISTS agree whatever the order among ties
+
+
+def test_lm_fewer_sub_quantisers_follow_rebuilds_and_new_codebooks(gpu):
+    """The 16-table view is derived state: a Build that replaces the lists, and codebooks set by the caller, must
+    both refresh it."""
+    dim, m = 128, 4
+    base = orc.random_vectors(6_000, dim, 77)
+    q = orc.random_vectors(64, dim, 78)
+    ref, ix = _pair(gpu, base, dim, 8, m=m)
+    assert_batch_equivalent(ref.search_batch(q, 10, nprobe=4), _s(ix, q, 10, nprobe=4), ctx="m=4 first build")
+    more = orc.random_vectors(3_000, dim, 79)
+    # IvfPqVectorIndex.Build re-trains from the buffer only and replaces the lists (IvfPqVectorIndex.cs:64,92)
+    ref.add_batch(more, ids=np.arange(6_000, 9_000))
+    ref.build()
+    ix.add(more)
+    ix.build()
+    assert_batch_equivalent(ref.search_batch(q, 10, nprobe=4), _s(ix, q, 10, nprobe=4), ctx="m=4 second build")
+    # a frozen copy with the first index's codebooks
+    cent = ix.centroids()
+    cb, _ = ix.codebooks()
+    fz = gpu.GpuIndex(gpu.IVF_PQ, dim, gpu.L2, nlist=8, m=m, k=256)
+    fz.set_codebooks(cent, cb)
+    fz.add(more)
+    fz.build()
+    a = _s(fz, q, 10, nprobe=4)
+    fz.set_codebooks(cent, cb[:, ::-1].copy())  # other codewords behind the same code bytes
+    fz.add(more)
+    fz.build()
+    b = _s(fz, q, 10, nprobe=4)
+    assert not np.array_equal(a[1], b[1])
+    assert fz.last_search_kernel()[0] == "ivfpq_lm_scan_kernel"
