@@ -43,6 +43,11 @@ def workload(name: str, scale: float) -> dict:
                  nprobe=64)
         w["n"] = max(4096, int(round(w["n"] * scale)))
         w["nlist"] = max(64, int(round(w["nlist"] * scale)))
+    elif name in ("c5m8", "c5m4"):  # C5's shape with fewer, longer sub-vectors (not BASELINE configs: the widened list-major scan)
+        w = dict(kind="IVF_PQ", metric="L2", dim=128, n=100_000_000, nq=10_000, topk=10, nlist=65536, m=int(name[3:]), k=256,
+                 nprobe=64)
+        w["n"] = max(4096, int(round(w["n"] * scale)))
+        w["nlist"] = max(64, int(round(w["nlist"] * scale)))
     elif name == "c4":
         w = dict(kind="FLAT", metric="IP", dim=768, n=10_000_000, nq=10_000, topk=100)
         w["n"] = max(4096, int(round(w["n"] * scale)))
@@ -59,7 +64,7 @@ def workload(name: str, scale: float) -> dict:
     else:
         raise SystemExit(f"unknown workload {name}")
     w["name"] = name
-    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5", "c2x"))
+    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5", "c2x", "c5m8", "c5m4"))
     return w
 
 

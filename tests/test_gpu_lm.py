@@ -258,7 +258,7 @@ def test_lm_fewer_sub_quantisers(gpu, dim, m):
         np.testing.assert_array_equal(rsc, got[1])  # the score LISTS agree whatever the order among ties
 
 
-def test_lm_fewer_sub_quantisers_follow_rebuilds_and_new_codebooks(gpu):
+def test_lm_fewer_sub_quantisers_follow_rebuilds_and_new_codebooks(gpu, monkeypatch):
     """The 16-table view is derived state: a Build that replaces the lists, and codebooks set by the caller, must
     both refresh it."""
     dim, m = 128, 4
@@ -281,9 +281,18 @@ def test_lm_fewer_sub_quantisers_follow_rebuilds_and_new_codebooks(gpu):
     fz.add(more)
     fz.build()
     a = _s(fz, q, 10, nprobe=4)
-    fz.set_codebooks(cent, cb[:, ::-1].copy())  # other codewords behind the same code bytes
+    cb2 = (cb * np.float32(0.9) + np.float32(0.01)).astype(np.float32)  # other codewords: other codes, other distances
+    fz.set_codebooks(cent, cb2)
     fz.add(more)
     fz.build()
     b = _s(fz, q, 10, nprobe=4)
     assert not np.array_equal(a[1], b[1])
     assert fz.last_search_kernel()[0] == "ivfpq_lm_scan_kernel"
+    monkeypatch.setenv("PYROPE_PQ_LM", "0")  # the query-major kernels read the index's own [m] tables
+    qm = gpu.GpuIndex(gpu.IVF_PQ, dim, gpu.L2, nlist=8, m=m, k=256)
+    qm.set_codebooks(cent, cb2)
+    qm.add(more)
+    qm.build()
+    c = _s(qm, q, 10, nprobe=4)
+    assert qm.last_search_kernel()[0] != "ivfpq_lm_scan_kernel"
+    assert_batch_equivalent(c, b, ctx="m=4 new codebooks: query-major vs list-major")
