@@ -504,24 +504,79 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
         pr_local = torch.full((per, P_eff), -1, dtype=torch.int64, device="cuda")
         pr_all = torch.empty((world * per, P_eff), dtype=torch.int64, device="cuda")
 
-    def step():
+    # the step's all-gathers: peer stores over NVLink through the library (csrc/peer.cu) unless --nccl-exchange, or unless
+    # some rank cannot map its peers' buffers (then every rank uses NCCL)
+    grp = None
+    if world > 1 and not args.nccl_exchange:
+        pbytes = per * P_eff * 8 if split_coarse else 16
+        ok = (nq * k) % 4 == 0 and pbytes % 16 == 0
+        try:
+            if ok:
+                grp = _lib.PeerGroup(world, rank, max(pbytes, nq * k * 8), 3)
+                mine = torch.frombuffer(bytearray(grp.handle()), dtype=torch.uint8).cuda()
+        except Exception as ex:
+            log(f"rank {rank}: peer exchange unavailable ({ex})")
+            ok = False
+        if not ok or grp is None:
+            ok, mine = False, torch.zeros(64, dtype=torch.uint8, device="cuda")
+        allh = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh.view(-1), mine)
+        if ok:
+            try:
+                grp.open(bytes(allh.cpu().numpy().tobytes()))
+            except Exception as ex:
+                log(f"rank {rank}: peer exchange unavailable ({ex})")
+                ok = False
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            if grp is not None:
+                grp.close()
+            grp = None
+    collective = "none" if world == 1 else ("peer stores over NVLink + epoch flags (pyrope_peer_allgather_device)" if grp else "nccl all_gather")
+
+    def step(marks=None):
+        """One search step.  marks: a list that receives (phase name, CUDA event) pairs - the per-phase breakdown of the
+        multi-GPU step (`step_phases_ms`), recorded outside the timed region only."""
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+        mark("start")
         if split_coarse:
             if qhi > qlo:
                 ix.coarse_probe_device(Q[qlo:qhi].data_ptr(), qhi - qlo, P_eff, pr_local.data_ptr(), stream=stream)
             lc = ix.last_search_launches()
-            dist.all_gather_into_tensor(pr_all.view(-1), pr_local.view(-1))
-            ix.search_probed_device(Q.data_ptr(), nq, k, P_eff, pr_all.data_ptr(), sc.data_ptr(), rw.data_ptr(),
+            mark("coarse_probe_own_queries")
+            if grp is not None:
+                probes_ptr = grp.allgather(0, pr_local.data_ptr(), per * P_eff * 8, stream=stream)
+                lc += 2
+            else:
+                dist.all_gather_into_tensor(pr_all.view(-1), pr_local.view(-1))
+                probes_ptr = pr_all.data_ptr()
+            mark("allgather_probes")
+            ix.search_probed_device(Q.data_ptr(), nq, k, P_eff, probes_ptr, sc.data_ptr(), rw.data_ptr(),
                                     cn.data_ptr(), stream=stream)
             launches[0] = lc + ix.last_search_launches()
         else:
             ix.search_device(Q.data_ptr(), nq, k, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), nprobe=nprobe, stream=stream)
             launches[0] = ix.last_search_launches()
+        mark("search_own_shard")
         if world > 1:
-            dist.all_gather_into_tensor(g_sc.view(-1), sc.view(-1))
-            dist.all_gather_into_tensor(g_rw.view(-1), rw.view(-1))
-            _lib.topk_merge_device(nq, world, k, k, g_sc.data_ptr(), g_rw.data_ptr(), m_sc.data_ptr(), m_rw.data_ptr(),
+            if grp is not None:
+                gs_ptr = grp.allgather(1, sc.data_ptr(), nq * k * 4, stream=stream)
+                gr_ptr = grp.allgather(2, rw.data_ptr(), nq * k * 8, stream=stream)
+                launches[0] += 4
+            else:
+                dist.all_gather_into_tensor(g_sc.view(-1), sc.view(-1))
+                dist.all_gather_into_tensor(g_rw.view(-1), rw.view(-1))
+                gs_ptr, gr_ptr = g_sc.data_ptr(), g_rw.data_ptr()
+            mark("allgather_results")
+            _lib.topk_merge_device(nq, world, k, k, gs_ptr, gr_ptr, m_sc.data_ptr(), m_rw.data_ptr(),
                                    m_cn.data_ptr(), stream=stream)
             launches[0] += 1
+            mark("merge")
 
     def barrier():
         torch.cuda.synchronize()
@@ -590,9 +645,13 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
     stage_ms = {"total": 0.0, "coarse": 0.0, "scan": 0.0, "merge": 0.0}
     reps = max(3, min(steps, 10))
     kname, kms_avg = "", 0.0
+    phases = {}
     for _ in range(reps):
-        step()
+        marks = []
+        step(marks)
         torch.cuda.synchronize()
+        for (_, e_a), (name, e_b) in zip(marks, marks[1:]):
+            phases[name] = phases.get(name, 0.0) + e_a.elapsed_time(e_b) / reps
         for kk, v in ix.last_search_ms().items():  # with a split coarse stage: the probed search only
             stage_ms[kk] += v / reps
         kname, kms = ix.last_search_kernel()
@@ -659,7 +718,8 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
     roofline = {"bound": alg["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": alg["unit"],
                 "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": kname,
                 "kernel_ms": round(dom_ms, 4), "algorithmic_per_launch": work, "peak_source": peak_src,
-                "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()}, **extra}
+                "stage_ms": {a: round(b, 4) for a, b in stage_ms.items()},
+                "step_phases_ms": {a: round(b, 4) for a, b in phases.items()}, **extra}
     if traffic_note:
         roofline["traffic_note"] = traffic_note
 
@@ -759,12 +819,16 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
             "details": {"l2_policy": "inputs larger than L2 (index "
                         f"{w['n'] * w.get('m', w['dim'] * 4) / 1e6:.0f} MB scanned region vs 126 MB L2)",
                         "parallelism": f"lists sharded list_id % {world}" if w["kind"] != "FLAT" else f"rows sharded in {world} blocks",
-                        **recall, "exchange": ("nccl all_gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
-                                    ("nccl all_gather of per-rank top-k + on-device merge" if world > 1 else "none") +
-                                    ("" if exchange == "none" else " + " + exchange), **build_info},
+                        **recall, "exchange": ("all-gather of probe lists (coarse stage split by query) + " if split_coarse else "") +
+                                    ("all-gather of per-rank top-k + on-device merge" if world > 1 else "none") +
+                                    ("" if exchange == "none" else " + " + exchange),
+                        "collective": collective, **build_info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches[0] * steps),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         }
+    if grp is not None:
+        torch.cuda.synchronize()
+        grp.close()
     ix.close()
     del ix
     torch.cuda.empty_cache()
@@ -992,6 +1056,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline AND the parity check against the oracle")
     ap.add_argument("--no-threshold-exchange", action="store_true",
                     help="multi-GPU IVF_PQ: do not share thresholds between the ranks' scan kernels")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="multi-GPU: all-gather probe lists and results with NCCL instead of the library's peer-memory exchange")
     ap.add_argument("--recall-queries", type=int, default=200, help="queries used for the recall@10 read-out (0 = skip)")
     ap.add_argument("--sharded-entry", action="store_true",
                     help="one process drives --gpus N devices through pyrope_sharded_* (no torchrun)")

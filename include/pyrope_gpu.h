@@ -274,6 +274,29 @@ int pyrope_sharded_search_batch_device(pyrope_sharded *s, int64_t nq, const floa
 int pyrope_sharded_last_search_ms(pyrope_sharded *s, float *ms_out);
 const char *pyrope_sharded_last_error(void);
 
+/* ---- exchange over peer memory (csrc/peer.cu): the all-gather steps of a sharded search when every GPU has its own
+ *      process (local top-k lists, and the probe lists of a coarse stage split by query), written as peer
+ *      stores over NVLink instead of a collective-library call.  One pyrope_peer_group per rank on that rank's current
+ *      device; `slot_bytes` bounds one rank's contribution to one call, `n_slots` independent exchanges (<= 8) can be
+ *      in use (e.g. slot 0 probes, 1 scores, 2 rows).  Every rank issues the same sequence of calls per slot.
+ *      pyrope_peer_allgather_device enqueues, on `stream`: a copy of d_src (16-byte aligned, bytes_per_rank a multiple
+ *      of 16) into every rank's buffer, a release of this call's epoch to the peers, and a wait for theirs; work
+ *      enqueued after it on the same stream sees *d_gathered_out = [world][bytes_per_rank].  The area is double-buffered
+ *      by call parity: consume the gathered data (on that stream) before the next-but-one call on the same slot.
+ *      A rank whose peers never arrive faults after ~5 s instead of hanging the device.  Errors: pyrope_peer_last_error(). */
+typedef struct pyrope_peer_group pyrope_peer_group;
+int pyrope_peer_group_create(int world, int rank, size_t slot_bytes, int n_slots, pyrope_peer_group **out);
+int pyrope_peer_group_destroy(pyrope_peer_group *g);
+/* one process per GPU: exchange the 64-byte handles out of band (e.g. torch.distributed), then open all of them */
+int pyrope_peer_group_handle(pyrope_peer_group *g, void *handle_out /* 64 bytes */);
+int pyrope_peer_group_open(pyrope_peer_group *g, const void *handles /* world x 64 bytes, own entry ignored */);
+/* one process, several GPUs (peer access enabled by the caller): hand over the peers' buffers directly */
+int pyrope_peer_group_buffer(pyrope_peer_group *g, void **d_buffer_out);
+int pyrope_peer_group_attach(pyrope_peer_group *g, void *const *buffers /* world entries, own entry ignored */);
+int pyrope_peer_allgather_device(pyrope_peer_group *g, int slot, const void *d_src, size_t bytes_per_rank,
+                                 const void **d_gathered_out, void *stream);
+const char *pyrope_peer_last_error(void);
+
 /* ---- Head+Tail on device: replaces DeltaVectorIndex (Vector/DeltaVectorIndex.cs) when BOTH sides are GPU
  *      indexes — a small mutable FLAT head and an IVF_FLAT / IVF_PQ / FLAT tail (VectorIndexRegistry.cs:110-111).
  *      Identity across the two sides is the row LABEL: the shim passes its id ordinal (Dictionary<string,long>) as

@@ -76,6 +76,14 @@ SIGNATURES = {
     "pyrope_sharded_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
     "pyrope_sharded_last_search_ms": (C.c_int, [vp, f32p]),
     "pyrope_sharded_last_error": (C.c_char_p, []),
+    "pyrope_peer_group_create": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(vp)]),
+    "pyrope_peer_group_destroy": (C.c_int, [vp]),
+    "pyrope_peer_group_handle": (C.c_int, [vp, vp]),
+    "pyrope_peer_group_open": (C.c_int, [vp, vp]),
+    "pyrope_peer_group_buffer": (C.c_int, [vp, C.POINTER(vp)]),
+    "pyrope_peer_group_attach": (C.c_int, [vp, C.POINTER(vp)]),
+    "pyrope_peer_allgather_device": (C.c_int, [vp, C.c_int, vp, C.c_size_t, C.POINTER(vp), vp]),
+    "pyrope_peer_last_error": (C.c_char_p, []),
     "pyrope_index_is_built": (C.c_int, [vp, i32p]),
     "pyrope_index_get_centroids": (C.c_int, [vp, vp, i32p]),
     "pyrope_index_get_codebooks": (C.c_int, [vp, vp, vp]),
@@ -364,6 +372,54 @@ class _BorrowedIndex(GpuIndex):
 
     def close(self):
         self._h = None
+
+    __del__ = close
+
+
+class PeerGroup:
+    """One rank's end of the all-gathers of a sharded search, over NVLink peer memory (pyrope_peer_*, csrc/peer.cu)."""
+
+    def __init__(self, world: int, rank: int, slot_bytes: int, n_slots: int = 1):
+        g = vp()
+        self._g = None
+        self._ck(load().pyrope_peer_group_create(world, rank, slot_bytes, n_slots, C.byref(g)))
+        self._g = g
+        self.world, self.rank = world, rank
+
+    @staticmethod
+    def _ck(rc: int):
+        if rc != OK:
+            msg = load().pyrope_peer_last_error()
+            raise PyropeGpuError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(load().pyrope_peer_group_handle(self._g, buf))
+        return buf.raw
+
+    def open(self, handles: bytes):
+        assert len(handles) == 64 * self.world
+        self._ck(load().pyrope_peer_group_open(self._g, C.create_string_buffer(handles, len(handles))))
+
+    def buffer(self) -> int:
+        out = vp()
+        self._ck(load().pyrope_peer_group_buffer(self._g, C.byref(out)))
+        return out.value
+
+    def attach(self, buffers):
+        arr = (vp * self.world)(*[vp(int(b)) if b else vp() for b in buffers])
+        self._ck(load().pyrope_peer_group_attach(self._g, arr))
+
+    def allgather(self, slot: int, src_ptr: int, bytes_per_rank: int, stream: int = 0) -> int:
+        """Enqueue the exchange on `stream`; returns the device address of [world][bytes_per_rank]."""
+        out = vp()
+        self._ck(load().pyrope_peer_allgather_device(self._g, slot, vp(src_ptr), bytes_per_rank, C.byref(out), vp(stream)))
+        return out.value
+
+    def close(self):
+        if getattr(self, "_g", None):
+            load().pyrope_peer_group_destroy(self._g)
+            self._g = None
 
     __del__ = close
 

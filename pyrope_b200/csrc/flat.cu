@@ -257,6 +257,60 @@ __global__ void __launch_bounds__(256) merge_pairs_kernel(int64_t nq, int parts,
     if (tid == 0 && out_c) out_c[q] = s_count;
 }
 
+// Few candidates per query (the multi-GPU merge: ranks x k): one WARP per query, eight queries per CTA, no block barriers.
+__global__ void __launch_bounds__(256) merge_pairs_warp_kernel(int64_t nq, int parts, int k_in, int k_out,
+                                                               const float* __restrict__ in_s,
+                                                               const int64_t* __restrict__ in_l,
+                                                               int64_t part_stride, int64_t q_stride,
+                                                               float* out_s, int64_t* out_l,
+                                                               int32_t* out_c, int P, int dedupe) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * P;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    const int total = parts * k_in;
+    for (int i = lane; i < P; i += 32) {
+        uint64_t key = 0;
+        if (i < total) {
+            const int part = i / k_in, j = i - part * k_in;
+            const int64_t a = part * part_stride + q * q_stride + j;
+            const int64_t lab = in_l[a];
+            if (lab >= 0) {
+                bool dup = false;
+                if (dedupe) {  // the same id in a lower part (the head) wins
+                    for (int pp = 0; pp < part && !dup; ++pp) {
+                        const int64_t b = pp * part_stride + q * q_stride;
+                        for (int jj = 0; jj < k_in; ++jj)
+                            if (in_l[b + jj] == lab) { dup = true; break; }
+                    }
+                }
+                if (!dup) key = make_key(in_s[a], (uint32_t)i);
+            }
+        }
+        keys[i] = key;
+    }
+    __syncwarp();
+    bitonic_sort_desc<true>(keys, P, lane, 32);
+    int local = 0;
+    for (int i = lane; i < k_out; i += 32) {
+        const uint64_t key = i < P ? keys[i] : 0ull;
+        if (key) {
+            const int idx = (int)key_pos(key);
+            const int part = idx / k_in, j = idx - part * k_in;
+            const int64_t a = part * part_stride + q * q_stride + j;
+            out_s[q * k_out + i] = in_s[a];
+            out_l[q * k_out + i] = in_l[a];
+            ++local;
+        } else {
+            out_s[q * k_out + i] = 0.f;
+            out_l[q * k_out + i] = -1;
+        }
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0 && out_c) out_c[q] = local;
+}
+
 }  // namespace
 
 int flat_scan_cap(int k) {
@@ -304,6 +358,12 @@ cudaError_t launch_merge_pairs(int64_t nq, int parts, int k_in, int k_out, const
     int total = parts * k_in;
     if (total > kMergeMaxCandidates) return cudaErrorInvalidValue;
     int P = next_pow2(total < 2 ? 2 : total);
+    if (P <= 256) {
+        merge_pairs_warp_kernel<<<(unsigned)((nq + 7) / 8), 256, sizeof(uint64_t) * (size_t)P * 8, st>>>(
+            nq, parts, k_in, k_out, in_scores, in_labels, part_stride, q_stride, out_scores, out_labels, out_counts, P,
+            dedupe ? 1 : 0);
+        return cudaGetLastError();
+    }
     merge_pairs_kernel<<<(unsigned)nq, 256, sizeof(uint64_t) * (size_t)P, st>>>(
         nq, parts, k_in, k_out, in_scores, in_labels, part_stride, q_stride, out_scores, out_labels,
         out_counts, P, dedupe ? 1 : 0);

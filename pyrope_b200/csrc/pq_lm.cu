@@ -972,6 +972,10 @@ struct LmFinalParams {
     int32_t* counts;           // nullable: results per query (when this kernel writes the search's final output)
 };
 
+// One CTA per query.  The k-th best APPROXIMATE distance is bounded with a 256-bucket histogram over the pool's range
+// (a bucket's upper edge, not a full sort: the pool holds a few hundred entries, the band a few dozen), everything within
+// the rounding band of it is compacted to the front and re-scored - one half warp per survivor - and only those
+// survivors are sorted.
 template <int SUB>
 __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -979,15 +983,21 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_n, s_m;
-    if (tid == 0) { s_n = 0; s_m = 0; }
+    __shared__ uint32_t s_lohi[2];
+    __shared__ int s_hist[256];
+    __shared__ float s_lim;
+    if (tid == 0) { s_n = 0; s_m = 0; s_lohi[0] = 0xffffffffu; s_lohi[1] = 0u; }
+    for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    // the probed lists' code ranges, once per query: a survivor's list is found by a shared-memory search below instead of
-    // dependent global loads per survivor
+    // the probed lists and their code ranges, once per query: a survivor's list is found by a shared-memory search below
+    // instead of dependent global loads per survivor
     long long* s_lo = reinterpret_cast<long long*>(keys + p.keys_cap);
     long long* s_hi = s_lo + p.P;
-    float* s_res = reinterpret_cast<float*>(s_hi + p.P) + warp * p.dim;  // m < 16: this warp's residual query
+    int* s_list = reinterpret_cast<int*>(s_hi + p.P);
+    float* s_res = reinterpret_cast<float*>(s_list + p.P) + (tid >> 4) * p.dim;  // m < 16: this half warp's residual query
     for (int sl = tid; sl < p.P; sl += blockDim.x) {
         const int64_t l = __ldg(p.probes + q * p.P + sl);
+        s_list[sl] = (int)l;
         s_lo[sl] = l >= 0 ? __ldg(p.list_off + l) : 0;
         s_hi[sl] = l >= 0 ? __ldg(p.list_off + l + 1) : 0;
     }
@@ -996,7 +1006,14 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
         const int c = min(p.pool_cnt[ps], p.kc);
         if (c > 0) {
             const int base = atomicAdd(&s_n, c);
-            for (int i = 0; i < c; ++i) keys[base + i] = p.pool[ps * p.kc + i];
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            for (int i = 0; i < c; ++i) {
+                const uint64_t key = p.pool[ps * p.kc + i];
+                keys[base + i] = key;
+                lo = min(lo, (uint32_t)(key >> 32)); hi = max(hi, (uint32_t)(key >> 32));
+            }
+            atomicMin(&s_lohi[0], lo);
+            atomicMax(&s_lohi[1], hi);
         }
     }
     __syncthreads();
@@ -1006,60 +1023,102 @@ __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     // best approximate distance can still belong to the true top k, so all of it is re-scored.
     int nres = n;
     if (n > kk) {
-        const int P2 = next_pow2(max(n, 2));
-        for (int i = n + tid; i < P2; i += blockDim.x) keys[i] = 0ull;
+        // distances run from dmin (the best score) to dmax; bucket b holds dmin + [b, b+1) / scale
+        const float dmin = -ord_to_score(s_lohi[1]), dmax = -ord_to_score(s_lohi[0]);
+        const float scale = dmax > dmin ? 255.f / (dmax - dmin) : 0.f;
+        for (int i = tid; i < n; i += blockDim.x)
+            atomicAdd(&s_hist[min(255, (int)((-key_score(keys[i]) - dmin) * scale))], 1);
         __syncthreads();
-        bitonic_sort_desc<false>(keys, P2, tid, blockDim.x);
-        const float err = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
-        const float dk = -key_score(keys[kk - 1]);
-        const float lim = dk + 2.f * err + 1e-5f * dk;
-        int mine = 0;
-        for (int i = kk + tid; i < n; i += blockDim.x) mine += (-key_score(keys[i]) <= lim);
-        if (mine) atomicAdd(&s_m, mine);  // sorted: the band is a prefix of the tail
+        if (warp == 0) {  // the first bucket where the running count reaches k: its upper edge bounds the k-th best
+            int c[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; tot += c[j]; }
+            int cum = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, cum, o);
+                if (lane >= o) cum += up;
+            }
+            const unsigned reach = __ballot_sync(0xffffffffu, cum >= kk);
+            if (lane == __ffs(reach) - 1) {
+                int run = cum - tot, b = lane * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    run += c[j];
+                    if (run >= kk) break;
+                    ++b;
+                }
+                const float edge = scale > 0.f ? fminf(dmax, dmin + (float)(b + 1) / scale * 1.00001f) : dmax;
+                const float err = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
+                s_lim = edge + 2.f * err + 2e-5f * edge;
+            }
+        }
         __syncthreads();
-        nres = kk + s_m;
+        const float lim = s_lim;
+        // compact the band to the front, a block of entries at a time (writes never pass the entries still to be read)
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            const uint64_t key = i < n ? keys[i] : 0ull;
+            const bool keep = i < n && -key_score(key) <= lim;
+            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            __syncthreads();
+            if (lane == 0 && mk) base = atomicAdd(&s_m, __popc(mk));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) keys[base + __popc(mk & ((1u << lane) - 1u))] = key;
+        }
+        __syncthreads();
+        nres = s_m;
     }
-    // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order
-    for (int i = warp; i < nres; i += blockDim.x / 32) {
-        const uint32_t pos = key_pos(keys[i]);
-        int lo = 0;  // the list holding pos is one of this query's probed lists: test them in parallel
-        for (int p0 = 0; p0 < p.P; p0 += 32) {
-            const bool hit = p0 + lane < p.P && s_lo[p0 + lane] <= (long long)pos && (long long)pos < s_hi[p0 + lane];
-            const unsigned mh = __ballot_sync(0xffffffffu, hit);
-            if (mh) { lo = (int)__ldg(p.probes + q * p.P + p0 + __ffs(mh) - 1); break; }
+    // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order; one half warp each
+    const int hl = tid & 15, hw = tid >> 4, nhw = blockDim.x >> 4;
+    const unsigned hmask = 0xffffu << (lane & 16);
+    for (int i0 = 0; i0 < nres; i0 += nhw) {  // uniform trip count: the shuffles below need the whole warp
+        const int i = i0 + hw;
+        const bool on = i < nres;
+        const uint32_t pos = key_pos(keys[on ? i : i0]);
+        int lo = 0;  // the list holding pos is one of this query's probed lists: test them sixteen at a time
+        for (int p0 = 0; p0 < p.P; p0 += 16) {
+            const bool hit = p0 + hl < p.P && s_lo[p0 + hl] <= (long long)pos && (long long)pos < s_hi[p0 + hl];
+            const unsigned mh = __ballot_sync(0xffffffffu, hit) & hmask;
+            if (mh) lo = s_list[p0 + ((__ffs(mh) - 1) & 15)];
+            if (__all_sync(0xffffffffu, mh != 0 || lo != 0)) break;  // both halves found theirs (list 0 is re-checked, harmlessly)
         }
         float dm = 0.f, dist = 0.f;
         if (p.m == 16) {
-            if (lane < 16) {
-                float r[SUB];
+            float r[SUB];
 #pragma unroll
-                for (int d = 0; d < SUB; ++d)
-                    r[d] = __fsub_rn(__ldg(p.Q + q * p.dim + lane * SUB + d), __ldg(p.centroids + (size_t)lo * p.dim + lane * SUB + d));
-                const int code = p.codes[(size_t)pos * 16 + lane];
-                dm = exact::a1_l2_fixed<SUB>(r, p.codebook + ((size_t)lane * p.ksub + code) * SUB);
-            }
+            for (int d = 0; d < SUB; ++d)
+                r[d] = __fsub_rn(__ldg(p.Q + q * p.dim + hl * SUB + d), __ldg(p.centroids + (size_t)lo * p.dim + hl * SUB + d));
+            const int code = p.codes[(size_t)pos * 16 + hl];
+            dm = exact::a1_l2_fixed<SUB>(r, p.codebook + ((size_t)hl * p.ksub + code) * SUB);
 #pragma unroll
-            for (int mi = 0; mi < 16; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, mi));
+            for (int mi = 0; mi < 16; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, (lane & 16) + mi));
         } else {
             // fewer, longer sub-vectors (dim/m = 16 .. 128): L2SquaredUnsafe's four-accumulator form applies from 32 on
             const int subr = p.dim / p.m;
-            for (int d = lane; d < p.dim; d += 32)
+            for (int d = hl; d < p.dim; d += 16)
                 s_res[d] = __fsub_rn(__ldg(p.Q + q * p.dim + d), __ldg(p.centroids + (size_t)lo * p.dim + d));
             __syncwarp();
-            if (lane < p.m) {
-                const int code = p.codes[(size_t)pos * p.m + lane];
-                dm = exact::a1_l2_eval(s_res + lane * subr, p.codebook + ((size_t)lane * p.ksub + code) * subr, subr);
+            if (hl < p.m) {
+                const int code = p.codes[(size_t)pos * p.m + hl];
+                dm = exact::a1_l2_eval(s_res + hl * subr, p.codebook + ((size_t)hl * p.ksub + code) * subr, subr);
             }
-            for (int mi = 0; mi < p.m; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, mi));
+            for (int mi = 0; mi < p.m; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, (lane & 16) + mi));
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) keys[i] = make_key(-dist, pos);
+        if (hl == 0 && on) keys[i] = make_key(-dist, pos);
     }
     __syncthreads();
     const int P3 = next_pow2(max(nres, 2));
     for (int i = nres + tid; i < P3; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
-    bitonic_sort_desc<false>(keys, P3, tid, blockDim.x);
+    if (P3 <= 64) {  // the usual case: one warp sorts without block barriers
+        if (warp == 0) bitonic_sort_desc<true>(keys, P3, lane, 32);
+        __syncthreads();
+    } else {
+        bitonic_sort_desc<false>(keys, P3, tid, blockDim.x);
+    }
     const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
     if (tid == 0 && p.counts) p.counts[q] = kk;
     for (int i = tid; i < p.k; i += blockDim.x) {
@@ -1255,8 +1314,8 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out; fp.counts = p.out_counts;
     fp.keys_cap = next_pow2(std::max(2, L.pool_cap));
     const int fthreads = L.pool_cap <= 2048 ? 128 : 256;
-    const size_t fsm = sizeof(uint64_t) * (size_t)fp.keys_cap + 2 * sizeof(long long) * (size_t)P +
-                       (p.m == 16 ? 0 : sizeof(float) * (size_t)(fthreads / 32) * p.dim);
+    const size_t fsm = sizeof(uint64_t) * (size_t)fp.keys_cap + (2 * sizeof(long long) + sizeof(int)) * (size_t)P +
+                       (p.m == 16 ? 0 : sizeof(float) * (size_t)(fthreads / 16) * p.dim);
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
     ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, fthreads, fsm, st>>>(fp);
