@@ -698,8 +698,10 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
         else:
             peak = peaks.get("bf16_tflops", 1590.0) / 2.0
             peak_src = "bf16 cuBLAS burst / 2 (TF32 dense assumed; TF32 itself unmeasured)"
-        extra["issued"] = round(3.0 * achieved, 2)          # the 3xTF32 split issues three MMAs per useful one
-        extra["issued_frac"] = round(3.0 * achieved / peak, 4)
+        terms = 1.0 if "1xTF32" in kname else 3.0          # the 3xTF32 split issues three MMAs per useful one
+        extra["mma_terms"] = int(terms)
+        extra["issued"] = round(terms * achieved, 2)
+        extra["issued_frac"] = round(terms * achieved / peak, 4)
     traffic, traffic_note = None, None
     try:
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

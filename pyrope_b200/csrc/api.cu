@@ -150,6 +150,7 @@ struct Segment {
 struct Workspace {
     DevBuf queue, pairs_s, pairs_l, cpairs_s, cpairs_l, probes, probes_raw, probe_scores, probe_cnt, allow, qnorm,
         qhi, qlo, tcq, tcc,  // tensor-core path: split queries, candidate queues, counts
+        q16, qbad,           // fp16 queries and the rows that do not fit fp16
         tcg, tct,            // two-pass threshold: group maxima, per-query tau
         q8,                  // SQ8: quantised queries
         hq, hs, hl, hc,      // h*: staging for the host-pointer entry point
@@ -162,7 +163,12 @@ struct TcOperand {
     DevBuf hi, lo, scale, bias, amax;
     int64_t rows_valid = 0;
     bool dirty = true;
-    void invalidate() { dirty = true; }
+    // fp16 copy for the one-term tensor passes (kernels.h: launch_tc_half): rows it covers, and whether every value lies
+    // within the range those passes are proven for (read back once per rebuild)
+    DevBuf h16, xabs;
+    int64_t h16_rows = 0;
+    bool h16_ok = false;
+    void invalidate() { dirty = true; h16_rows = 0; }
 };
 
 }  // namespace
@@ -1039,7 +1045,8 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         if (&op == &h->tc_seg && h->kind == PYROPE_FLAT) {
             tp.ev_k0 = h->evk[0]; tp.ev_k1 = h->evk[1];
             h->evk_valid = true;
-            h->dom_kernel = "flat_tc_kernel";
+            // one TF32 term + rigorous band (tau_ws without the two-pass maxima), or the three-term split
+            h->dom_kernel = (tp.tau_ws && !tp.gmax_ws) ? "flat_tc_kernel (1xTF32 + band)" : "flat_tc_kernel (3xTF32)";
         }
         CK(launch_flat_tc(tp, st));
         launches += 2;
@@ -1057,9 +1064,34 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
     } else if (use_ctc) {
         TcOperand& op = h->tc_cent;
         if (op.dirty || op.rows_valid < h->nc) ++launches;
+        if (op.dirty || op.rows_valid < h->nc) op.h16_rows = 0;
         TRY(ensure_tc_operand(op, h->centroids.as<float>(), h->nc, dim, h->metric, nullptr, st));
         TRY(ws.ctc.ensure(coarse_tc_scratch_bytes(nq, h->nc, g_num_sms), 0, st));
         CoarseTcParams cp{};
+        // L2 / IP, rows a multiple of 16 bytes in fp16: the tensor passes run on fp16 copies (twice the MMA rate, half the
+        // operand bytes, the same 10-bit mantissa)
+        static const bool no_f16 = getenv("PYROPE_COARSE_TF32") != nullptr;
+        if (!no_f16 && h->metric != kCosine && dim % 8 == 0) {
+            if (op.h16_rows != h->nc) {
+                TRY(op.h16.ensure(sizeof(uint16_t) * (size_t)h->nc * dim, 0, st));
+                TRY(op.xabs.ensure(sizeof(float), 0, st, true));
+                CK(cudaMemsetAsync(op.xabs.p, 0, sizeof(float), st));
+                CK(launch_tc_half(h->centroids.as<float>(), (int64_t)h->nc * dim, op.h16.p, op.xabs.as<float>(), st));
+                float xabs = 0.f;
+                CK(cudaMemcpyAsync(&xabs, op.xabs.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                op.h16_ok = xabs <= kTcHalfMaxAbs;
+                op.h16_rows = h->nc;
+                ++launches;
+            }
+            if (op.h16_ok) {
+                TRY(ws.q16.ensure(sizeof(uint16_t) * (size_t)nq * dim, 0, st));
+                TRY(ws.qbad.ensure((size_t)nq, 0, st));
+                CK(launch_tc_half_rows(dQ, nq, dim, ws.q16.p, ws.qbad.as<uint8_t>(), st));
+                ++launches;
+                cp.Q16 = ws.q16.p; cp.C16 = op.h16.p; cp.qbad = ws.qbad.as<uint8_t>();
+            }
+        }
         cp.Q = dQ; cp.Qhi = ws.qhi.as<float>(); cp.nq = nq; cp.dim = dim; cp.metric = h->metric;
         cp.C = h->centroids.as<float>(); cp.Chi = op.hi.as<float>(); cp.cnorms = h->cnorms.as<float>(); cp.nc = h->nc;
         cp.scale = op.scale.as<float>(); cp.bias = op.bias.as<float>(); cp.amax = op.amax.as<float>();

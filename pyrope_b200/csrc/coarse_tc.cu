@@ -103,6 +103,13 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -142,6 +149,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
 constexpr uint32_t kCoarseIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16 with fp16 operands (format 0), fp32 accumulate: the same 10-bit mantissa as tf32 at twice the rate and half the
+// operand bytes - a 128-byte swizzle atom holds 64 elements, one MMA consumes 16
+constexpr uint32_t kCoarseIdescF16 = (1u << 4) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct CoarseParams {
     int64_t nq, n_scan;
@@ -159,7 +169,7 @@ struct CoarseParams {
     int cap, parts;
 };
 
-template <bool PASS_B>
+template <bool PASS_B, bool F16>
 __global__ void __launch_bounds__(C_THREADS, 1)
 coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, CoarseParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -178,7 +188,9 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int64_t total = p.qtiles * p.ntiles;
     const int64_t u0 = total * (int64_t)blockIdx.x / gridDim.x, u1 = total * ((int64_t)blockIdx.x + 1) / gridDim.x;
     const int nunit = (int)(u1 - u0);
-    const int KC = (p.dim + CBK - 1) / CBK;
+    constexpr int CBE = F16 ? 2 * CBK : CBK;  // elements per 128-byte K chunk
+    constexpr int KI = F16 ? 16 : 8;          // elements one MMA consumes (32 bytes either way)
+    const int KC = (p.dim + CBE - 1) / CBE;
 
     if (tid == 0) {
         for (int i = 0; i < XSTAGES; ++i) { mbar_init(xfull0 + 8 * i, 1); mbar_init(xempty0 + 8 * i, 1); }
@@ -214,7 +226,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     if (qloads > 0) mbar_wait(qempty, (qloads - 1) & 1);
                     mbar_expect_tx(qfull, (uint32_t)(KC * QCHUNK_BYTES));
                     for (int kc = 0; kc < KC; ++kc)
-                        tma_load_2d(smem_u32(qs + kc * QCHUNK_BYTES), &map_q, qfull, kc * CBK, (int)(qt * CQ));
+                        tma_load_2d(smem_u32(qs + kc * QCHUNK_BYTES), &map_q, qfull, kc * CBE, (int)(qt * CQ));
                     ++qloads;
                     newq = false;
                 }
@@ -222,7 +234,7 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(xempty0 + 8 * s, ph ^ 1);
                     mbar_expect_tx(xfull0 + 8 * s, XSTAGE_BYTES);
-                    tma_load_2d(smem_u32(xs) + s * XSTAGE_BYTES, &map_x, xfull0 + 8 * s, kc * CBK, n0);
+                    tma_load_2d(smem_u32(xs) + s * XSTAGE_BYTES, &map_x, xfull0 + 8 * s, kc * CBE, n0);
                     if (++s == XSTAGES) { s = 0; ph ^= 1; }
                 }
                 if (++nt == ntiles_i) { nt = 0; ++qt; newq = true; }
@@ -256,11 +268,16 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         const uint64_t xd = xd_base + (uint64_t)s * kXStep;
                         const uint64_t qd0 = qd_base + (uint64_t)kc * kQStep, qd1 = qd0 + kHalf;
 #pragma unroll
-                        for (int k4 = 0; k4 < CBK / 8; ++k4) {
-                            if (kc * CBK + k4 * 8 < p.dim) {
-                                const uint64_t adv = (uint64_t)(k4 * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                                tc_mma_tf32(d0, qd0 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
-                                tc_mma_tf32(d0 + CN, qd1 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            if (kc * CBE + k4 * KI < p.dim) {
+                                const uint64_t adv = (uint64_t)(k4 * 2);  // one MMA's K slice = 32 bytes = 2 x 16-byte units
+                                if (F16) {
+                                    tc_mma_f16(d0, qd0 + adv, xd + adv, kCoarseIdescF16, (kc | k4) != 0);
+                                    tc_mma_f16(d0 + CN, qd1 + adv, xd + adv, kCoarseIdescF16, (kc | k4) != 0);
+                                } else {
+                                    tc_mma_tf32(d0, qd0 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
+                                    tc_mma_tf32(d0 + CN, qd1 + adv, xd + adv, kCoarseIdesc, (kc | k4) != 0);
+                                }
                             }
                         }
                         tc_commit(xempty0 + 8 * s);  // frees the centroid stage when these MMAs retire
@@ -405,7 +422,8 @@ template <int R>  // registers per lane: groups <= 32 R
 __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict__ umax, int64_t nq_pad, int ntiles, int64_t nq,
                                                         int kprime, const float* __restrict__ Q, int dim,
                                                         const float* __restrict__ amax, float* tau_out,
-                                                        const float* __restrict__ C, int64_t c_bytes, float eband) {
+                                                        const float* __restrict__ C, int64_t c_bytes, float eband, float under,
+                                                        float smax, const uint8_t* __restrict__ qbad) {
     extern __shared__ float s_u[];  // [32][ntiles + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // The exact ranking (two kernels from now) reads ~100 scattered fp32 centroid rows per query: pull the table from
@@ -462,12 +480,14 @@ __global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict
             float qq = 0.f;
             for (int d = lane; d < dim; d += 32) { const float v = __ldg(Q + q * dim + d); qq = fmaf(v, v, qq); }
             qq = warp_sum(qq);
-            const float E = eband * sqrtf(qq) * __ldg(amax);  // 2^-10 (1 + 2^-7) |q| A
+            // 2^-10 (1 + 2^-7) |q| A; fp16 operands add the absolute error of values below 2^-14 (<= 2^-25 each)
+            const float E = eband * sqrtf(qq) * __ldg(amax) + under * (smax * sqrtf(qq) + __ldg(amax));
             // accept s > tau: everything >= G - 2E, with room for the fp32 rounding of the proxy itself and for the
             // difference between exact arithmetic and the reference's evaluation order (both ~1e-6 relative)
             tau = G - 2.f * E - 4e-6f * fabsf(G) - 1e-30f;
             tau = fminf(tau, G);
             tau = tau > -INFINITY ? nextafterf(tau, -INFINITY) : tau;
+            if (qbad && qbad[q]) tau = -INFINITY;  // a component beyond the fp16 range: no bound holds, rank everything exactly
         }
         if (lane == 0) tau_out[q] = tau;
     }
@@ -596,14 +616,14 @@ EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dim, int box_rows) {
+bool make_map(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows, bool f16 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)dim * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)CBK, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * CBK : CBK), (cuuint32_t)box_rows};  // 128 bytes wide either way
     cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -637,10 +657,63 @@ CoarseLayout coarse_layout(int64_t nq, int64_t nc, int num_sms) {
     return L;
 }
 
+// ---- fp16 operand copies ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t f2h_sat(float x) {
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+}
+__global__ void __launch_bounds__(256) tc_half_kernel(const float* __restrict__ X, int64_t n, uint16_t* __restrict__ out, float* absmax) {
+    float mx = 0.f;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < n) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(X + i));
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            const uint32_t lo = (uint32_t)f2h_sat(v.x) | ((uint32_t)f2h_sat(v.y) << 16);
+            const uint32_t hi = (uint32_t)f2h_sat(v.z) | ((uint32_t)f2h_sat(v.w) << 16);
+            *reinterpret_cast<uint2*>(out + i) = make_uint2(lo, hi);
+        } else {
+            for (int64_t j = i; j < n; ++j) { mx = fmaxf(mx, fabsf(X[j])); out[j] = f2h_sat(X[j]); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // NaN compares false everywhere above: it never raises the maximum, and its fp16 copy is NaN (scores NaN, as the
+    // reference's own arithmetic would give)
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(mx));
+}
+__global__ void __launch_bounds__(256) tc_half_rows_kernel(const float* __restrict__ Q, int64_t nq, int dim, uint16_t* __restrict__ out,
+                                                           uint8_t* __restrict__ bad) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nq) return;
+    float mx = 0.f;
+    for (int d = lane; d < dim; d += 32) {
+        const float v = __ldg(Q + r * dim + d);
+        mx = fmaxf(mx, fabsf(v));
+        out[r * dim + d] = f2h_sat(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) bad[r] = !(mx <= kTcHalfMaxAbs);
+}
+
 }  // namespace
 
 // The unit maxima only bound the k'-th best score when there are comfortably more units than k'; smaller tables and
 // dim > 128 stay on the streaming kernel (flat_tc.cu).
+cudaError_t launch_tc_half(const float* X, int64_t n_elems, void* out16, float* absmax, cudaStream_t st) {
+    if (n_elems <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_elems / 4 + 255) / 256 + 1, 148 * 32);
+    tc_half_kernel<<<grid, 256, 0, st>>>(X, n_elems, static_cast<uint16_t*>(out16), absmax);
+    return cudaGetLastError();
+}
+cudaError_t launch_tc_half_rows(const float* Q, int64_t nq, int dim, void* out16, uint8_t* bad, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    tc_half_rows_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(Q, nq, dim, static_cast<uint16_t*>(out16), bad);
+    return cudaGetLastError();
+}
+
 bool coarse_tc_supported(int dim, int64_t nc, int nprobe) {
     int fine = 0;
     return dim % 4 == 0 && dim >= 8 && dim <= CKC * CBK && nprobe >= 1 && nprobe <= kCoarseTcCap / 2 &&
@@ -657,8 +730,15 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     CUtensorMap mq, mx;
     // (Feeding the fp32 table itself to kind::tf32 - truncation, band 1.5x - was measured: 45% more survivors on the
     // C5 centroids, and the exact ranking gathers them from HBM either way: 0.35 ms instead of 0.28.)
-    const float eband = 9.85e-4f;  // 2^-10 (1 + 2^-7): both operands rounded to nearest tf32
-    if (!make_map(&mq, a.Qhi, a.nq, a.dim, CQ) || !make_map(&mx, a.Chi, a.nc, a.dim, CN)) return cudaErrorInvalidValue;
+    const float eband = 9.85e-4f;  // 2^-10 (1 + 2^-7): both operands rounded to nearest tf32 - or to nearest fp16
+    const bool f16 = a.Q16 && a.C16;
+    // fp16: a value below 2^-14 is rounded with an ABSOLUTE error of at most 2^-25; summed over the row,
+    // sum_i (|q_i| + |c_i|) 2^-25 <= 2^-25 sqrt(d) (|q| + |c|)   (twice that, for the products of two such errors and slack)
+    const float under = f16 ? 5.97e-8f * sqrtf((float)a.dim) : 0.f;
+    const float smax = a.metric == kL2 ? 2.f : 1.f;  // |scale| of the proxy score (launch_tc_prepare)
+    if (f16 ? (!make_map(&mq, a.Q16, a.nq, a.dim, CQ, true) || !make_map(&mx, a.C16, a.nc, a.dim, CN, true))
+            : (!make_map(&mq, a.Qhi, a.nq, a.dim, CQ) || !make_map(&mx, a.Chi, a.nc, a.dim, CN)))
+        return cudaErrorInvalidValue;
     CoarseParams p{};
     p.nq = a.nq; p.n_scan = a.nc; p.dim = a.dim; p.qtiles = L.qtiles; p.ntiles = L.ntiles; p.nq_pad = L.nq_pad;
     p.scale = a.scale; p.bias = a.bias;
@@ -669,9 +749,11 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     p.cap = L.cap; p.parts = L.parts;
     cudaError_t e = cudaMemsetAsync(p.qcnt, 0, sizeof(int32_t) * (size_t)L.nq_pad * L.parts, st);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(coarse_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
+    auto* passA = f16 ? coarse_tc_kernel<false, true> : coarse_tc_kernel<false, false>;
+    auto* passB = f16 ? coarse_tc_kernel<true, true> : coarse_tc_kernel<true, false>;
+    e = cudaFuncSetAttribute(passA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(coarse_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
+    e = cudaFuncSetAttribute(passB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM);
     if (e != cudaSuccess) return e;
     static const bool dbg = getenv("PYROPE_COARSE_DEBUG") != nullptr;
     cudaEvent_t dev[5];
@@ -682,23 +764,23 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     if (ngroups <= 0) return cudaErrorInvalidValue;
     const size_t tsm = sizeof(float) * 32 * ((size_t)ngroups + 1);
     mark(0);
-    coarse_tc_kernel<false><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
+    passA<<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
     mark(1);
     if (ngroups <= 512) {
         e = cudaFuncSetAttribute(coarse_tau_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return e;
         coarse_tau_kernel<16><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
             p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau), a.C,
-            (int64_t)sizeof(float) * a.nc * a.dim, eband);
+            (int64_t)sizeof(float) * a.nc * a.dim, eband, under, smax, f16 ? a.qbad : nullptr);
     } else {
         e = cudaFuncSetAttribute(coarse_tau_kernel<TAU_MAXU / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return e;
         coarse_tau_kernel<TAU_MAXU / 32><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
             p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau), a.C,
-            (int64_t)sizeof(float) * a.nc * a.dim, eband);
+            (int64_t)sizeof(float) * a.nc * a.dim, eband, under, smax, f16 ? a.qbad : nullptr);
     }
     mark(2);
-    coarse_tc_kernel<true><<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
+    passB<<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
     mark(3);
     const size_t rsm = sizeof(uint64_t) * RANK_KEYS + sizeof(uint32_t) * RANK_SPOS + sizeof(float) * (size_t)a.dim;
     if (a.metric == kL2)

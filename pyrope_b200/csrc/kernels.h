@@ -98,10 +98,18 @@ struct CoarseTcParams {
     const float* Q; const float* Qhi; int64_t nq; int dim; int metric;
     const float* C; const float* Chi; const float* cnorms; int64_t nc;
     const float* scale; const float* bias; const float* amax;   // proxy terms of the centroid operand (TcOperand)
+    // optional fp16 copies of both operands (launch_tc_half*): the tensor passes then run kind::f16.  Only for tables whose
+    // values all fit the fp16 range; qbad [nq] marks queries that do not (they are ranked exhaustively).  L2 / IP only.
+    const void* Q16 = nullptr; const void* C16 = nullptr; const uint8_t* qbad = nullptr;
     int nprobe; int64_t* probes_out;
     void* scratch; int num_sms;
 };
 bool coarse_tc_supported(int dim, int64_t nc, int nprobe);
+// fp16 copy of a table, round to nearest, saturating; absmax (device, zero-initialised by the caller) receives max |x|
+cudaError_t launch_tc_half(const float* X, int64_t n_elems, void* out16, float* absmax, cudaStream_t st);
+// the same per query row; bad[q] = 1 when a component of row q lies beyond the range the fp16 passes are proven for
+cudaError_t launch_tc_half_rows(const float* Q, int64_t nq, int dim, void* out16, uint8_t* bad, cudaStream_t st);
+constexpr float kTcHalfMaxAbs = 32768.f;
 size_t coarse_tc_scratch_bytes(int64_t nq, int64_t nc, int num_sms);
 int coarse_tc_launches();
 cudaError_t launch_coarse_tc(const CoarseTcParams& p, cudaStream_t st);

@@ -179,4 +179,4 @@ def test_flat_tc_two_pass_one_term_many_splits(gpu, force_tc, nq, metric):
     ix.add(base)
     for k in (40, 100):
         assert_batch_equivalent(ref.search_batch(q, k), _s(ix, q, k), ctx=f"two-pass one-term nq={nq} k={k}")
-    assert ix.last_search_kernel()[0] == "flat_tc_kernel"
+    assert ix.last_search_kernel()[0].startswith("flat_tc_kernel")
