@@ -698,7 +698,10 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
         else:
             peak = peaks.get("bf16_tflops", 1590.0) / 2.0
             peak_src = "bf16 cuBLAS burst / 2 (TF32 dense assumed; TF32 itself unmeasured)"
-        terms = 1.0 if "1xTF32" in kname else 3.0          # the 3xTF32 split issues three MMAs per useful one
+        terms = 1.0 if "1x" in kname else 3.0              # the 3xTF32 split issues three MMAs per useful one
+        if "FP16" in kname and peaks.get("bf16_tflops"):   # kind::f16 runs at the bf16 rate: that is this pass's pipe peak
+            peak, peak_src = round(float(peaks["bf16_tflops"]), 1), "MEASURED_PEAKS.json bf16_tflops (kind::f16 pass)"
+            extra["tf32_peak"] = round(tp["tflops"], 1) if tp["tflops"] else None
         extra["mma_terms"] = int(terms)
         extra["issued"] = round(terms * achieved, 2)
         extra["issued_frac"] = round(terms * achieved / peak, 4)

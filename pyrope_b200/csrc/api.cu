@@ -1036,6 +1036,30 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             tp.tau_ws = ws.tct.as<float>();
             tp.amax = op.amax.as<float>();
             launches += 2;
+            // L2 / IP: the pass runs on fp16 copies of both operands when every table value fits the fp16 range
+            static const bool no_f16 = getenv("PYROPE_FLAT_TF32") != nullptr;
+            if (!no_f16 && h->metric != kCosine && dim % 8 == 0) {
+                if (op.h16_rows < n_rows) {
+                    // the copy covers whole tables only (rows appended since are converted together with the rest)
+                    TRY(op.h16.ensure(sizeof(uint16_t) * (size_t)n_rows * dim, 0, st));
+                    TRY(op.xabs.ensure(sizeof(float), 0, st, true));
+                    CK(cudaMemsetAsync(op.xabs.p, 0, sizeof(float), st));
+                    CK(launch_tc_half(X, n_rows * dim, op.h16.p, op.xabs.as<float>(), st));
+                    float xabs = 0.f;
+                    CK(cudaMemcpyAsync(&xabs, op.xabs.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    op.h16_ok = xabs <= kTcHalfMaxAbs;
+                    op.h16_rows = n_rows;
+                    ++launches;
+                }
+                if (op.h16_ok) {
+                    TRY(ws.q16.ensure(sizeof(uint16_t) * (size_t)nq * dim, 0, st));
+                    TRY(ws.qbad.ensure((size_t)nq, 0, st));
+                    CK(launch_tc_half_rows(dQ, nq, dim, ws.q16.p, ws.qbad.as<uint8_t>(), st));
+                    ++launches;
+                    tp.Q16 = ws.q16.p; tp.X16 = op.h16.p; tp.qbad = ws.qbad.as<uint8_t>();
+                }
+            }
         }
         const int64_t nq_pad = flat_tc_nq_pad(nq);
         const size_t tparts = (size_t)tp.splits * flat_tc_parts_per_split(tp);
@@ -1046,7 +1070,8 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             tp.ev_k0 = h->evk[0]; tp.ev_k1 = h->evk[1];
             h->evk_valid = true;
             // one TF32 term + rigorous band (tau_ws without the two-pass maxima), or the three-term split
-            h->dom_kernel = (tp.tau_ws && !tp.gmax_ws) ? "flat_tc_kernel (1xTF32 + band)" : "flat_tc_kernel (3xTF32)";
+            h->dom_kernel = (tp.tau_ws && !tp.gmax_ws) ? (tp.X16 ? "flat_tc_kernel (1xFP16 + band)" : "flat_tc_kernel (1xTF32 + band)")
+                                                       : "flat_tc_kernel (3xTF32)";
         }
         CK(launch_flat_tc(tp, st));
         launches += 2;

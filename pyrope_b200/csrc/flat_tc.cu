@@ -90,6 +90,13 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -118,6 +125,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16, fp16 operands (format 0), fp32 accumulate: 16 elements per MMA, 64 per 128-byte chunk
+constexpr uint32_t kInstrDescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// one-term passes load one Q and one X chunk per stage (48 KiB): four stages fit where the three-term split holds two
+constexpr int STAGES1 = 4, STAGE1_BYTES = QH_BYTES + XH_BYTES;
+static_assert(STAGES1 * STAGE1_BYTES == STAGES * STAGE_BYTES, "both layouts fill the same shared memory");
 
 struct TcParams {
     int64_t nq, n_scan;
@@ -132,7 +144,8 @@ struct TcParams {
     // maximum proxy score of every 32-row group; pass B starts every query at tau_init instead of -inf
     float uscale;        // metric with one scale for every row (L2: 2, IP: 1): skip the per-row scale loads
     int has_uscale;
-    int one_term;        // pass A only: D = Qhi.Xhi (1xTF32, hi tiles only); the select step covers the error
+    int one_term;        // D = Qhi.Xhi only (one product per K slice; the band / select step covers the error)
+    int f16;             // one_term with fp16 operands behind map_qhi / map_xhi (kind::f16)
     float* gmax;         // [nq_pad][gstride]
     int64_t gstride;     // groups per query = ntiles * 8
     const float* tau_init;  // [nq_pad] nullable
@@ -159,18 +172,22 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     float* sterms = reinterpret_cast<float*>(tmem_ptr_s + 4);  // [4 warps][bias 2*BN | scale 2*BN]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES1]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES1]), tempty0 = smem_u32(&bars[2 * STAGES1 + 2]);
+    // stage ring: four 48 KiB stages (one Q chunk, one X chunk) for one-term passes, two 96 KiB stages (hi and lo of both)
+    const uint32_t nsm = p.one_term ? STAGES1 - 1 : STAGES - 1, nsh = p.one_term ? 2 : 1;
+    const uint32_t stage_bytes = p.one_term ? STAGE1_BYTES : STAGE_BYTES, xoff = p.one_term ? QH_BYTES : 2 * QH_BYTES;
+    const int BKE = p.f16 ? 2 * BK : BK;  // elements per 128-byte K chunk
 
     const int64_t qtiles = (p.nq + BM - 1) / BM;
     const int64_t qt = blockIdx.x % qtiles, sp = blockIdx.x / qtiles;
     const int64_t t_begin = sp * p.tiles_per_split;
     const int64_t t_end = min(p.ntiles, t_begin + p.tiles_per_split);
     const int ntile = (int)max((int64_t)0, t_end - t_begin);
-    const int KC = (p.dim + BK - 1) / BK;
+    const int KC = (p.dim + BKE - 1) / BKE;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < STAGES1; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4 * p.halves); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -190,12 +207,12 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             for (int ti = 0; ti < ntile; ++ti) {
                 const int n0 = (int)((t_begin + ti) * BN);
                 for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t s = it & nsm, ph = (it >> nsh) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    const uint32_t sb = smem_u32(stage_base + s * STAGE_BYTES);
-                    mbar_expect_tx(full0 + 8 * s, p.one_term ? QH_BYTES + XH_BYTES : STAGE_BYTES);
-                    tma_load_2d(sb, &map_qhi, full0 + 8 * s, kc * BK, (int)(qt * BM));
-                    tma_load_2d(sb + 2 * QH_BYTES, &map_xhi, full0 + 8 * s, kc * BK, n0);
+                    const uint32_t sb = smem_u32(stage_base) + s * stage_bytes;
+                    mbar_expect_tx(full0 + 8 * s, stage_bytes);
+                    tma_load_2d(sb, &map_qhi, full0 + 8 * s, kc * BKE, (int)(qt * BM));
+                    tma_load_2d(sb + xoff, &map_xhi, full0 + 8 * s, kc * BKE, n0);
                     if (!p.one_term) {
                         tma_load_2d(sb + QH_BYTES, &map_qlo, full0 + 8 * s, kc * BK, (int)(qt * BM));
                         tma_load_2d(sb + 2 * QH_BYTES + XH_BYTES, &map_xlo, full0 + 8 * s, kc * BK, n0);
@@ -213,16 +230,18 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t s = it & nsm, ph = (it >> nsh) & 1;
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t sb = smem_u32(stage_base + s * STAGE_BYTES);
+                    const uint32_t sb = smem_u32(stage_base) + s * stage_bytes;
                     const uint64_t qhi = make_sw128_desc(sb), qlo = make_sw128_desc(sb + QH_BYTES);
-                    const uint64_t xhi = make_sw128_desc(sb + 2 * QH_BYTES), xlo = make_sw128_desc(sb + 2 * QH_BYTES + XH_BYTES);
+                    const uint64_t xhi = make_sw128_desc(sb + xoff), xlo = make_sw128_desc(sb + 2 * QH_BYTES + XH_BYTES);
 #pragma unroll
                     for (int k4 = 0; k4 < BK / 8; ++k4) {
                         const uint64_t adv = (uint64_t)(k4 * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                        if (p.one_term) {
+                        if (p.f16) {
+                            tc_mma_f16(d_tmem, qhi + adv, xhi + adv, kInstrDescF16, (kc | k4) != 0);
+                        } else if (p.one_term) {
                             tc_mma_tf32(d_tmem, qhi + adv, xhi + adv, kInstrDesc, (kc | k4) != 0);
                         } else {
                             tc_mma_tf32(d_tmem, qlo + adv, xhi + adv, kInstrDesc, (kc | k4) != 0);
@@ -507,8 +526,11 @@ __global__ void __launch_bounds__(128) tc_gmax_select_kernel(const float* __rest
 
 // ---- single one-TF32 pass (long K: the FLAT scan of BASELINE config 4): no pass A, every query starts cold and prunes
 // with the rounding band of the one-term product, eps_q = 2 x 2^-10 (1 + 2^-7) |q| max_r(|scale_r| |x_r|) (see above).
+// fp16 operands: + the absolute error of components below 2^-14 (under = 2^-24 sqrt(d), smax = |scale|); a query with a
+// component beyond the fp16 range gets an infinite band - its queue overflows and the three-term pass redoes the batch.
 __global__ void __launch_bounds__(128) tc_band_kernel(const float* __restrict__ Q, int dim, int64_t nq, const float* __restrict__ amax,
-                                                     float* band_out, int* overflow) {
+                                                     float* band_out, int* overflow, float under, float smax,
+                                                     const uint8_t* __restrict__ qbad) {
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 0;
@@ -516,7 +538,12 @@ __global__ void __launch_bounds__(128) tc_band_kernel(const float* __restrict__ 
     float qq = 0.f;
     for (int d = lane; d < dim; d += 32) { const float v = __ldg(Q + q * dim + d); qq = fmaf(v, v, qq); }
     qq = warp_sum(qq);
-    if (lane == 0) band_out[q] = 2.f * 9.85e-4f * sqrtf(qq) * __ldg(amax) * 1.0001f + 1e-30f;
+    if (lane == 0) {
+        const float A = __ldg(amax), qn = sqrtf(qq);
+        float b = 2.f * (9.85e-4f * qn * A + under * (smax * qn + A)) * 1.0001f + 1e-30f;
+        if (qbad && qbad[q]) b = INFINITY;
+        band_out[q] = b;
+    }
 }
 
 // ---- exact fp32 re-score of the survivors + final ordering -------------------------------------
@@ -736,14 +763,14 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dim, int box_rows) {
+bool make_map(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows, bool f16 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)dim * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * BK : BK), (cuuint32_t)box_rows};  // 128 bytes wide either way
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -863,8 +890,11 @@ cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
         // ONE one-TF32 pass with band pruning (a third of the MMAs and half the operand traffic of the 3xTF32 split);
         // a queue that cannot be pruned below its capacity raises the flag and the three-term pass behind redoes the batch
         const int64_t nq_pad = flat_tc_nq_pad(a.nq);
+        const bool f16 = a.Q16 && a.X16;
         tc_band_kernel<<<(unsigned)((a.nq + 3) / 4), 128, 0, st>>>(a.Q, a.dim, a.nq, a.amax, a.tau_ws + nq_pad,
-                                                                   reinterpret_cast<int*>(a.tau_ws + 2 * nq_pad));
+                                                                   reinterpret_cast<int*>(a.tau_ws + 2 * nq_pad),
+                                                                   f16 ? 5.97e-8f * sqrtf((float)a.dim) : 0.f,
+                                                                   a.metric == kL2 ? 2.f : 1.f, f16 ? a.qbad : nullptr);
         cudaError_t e = launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st, 1);
         if (e != cudaSuccess) return e;
         return launch_flat_tc_pass(a, a.splits, nullptr, nullptr, st, 2);
@@ -893,10 +923,13 @@ cudaError_t launch_flat_tc_select(const FlatTcParams& a, cudaStream_t st) {
 static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float* gmax, const float* tau_init, cudaStream_t st,
                                        int mode) {
     CUtensorMap mqh, mql, mxh, mxl;
-    if (!make_map(&mqh, a.Qhi, a.nq, a.dim, BM) || !make_map(&mql, a.Qlo, a.nq, a.dim, BM) ||
-        !make_map(&mxh, a.Xhi, a.n_rows, a.dim, BN) || !make_map(&mxl, a.Xlo, a.n_rows, a.dim, BN))
+    const bool f16 = mode == 1 && !gmax && a.Q16 && a.X16;  // the single one-term pass on fp16 copies
+    if (!make_map(&mql, a.Qlo, a.nq, a.dim, BM) || !make_map(&mxl, a.Xlo, a.n_rows, a.dim, BN)) return cudaErrorInvalidValue;
+    if (f16 ? (!make_map(&mqh, a.Q16, a.nq, a.dim, BM, true) || !make_map(&mxh, a.X16, a.n_rows, a.dim, BN, true))
+            : (!make_map(&mqh, a.Qhi, a.nq, a.dim, BM) || !make_map(&mxh, a.Xhi, a.n_rows, a.dim, BN)))
         return cudaErrorInvalidValue;
     TcParams p{};
+    p.f16 = f16 ? 1 : 0;
     p.nq = a.nq; p.n_scan = a.n_scan; p.dim = a.dim; p.kprime = a.kprime; p.cap = a.cap; p.splits = splits;
     p.ntiles = (a.n_scan + BN - 1) / BN;
     p.tiles_per_split = (p.ntiles + splits - 1) / splits;

@@ -49,6 +49,9 @@ struct FlatTcParams {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded around the tcgen05 kernel alone
     uint64_t* queue; int32_t* counts;        // scratch [splits][nq_pad][cap], [splits][nq_pad]
     const float* amax = nullptr;             // optional: max_r |scale_r||x_r| of the operand => pass A runs 1xTF32
+    // optional fp16 copies (launch_tc_half*) for the single one-term pass (L2 / IP, every table value within the fp16
+    // range; qbad [nq] marks queries that are not): kind::f16 at twice the tf32 rate and half the operand bytes
+    const void* Q16 = nullptr; const void* X16 = nullptr; const uint8_t* qbad = nullptr;
     float* gmax_ws = nullptr;                // optional two-pass threshold scratch: flat_tc_gmax_floats() floats
     float* tau_ws = nullptr;                 //   and flat_tc_nq_pad() floats (both set => two passes)
     PairOut out;                             // writes ONE part (splits are reduced by the re-score)

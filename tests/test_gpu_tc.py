@@ -180,3 +180,55 @@ def test_flat_tc_two_pass_one_term_many_splits(gpu, force_tc, nq, metric):
     for k in (40, 100):
         assert_batch_equivalent(ref.search_batch(q, k), _s(ix, q, k), ctx=f"two-pass one-term nq={nq} k={k}")
     assert ix.last_search_kernel()[0].startswith("flat_tc_kernel")
+
+
+# ------------------------------------------------------------------------------------------------
+# long rows (d > 256, >= 65,536 rows): ONE product per K slice on fp16 copies + rigorous band + exact re-score
+# ------------------------------------------------------------------------------------------------
+def _flat_pair(gpu, metric, base):
+    ref = orc.FlatIndex(base.shape[1], metric)
+    ref.add_batch(base)
+    ix = gpu.GpuIndex(gpu.FLAT, base.shape[1], gpu.L2 if metric == orc.L2 else gpu.INNER_PRODUCT)
+    ix.add(base)
+    return ref, ix
+
+
+@pytest.mark.parametrize("metric", [orc.L2, orc.IP])
+def test_flat_one_term_fp16_pass_matches_oracle(gpu, metric):
+    rng = np.random.default_rng(310)
+    base = rng.random((70_000, 320), dtype=np.float32)
+    base[300:340] = base[299] + rng.random((40, 320), dtype=np.float32) * 1e-4   # a cluster inside one rounding band
+    q = rng.random((150, 320), dtype=np.float32)
+    q[:4] = base[299] + 1e-3
+    ref, ix = _flat_pair(gpu, metric, base)
+    for k in (10, 100):
+        rid, rsc, rcn = ref.search_batch(q, k)
+        got = _s(ix, q, k)
+        assert ix.last_search_kernel()[0] == "flat_tc_kernel (1xFP16 + band)"
+        assert_batch_equivalent((rid, rsc, rcn), got, ctx=f"one-term fp16 k={k}")
+        same = rid == got[0]
+        np.testing.assert_array_equal(rsc[same], got[1][same])   # scores come from the exact re-score
+
+
+def test_flat_one_term_fp16_range_edges(gpu):
+    rng = np.random.default_rng(311)
+    # every value below fp16's smallest normal
+    tiny = (rng.random((66_000, 264), dtype=np.float32) * np.float32(2e-5)).astype(np.float32)
+    ref, ix = _flat_pair(gpu, orc.IP, tiny)
+    q = (rng.random((40, 264), dtype=np.float32) * np.float32(2e-5)).astype(np.float32)
+    assert_batch_equivalent(ref.search_batch(q, 20), _s(ix, q, 20), ctx="fp16 underflow")
+    # magnitudes eight orders apart inside a row
+    mag = np.where(np.arange(264) % 3 == 0, np.float32(1.5e4), np.float32(1e-4)).astype(np.float32)
+    mixed = (rng.random((66_000, 264), dtype=np.float32) * mag).astype(np.float32)
+    ref, ix = _flat_pair(gpu, orc.L2, mixed)
+    q = (rng.random((40, 264), dtype=np.float32) * mag).astype(np.float32)
+    assert_batch_equivalent(ref.search_batch(q, 20), _s(ix, q, 20), ctx="fp16 mixed magnitudes")
+    # one query beyond fp16: its band is infinite, the three-term pass redoes the batch
+    q[7, 0] = np.float32(2.0e5)
+    assert_batch_equivalent(ref.search_batch(q, 20), _s(ix, q, 20), ctx="query beyond fp16")
+    # a table value beyond fp16: the tf32 one-term pass is kept
+    mixed[123, 3] = np.float32(1.0e6)
+    ref, ix = _flat_pair(gpu, orc.L2, mixed)
+    q = (rng.random((40, 264), dtype=np.float32) * mag).astype(np.float32)
+    assert_batch_equivalent(ref.search_batch(q, 20), _s(ix, q, 20), ctx="table beyond fp16")
+    assert ix.last_search_kernel()[0] == "flat_tc_kernel (1xTF32 + band)"
