@@ -78,10 +78,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same into the shared memory of every CTA of the cluster named in `mask` (same offset), completing bytes on each
+// CTA's own barrier at the same offset
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -146,6 +162,14 @@ struct TcParams {
     int has_uscale;
     int one_term;        // D = Qhi.Xhi only (one product per K slice; the band / select step covers the error)
     int f16;             // one_term with fp16 operands behind map_qhi / map_xhi (kind::f16)
+    // one_term, launched as clusters of two CTAs (neighbouring query tiles, same row range): each CTA fetches HALF of every X
+    // chunk and multicasts it into both (map_xlo = the half-height X box), so a chunk costs 32 KiB of L2 -> SM traffic per
+    // SM instead of 48.  qtiles_grid = query tiles rounded up to a whole number of clusters: the CTAs past the last real
+    // tile are ghosts that only fetch and release.  (Measured on C4: 159 -> 147 ms per batch at 2 CTAs, no further gain at
+    // 4; an L2 prefetch of the next tile's rows made it slower.  The kernel runs under the board's power cap - SM clock
+    // ~1.1-1.45 GHz of 1.965 - so what counts is energy per MMA, not bytes in flight.)
+    int cluster;         // CTAs per cluster (0: none, 2 or 4): each fetches 1/cluster of every X chunk
+    int64_t qtiles_grid;
     float* gmax;         // [nq_pad][gstride]
     int64_t gstride;     // groups per query = ntiles * 8
     const float* tau_init;  // [nq_pad] nullable
@@ -180,14 +204,19 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     const int BKE = p.f16 ? 2 * BK : BK;  // elements per 128-byte K chunk
 
     const int64_t qtiles = (p.nq + BM - 1) / BM;
-    const int64_t qt = blockIdx.x % qtiles, sp = blockIdx.x / qtiles;
+    const int64_t qtg = p.cluster ? p.qtiles_grid : qtiles;
+    const int64_t qt = blockIdx.x % qtg, sp = blockIdx.x / qtg;
+    const bool ghost = qt >= qtiles;
+    uint32_t crank = 0;
+    if (p.cluster) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
     const int64_t t_begin = sp * p.tiles_per_split;
     const int64_t t_end = min(p.ntiles, t_begin + p.tiles_per_split);
     const int ntile = (int)max((int64_t)0, t_end - t_begin);
     const int KC = (p.dim + BKE - 1) / BKE;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES1; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < STAGES1; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, p.cluster ? p.cluster : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4 * p.halves); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -198,12 +227,27 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster) cluster_sync_all();  // the partner's barriers exist before anything is multicast at them
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
             uint32_t it = 0;
+            if (p.cluster) {
+                for (int ti = 0; ti < ntile; ++ti) {
+                    const int n0 = (int)((t_begin + ti) * BN);
+                    for (int kc = 0; kc < KC; ++kc, ++it) {
+                        const uint32_t s = it & nsm, ph = (it >> nsh) & 1;
+                        mbar_wait(empty0 + 8 * s, ph ^ 1);  // both CTAs have finished with the stage
+                        const uint32_t sb = smem_u32(stage_base) + s * stage_bytes;
+                        mbar_expect_tx(full0 + 8 * s, ghost ? XH_BYTES : stage_bytes);
+                        if (!ghost) tma_load_2d(sb, &map_qhi, full0 + 8 * s, kc * BKE, (int)(qt * BM));
+                        tma_load_2d_mc(sb + xoff + crank * (XH_BYTES / p.cluster), &map_xlo, full0 + 8 * s, kc * BKE,
+                                       n0 + (int)crank * (BN / p.cluster), cmask);
+                    }
+                }
+            } else
             for (int ti = 0; ti < ntile; ++ti) {
                 const int n0 = (int)((t_begin + ti) * BN);
                 for (int kc = 0; kc < KC; ++kc, ++it) {
@@ -224,6 +268,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         // ================= MMA issuer =================
         if (elect_one()) {
             uint32_t it = 0;
+            if (ghost) {  // no queries here: take delivery of every stage and hand it back
+                for (int64_t n = (int64_t)ntile * KC; n > 0; --n, ++it) {
+                    const uint32_t s = it & nsm, ph = (it >> nsh) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_commit_mc(empty0 + 8 * s, cmask);
+                }
+            } else
             for (int ti = 0; ti < ntile; ++ti) {
                 const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
                 mbar_wait(tempty0 + 8 * buf, aph ^ 1);
@@ -249,12 +300,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                             tc_mma_tf32(d_tmem, qhi + adv, xhi + adv, kInstrDesc, 1);
                         }
                     }
-                    tc_commit(empty0 + 8 * s);  // frees the shared-memory stage when these MMAs retire
+                    // frees the shared-memory stage when these MMAs retire (in both CTAs of a cluster: the partner writes here too)
+                    if (p.cluster) tc_commit_mc(empty0 + 8 * s, cmask); else tc_commit(empty0 + 8 * s);
                 }
                 tc_commit(tfull0 + 8 * buf);    // accumulator tile complete
             }
         }
-    } else if (warp >= 4 && warp < 4 + 4 * p.halves) {
+    } else if (warp >= 4 && warp < 4 + 4 * p.halves && !ghost) {
         // ================= epilogue: thread <-> query (x column half) =================
         const int ew = (warp - 4) & 3;                 // TMEM lane quarter
         const int hf = (warp - 4) >> 2;                // column half of every tile this warp reads
@@ -451,6 +503,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster) cluster_sync_all();  // the partner may still be multicasting data and arrivals into this CTA
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -930,6 +983,11 @@ static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float*
         return cudaErrorInvalidValue;
     TcParams p{};
     p.f16 = f16 ? 1 : 0;
+    static const bool no_cluster = getenv("PYROPE_FLAT_NOCLUSTER") != nullptr;
+    const bool cluster = mode == 1 && !gmax && !no_cluster;
+    static const int csize = getenv("PYROPE_FLAT_CLUSTER") ? atoi(getenv("PYROPE_FLAT_CLUSTER")) : 2;
+    const int CS = csize == 4 ? 4 : 2;
+    if (cluster && !make_map(&mxl, f16 ? a.X16 : static_cast<const void*>(a.Xhi), a.n_rows, a.dim, BN / CS, f16)) return cudaErrorInvalidValue;
     p.nq = a.nq; p.n_scan = a.n_scan; p.dim = a.dim; p.kprime = a.kprime; p.cap = a.cap; p.splits = splits;
     p.ntiles = (a.n_scan + BN - 1) / BN;
     p.tiles_per_split = (p.ntiles + splits - 1) / splits;
@@ -948,7 +1006,24 @@ static cudaError_t launch_flat_tc_pass(const FlatTcParams& a, int splits, float*
     cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (a.ev_k0 && !gmax && mode != 2) cudaEventRecord(a.ev_k0, st);
-    flat_tc_kernel<<<(unsigned)(qtiles * splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
+    if (cluster) {
+        p.cluster = CS;
+        p.qtiles_grid = (qtiles + CS - 1) / CS * CS;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(p.qtiles_grid * splits));
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)CS; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, flat_tc_kernel, mqh, mql, mxh, mxl, p);
+        if (e != cudaSuccess) return e;
+    } else {
+        flat_tc_kernel<<<(unsigned)(qtiles * splits), TC_THREADS, smem, st>>>(mqh, mql, mxh, mxl, p);
+    }
     if (a.ev_k1 && !gmax && mode != 2) cudaEventRecord(a.ev_k1, st);
     return cudaGetLastError();
 }
