@@ -322,6 +322,11 @@ int pyrope_delta_search_batch_device(pyrope_delta *d, int64_t nq, const float *d
  * IvfFlatVectorIndex.cs:47), every head row is tombstoned, then the tail is built.  moved_out = rows moved;
  * tail_rows_out (nullable, one entry per moved row in head scan order) = the tail row ordinal now holding it. */
 int pyrope_delta_compact(pyrope_delta *d, int64_t *moved_out, int64_t *tail_rows_out);
+/* The same in two calls: the move (head rows into the tail's buffer, head tombstoned) and the tail's Build.  A shim that
+ * keeps id tables records tail_rows_out after the move whatever the build then returns, so a failed build (e.g. out of
+ * memory while training) leaves every id addressable and can simply be retried. */
+int pyrope_delta_move(pyrope_delta *d, int64_t *moved_out, int64_t *tail_rows_out);
+int pyrope_delta_build_tail(pyrope_delta *d);
 /* DeltaVectorIndex.GetStats :224-239: head count + tail count (duplicates counted twice, as there). */
 int pyrope_delta_stats(pyrope_delta *d, int64_t *count_out);
 /* DeltaVectorIndex.Snapshot / Load :160-222: path + ".head", path + ".tail" and a manifest at path. */

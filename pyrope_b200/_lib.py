@@ -110,6 +110,8 @@ SIGNATURES = {
     "pyrope_delta_search_batch": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp]),
     "pyrope_delta_search_batch_device": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp]),
     "pyrope_delta_compact": (C.c_int, [vp, i64p, vp]),
+    "pyrope_delta_move": (C.c_int, [vp, i64p, vp]),
+    "pyrope_delta_build_tail": (C.c_int, [vp]),
     "pyrope_delta_stats": (C.c_int, [vp, i64p]),
     "pyrope_delta_snapshot": (C.c_int, [vp, C.c_char_p]),
     "pyrope_delta_load": (C.c_int, [vp, C.c_char_p]),

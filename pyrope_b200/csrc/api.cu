@@ -2326,7 +2326,12 @@ int pyrope_delta_search_batch(pyrope_delta* d, int64_t nq, const float* Q, int t
     return PYROPE_OK;
 }
 
-int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows_out) {
+}  // extern "C"
+
+namespace {
+// DeltaVectorIndex.Build :124-158 in two steps a caller can take apart: MOVE (head rows -> tail buffer, head tombstoned)
+// and BUILD (the tail's Build).  A host that keeps id tables updates them after the move whatever the build returns.
+int delta_compact_impl(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows_out, bool do_move, bool do_build) {
     if (!d) return fail(PYROPE_ERR_INVALID_ARG, "delta handle is null");
     if (moved_out) *moved_out = 0;
     std::lock_guard<std::mutex> g(d->mu);
@@ -2339,7 +2344,7 @@ int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows
     cudaStream_t st = tl->stream;
     Segment& hs = hd->seg;
     const int dim = hd->dim;
-    const int64_t n = hs.live;
+    const int64_t n = do_move ? hs.live : 0;
     if (n > 0) {
         // 1. the head's live rows in scan order (bfHead.Scan(), DeltaVectorIndex.cs:133)
         std::vector<int64_t> slots;
@@ -2466,10 +2471,22 @@ int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows
         if (moved_out) *moved_out = n;
     }
     // 4. _head.Build() is a no-op for FLAT; _tail.Build() (:151-152)
+    if (!do_build) return PYROPE_OK;
     if (tl->kind == PYROPE_IVF_FLAT) return build_ivfflat(tl);
     if (tl->kind == PYROPE_IVF_PQ) return build_ivfpq(tl);
     return PYROPE_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int pyrope_delta_compact(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows_out) {
+    return delta_compact_impl(d, moved_out, tail_rows_out, true, true);
+}
+int pyrope_delta_move(pyrope_delta* d, int64_t* moved_out, int64_t* tail_rows_out) {
+    return delta_compact_impl(d, moved_out, tail_rows_out, true, false);
+}
+int pyrope_delta_build_tail(pyrope_delta* d) { return delta_compact_impl(d, nullptr, nullptr, false, true); }
 
 int pyrope_delta_stats(pyrope_delta* d, int64_t* count_out) {
     if (!d || !count_out) return fail(PYROPE_ERR_INVALID_ARG, "null argument");

@@ -504,7 +504,9 @@ int pyrope_vindex_build(pyrope_vindex* v) {
     std::vector<int64_t> tail_rows(moved_gids.size() + 1, -1);
     int64_t moved = 0;
     const bool had_buffer = !tl->buffered.empty() || !moved_gids.empty();
-    VTRY(pyrope_delta_compact(v->d, &moved, tail_rows.data()));
+    // move first, book-keeping second, the tail's Build last: if the build fails (out of memory in k-means, say) the id
+    // tables already describe where every row is, so Delete / Upsert / Snapshot keep working and Build can be retried
+    VTRY(pyrope_delta_move(v->d, &moved, tail_rows.data()));
     if (moved != (int64_t)moved_gids.size())
         return vfail(PYROPE_ERR_INVALID_STATE, "compaction moved %lld rows, the id table expected %zu", (long long)moved,
                      moved_gids.size());
@@ -518,6 +520,7 @@ int pyrope_vindex_build(pyrope_vindex* v) {
     }
     std::fill(hd->gid_of_row.begin(), hd->gid_of_row.end(), (int64_t)-1);  // _head.Delete(id) for every moved id
     hd->drop_all();
+    VTRY(pyrope_delta_build_tail(v->d));
     leaf_after_build(tl, had_buffer);
     return PYROPE_OK;
 }

@@ -159,7 +159,8 @@ class _VectorIndex:
         scores = np.zeros((nq, kk), np.float32)
         ids = np.full((nq, kk), -1, np.int64)
         counts = np.zeros(nq, np.int32)
-        ms = -1 if options is None or options.MaxScans is None else int(options.MaxScans)
+        # null = no budget (-1 on the ABI); a caller's value <= 0 scans nothing in the reference and must not become "no budget"
+        ms = -1 if options is None or options.MaxScans is None else max(int(options.MaxScans), 0)
         npb = -1 if options is None or options.NProbe is None else int(options.NProbe)
         _ck(_lib.load().pyrope_vindex_search(self._v, nq, _p(Q), ln, int(topK), ms, npb, _p(scores), _p(ids), _p(counts)))
         names = _id_strings(ids.reshape(-1))  # one call, one lock for the whole result list

@@ -70,6 +70,9 @@ def test_bruteforce_maxscans_zero_is_empty(vi):  # :56-65
     index.Add("a", [1.0, 0.0])
     index.Add("b", [0.0, 1.0])
     assert index.Search([1.0, 0.0], 1, vi.SearchOptions(MaxScans=0)) == []
+    # scanLimit = min(MaxScans, count) <= 0 -> empty (BruteForceVectorIndex.cs:288-289): a negative budget is NOT "no budget"
+    assert index.Search([1.0, 0.0], 1, vi.SearchOptions(MaxScans=-3)) == []
+    assert len(index.Search([1.0, 0.0], 2, vi.SearchOptions(MaxScans=None))) == 2
 
 
 def test_bruteforce_deleted_id_can_be_added_again(vi):  # Delete drops the id from _idMap (:240), Add appends
