@@ -709,7 +709,7 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
     try:
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         tr = json.load(open(tpath))
-        ent = tr.get(f"{kname}:{w['name']}:{args.scale:g}") if world == 1 else None
+        ent = tr.get(f"{kname.split(' ')[0]}:{w['name']}:{args.scale:g}") if world == 1 else None
         if isinstance(ent, dict):
             traffic = ent.get("bytes")
             srcs = [os.path.join(ROOT, "pyrope_b200", "csrc", s) for s in ent.get("sources", [])]
