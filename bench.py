@@ -712,8 +712,13 @@ def bench_workload(args, torch, pg, dist, w: dict, steps: int, warmup: int, rank
         ent = tr.get(f"{kname.split(' ')[0]}:{w['name']}:{args.scale:g}") if world == 1 else None
         if isinstance(ent, dict):
             traffic = ent.get("bytes")
-            srcs = [os.path.join(ROOT, "pyrope_b200", "csrc", s) for s in ent.get("sources", [])]
-            if any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(tpath) for s in srcs):
+            import hashlib
+            stale = False
+            for fn, digest in dict(ent.get("sources", {})).items():  # {file: sha256 prefix at capture time}
+                fp = os.path.join(ROOT, "pyrope_b200", "csrc", fn)
+                if os.path.exists(fp) and hashlib.sha256(open(fp, "rb").read()).hexdigest()[:16] != digest:
+                    stale = True
+            if stale:
                 traffic_note = "profiles/traffic.json predates the kernel source: re-capture with ncu --set full"
                 log("WARNING: " + traffic_note)
         elif ent is not None:

@@ -1005,15 +1005,22 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
         qnorm = ws.qnorm.as<float>();
     }
 
-    if (use_tc_seg || use_tc_coarse || use_ctc) {
+    // tf32 hi / lo copies of the queries: made once per search, by the first stage that needs them (the coarse probe on
+    // fp16 copies followed by an ADC scan never does)
+    bool qsplit_done = false;
+    auto need_qsplit = [&]() -> int {
+        if (qsplit_done) return PYROPE_OK;
         TRY(ws.qhi.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
         TRY(ws.qlo.ensure(sizeof(float) * (size_t)nq * dim, 0, st));
         CK(launch_tc_prepare(dQ, nq, dim, h->metric, nullptr, ws.qhi.as<float>(), ws.qlo.as<float>(), nullptr, nullptr, 0, st));
         ++launches;
-    }
+        qsplit_done = true;
+        return PYROPE_OK;
+    };
     auto run_tc = [&](TcOperand& op, const float* X, int64_t n_rows, int64_t n_scan_rows, const uint8_t* dead,
                       const float* xnorm, const int64_t* labels, int kk, PairOut po) -> int {
         if (op.dirty || op.rows_valid < n_rows) ++launches;
+        TRY(need_qsplit());
         TRY(ensure_tc_operand(op, X, n_rows, dim, h->metric, dead, st));
         FlatTcParams tp{};
         tp.Q = dQ; tp.Qhi = ws.qhi.as<float>(); tp.Qlo = ws.qlo.as<float>(); tp.nq = nq; tp.dim = dim;
@@ -1117,6 +1124,7 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                 cp.Q16 = ws.q16.p; cp.C16 = op.h16.p; cp.qbad = ws.qbad.as<uint8_t>();
             }
         }
+        if (!cp.Q16) TRY(need_qsplit());
         cp.Q = dQ; cp.Qhi = ws.qhi.as<float>(); cp.nq = nq; cp.dim = dim; cp.metric = h->metric;
         cp.C = h->centroids.as<float>(); cp.Chi = op.hi.as<float>(); cp.cnorms = h->cnorms.as<float>(); cp.nc = h->nc;
         cp.scale = op.scale.as<float>(); cp.bias = op.bias.as<float>(); cp.amax = op.amax.as<float>();
