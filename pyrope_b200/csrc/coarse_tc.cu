@@ -10,9 +10,10 @@
 // kernel re-fetches its 128-query tile with every 256-row tile (192 KiB of L2 -> shared-memory traffic per 2,048
 // MMA cycles = 26 TB/s chip-wide, twice what L2 delivers), so it was bound by operand traffic, and its pass B by a
 // divergent per-lane filter.  Here:
-//   * one CTA keeps a 256-query tile (two UMMA M = 128 halves, hi = tf32(q) only) RESIDENT in 128 KiB of shared
-//     memory and streams centroid tiles of 128 rows (16 KiB per 32-float K chunk, 5 TMA stages): 64 KiB of L2
-//     traffic per (256 x 128) unit, a third of before per score;
+//   * one CTA keeps a 256-query tile (two UMMA M = 128 halves) RESIDENT in shared memory and streams centroid tiles
+//     of 128 rows (16 KiB per 128-byte K chunk, 5 TMA stages).  Operands are fp16 copies (kind::f16: the mantissa of
+//     tf32 at twice the rate and half the bytes; L2 / IP, values within the fp16 range - launch_coarse_tc) or
+//     tf32(x) copies (kind::tf32): one product per K slice either way, never the three-term split;
 //   * accumulators: 2 halves x 2 buffers x 128 TMEM columns; eight epilogue warps (lane quarter x half) read them
 //     with tcgen05.ld while the next unit's MMAs run;
 //   * work units (query tile, centroid tile) are dealt to the 148 persistent CTAs as equal contiguous ranges (a
@@ -21,7 +22,8 @@
 //     coarse_tau_kernel takes the k'-th largest of a query's unit maxima (each of the k' best units holds a row at
 //     least that good) minus twice the rounding bound of the one-TF32 product as that query's threshold;
 //   * pass B recomputes the same scores and appends the POSITIONS of everything above the threshold to the query's
-//     candidate list (a 32-bit hit mask per 32 columns, one atomicAdd per hit; ~110 survivors per query at C5);
+//     candidate list (a 32-bit hit mask per 32 columns; lists private to one thread, plain stores; ~170 survivors
+//     per query on C5's trained centroids);
 //   * coarse_rank_kernel scores the survivors exactly, in the reference's order, sorts and writes the nprobe best.
 //     A query whose list overflowed (thousands of centroids inside one rounding band) is ranked exhaustively.
 #include <cuda.h>

@@ -16,7 +16,12 @@
 // threshold, append survivors to its private queue in L2; a full queue is sorted by the whole warp).
 // The k' = k + margin survivors per (query, split) are re-scored with exact fp32 arithmetic by
 // flat_rescore_kernel, which also does the final ordering — reported distances never come from
-// the TF32 path.
+// the tensor path.
+//
+// Long rows (d > 256, >= 65,536 rows: BASELINE config 4) take ONE product per K slice instead of three — on fp16
+// copies of both operands (kind::f16) when the values fit, else on the tf32 hi copies — with a rigorous rounding
+// band per query (tc_band_kernel) and a three-term pass behind that only runs if a queue overflowed; one-term
+// passes use four 48 KiB stages and are launched in clusters of two CTAs that multicast the X chunks to each other.
 #include <cuda.h>
 
 #include <algorithm>
