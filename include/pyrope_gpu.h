@@ -283,7 +283,7 @@ const char *pyrope_sharded_last_error(void);
  *      of 16) into every rank's buffer, a release of this call's epoch to the peers, and a wait for theirs; work
  *      enqueued after it on the same stream sees *d_gathered_out = [world][bytes_per_rank].  The area is double-buffered
  *      by call parity: consume the gathered data (on that stream) before the next-but-one call on the same slot.
- *      A rank whose peers never arrive faults after ~5 s instead of hanging the device.  Errors: pyrope_peer_last_error(). */
+ *      A rank whose peers never arrive faults after ~20 s instead of hanging the device.  Errors: pyrope_peer_last_error(). */
 typedef struct pyrope_peer_group pyrope_peer_group;
 int pyrope_peer_group_create(int world, int rank, size_t slot_bytes, int n_slots, pyrope_peer_group **out);
 int pyrope_peer_group_destroy(pyrope_peer_group *g);

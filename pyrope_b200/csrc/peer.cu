@@ -75,7 +75,7 @@ __global__ void peer_signal_wait_kernel(PeerPtrs pp, int world, int rank, int sl
         unsigned long long spins = 0;
         while (*mine < epoch) {
             __nanosleep(200);
-            if (++spins > (1ull << 24)) __trap();  // ~5 s: a peer that never arrives must fault, not hang the GPU
+            if (++spins > (1ull << 26)) __trap();  // ~20 s: a peer that never arrives must fault, not hang the GPU
         }
         __threadfence_system();
     }
