@@ -20,9 +20,11 @@
  *    search returns instead of the ordinal (used for global row numbers when sharded across GPUs).
  *  - scores are "higher is better" for every metric: L2 -> -||q-x||^2, InnerProduct -> q.x,
  *    Cosine -> q.x/(|q||x|) (0 if either norm < 1e-6), as in the reference.
- *  - one process drives one GPU (torch.distributed / NCCL provides the cross-GPU exchange in the
- *    harness); search is thread-safe for concurrent callers on one handle, mutation must be
- *    serialised by the caller (the shim's ReaderWriterLockSlim already does).
+ *  - a pyrope_index lives on one GPU.  N GPUs: one process drives them all through pyrope_sharded_*,
+ *    or one process per GPU shards with pyrope_index_set_shard and exchanges probe lists / top-k lists
+ *    with pyrope_peer_* (peer stores over NVLink) or any all-gather of its own.  Search is thread-safe
+ *    for concurrent callers on one handle, mutation must be serialised by the caller (the shim's
+ *    ReaderWriterLockSlim already does).
  */
 #ifndef PYROPE_GPU_H
 #define PYROPE_GPU_H
@@ -117,7 +119,7 @@ int pyrope_index_set_codebooks(pyrope_index *h, int n_centroids, const float *ce
 /* Multi-GPU sharding of an IVF index: this process keeps only the inverted lists with
  * list_id % world == rank (centroids and PQ codebooks stay replicated); rows assigned to other lists
  * are dropped at the next pyrope_index_build.  Every rank sees all rows and all queries; per-rank
- * top-k lists are exchanged with NCCL allgather and reduced by pyrope_topk_merge_device. */
+ * top-k lists are all-gathered (pyrope_peer_allgather_device, or NCCL) and reduced by pyrope_topk_merge_device. */
 int pyrope_index_set_shard(pyrope_index *h, int rank, int world);
 /* Multi-GPU IVF_PQ (list-major scan): share per-query thresholds between the ranks while their scan kernels run.  A
  * bound one rank proves for a query (k candidates at or below it) holds on every rank, so every tightening is also
@@ -219,7 +221,7 @@ int pyrope_batcher_search(pyrope_batcher *b, const float *query, int topk, int64
 int pyrope_batcher_stats(pyrope_batcher *b, int64_t *batches_out, int64_t *queries_out);
 const char *pyrope_batcher_last_error(void);
 
-/* ---- cross-shard merge (the step after ncclAllGather; semantics of DeltaVectorIndex.cs:95-121
+/* ---- cross-shard merge (the step after the all-gather of the per-shard lists; semantics of DeltaVectorIndex.cs:95-121
  *      without the id-dedupe, which sharding makes unnecessary): parts x nq x k_in candidate lists
  *      -> nq x k_out, best first, ties to the lower part index.  rows < 0 mark empty slots. */
 int pyrope_topk_merge_device(int64_t nq, int parts, int k_in, int k_out, const float *d_scores,
