@@ -266,68 +266,72 @@ __global__ void __launch_bounds__(256) lm_cmax_kernel(const float* __restrict__ 
     if (e < 16) cmax[e] = __uint_as_float(s_mx[e]);
 }
 __global__ void __launch_bounds__(256) lm_prepare_kernel(LmPrep a) {
-    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (w >= a.ioff[a.nlist]) return;
-    const int l = a.item_list[w], rel = w - a.ioff[l];
-    const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
-    const int g = rel;
-    const int pbeg = a.loff[l], pend = a.loff[l + 1];
-    int qid[LM_QS], psl[LM_QS];
-#pragma unroll
-    for (int j = 0; j < LM_QS; ++j) {
-        const int idx = pbeg + LM_QS * g + j;
-        qid[j] = idx < pend ? a.pairq[idx] : -1;
-        psl[j] = idx < pend ? a.pairp[idx] : 0;
-    }
-    unsigned char* blkp = a.iblk + (size_t)w * a.blk;
-    const int sub = a.dim >> 4, D0 = lane * 4;
-    const bool on = lane * 4 < a.dim;
-    const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;  // the lane's four dimensions lie in one sub-vector
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
-    float scale[LM_QS];
-#pragma unroll
-    for (int h = 0; h < LM_QS / 4; ++h) {  // queries 4h .. 4h+3 form one float4-interleaved half
-        float4 t[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 q = c;
-            if (on && qid[4 * h + j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[4 * h + j] * a.dim) + lane);
-            t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
-            // fixed-point scale: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
-            float r2 = 0.25f * (t[j].x * t[j].x + t[j].y * t[j].y + t[j].z * t[j].z + t[j].w * t[j].w);
-            if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
-            float b = on ? sqrtf(r2) * 1.000001f + cm : 0.f;
-            b *= b;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-            scale[4 * h + j] = qid[4 * h + j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
+    const int lane = threadIdx.x & 31;
+    const int n_items = a.ioff[a.nlist];
+    const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
+    // a resident grid walks the items (one warp per item at a time): 100 k short-lived blocks kept the SMs a third full
+    for (int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < n_items; w += wstride) {
+        const int l = a.item_list[w], rel = w - a.ioff[l];
+        const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
+        const int g = rel;
+        const int pbeg = a.loff[l], pend = a.loff[l + 1];
+        int qid[LM_QS], psl[LM_QS];
+    #pragma unroll
+        for (int j = 0; j < LM_QS; ++j) {
+            const int idx = pbeg + LM_QS * g + j;
+            qid[j] = idx < pend ? a.pairq[idx] : -1;
+            psl[j] = idx < pend ? a.pairp[idx] : 0;
         }
-        if (on) {
-            // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
-            // table build read 256 contiguous bytes per d (no bank conflicts)
-            float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR + (size_t)h * a.dim * 16);
-            dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
-            dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
-            dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
-            dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+        unsigned char* blkp = a.iblk + (size_t)w * a.blk;
+        const int sub = a.dim >> 4, D0 = lane * 4;
+        const bool on = lane * 4 < a.dim;
+        const float cm = on ? __ldg(a.cmax + D0 / sub) : 0.f;  // the lane's four dimensions lie in one sub-vector
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) c = __ldg(reinterpret_cast<const float4*>(a.centroids + (size_t)l * a.dim) + lane);
+        float scale[LM_QS];
+    #pragma unroll
+        for (int h = 0; h < LM_QS / 4; ++h) {  // queries 4h .. 4h+3 form one float4-interleaved half
+            float4 t[4];
+    #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 q = c;
+                if (on && qid[4 * h + j] >= 0) q = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)qid[4 * h + j] * a.dim) + lane);
+                t[j] = make_float4(-2.f * (q.x - c.x), -2.f * (q.y - c.y), -2.f * (q.z - c.z), -2.f * (q.w - c.w));
+                // fixed-point scale: every table value |r_m - p|^2 is at most B = max_m (|r_m| + max_e |p_m,e|)^2
+                float r2 = 0.25f * (t[j].x * t[j].x + t[j].y * t[j].y + t[j].z * t[j].z + t[j].w * t[j].w);
+                if (sub == 8) r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
+                float b = on ? sqrtf(r2) * 1.000001f + cm : 0.f;
+                b *= b;
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+                scale[4 * h + j] = qid[4 * h + j] >= 0 ? LM_QMAX / (b * 1.00001f + 1e-30f) : 0.f;
+            }
+            if (on) {
+                // dimension D = mi*sub + d is stored at slot d*16 + mi, so the 16 sub-quantiser lanes of the
+                // table build read 256 contiguous bytes per d (no bank conflicts)
+                float4* dst = reinterpret_cast<float4*>(blkp + LM_HDR + (size_t)h * a.dim * 16);
+                dst[((D0 + 0) % sub) * 16 + (D0 + 0) / sub] = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+                dst[((D0 + 1) % sub) * 16 + (D0 + 1) / sub] = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+                dst[((D0 + 2) % sub) * 16 + (D0 + 2) / sub] = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+                dst[((D0 + 3) % sub) * 16 + (D0 + 3) / sub] = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+            }
         }
-    }
-    if (lane == 0) {
-        LmHeader h{};
-        h.list = l;
-        h.vbeg = beg;
-        h.nvec = (int)len;
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = (short)psl[j]; h.s[j] = scale[j]; }
-        *reinterpret_cast<LmHeader*>(blkp) = h;
-    }
-    if (lane < LM_QS) {
-        float mys = 0.f;
-        int myq = -1;
-#pragma unroll
-        for (int j = 0; j < LM_QS; ++j) { mys = lane == j ? scale[j] : mys; myq = lane == j ? qid[j] : myq; }
-        if (myq >= 0) atomicMax(a.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
+        if (lane == 0) {
+            LmHeader h{};
+            h.list = l;
+            h.vbeg = beg;
+            h.nvec = (int)len;
+    #pragma unroll
+            for (int j = 0; j < LM_QS; ++j) { h.qid[j] = qid[j]; h.pslot[j] = (short)psl[j]; h.s[j] = scale[j]; }
+            *reinterpret_cast<LmHeader*>(blkp) = h;
+        }
+        if (lane < LM_QS) {
+            float mys = 0.f;
+            int myq = -1;
+    #pragma unroll
+            for (int j = 0; j < LM_QS; ++j) { mys = lane == j ? scale[j] : mys; myq = lane == j ? qid[j] : myq; }
+            if (myq >= 0) atomicMax(a.sinv_max + myq, __float_as_uint(1.f / mys));  // positive floats order like their bits
+        }
     }
 }
 
@@ -964,7 +968,7 @@ struct LmFinalParams {
     const float* Q; int dim;
     const float* centroids; const float* codebook; int ksub; int m;  // the index's own quantiser: [m][ksub][dim/m]
     const uint8_t* codes; const int64_t* list_off; int nlist; const int64_t* labels;  // codes [total][m]
-    const int64_t* probes; int P;
+    const int64_t* probes; int P; int64_t nq;
     const unsigned long long* pool; const int32_t* pool_cnt; int pslots; int k; int kc;
     const uint32_t* sinv_max;  // [nq] max 1/scale over the query's items (float bits): bounds every pool entry's error
     int keys_cap;              // keys in the sort window (the list ranges sit behind it in shared memory)
@@ -980,156 +984,158 @@ template <int SUB>
 __global__ void __launch_bounds__(256) ivfpq_lm_final_kernel(LmFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [next_pow2(pool_cap)]
-    const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_n, s_m;
     __shared__ uint32_t s_lohi[2];
     __shared__ int s_hist[256];
     __shared__ float s_lim;
-    if (tid == 0) { s_n = 0; s_m = 0; s_lohi[0] = 0xffffffffu; s_lohi[1] = 0u; }
-    for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    // the probed lists and their code ranges, once per query: a survivor's list is found by a shared-memory search below
-    // instead of dependent global loads per survivor
-    long long* s_lo = reinterpret_cast<long long*>(keys + p.keys_cap);
-    long long* s_hi = s_lo + p.P;
-    int* s_list = reinterpret_cast<int*>(s_hi + p.P);
-    float* s_res = reinterpret_cast<float*>(s_list + p.P) + (tid >> 4) * p.dim;  // m < 16: this half warp's residual query
-    for (int sl = tid; sl < p.P; sl += blockDim.x) {
-        const int64_t l = __ldg(p.probes + q * p.P + sl);
-        s_list[sl] = (int)l;
-        s_lo[sl] = l >= 0 ? __ldg(p.list_off + l) : 0;
-        s_hi[sl] = l >= 0 ? __ldg(p.list_off + l + 1) : 0;
-    }
-    for (int sl = tid; sl < p.pslots; sl += blockDim.x) {  // gather the pairs' private regions
-        const size_t ps = (size_t)q * p.pslots + sl;
-        const int c = min(p.pool_cnt[ps], p.kc);
-        if (c > 0) {
-            const int base = atomicAdd(&s_n, c);
-            uint32_t lo = 0xffffffffu, hi = 0u;
-            for (int i = 0; i < c; ++i) {
-                const uint64_t key = p.pool[ps * p.kc + i];
-                keys[base + i] = key;
-                lo = min(lo, (uint32_t)(key >> 32)); hi = max(hi, (uint32_t)(key >> 32));
-            }
-            atomicMin(&s_lohi[0], lo);
-            atomicMax(&s_lohi[1], hi);
-        }
-    }
-    __syncthreads();
-    const int n = s_n;
-    const int kk = min(n, p.k);
-    // Pool distances are approximate (fixed-point tables): |d - true| <= err.  Everything within 2 err of the k-th
-    // best approximate distance can still belong to the true top k, so all of it is re-scored.
-    int nres = n;
-    if (n > kk) {
-        // distances run from dmin (the best score) to dmax; bucket b holds dmin + [b, b+1) / scale
-        const float dmin = -ord_to_score(s_lohi[1]), dmax = -ord_to_score(s_lohi[0]);
-        const float scale = dmax > dmin ? 255.f / (dmax - dmin) : 0.f;
-        for (int i = tid; i < n; i += blockDim.x)
-            atomicAdd(&s_hist[min(255, (int)((-key_score(keys[i]) - dmin) * scale))], 1);
+    for (int64_t q = blockIdx.x; q < p.nq; q += gridDim.x) {  // launched with one CTA per query
+        if (tid == 0) { s_n = 0; s_m = 0; s_lohi[0] = 0xffffffffu; s_lohi[1] = 0u; }
+        for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
-        if (warp == 0) {  // the first bucket where the running count reaches k: its upper edge bounds the k-th best
-            int c[8], tot = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; tot += c[j]; }
-            int cum = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, cum, o);
-                if (lane >= o) cum += up;
-            }
-            const unsigned reach = __ballot_sync(0xffffffffu, cum >= kk);
-            if (lane == __ffs(reach) - 1) {
-                int run = cum - tot, b = lane * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    run += c[j];
-                    if (run >= kk) break;
-                    ++b;
+        // the probed lists and their code ranges, once per query: a survivor's list is found by a shared-memory search below
+        // instead of dependent global loads per survivor
+        long long* s_lo = reinterpret_cast<long long*>(keys + p.keys_cap);
+        long long* s_hi = s_lo + p.P;
+        int* s_list = reinterpret_cast<int*>(s_hi + p.P);
+        float* s_res = reinterpret_cast<float*>(s_list + p.P) + (tid >> 4) * p.dim;  // m < 16: this half warp's residual query
+        for (int sl = tid; sl < p.P; sl += blockDim.x) {
+            const int64_t l = __ldg(p.probes + q * p.P + sl);
+            s_list[sl] = (int)l;
+            s_lo[sl] = l >= 0 ? __ldg(p.list_off + l) : 0;
+            s_hi[sl] = l >= 0 ? __ldg(p.list_off + l + 1) : 0;
+        }
+        for (int sl = tid; sl < p.pslots; sl += blockDim.x) {  // gather the pairs' private regions
+            const size_t ps = (size_t)q * p.pslots + sl;
+            const int c = min(p.pool_cnt[ps], p.kc);
+            if (c > 0) {
+                const int base = atomicAdd(&s_n, c);
+                uint32_t lo = 0xffffffffu, hi = 0u;
+                for (int i = 0; i < c; ++i) {
+                    const uint64_t key = p.pool[ps * p.kc + i];
+                    keys[base + i] = key;
+                    lo = min(lo, (uint32_t)(key >> 32)); hi = max(hi, (uint32_t)(key >> 32));
                 }
-                const float edge = scale > 0.f ? fminf(dmax, dmin + (float)(b + 1) / scale * 1.00001f) : dmax;
-                const float err = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
-                s_lim = edge + 2.f * err + 2e-5f * edge;
+                atomicMin(&s_lohi[0], lo);
+                atomicMax(&s_lohi[1], hi);
             }
         }
         __syncthreads();
-        const float lim = s_lim;
-        // compact the band to the front, a block of entries at a time (writes never pass the entries still to be read)
-        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + tid;
-            const uint64_t key = i < n ? keys[i] : 0ull;
-            const bool keep = i < n && -key_score(key) <= lim;
-            const unsigned mk = __ballot_sync(0xffffffffu, keep);
-            int base = 0;
+        const int n = s_n;
+        const int kk = min(n, p.k);
+        // Pool distances are approximate (fixed-point tables): |d - true| <= err.  Everything within 2 err of the k-th
+        // best approximate distance can still belong to the true top k, so all of it is re-scored.
+        int nres = n;
+        if (n > kk) {
+            // distances run from dmin (the best score) to dmax; bucket b holds dmin + [b, b+1) / scale
+            const float dmin = -ord_to_score(s_lohi[1]), dmax = -ord_to_score(s_lohi[0]);
+            const float scale = dmax > dmin ? 255.f / (dmax - dmin) : 0.f;
+            for (int i = tid; i < n; i += blockDim.x)
+                atomicAdd(&s_hist[min(255, (int)((-key_score(keys[i]) - dmin) * scale))], 1);
             __syncthreads();
-            if (lane == 0 && mk) base = atomicAdd(&s_m, __popc(mk));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) keys[base + __popc(mk & ((1u << lane) - 1u))] = key;
-        }
-        __syncthreads();
-        nres = s_m;
-    }
-    // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order; one half warp each
-    const int hl = tid & 15, hw = tid >> 4, nhw = blockDim.x >> 4;
-    const unsigned hmask = 0xffffu << (lane & 16);
-    for (int i0 = 0; i0 < nres; i0 += nhw) {  // uniform trip count: the shuffles below need the whole warp
-        const int i = i0 + hw;
-        const bool on = i < nres;
-        const uint32_t pos = key_pos(keys[on ? i : i0]);
-        int lo = 0;  // the list holding pos is one of this query's probed lists: test them sixteen at a time
-        for (int p0 = 0; p0 < p.P; p0 += 16) {
-            const bool hit = p0 + hl < p.P && s_lo[p0 + hl] <= (long long)pos && (long long)pos < s_hi[p0 + hl];
-            const unsigned mh = __ballot_sync(0xffffffffu, hit) & hmask;
-            if (mh) lo = s_list[p0 + ((__ffs(mh) - 1) & 15)];
-            if (__all_sync(0xffffffffu, mh != 0 || lo != 0)) break;  // both halves found theirs (list 0 is re-checked, harmlessly)
-        }
-        float dm = 0.f, dist = 0.f;
-        if (p.m == 16) {
-            float r[SUB];
-#pragma unroll
-            for (int d = 0; d < SUB; ++d)
-                r[d] = __fsub_rn(__ldg(p.Q + q * p.dim + hl * SUB + d), __ldg(p.centroids + (size_t)lo * p.dim + hl * SUB + d));
-            const int code = p.codes[(size_t)pos * 16 + hl];
-            dm = exact::a1_l2_fixed<SUB>(r, p.codebook + ((size_t)hl * p.ksub + code) * SUB);
-#pragma unroll
-            for (int mi = 0; mi < 16; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, (lane & 16) + mi));
-        } else {
-            // fewer, longer sub-vectors (dim/m = 16 .. 128): L2SquaredUnsafe's four-accumulator form applies from 32 on
-            const int subr = p.dim / p.m;
-            for (int d = hl; d < p.dim; d += 16)
-                s_res[d] = __fsub_rn(__ldg(p.Q + q * p.dim + d), __ldg(p.centroids + (size_t)lo * p.dim + d));
-            __syncwarp();
-            if (hl < p.m) {
-                const int code = p.codes[(size_t)pos * p.m + hl];
-                dm = exact::a1_l2_eval(s_res + hl * subr, p.codebook + ((size_t)hl * p.ksub + code) * subr, subr);
+            if (warp == 0) {  // the first bucket where the running count reaches k: its upper edge bounds the k-th best
+                int c[8], tot = 0;
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; tot += c[j]; }
+                int cum = tot;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, cum, o);
+                    if (lane >= o) cum += up;
+                }
+                const unsigned reach = __ballot_sync(0xffffffffu, cum >= kk);
+                if (lane == __ffs(reach) - 1) {
+                    int run = cum - tot, b = lane * 8;
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        run += c[j];
+                        if (run >= kk) break;
+                        ++b;
+                    }
+                    const float edge = scale > 0.f ? fminf(dmax, dmin + (float)(b + 1) / scale * 1.00001f) : dmax;
+                    const float err = LM_QERR * 1.001f * __uint_as_float(__ldg(p.sinv_max + q));
+                    s_lim = edge + 2.f * err + 2e-5f * edge;
+                }
             }
-            for (int mi = 0; mi < p.m; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, (lane & 16) + mi));
-            __syncwarp();
+            __syncthreads();
+            const float lim = s_lim;
+            // compact the band to the front, a block of entries at a time (writes never pass the entries still to be read)
+            for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+                const int i = i0 + tid;
+                const uint64_t key = i < n ? keys[i] : 0ull;
+                const bool keep = i < n && -key_score(key) <= lim;
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                int base = 0;
+                __syncthreads();
+                if (lane == 0 && mk) base = atomicAdd(&s_m, __popc(mk));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) keys[base + __popc(mk & ((1u << lane) - 1u))] = key;
+            }
+            __syncthreads();
+            nres = s_m;
         }
-        if (hl == 0 && on) keys[i] = make_key(-dist, pos);
-    }
-    __syncthreads();
-    const int P3 = next_pow2(max(nres, 2));
-    for (int i = nres + tid; i < P3; i += blockDim.x) keys[i] = 0ull;
-    __syncthreads();
-    if (P3 <= 64) {  // the usual case: one warp sorts without block barriers
-        if (warp == 0) bitonic_sort_desc<true>(keys, P3, lane, 32);
+        // exact re-score of the survivors: IvfPqVectorIndex.cs:161-166,182-186 in the reference's order; one half warp each
+        const int hl = tid & 15, hw = tid >> 4, nhw = blockDim.x >> 4;
+        const unsigned hmask = 0xffffu << (lane & 16);
+        for (int i0 = 0; i0 < nres; i0 += nhw) {  // uniform trip count: the shuffles below need the whole warp
+            const int i = i0 + hw;
+            const bool on = i < nres;
+            const uint32_t pos = key_pos(keys[on ? i : i0]);
+            int lo = 0;  // the list holding pos is one of this query's probed lists: test them sixteen at a time
+            for (int p0 = 0; p0 < p.P; p0 += 16) {
+                const bool hit = p0 + hl < p.P && s_lo[p0 + hl] <= (long long)pos && (long long)pos < s_hi[p0 + hl];
+                const unsigned mh = __ballot_sync(0xffffffffu, hit) & hmask;
+                if (mh) lo = s_list[p0 + ((__ffs(mh) - 1) & 15)];
+                if (__all_sync(0xffffffffu, mh != 0 || lo != 0)) break;  // both halves found theirs (list 0 is re-checked, harmlessly)
+            }
+            float dm = 0.f, dist = 0.f;
+            if (p.m == 16) {
+                float r[SUB];
+    #pragma unroll
+                for (int d = 0; d < SUB; ++d)
+                    r[d] = __fsub_rn(__ldg(p.Q + q * p.dim + hl * SUB + d), __ldg(p.centroids + (size_t)lo * p.dim + hl * SUB + d));
+                const int code = p.codes[(size_t)pos * 16 + hl];
+                dm = exact::a1_l2_fixed<SUB>(r, p.codebook + ((size_t)hl * p.ksub + code) * SUB);
+    #pragma unroll
+                for (int mi = 0; mi < 16; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, (lane & 16) + mi));
+            } else {
+                // fewer, longer sub-vectors (dim/m = 16 .. 128): L2SquaredUnsafe's four-accumulator form applies from 32 on
+                const int subr = p.dim / p.m;
+                for (int d = hl; d < p.dim; d += 16)
+                    s_res[d] = __fsub_rn(__ldg(p.Q + q * p.dim + d), __ldg(p.centroids + (size_t)lo * p.dim + d));
+                __syncwarp();
+                if (hl < p.m) {
+                    const int code = p.codes[(size_t)pos * p.m + hl];
+                    dm = exact::a1_l2_eval(s_res + hl * subr, p.codebook + ((size_t)hl * p.ksub + code) * subr, subr);
+                }
+                for (int mi = 0; mi < p.m; ++mi) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dm, (lane & 16) + mi));
+                __syncwarp();
+            }
+            if (hl == 0 && on) keys[i] = make_key(-dist, pos);
+        }
         __syncthreads();
-    } else {
-        bitonic_sort_desc<false>(keys, P3, tid, blockDim.x);
-    }
-    const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
-    if (tid == 0 && p.counts) p.counts[q] = kk;
-    for (int i = tid; i < p.k; i += blockDim.x) {
-        if (i < kk) {
-            const uint64_t key = keys[i];
-            p.out.scores[ob + i] = key_score(key);
-            p.out.labels[ob + i] = p.labels[key_pos(key)];
+        const int P3 = next_pow2(max(nres, 2));
+        for (int i = nres + tid; i < P3; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        if (P3 <= 64) {  // the usual case: one warp sorts without block barriers
+            if (warp == 0) bitonic_sort_desc<true>(keys, P3, lane, 32);
+            __syncthreads();
         } else {
-            p.out.scores[ob + i] = 0.f;
-            p.out.labels[ob + i] = -1;
+            bitonic_sort_desc<false>(keys, P3, tid, blockDim.x);
         }
+        const int64_t ob = (q * p.out.parts_total + p.out.part_base) * (int64_t)p.k;
+        if (tid == 0 && p.counts) p.counts[q] = kk;
+        for (int i = tid; i < p.k; i += blockDim.x) {
+            if (i < kk) {
+                const uint64_t key = keys[i];
+                p.out.scores[ob + i] = key_score(key);
+                p.out.labels[ob + i] = p.labels[key_pos(key)];
+            } else {
+                p.out.scores[ob + i] = 0.f;
+                p.out.labels[ob + i] = -1;
+            }
+        }
+        __syncthreads();  // the next query re-uses every shared array
     }
 }
 
@@ -1266,7 +1272,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     pa.Q = p.Q; pa.centroids = p.centroids; pa.dim = p.dim; pa.iblk = iblk; pa.blk = L.blk;
     pa.cmax = cmax; pa.sinv_max = sinv_max;
     mark();
-    lm_prepare_kernel<<<(unsigned)((L.max_items * 32 + 255) / 256), 256, 0, st>>>(pa);
+    lm_prepare_kernel<<<(unsigned)std::min<int64_t>((L.max_items * 32 + 255) / 256, (int64_t)num_sms * 8), 256, 0, st>>>(pa);
     mark();
 
     if (!fork) {
@@ -1310,7 +1316,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
     LmFinalParams fp{};
     fp.Q = p.Q; fp.dim = p.dim; fp.centroids = p.centroids; fp.codebook = p.codebook; fp.ksub = p.ksub; fp.m = p.m;
     fp.codes = p.codes; fp.list_off = p.list_off; fp.nlist = p.nlist; fp.labels = p.labels;
-    fp.probes = p.probes; fp.P = P;
+    fp.probes = p.probes; fp.P = P; fp.nq = p.nq;
     fp.pool = pool; fp.pool_cnt = pool_cnt; fp.pslots = L.pslots; fp.k = p.k; fp.kc = L.kc; fp.sinv_max = sinv_max; fp.out = p.out; fp.counts = p.out_counts;
     fp.keys_cap = next_pow2(std::max(2, L.pool_cap));
     const int fthreads = L.pool_cap <= 2048 ? 128 : 256;
@@ -1318,6 +1324,7 @@ cudaError_t launch_lm(const IvfPqScanParams& p, void* scratch, int num_sms, cuda
                        (p.m == 16 ? 0 : sizeof(float) * (size_t)(fthreads / 16) * p.dim);
     e = cudaFuncSetAttribute(ivfpq_lm_final_kernel<SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     if (e != cudaSuccess) return e;
+    // one CTA per query (a resident grid walking the queries measured slower: 0.164 against 0.133 ms on C5)
     ivfpq_lm_final_kernel<SUB><<<(unsigned)p.nq, fthreads, fsm, st>>>(fp);
     mark();
     if (stage_dbg && nsev == 7) {
