@@ -1,7 +1,12 @@
 """The peer-memory all-gather of the sharded search (csrc/peer.cu).  One GPU is enough to exercise the protocol: two
 ranks of one group live on the same device, on two streams, and hand each other their buffers directly
 (pyrope_peer_group_attach) — the kernels, epochs, parity halves and flag words are the ones a multi-GPU run uses; the
-real NVLink path runs in bench.py under torchrun (`details.collective`)."""
+real NVLink path runs in bench.py under torchrun (`details.collective`).
+
+Ranks that SHARE a device must not allocate or free device memory while an exchange is in flight: cudaMalloc / cudaFree
+may wait for the whole device, i.e. for this rank's own wait kernel, which waits for a peer whose host thread sits in
+the same kind of call — a deadlock that separate devices cannot have.  Hence every buffer below is allocated, and every
+library workspace grown, before the rank threads start."""
 import numpy as np
 import pytest
 
@@ -59,12 +64,13 @@ def test_allgather_rounds_on_one_device(gpu, world):
         host = [rng.integers(0, 256, nbytes, dtype=np.uint8) for _ in range(world)]
         src = [torch.from_numpy(h).cuda() for h in host]
         torch.cuda.synchronize()
-        outs = [None] * world
+        outs = [torch.empty(world * nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        torch.cuda.synchronize()
 
         def run(r):
             with torch.cuda.stream(streams[r]):
                 ptr = gs[r].allgather(slot, src[r].data_ptr(), nbytes, stream=streams[r].cuda_stream)
-                outs[r] = torch.as_tensor(_Raw(ptr, world * nbytes), device="cuda").clone()  # consumer on the same stream
+                outs[r].copy_(torch.as_tensor(_Raw(ptr, world * nbytes), device="cuda"))  # consumer on the same stream
 
         _in_threads(run, world)
         torch.cuda.synchronize()
@@ -125,27 +131,30 @@ def test_sharded_search_through_the_peer_exchange(gpu):
     gs = _groups(gpu, world, max(per * P * 8, nq * k * 8), 3)
     streams = [torch.cuda.Stream() for _ in range(world)]
     Q = torch.from_numpy(q).cuda()
-    res = [None] * world
-    for ix in shards:  # workspaces allocated before the ranks start waiting for each other
-        ix.search(q[:8], k, nprobe=P)
-    torch.cuda.synchronize()
+    res = []
+    for r in range(world):  # every buffer of the exchange, and every library workspace, exists before the ranks start
+        mine = torch.full((per, P), -1, dtype=torch.int64, device="cuda")
+        sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        rw = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        cn = torch.empty((nq,), dtype=torch.int32, device="cuda")
+        res.append((torch.empty_like(sc), torch.empty_like(rw), torch.empty_like(cn), mine, sc, rw, cn))
+        full = torch.empty((nq, P), dtype=torch.int64, device="cuda")
+        st0 = torch.cuda.current_stream().cuda_stream
+        shards[r].coarse_probe_device(Q.data_ptr(), nq, P, full.data_ptr(), stream=st0)   # same shapes as below, or larger
+        shards[r].search_probed_device(Q.data_ptr(), nq, k, P, full.data_ptr(), sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), stream=st0)
+        torch.cuda.synchronize()
 
     def run(r):
         with torch.cuda.stream(streams[r]):
             st = streams[r].cuda_stream
             lo, hi, _ = query_slice(nq, r, world)
-            mine = torch.full((per, P), -1, dtype=torch.int64, device="cuda")
+            m_sc, m_rw, m_cn, mine, sc, rw, cn = res[r]
             shards[r].coarse_probe_device(Q[lo:hi].data_ptr(), hi - lo, P, mine.data_ptr(), stream=st)
             probes = gs[r].allgather(0, mine.data_ptr(), per * P * 8, stream=st)
-            sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-            rw = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-            cn = torch.empty((nq,), dtype=torch.int32, device="cuda")
             shards[r].search_probed_device(Q.data_ptr(), nq, k, P, probes, sc.data_ptr(), rw.data_ptr(), cn.data_ptr(), stream=st)
             g_s = gs[r].allgather(1, sc.data_ptr(), nq * k * 4, stream=st)
             g_r = gs[r].allgather(2, rw.data_ptr(), nq * k * 8, stream=st)
-            m_sc, m_rw, m_cn = torch.empty_like(sc), torch.empty_like(rw), torch.empty_like(cn)
             _lib.topk_merge_device(nq, world, k, k, g_s, g_r, m_sc.data_ptr(), m_rw.data_ptr(), m_cn.data_ptr(), stream=st)
-            res[r] = (m_sc, m_rw, m_cn, mine, sc, rw, cn)
 
     _in_threads(run, world)
     torch.cuda.synchronize()
