@@ -418,34 +418,25 @@ coarse_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // E = 2^-10 (1 + 2^-7) |q| max_r(|scale_r| |x_r|)  (Cauchy-Schwarz).  There are at least k' rows scoring >= G (the k'-th
 // unit maximum) in this arithmetic, hence exactly >= G - E; a row of the exact top k' therefore scores >= G - 2E here.
 // 32 queries per block: the unit maxima arrive [unit][query] (coalesced), are transposed through shared memory and
-// each warp runs a register-resident bisection for 8 queries.
+// each of the 16 warps runs a register-resident bisection for 2 queries (the kernel's time is that serial chain: with 4
+// warps x 8 queries it cost 0.047 ms whatever the batch size).
 constexpr int TAU_MAXU = 1024;  // units per query handled in registers (32 per lane): 131,072 centroids
 template <int R>  // registers per lane: groups <= 32 R
-__global__ void __launch_bounds__(128) coarse_tau_kernel(const float* __restrict__ umax, int64_t nq_pad, int ntiles, int64_t nq,
+__global__ void __launch_bounds__(512) coarse_tau_kernel(const float* __restrict__ umax, int64_t nq_pad, int ntiles, int64_t nq,
                                                         int kprime, const float* __restrict__ Q, int dim,
                                                         const float* __restrict__ amax, float* tau_out,
-                                                        const float* __restrict__ C, int64_t c_bytes, float eband, float under,
+                                                        float eband, float under,
                                                         float smax, const uint8_t* __restrict__ qbad) {
     extern __shared__ float s_u[];  // [32][ntiles + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // The exact ranking (two kernels from now) reads ~100 scattered fp32 centroid rows per query: pull the table from
-    // HBM into L2 now, one slice per block (the tensor passes stream the tf32 copy, not this one).
-    if (tid == 0 && C) {
-        const int64_t slice = ((c_bytes + gridDim.x - 1) / gridDim.x + 4095) & ~(int64_t)4095;
-        const int64_t b0 = (int64_t)blockIdx.x * slice;
-        for (int64_t o = b0; o < min(c_bytes, b0 + slice); o += 32768) {
-            const uint32_t n = (uint32_t)min((int64_t)32768, min(c_bytes, b0 + slice) - o) & ~15u;
-            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(C) + o), "r"(n) : "memory");
-        }
-    }
     const int64_t q0 = (int64_t)blockIdx.x * 32;
     const int ld = ntiles + 1;
-    for (int i = tid; i < 32 * ntiles; i += 128) {
+    for (int i = tid; i < 32 * ntiles; i += blockDim.x) {
         const int t = i >> 5, ql = i & 31;
         s_u[ql * ld + t] = (q0 + ql < nq) ? __ldg(umax + (int64_t)t * nq_pad + q0 + ql) : -INFINITY;
     }
     __syncthreads();
-    for (int ql = warp; ql < 32; ql += 4) {
+    for (int ql = warp; ql < 32; ql += (int)(blockDim.x >> 5)) {
         const int64_t q = q0 + ql;
         if (q >= nq) break;
         float tau = -INFINITY;
@@ -771,15 +762,15 @@ cudaError_t launch_coarse_tc(const CoarseTcParams& a, cudaStream_t st) {
     if (ngroups <= 512) {
         e = cudaFuncSetAttribute(coarse_tau_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return e;
-        coarse_tau_kernel<16><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
-            p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau), a.C,
-            (int64_t)sizeof(float) * a.nc * a.dim, eband, under, smax, f16 ? a.qbad : nullptr);
+        coarse_tau_kernel<16><<<(unsigned)((a.nq + 31) / 32), 512, tsm, st>>>(
+            p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau),
+            eband, under, smax, f16 ? a.qbad : nullptr);
     } else {
         e = cudaFuncSetAttribute(coarse_tau_kernel<TAU_MAXU / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return e;
-        coarse_tau_kernel<TAU_MAXU / 32><<<(unsigned)((a.nq + 31) / 32), 128, tsm, st>>>(
-            p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau), a.C,
-            (int64_t)sizeof(float) * a.nc * a.dim, eband, under, smax, f16 ? a.qbad : nullptr);
+        coarse_tau_kernel<TAU_MAXU / 32><<<(unsigned)((a.nq + 31) / 32), 512, tsm, st>>>(
+            p.umax, L.nq_pad, ngroups, a.nq, kprime, a.Q, a.dim, a.amax, reinterpret_cast<float*>(base + L.tau),
+            eband, under, smax, f16 ? a.qbad : nullptr);
     }
     mark(2);
     passB<<<grid, C_THREADS, C_SMEM, st>>>(mq, mx, p);
