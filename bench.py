@@ -57,6 +57,10 @@ def workload(name: str, scale: float) -> dict:
         w = dict(kind="IVF_FLAT", metric="L2", dim=128, n=10_000_000, nq=10_000, topk=10, nlist=4096, nprobe=16)
         w["n"] = max(4096, int(round(w["n"] * scale)))
         w["nlist"] = max(64, int(round(w["nlist"] * scale)))
+    elif name == "c2w":  # the same with rows of 768 floats (the wide list-major kernels)
+        w = dict(kind="IVF_FLAT", metric="L2", dim=768, n=2_000_000, nq=10_000, topk=10, nlist=1024, nprobe=16)
+        w["n"] = max(4096, int(round(w["n"] * scale)))
+        w["nlist"] = max(64, int(round(w["nlist"] * scale)))
     elif name == "c2":
         w = dict(kind="IVF_FLAT", metric="L2", dim=128, n=10_000, nq=100, topk=10, nlist=100, nprobe=3)
     elif name == "c3":
@@ -64,7 +68,7 @@ def workload(name: str, scale: float) -> dict:
     else:
         raise SystemExit(f"unknown workload {name}")
     w["name"] = name
-    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5", "c2x", "c5m8", "c5m4"))
+    w["reduced"] = bool(scale != 1.0 and name in ("c4", "c5", "c2x", "c2w", "c5m8", "c5m4"))
     return w
 
 

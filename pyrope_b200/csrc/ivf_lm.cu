@@ -20,7 +20,8 @@
 //   ivf_lm_final_kernel  best k of the pool, RE-SCORED in the reference's evaluation order
 //                        (VectorMath.L2Squared / DotProduct, VectorMath.cs:8-70) so reported scores are the
 //                        oracle's bit for bit, then ordered.
-// Shapes: L2 / inner product / cosine, dim % 4 == 0 and dim <= 128, no MaxScans budget; everything else takes ivf.cu.
+// Shapes: L2 / inner product / cosine, dim % 4 == 0 and dim <= 1024 (rows wider than 128 floats take the *_wide kernels),
+// no MaxScans budget; everything else takes ivf.cu.
 #include <cub/cub.cuh>
 
 #include <cstdio>
@@ -197,6 +198,65 @@ struct FlParams {
     const float* norms;  // Cosine: |x| per list entry
 };
 
+// ---- after an item: hand at most k candidates per slot to the pair's private pool region, tighten the threshold ------
+__device__ __forceinline__ void fl_hand_over(const FlParams& p, int it, uint64_t* qkeys, int* s_qcnt, const int* s_qid,
+                                             const int* s_psl, int warp, int lane) {
+    for (int j = warp; j < FG; j += FT / 32) {
+        const int n = s_qcnt[j];
+        const int q = s_qid[j];
+        if (n > 0 && q >= 0) {
+            uint64_t* kq = qkeys + j * FQC;
+            if (n > FQC) {
+                if (lane == 0) p.redo[atomicAdd(p.redo_cnt, 1)] = make_int2(q, it * FG + j);
+            } else {
+                const size_t ps = (size_t)q * p.pslots + s_psl[j];
+                unsigned long long* dst = p.pool + ps * p.k;
+                uint64_t mink = ~0ull;
+                int kept;
+                if (n > p.k && n <= 64) {  // select by rank counting inside the warp
+                    const uint64_t a = lane < n ? kq[lane] : 0ull, b = lane + 32 < n ? kq[lane + 32] : 0ull;
+                    int ra = 0, rb = 0;
+                    for (int i = 0; i < n; ++i) {
+                        const uint64_t x = kq[i];
+                        ra += x > a;
+                        rb += x > b;
+                    }
+                    const bool ka = lane < n && ra < p.k, kb = lane + 32 < n && rb < p.k;
+                    const unsigned ma = __ballot_sync(0xffffffffu, ka), mb = __ballot_sync(0xffffffffu, kb);
+                    kept = __popc(ma) + __popc(mb);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (ka) { dst[__popc(ma & below)] = a; mink = a; }
+                    if (kb) { dst[__popc(ma) + __popc(mb & below)] = b; mink = b < mink ? b : mink; }
+                } else {
+                    if (n > p.k) {
+                        const int P2 = next_pow2(n);
+                        for (int i = n + lane; i < P2; i += 32) kq[i] = 0ull;
+                        __syncwarp();
+                        bitonic_sort_desc<true>(kq, P2, lane, 32);
+                    }
+                    kept = min(n, p.k);
+                    for (int i = lane; i < kept; i += 32) {
+                        const uint64_t x = kq[i];
+                        dst[i] = x;
+                        mink = x < mink ? x : mink;
+                    }
+                }
+                if (lane == 0) p.pool_cnt[ps] = kept;
+                if (kept >= p.k) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const uint64_t x = __shfl_xor_sync(0xffffffffu, mink, o);
+                        mink = x < mink ? x : mink;
+                    }
+                    if (lane == 0) atomicMax(p.pool_thr + q, (uint32_t)(mink >> 32));
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) s_qcnt[j] = 0;
+    }
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(FT, 2) ivf_lm_scan_kernel(FlParams p) {
     __shared__ uint64_t qkeys[FG * FQC];
@@ -294,61 +354,208 @@ __global__ void __launch_bounds__(FT, 2) ivf_lm_scan_kernel(FlParams p) {
             }
         }
         __syncthreads();
-        // ---- hand at most k candidates per slot to the pair's private pool region, tighten the threshold
-        for (int j = warp; j < FG; j += FT / 32) {
-            const int n = s_qcnt[j];
-            const int q = s_qid[j];
-            if (n > 0 && q >= 0) {
-                uint64_t* kq = qkeys + j * FQC;
-                if (n > FQC) {
-                    if (lane == 0) p.redo[atomicAdd(p.redo_cnt, 1)] = make_int2(q, it * FG + j);
-                } else {
-                    const size_t ps = (size_t)q * p.pslots + s_psl[j];
-                    unsigned long long* dst = p.pool + ps * p.k;
-                    uint64_t mink = ~0ull;
-                    int kept;
-                    if (n > p.k && n <= 64) {  // select by rank counting inside the warp
-                        const uint64_t a = lane < n ? kq[lane] : 0ull, b = lane + 32 < n ? kq[lane + 32] : 0ull;
-                        int ra = 0, rb = 0;
-                        for (int i = 0; i < n; ++i) {
-                            const uint64_t x = kq[i];
-                            ra += x > a;
-                            rb += x > b;
-                        }
-                        const bool ka = lane < n && ra < p.k, kb = lane + 32 < n && rb < p.k;
-                        const unsigned ma = __ballot_sync(0xffffffffu, ka), mb = __ballot_sync(0xffffffffu, kb);
-                        kept = __popc(ma) + __popc(mb);
-                        const unsigned below = (1u << lane) - 1u;
-                        if (ka) { dst[__popc(ma & below)] = a; mink = a; }
-                        if (kb) { dst[__popc(ma) + __popc(mb & below)] = b; mink = b < mink ? b : mink; }
-                    } else {
-                        if (n > p.k) {
-                            const int P2 = next_pow2(n);
-                            for (int i = n + lane; i < P2; i += 32) kq[i] = 0ull;
-                            __syncwarp();
-                            bitonic_sort_desc<true>(kq, P2, lane, 32);
-                        }
-                        kept = min(n, p.k);
-                        for (int i = lane; i < kept; i += 32) {
-                            const uint64_t x = kq[i];
-                            dst[i] = x;
-                            mink = x < mink ? x : mink;
+        fl_hand_over(p, it, qkeys, s_qcnt, s_qid, s_psl, warp, lane);
+        __syncthreads();
+    }
+}
+
+// ---- rows wider than 128 floats (d <= 1024) ---------------------------------------------------------------------
+// Same item / pool / threshold scheme; what changes is where the 16 queries live.  A lane cannot hold d/32 dimensions of 16
+// queries in registers, so the item's queries are staged in shared memory once, interleaved per 128-dimension chunk, and
+// the loop nest is turned inside out: a warp owns a block of 32 rows, walks the chunks, re-loads its query registers
+// once per (block, chunk) - 32 LDS.64 for 16 row pairs - and keeps the running (row, query) sums of the block in a
+// private strip of shared memory (lane i always touches the same 16 slots: no synchronisation).
+constexpr int FW_MAX_DIM = 1024;
+constexpr int FWR = 32;      // rows per warp and pass
+constexpr int FSEEDW = FSEED;  // rows sampled per query for the starting threshold: as many as for narrow rows - with 64 the
+                               // k-th of the sample let 15 % of a list through, most pairs overflowed their queue and the
+                               // redo kernel (one CTA per pair) ran for 0.75 s next to a 0.1 s scan
+
+template <int METRIC>
+__device__ __forceinline__ float warp_score_wide(const float* __restrict__ q, const float* __restrict__ x, int dim, int lane) {
+    float a = 0.f;
+    for (int c = lane * 4; c < dim; c += 128) {
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(q + c)), xv = __ldg(reinterpret_cast<const float4*>(x + c));
+        if (METRIC == kL2) {
+            const float d0 = qv.x - xv.x, d1 = qv.y - xv.y, d2 = qv.z - xv.z, d3 = qv.w - xv.w;
+            a = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, a))));
+        } else {
+            a = fmaf(qv.x, xv.x, fmaf(qv.y, xv.y, fmaf(qv.z, xv.z, fmaf(qv.w, xv.w, a))));
+        }
+    }
+    a = warp_sum(a);
+    return METRIC == kL2 ? -a : a;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256) ivf_lm_seed_wide_kernel(FlSeed a) {
+    const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= a.nq) return;
+    constexpr int U = FSEEDW / 32;
+    float sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sc[u] = -INFINITY;
+    const int want = FSEEDW;
+    int got = 0;
+    for (int pr = 0; pr < a.P && got < want; ++pr) {
+        const int64_t l = a.probes[q * a.P + pr];
+        if (l < 0) continue;
+        const int64_t beg = a.list_off[l], len = a.list_off[l + 1] - beg;
+        for (int64_t v = 0; v < len && got < want; ++v) {
+            if (a.dead && a.dead[beg + v]) continue;  // warp-uniform
+            float s = warp_score_wide<METRIC>(a.Q + q * a.dim, a.vecs + (beg + v) * a.dim, a.dim, lane);
+            if (METRIC == kCosine) s *= inv_norm(a.norms, beg + v);
+#pragma unroll
+            for (int w = 0; w < U; ++w)
+                if ((got >> 5) == w && (got & 31) == lane) sc[w] = s;
+            ++got;
+        }
+    }
+    if (got < a.k) return;  // fewer candidates than k so far: no threshold (everything is kept)
+    uint32_t o[U], lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        o[u] = sc[u] == -INFINITY ? 0u : score_to_ord(sc[u]);
+        if (o[u]) { lo = min(lo, o[u]); hi = max(hi, o[u]); }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    while (lo < hi) {  // k-th largest of the sampled scores
+        const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) c += o[u] >= mid;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= a.k) lo = mid; else hi = mid - 1u;
+    }
+    if (lane == 0) {
+        const float t = ord_to_score(lo);
+        const float tl = t - 2e-5f * fabsf(t) - 1e-30f;  // the scan kernel sums the same products in another order
+        a.pool_thr[q] = score_to_ord(tl) - 1u;
+    }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(FT, 2) ivf_lm_scan_wide_kernel(FlParams p, int nchunk) {
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    float2* s_q2 = reinterpret_cast<float2*>(fw_smem);                        // [nchunk][8 query pairs][4 dims][32 lanes]
+    float* s_part = reinterpret_cast<float*>(s_q2 + (size_t)nchunk * 1024);   // [8 warps][FWR rows x 16 queries]
+    __shared__ uint64_t qkeys[FG * FQC];
+    __shared__ int s_qcnt[FG];
+    __shared__ int s_qid[FG], s_psl[FG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_items = *p.n_items;
+    const int dim = p.dim;
+    if (tid < FG) s_qcnt[tid] = 0;
+    __syncthreads();
+
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int2 item = __ldg(&p.items[it]);
+        const int l = item.x, g = item.y;
+        const int64_t beg = __ldg(p.list_off + l), len = __ldg(p.list_off + l + 1) - beg;
+        const int pbeg = __ldg(p.pair_off + l), pend = __ldg(p.pair_off + l + 1);
+        if (tid < FG) {
+            const int idx = pbeg + FG * g + tid;
+            s_qid[tid] = idx < pend ? __ldg(p.pairq + idx) : -1;
+            s_psl[tid] = idx < pend ? __ldg(p.pairp + idx) : 0;
+        }
+        __syncthreads();
+        // the item's queries, pair (2j, 2j+1) interleaved: entry ((c*8 + j)*4 + d)*32 + lane = dimension c*128 + lane*4 + d
+        for (int i = tid; i < nchunk * 1024; i += FT) {
+            const int ln = i & 31, d = (i >> 5) & 3, j = (i >> 7) & 7, c = i >> 10;
+            const int dd = c * 128 + ln * 4 + d;
+            const int qa = s_qid[2 * j], qb = s_qid[2 * j + 1];
+            float a = 0.f, b = 0.f;
+            if (dd < dim) {
+                if (qa >= 0) a = __ldg(p.Q + (size_t)qa * dim + dd);
+                if (qb >= 0) b = __ldg(p.Q + (size_t)qb * dim + dd);
+            }
+            s_q2[i] = make_float2(a, b);
+        }
+        __syncthreads();
+        const int myq = s_qid[lane & 15];  // after the reduce-scatter a lane holds (row = lane / 16, query = lane % 16)
+        float thr = INFINITY;              // nothing passes for an empty slot
+        if (myq >= 0) {
+            const uint32_t u = __ldcg(p.pool_thr + myq);
+            thr = u ? ord_to_score(u) : -INFINITY;
+        }
+        const float4* rows = reinterpret_cast<const float4*>(p.vecs + (size_t)beg * dim);
+        const int rstride = dim / 4;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* part = s_part + warp * (FWR * 16);
+        for (int64_t rb = (int64_t)warp * FWR; rb < len; rb += (int64_t)(FT / 32) * FWR) {
+            const int npair = (int)min((int64_t)(FWR / 2), (len - rb + 1) / 2);
+            for (int c = 0; c < nchunk; ++c) {
+                unsigned long long qp[FG / 2][4];
+#pragma unroll
+                for (int j = 0; j < FG / 2; ++j)
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+                        qp[j][d] = *reinterpret_cast<const unsigned long long*>(&s_q2[((c * 8 + j) * 4 + d) * 32 + lane]);
+                const bool lane_on = c * 128 + lane * 4 < dim;
+                const float4* rc = rows + c * 32 + lane;
+                float4 n0 = zero4, n1 = zero4;
+                if (lane_on) n0 = __ldg(rc + rb * rstride);
+                if (lane_on && rb + 1 < len) n1 = __ldg(rc + (rb + 1) * rstride);
+#pragma unroll 1
+                for (int rp = 0; rp < npair; ++rp) {
+                    const float4 x0 = n0, x1 = n1;
+                    const int64_t vn = rb + 2 * (rp + 1);
+                    n0 = zero4; n1 = zero4;
+                    if (lane_on && rp + 1 < npair) n0 = __ldg(rc + vn * rstride);
+                    if (lane_on && rp + 1 < npair && vn + 1 < len) n1 = __ldg(rc + (vn + 1) * rstride);
+                    float vals[32];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float4 x = r ? x1 : x0;
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int j = 0; j < FG / 2; ++j) {
+                            unsigned long long acc = 0ull;
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) {
+                                if (METRIC == kL2) {
+                                    const unsigned long long df = fadd2(qp[j][d], pack2(-xs[d], -xs[d]));
+                                    acc = ffma2(df, df, acc);
+                                } else {
+                                    acc = ffma2(qp[j][d], pack2(xs[d], xs[d]), acc);
+                                }
+                            }
+                            unpack2(acc, vals[r * 16 + 2 * j], vals[r * 16 + 2 * j + 1]);
                         }
                     }
-                    if (lane == 0) p.pool_cnt[ps] = kept;
-                    if (kept >= p.k) {
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const uint64_t x = __shfl_xor_sync(0xffffffffu, mink, o);
-                            mink = x < mink ? x : mink;
+                    for (int s2 = 16; s2 >= 1; s2 >>= 1) {  // butterfly reduce-scatter: lane i ends with the total of value i
+                        const bool upper = (lane & s2) != 0;
+#pragma unroll
+                        for (int i = 0; i < s2; ++i) {
+                            const float send = upper ? vals[i] : vals[i + s2];
+                            const float keep = upper ? vals[i + s2] : vals[i];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
                         }
-                        if (lane == 0) atomicMax(p.pool_thr + q, (uint32_t)(mink >> 32));
+                    }
+                    float* ps = part + rp * 32 + lane;  // (row 2 rp + lane / 16, query lane % 16)
+                    *ps = c == 0 ? vals[0] : *ps + vals[0];
+                }
+            }
+            for (int rp = 0; rp < npair; ++rp) {
+                const int64_t row = rb + 2 * rp + (lane >> 4);
+                float score = part[rp * 32 + lane];
+                if (METRIC == kL2) score = -score;
+                if (METRIC == kCosine && row < len) score *= inv_norm(p.norms, beg + row);
+                if (row < len && score > thr) {
+                    const int64_t gpos = beg + row;
+                    if (!(p.dead && p.dead[gpos])) {
+                        const int j = lane & 15;
+                        const int pos = atomicAdd(&s_qcnt[j], 1);
+                        if (pos < FQC) qkeys[j * FQC + pos] = make_key(score, (uint32_t)gpos);
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) s_qcnt[j] = 0;
         }
+        __syncthreads();
+        fl_hand_over(p, it, qkeys, s_qcnt, s_qid, s_psl, warp, lane);
         __syncthreads();
     }
 }
@@ -383,13 +590,15 @@ __global__ void __launch_bounds__(256) ivf_lm_redo_kernel(FlRedo a) {
         if (tid == 0) s_thr = (uint64_t)__ldcg(a.pool_thr + en.x) << 32;  // keys at or below it cannot be in the top k
         __syncthreads();
         float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane * 4 < a.dim) qv = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)en.x * a.dim) + lane);
+        const bool wide = a.dim > 128;
+        if (!wide && lane * 4 < a.dim) qv = __ldg(reinterpret_cast<const float4*>(a.Q + (size_t)en.x * a.dim) + lane);
         for (int64_t c0 = 0; c0 < len; c0 += 256) {
             if (s_cnt + 256 > FREDO_QCAP) Qu.prune(tid, 256);
             for (int64_t v = c0 + warp; v < min(len, c0 + 256); v += 8) {
                 float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane * 4 < a.dim) xv = __ldg(reinterpret_cast<const float4*>(a.vecs + (beg + v) * a.dim) + lane);
-                float s = warp_score<METRIC>(qv, xv);
+                if (!wide && lane * 4 < a.dim) xv = __ldg(reinterpret_cast<const float4*>(a.vecs + (beg + v) * a.dim) + lane);
+                float s = wide ? warp_score_wide<METRIC>(a.Q + (size_t)en.x * a.dim, a.vecs + (beg + v) * a.dim, a.dim, lane)
+                               : warp_score<METRIC>(qv, xv);
                 if (METRIC == kCosine) s *= inv_norm(a.norms, beg + v);
                 if (lane == 0 && !(a.dead && a.dead[beg + v])) Qu.push(make_key(s, (uint32_t)(beg + v)));
             }
@@ -540,7 +749,12 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
     FlSeed sd{};
     sd.Q = p.Q; sd.nq = p.nq; sd.dim = p.dim; sd.probes = p.probes; sd.P = P; sd.vecs = p.vecs; sd.dead = p.dead;
     sd.list_off = p.list_off; sd.pool_thr = pool_thr; sd.k = p.k; sd.norms = p.norms;
-    if (p.k <= FSEED) ivf_lm_seed_kernel<METRIC><<<(unsigned)((p.nq + 7) / 8), 256, 0, st>>>(sd);
+    const bool wide = p.dim > 128;
+    if (wide) {
+        if (p.k <= FSEEDW) ivf_lm_seed_wide_kernel<METRIC><<<(unsigned)((p.nq + 7) / 8), 256, 0, st>>>(sd);
+    } else if (p.k <= FSEED) {
+        ivf_lm_seed_kernel<METRIC><<<(unsigned)((p.nq + 7) / 8), 256, 0, st>>>(sd);
+    }
 
     FlParams sp{};
     sp.Q = p.Q; sp.dim = p.dim; sp.vecs = p.vecs; sp.dead = p.dead; sp.list_off = p.list_off;
@@ -548,7 +762,15 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
     sp.pool = pool; sp.pool_cnt = pool_cnt; sp.pool_thr = pool_thr; sp.pslots = P; sp.k = p.k;
     sp.redo = redo; sp.redo_cnt = redo_cnt; sp.norms = p.norms;
     if (p.ev_k0) cudaEventRecord(p.ev_k0, st);
-    ivf_lm_scan_kernel<METRIC><<<(unsigned)std::min<int64_t>(2 * num_sms, L.max_items), FT, 0, st>>>(sp);
+    if (wide) {
+        const int nchunk = (p.dim + 127) / 128;
+        const size_t wsm = (size_t)nchunk * 1024 * sizeof(float2) + (size_t)(FT / 32) * FWR * 16 * sizeof(float);
+        e = cudaFuncSetAttribute(ivf_lm_scan_wide_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+        if (e != cudaSuccess) return e;
+        ivf_lm_scan_wide_kernel<METRIC><<<(unsigned)std::min<int64_t>(2 * num_sms, L.max_items), FT, wsm, st>>>(sp, nchunk);
+    } else {
+        ivf_lm_scan_kernel<METRIC><<<(unsigned)std::min<int64_t>(2 * num_sms, L.max_items), FT, 0, st>>>(sp);
+    }
     if (p.ev_k1) cudaEventRecord(p.ev_k1, st);
 
     FlRedo rd{};
@@ -571,7 +793,7 @@ cudaError_t launch_fl(const IvfFlatScanParams& p, int nlist, void* scratch, int 
 
 bool ivfflat_lm_supported(int dim, int metric, int nprobe, int k, int64_t nq, int64_t list_total, bool has_budget) {
     if (has_budget || (metric != kL2 && metric != kIP && metric != kCosine)) return false;
-    if (dim % 4 != 0 || dim > 128 || dim < 4) return false;
+    if (dim % 4 != 0 || dim > FW_MAX_DIM || dim < 4) return false;  // d > 128: the wide kernels (queries staged in shared memory)
     if (k < 1 || k > kMaxTopK || (int64_t)nprobe * k > 16384) return false;
     if (nq * nprobe >= ((int64_t)1 << 29) || list_total >= ((int64_t)1 << 32)) return false;
     return true;

@@ -121,3 +121,33 @@ def test_ivf_lm_cosine_matches_oracle(gpu):
         sc, rows, cnt = ix.search(Q, k, nprobe=nprobe)
         assert ix.last_search_kernel()[0] == "ivf_lm_scan_kernel"
         assert_batch_equivalent(ref.search_batch(Q, k, nprobe=nprobe), (rows, sc, cnt), ctx=f"ivf lm cosine k={k} nprobe={nprobe}")
+
+
+# ------------------------------------------------------------------------------------------------
+# rows wider than 128 floats: queries staged in shared memory, 128-dimension chunks (ivf_lm_scan_wide_kernel)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,metric", [(256, "l2"), (768, "ip"), (136, "l2"), (384, "cos"), (1024, "l2")])
+def test_ivfflat_lm_wide_rows(gpu, dim, metric):
+    mo, mg = {"l2": (orc.L2, gpu.L2), "ip": (orc.IP, gpu.INNER_PRODUCT), "cos": (orc.COSINE, gpu.COSINE)}[metric]
+    base = orc.random_vectors(6_000, dim, 50 + dim)
+    q = orc.random_vectors(130, dim, 51 + dim)
+    ref, ix = _pair(gpu, base, dim, 16, mo, mg)
+    for k, nprobe in ((10, 3), (100, 6), (1, 16), (600, 2)):   # k = 600 > the seed sample: cold start + redo path
+        rid, rsc, rcn = ref.search_batch(q, k, nprobe=nprobe)
+        gid, gsc, gcn = _s(ix, q, k, nprobe=nprobe)
+        assert ix.last_search_kernel()[0] == "ivf_lm_scan_kernel"
+        assert_batch_equivalent((rid, rsc, rcn), (gid, gsc, gcn), ctx=f"ivf lm wide d={dim} {metric} k={k} nprobe={nprobe}")
+        same = rid == gid
+        assert same.mean() > 0.99
+        np.testing.assert_array_equal(rsc[same], gsc[same])   # survivors re-scored in the reference's order
+
+
+def test_ivfflat_lm_wide_rows_with_deletes_and_ragged_lists(gpu):
+    dim = 320
+    base = orc.random_vectors(5_000, dim, 77)
+    q = orc.random_vectors(90, dim, 78)
+    ref, ix = _pair(gpu, base, dim, 24, orc.L2, gpu.L2)     # ~208 rows per list: blocks of 32 rows end ragged, odd lengths
+    rng = np.random.default_rng(3)
+    for r in (int(x) for x in rng.choice(5_000, 200, replace=False)):
+        assert ref.delete(r) and ix.delete_row(r)
+    assert_batch_equivalent(ref.search_batch(q, 10, nprobe=8), _s(ix, q, 10, nprobe=8), ctx="ivf lm wide deletes")
