@@ -126,12 +126,15 @@ int pyrope_peer_group_create(int world, int rank, size_t slot_bytes, int n_slots
 
 int pyrope_peer_group_destroy(pyrope_peer_group* g) {
     if (!g) return PYROPE_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(g->device);
     cudaDeviceSynchronize();
     if (g->ipc)
         for (int r = 0; r < g->world; ++r)
             if (r != g->rank && g->peers[r]) cudaIpcCloseMemHandle(g->peers[r]);
     if (g->local) cudaFree(g->local);
+    if (prev >= 0) cudaSetDevice(prev);  // the caller's current device is not ours to change
     delete g;
     return PYROPE_OK;
 }
@@ -194,7 +197,7 @@ int pyrope_peer_allgather_device(pyrope_peer_group* g, int slot, const void* d_s
     if (bytes_per_rank == 0 || bytes_per_rank > g->slot_bytes || (bytes_per_rank & 15) || (reinterpret_cast<uintptr_t>(d_src) & 15))
         return pfail(PYROPE_ERR_INVALID_ARG, "contribution must be 16-byte aligned, a multiple of 16 bytes and at most %zu bytes", g->slot_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned long long epoch = ++g->epoch[slot];
+    const unsigned long long epoch = g->epoch[slot] + 1;  // committed below, once both kernels are enqueued
     // [slot][parity][rank][bytes_per_rank]: the ranks' contributions are contiguous, like an all-gather's output
     const size_t half = kFlagBytes + ((size_t)slot * 2 + (epoch & 1)) * g->world * g->slot_bytes;
     PeerPtrs pp{};
@@ -205,6 +208,7 @@ int pyrope_peer_allgather_device(pyrope_peer_group* g, int slot, const void* d_s
                                                                         static_cast<const uint4*>(d_src), n16);
     peer_signal_wait_kernel<<<1, 32, 0, st>>>(pp, g->world, g->rank, slot, epoch);
     PCK(cudaGetLastError());
+    g->epoch[slot] = epoch;
     *d_gathered_out = g->local + half;
     return PYROPE_OK;
 }
