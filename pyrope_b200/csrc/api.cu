@@ -1047,11 +1047,14 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
             static const bool no_f16 = getenv("PYROPE_FLAT_TF32") != nullptr;
             if (!no_f16 && h->metric != kCosine && dim % 8 == 0) {
                 if (op.h16_rows < n_rows) {
-                    // the copy covers whole tables only (rows appended since are converted together with the rest)
-                    TRY(op.h16.ensure(sizeof(uint16_t) * (size_t)n_rows * dim, 0, st));
+                    // rows appended since the last search are converted on their own (an in-place change invalidates the
+                    // operand and starts from row 0); the running maximum covers every row converted so far
+                    const int64_t from = op.h16_rows;
+                    TRY(op.h16.ensure(sizeof(uint16_t) * (size_t)n_rows * dim, sizeof(uint16_t) * (size_t)from * dim, st));
                     TRY(op.xabs.ensure(sizeof(float), 0, st, true));
-                    CK(cudaMemsetAsync(op.xabs.p, 0, sizeof(float), st));
-                    CK(launch_tc_half(X, n_rows * dim, op.h16.p, op.xabs.as<float>(), st));
+                    if (from == 0) CK(cudaMemsetAsync(op.xabs.p, 0, sizeof(float), st));
+                    CK(launch_tc_half(X + (size_t)from * dim, (n_rows - from) * dim, op.h16.as<uint16_t>() + (size_t)from * dim,
+                                      op.xabs.as<float>(), st));
                     float xabs = 0.f;
                     CK(cudaMemcpyAsync(&xabs, op.xabs.p, sizeof(float), cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));

@@ -232,3 +232,26 @@ def test_flat_one_term_fp16_range_edges(gpu):
     q = (rng.random((40, 264), dtype=np.float32) * mag).astype(np.float32)
     assert_batch_equivalent(ref.search_batch(q, 20), _s(ix, q, 20), ctx="table beyond fp16")
     assert ix.last_search_kernel()[0] == "flat_tc_kernel (1xTF32 + band)"
+
+
+def test_flat_one_term_fp16_follows_appends_and_updates(gpu):
+    """The fp16 copy is derived state: rows appended between searches are converted on their own, an in-place update
+    starts it over.  Both must show up in the next search."""
+    rng = np.random.default_rng(312)
+    base = rng.random((66_000, 264), dtype=np.float32)
+    ref, ix = _flat_pair(gpu, orc.IP, base)
+    q = rng.random((64, 264), dtype=np.float32)
+    assert_batch_equivalent(ref.search_batch(q, 10), _s(ix, q, 10), ctx="before appends")
+    assert ix.last_search_kernel()[0] == "flat_tc_kernel (1xFP16 + band)"
+    more = (q[:20] * np.float32(1.5)).astype(np.float32)          # the new best matches of the first 20 queries
+    ref.add_batch(more, ids=np.arange(66_000, 66_020))
+    ix.add(more)
+    got = _s(ix, q, 10)
+    assert_batch_equivalent(ref.search_batch(q, 10), got, ctx="after appends")
+    assert (got[0][:20, 0] == np.arange(66_000, 66_020)).all()
+    upd = (q[30] * np.float32(3.0)).astype(np.float32)             # an in-place update of an old row
+    ref.upsert(5, upd)
+    ix.update_row(5, upd)
+    got = _s(ix, q, 10)
+    assert_batch_equivalent(ref.search_batch(q, 10), got, ctx="after an update")
+    assert got[0][30, 0] == 5
