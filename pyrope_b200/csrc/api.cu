@@ -1050,7 +1050,13 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                     // rows appended since the last search are converted on their own (an in-place change invalidates the
                     // operand and starts from row 0); the running maximum covers every row converted so far
                     const int64_t from = op.h16_rows;
-                    TRY(op.h16.ensure(sizeof(uint16_t) * (size_t)n_rows * dim, sizeof(uint16_t) * (size_t)from * dim, st));
+                    if (op.h16.ensure(sizeof(uint16_t) * (size_t)n_rows * dim, sizeof(uint16_t) * (size_t)from * dim, st) != PYROPE_OK) {
+                        // no room for another half-size copy of the table: the tf32 pass needs none
+                        op.h16.release();
+                        op.h16_ok = false;
+                        op.h16_rows = n_rows;
+                        goto half_done;
+                    }
                     TRY(op.xabs.ensure(sizeof(float), 0, st, true));
                     if (from == 0) CK(cudaMemsetAsync(op.xabs.p, 0, sizeof(float), st));
                     CK(launch_tc_half(X + (size_t)from * dim, (n_rows - from) * dim, op.h16.as<uint16_t>() + (size_t)from * dim,
@@ -1062,7 +1068,8 @@ int search_device(Index* h, int64_t nq, const float* dQ, int topk, int64_t max_s
                     op.h16_rows = n_rows;
                     ++launches;
                 }
-                if (op.h16_ok) {
+            half_done:
+                if (op.h16_ok && op.h16.p) {
                     TRY(ws.q16.ensure(sizeof(uint16_t) * (size_t)nq * dim, 0, st));
                     TRY(ws.qbad.ensure((size_t)nq, 0, st));
                     CK(launch_tc_half_rows(dQ, nq, dim, ws.q16.p, ws.qbad.as<uint8_t>(), st));
