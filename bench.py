@@ -345,6 +345,12 @@ def oracle_index_from_gpu(ix, w: dict, torch=None):
         o.add_batch(base_rows_host(torch, w, w["n"]))
         o.build()
         return o, w["n"], "an oracle-built index over the same rows"
+    if w["kind"] == "IVF_FLAT" and w["n"] * w["dim"] * 4 <= (12 << 30):  # the rows fit on the host twice over
+        o = orc.IvfFlatIndex(w["dim"], metric, nlist=w["nlist"])
+        off, rows, _ = ix.lists()
+        base = base_rows_host(torch, w, w["n"])
+        o.adopt(ix.centroids(), off, rows, base[rows])   # list-major copy of the same rows
+        return o, w["n"], "the GPU-built index (same centroids and lists)"
     raise NotImplementedError
 
 

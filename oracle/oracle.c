@@ -1085,6 +1085,37 @@ void orc_ivfflat_get_list(const orc_ivfflat *ix, int list, int64_t *ids_out) {
     memcpy(ids_out, ix->lists[list].ids, sizeof(int64_t) * (size_t)ix->lists[list].n);
 }
 
+/* Test infrastructure: take over centroids and inverted lists built elsewhere (the GPU index under test), so that a
+ * search compares the scan alone at sizes where re-running k-means on the CPU would take hours.  vecs is list-major like
+ * ids; norms are recomputed the way Add does (:347). */
+void orc_ivfflat_adopt(orc_ivfflat *ix, int nlist, const float *centroids, const int64_t *offs, const int64_t *ids,
+                       const float *vecs) {
+    int dim = ix->dim;
+    ivfflat_free_lists(ix);
+    ix->nc = nlist;
+    ix->centroids = (float *)malloc(sizeof(float) * (size_t)nlist * (size_t)dim);
+    memcpy(ix->centroids, centroids, sizeof(float) * (size_t)nlist * (size_t)dim);
+    ix->cnorms = (float *)malloc(sizeof(float) * (size_t)nlist);
+    for (int c = 0; c < nlist; c++)
+        ix->cnorms[c] = ix->metric == ORC_COSINE ? orc_norm(ix->centroids + (size_t)c * dim, dim) : 0.0f;
+    ix->lists = (flist_t *)calloc((size_t)nlist, sizeof(flist_t));
+    for (int c = 0; c < nlist; c++) {
+        int64_t n = offs[c + 1] - offs[c];
+        flist_t *l = &ix->lists[c];
+        l->n = l->cap = (int)n;
+        if (n == 0) continue;
+        l->ids = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+        l->vecs = (float *)malloc(sizeof(float) * (size_t)n * (size_t)dim);
+        l->norms = (float *)malloc(sizeof(float) * (size_t)n);
+        memcpy(l->ids, ids + offs[c], sizeof(int64_t) * (size_t)n);
+        memcpy(l->vecs, vecs + (size_t)offs[c] * (size_t)dim, sizeof(float) * (size_t)n * (size_t)dim);
+        for (int64_t i = 0; i < n; i++)
+            l->norms[i] = ix->metric == ORC_COSINE ? orc_norm(l->vecs + (size_t)i * dim, dim) : 0.0f;
+    }
+    ndict_clear(&ix->buffer);
+    ix->built = 1;
+}
+
 /* rank all centroids: score each (:186-193), List.Sort descending (:196) */
 static res_t *rank_centroids(int metric, const float *q, float qn, const float *cent,
                              const float *cnorms, int nc, int dim) {

@@ -95,6 +95,9 @@ int orc_ivfflat_delete(orc_ivfflat *ix, int64_t id);             /* :62-83 */
 void orc_ivfflat_build(orc_ivfflat *ix);                         /* :85-145 */
 int orc_ivfflat_is_built(const orc_ivfflat *ix);
 int orc_ivfflat_ncentroids(const orc_ivfflat *ix);
+/* test infrastructure: adopt centroids and inverted lists (offsets [nlist+1], ids / vecs list-major) built elsewhere */
+void orc_ivfflat_adopt(orc_ivfflat *ix, int nlist, const float *centroids, const int64_t *offs, const int64_t *ids,
+                       const float *vecs);
 void orc_ivfflat_get_centroids(const orc_ivfflat *ix, float *out);
 int orc_ivfflat_count(const orc_ivfflat *ix);                    /* GetStats :300-312 */
 int orc_ivfflat_list_size(const orc_ivfflat *ix, int list);

@@ -87,6 +87,7 @@ def lib():
     sig("orc_ivfflat_ncentroids", C.c_int, vp)
     sig("orc_ivfflat_get_centroids", None, vp, f32p)
     sig("orc_ivfflat_count", C.c_int, vp)
+    sig("orc_ivfflat_adopt", None, vp, C.c_int, f32p, i64p, i64p, f32p)
     sig("orc_ivfflat_list_size", C.c_int, vp, C.c_int)
     sig("orc_ivfflat_get_list", None, vp, C.c_int, i64p)
     sig("orc_ivfflat_search", C.c_int, vp, f32p, C.c_int, C.c_int64, C.c_int, i64p, f32p)
@@ -388,6 +389,15 @@ class IvfFlatIndex(_Index):
 
     def count(self):
         return lib().orc_ivfflat_count(self._h)
+
+    def adopt(self, centroids, list_offsets, ids, vecs):
+        """Take over an index built elsewhere (the GPU index under test): searches then compare the scan alone."""
+        c, pc = _f32(centroids)
+        off, poff = _i64(list_offsets)
+        ids, pids = _i64(ids)
+        v, pv = _f32(vecs)
+        assert v.shape == (len(ids), self.dim) and off[-1] == len(ids)
+        lib().orc_ivfflat_adopt(self._h, c.shape[0], pc, poff, pids, pv)
 
     def lists(self):
         nc = lib().orc_ivfflat_ncentroids(self._h)

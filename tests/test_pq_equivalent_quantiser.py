@@ -43,3 +43,23 @@ def test_sixteen_table_view_gives_the_same_adc_distance(dim, m):
         # and the pieces really are pieces: every table of the original is the sum of its 16/m virtual tables
         per = 16 // m
         np.testing.assert_allclose(t16.reshape(m, per, k).astype(np.float64).sum(axis=1), t.astype(np.float64), rtol=2e-6, atol=1e-7)
+
+
+def test_ivfflat_adopt_reproduces_the_built_index():
+    """orc_ivfflat_adopt (what bench.py uses to hand a GPU-built IVF_FLAT index to the oracle at sizes where CPU k-means
+    would take hours): an index rebuilt from another one's centroids and lists answers identically."""
+    for metric in (orc.L2, orc.IP, orc.COSINE):
+        base = orc.random_vectors(3_000, 24, 9)
+        a = orc.IvfFlatIndex(24, metric, nlist=12)
+        a.add_batch(base)
+        a.build()
+        lists = a.lists()
+        off = np.zeros(len(lists) + 1, np.int64)
+        off[1:] = np.cumsum([len(x) for x in lists])
+        ids = np.concatenate(lists)
+        b = orc.IvfFlatIndex(24, metric, nlist=12)
+        b.adopt(a.centroids(), off, ids, base[ids])
+        q = orc.random_vectors(40, 24, 10)
+        ra, rb = a.search_batch(q, 10, nprobe=4), b.search_batch(q, 10, nprobe=4)
+        for x, y in zip(ra, rb):
+            np.testing.assert_array_equal(x, y)
